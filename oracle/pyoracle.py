@@ -1,0 +1,206 @@
+"""ctypes door onto oracle/liboracle.so and oracle/_ref/*.so -- TEST INFRASTRUCTURE ONLY.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs.  The product never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PC_NONE, PC_DIAG, PC_ILU0, PC_SPLIT = 0, 1, 2, 3
+
+_DT = {"f32": np.float32, "f64": np.float64, "f32f64": np.float32}
+_FT = {"f32": np.float32, "f64": np.float64, "f32f64": np.float64}
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) or (
+        os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(_HERE, "_ref", "libilupp.so"))
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-j4"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+_ilupp = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+    return _lib
+
+
+def ref():
+    """Reference's own CPU translation units (oracle/_ref/libref.so); None if not built."""
+    global _ref
+    p = os.path.join(_HERE, "_ref", "libref.so")
+    if _ref is None and os.path.exists(p):
+        _ref = C.CDLL(p)
+    return _ref
+
+
+def ilupp():
+    global _ilupp
+    p = os.path.join(_HERE, "_ref", "libilupp.so")
+    if _ilupp is None and os.path.exists(p):
+        _ilupp = C.CDLL(p)
+        _ilupp.ilupp_create.restype = C.c_void_p
+    return _ilupp
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _PcStruct(C.Structure):
+    _fields_ = [("kind", C.c_int), ("n", C.c_int), ("dinv", C.c_void_p), ("lv", C.c_void_p), ("uv", C.c_void_p),
+                ("lp", C.c_void_p), ("li", C.c_void_p), ("up", C.c_void_p), ("ui", C.c_void_p),
+                ("middle", C.c_void_p), ("lscale", C.c_void_p), ("rscale", C.c_void_p),
+                ("permRow", C.c_void_p), ("permCol", C.c_void_p)]
+
+
+class Precond:
+    """Flat description of a reference Preconditioner object for the oracle."""
+
+    def __init__(self, kind, n, mode="f64", **kw):
+        self.kind, self.n, self.mode = kind, n, mode
+        R, F = _DT[mode], _FT[mode]
+        self._keep = {}
+        s = _PcStruct()
+        s.kind, s.n = kind, n
+        for name, dt in (("dinv", R), ("lv", F), ("uv", F), ("middle", R), ("lscale", R), ("rscale", R)):
+            if kw.get(name) is not None:
+                self._keep[name] = np.ascontiguousarray(kw[name], dtype=dt)
+                setattr(s, name, self._keep[name].ctypes.data)
+        for name in ("lp", "li", "up", "ui", "permRow", "permCol"):
+            if kw.get(name) is not None:
+                self._keep[name] = _i32(kw[name])
+                setattr(s, name, self._keep[name].ctypes.data)
+        self.struct = s
+
+    def apply(self, which, vec):
+        R = _DT[self.mode]
+        vin = np.ascontiguousarray(vec, dtype=R)
+        out = np.zeros_like(vin)
+        getattr(lib(), "orc_precond_apply_" + self.mode)(C.byref(self.struct), C.c_int(which), _p(vin), _p(out))
+        return out
+
+
+def spmv(rowptr, col, val, x, mode="f64"):
+    R = _DT[mode]
+    val = np.ascontiguousarray(val, dtype=R); x = np.ascontiguousarray(x, dtype=R)
+    out = np.zeros(len(rowptr) - 1, dtype=R)
+    getattr(lib(), "orc_spmv_" + ("f32" if R == np.float32 else "f64"))(
+        _p(out), _p(val), _p(_i32(rowptr)), _p(_i32(col)), _p(x), C.c_int(len(rowptr) - 1))
+    return out
+
+
+def generate_level(rowptr, col, val, mode="f32"):
+    """leftILU.cu generateLevel + bucketing -> (level, levelPtr, nodes)."""
+    R = _DT[mode]; n = len(rowptr) - 1
+    val = np.ascontiguousarray(val, dtype=R)
+    level = np.zeros(n, dtype=np.int32)
+    getattr(lib(), "orc_generate_level_" + mode)(C.c_int(n), _p(val), _p(_i32(rowptr)), _p(_i32(col)), _p(level))
+    return (level,) + bucket_levels(level)
+
+
+def bucket_levels(level):
+    level = _i32(level); n = len(level)
+    nl = int(level.max()) + 1 if n else 0
+    lp = np.zeros(nl + 1, dtype=np.int32); nodes = np.zeros(n, dtype=np.int32)
+    lib().orc_bucket_levels(C.c_int(n), _p(level), _p(lp), _p(nodes))
+    return lp, nodes
+
+
+def get_level(is_l, rowptr, col, val, mode="f32"):
+    R = _DT[mode]; n = len(rowptr) - 1
+    val = np.ascontiguousarray(val, dtype=R)
+    level = np.zeros(n, dtype=np.int32)
+    getattr(lib(), "orc_get_level_" + mode)(C.c_int(int(is_l)), _p(val), _p(_i32(rowptr)), _p(_i32(col)), _p(level), C.c_int(n))
+    return level
+
+
+def ilu0(rowptr, col, val, mode="f32"):
+    """leftILU CPU semantics.  Returns dict(lp,li,lv,up,ui,uv,level,levelPtr,nodes,fval,fcol)."""
+    R = _DT[mode]; n = len(rowptr) - 1; nnz = int(rowptr[-1])
+    rowptr, col = _i32(rowptr), _i32(col); val = np.ascontiguousarray(val, dtype=R)
+    f = getattr(lib(), "orc_ilu0_" + mode)
+    lp = np.zeros(n + 1, dtype=np.int32); up = np.zeros(n + 1, dtype=np.int32)
+    nl = C.c_int(0)
+    f(C.c_int(n), _p(val), _p(rowptr), _p(col), _p(lp), None, None, _p(up), None, None, None, C.byref(nl), None, None, None, None)
+    lv = np.zeros(lp[-1], dtype=R); li = np.zeros(lp[-1], dtype=np.int32)
+    uv = np.zeros(up[-1], dtype=R); ui = np.zeros(up[-1], dtype=np.int32)
+    level = np.zeros(n, dtype=np.int32); levelPtr = np.zeros(nl.value + 1, dtype=np.int32)
+    nodes = np.zeros(n, dtype=np.int32); fval = np.zeros(nnz, dtype=R); fcol = np.zeros(nnz, dtype=np.int32)
+    f(C.c_int(n), _p(val), _p(rowptr), _p(col), _p(lp), _p(lv), _p(li), _p(up), _p(uv), _p(ui), _p(level),
+      C.byref(nl), _p(levelPtr), _p(nodes), _p(fval), _p(fcol))
+    return dict(lp=lp, li=li, lv=lv, up=up, ui=ui, uv=uv, level=level, levelPtr=levelPtr, nodes=nodes,
+                fval=fval, fcol=fcol)
+
+
+def gmres(rowptr, col, val, b, x0, m, max_iter, tol, pc: Precond, hist_cap=0):
+    """Reference host GMRES / GMRESilu.  Returns (flag, x, iters, resid, hist)."""
+    mode = pc.mode; R = _DT[mode]; n = len(rowptr) - 1
+    val = np.ascontiguousarray(val, dtype=R); b = np.ascontiguousarray(b, dtype=R)
+    x = np.array(x0, dtype=R, copy=True)
+    it = C.c_int(max_iter)
+    t = (C.c_float if R == np.float32 else C.c_double)(tol)
+    hist = np.zeros(max(hist_cap, 1), dtype=R); hl = C.c_int(0)
+    fn = getattr(lib(), "orc_gmres_" + mode); fn.restype = C.c_int
+    flag = fn(_p(val), _p(_i32(rowptr)), _p(_i32(col)), _p(x), _p(b), C.c_int(n), C.c_int(m), C.byref(it),
+              C.byref(t), C.byref(pc.struct), _p(hist), C.c_int(hist_cap), C.byref(hl))
+    return flag, x, it.value, t.value, hist[: hl.value].copy()
+
+
+def partition(Ap, Ai, npart, n_nodes):
+    m = len(Ap) - 1
+    Ap = np.ascontiguousarray(Ap, dtype=np.int64); Ai = np.ascontiguousarray(Ai, dtype=np.int64)
+    ps = np.zeros(npart + 1, dtype=np.int64); npt = np.zeros(m, dtype=np.int64)
+    pinv = np.zeros(m, dtype=np.int64); q = np.zeros(m, dtype=np.int64)
+    lib().orc_partition(C.c_int64(m), _p(Ap), _p(Ai), C.c_int(npart), C.c_int64(n_nodes), _p(ps), _p(npt), _p(pinv), _p(q))
+    return ps, npt, pinv, q
+
+
+def ilupp_factor(n, Ap, Ai, Ax, threshold=1.2, mem_factor=1.0):
+    """Run the reference's vendored ILU++ (oracle/_ref/libilupp.so) like mna_solve_gpu_gmres.cpp:316-405."""
+    L = ilupp()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libilupp.so not built")
+    Ap = _i32(Ap); Ai = _i32(Ai); Ax = np.ascontiguousarray(Ax, dtype=np.float64)
+    h = C.c_void_p(L.ilupp_create(C.c_int(n), _p(Ap), _p(Ai), _p(Ax), C.c_double(threshold), C.c_double(mem_factor)))
+    nl, nu, fill = C.c_int(0), C.c_int(0), C.c_double(0)
+    L.ilupp_sizes(h, C.byref(nl), C.byref(nu), C.byref(fill))
+    r = dict(lp=np.zeros(n + 1, np.int32), li=np.zeros(nl.value, np.int32), lv=np.zeros(nl.value),
+             up=np.zeros(n + 1, np.int32), ui=np.zeros(nu.value, np.int32), uv=np.zeros(nu.value),
+             middle=np.zeros(n), permRow=np.zeros(n, np.int32), permCol=np.zeros(n, np.int32),
+             lscale=np.zeros(n), rscale=np.zeros(n))
+    L.ilupp_get(h, *[_p(r[k]) for k in ("lp", "li", "lv", "up", "ui", "uv", "middle", "permRow", "permCol", "lscale", "rscale")])
+    r["fill"] = fill.value
+    r["_handle"] = h
+    return r
+
+
+def ilupp_gmres(fac, b, restart=100, max_iter=6000, rel_tol=8.0, abs_tol=8.0):
+    L = ilupp(); n = len(b)
+    b = np.ascontiguousarray(b, dtype=np.float64); x = np.zeros(n)
+    rt, at = C.c_double(rel_tol), C.c_double(abs_tol)
+    L.ilupp_gmres.restype = C.c_int
+    it = L.ilupp_gmres(fac["_handle"], _p(b), _p(x), C.c_int(restart), C.c_int(max_iter), C.byref(rt), C.byref(at))
+    return x, it, rt.value, at.value
+
+
+def ilupp_free(fac):
+    ilupp().ilupp_destroy(fac.pop("_handle"))
