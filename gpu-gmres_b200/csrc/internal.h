@@ -1,0 +1,163 @@
+// internal.h -- shared declarations of libb200gmres (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b200gmres.h"
+#include "../host/host_algos.h"
+
+namespace bg {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define BG_CUDA(call)                                                    \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return bg::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define BG_TRY(call)              \
+  do {                            \
+    int rc__ = (call);            \
+    if (rc__ < 0) return rc__;    \
+  } while (0)
+
+inline size_t dtype_size(int dt) { return dt == BG_F64 ? 8 : 4; }
+
+// simple owning device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t b);
+  int upload(const void* h, size_t b, cudaStream_t s);
+  void release();
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace bg
+
+struct bg_context_s {
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  size_t smem_optin = 0;
+};
+
+struct bg_matrix_s {
+  bg_context_t ctx = nullptr;
+  int n = 0, dtype = BG_F64, format = BG_SPMV_CSR_VECTOR, lanes = 4;
+  int64_t nnz = 0;
+  bg::SpmvPlan plan;
+  bg::DevBuf rp, ci, val;            // CSR
+  bg::DevBuf s_ptr, s_col, s_val;    // sliced ELL
+  int sell_rpt = 1, sell_height = 32, sell_slices = 0;
+};
+
+// ---- device-side argument bundles --------------------------------------------------------
+namespace bg {
+
+struct TrsvXform {      // prologue / epilogue of the split preconditioner
+  int pro = 0;          // 0 plain, 1 left-split (in[perm]/lscale[perm]), 2 right-split (in*middle)
+  int epi = 0;          // 0 plain, 1 right-split scatter (out[ipc[r]] = x/rscale[ipc[r]])
+  const int* perm = nullptr;   // permRow (pro 1) / inverse permCol (epi 1)
+  const void* scale_pro = nullptr;  // lscale or middle   (vector dtype)
+  const void* scale_epi = nullptr;  // rscale
+};
+
+struct LevelStreamDev {
+  int n = 0, n_levels = 0, max_level_rows = 0;
+  DevBuf lev_ptr, lev_K, lev_off, rows, cols, vals, diag;
+  std::vector<int> seg_begin, seg_end, seg_single, h_lev_ptr;
+  std::vector<int> level;
+  int64_t bytes = 0;
+};
+
+struct BlockStreamDev {
+  int n = 0, nblocks = 0, K = 0, CS = 0, max_rows = 0, max_levels = 0;
+  int64_t chunk_bytes = 0, bytes = 0;
+  DevBuf grow, blk_row_ptr, blk_lev_ptr, lev_slot, blk_chunk_ptr, stream;
+};
+
+// state shared by the orthogonalisation / Givens kernels (all double, device memory)
+struct GmresDev {
+  int* flags;      // [0] converged (1 in-cycle, 2 at residual check) [1] k_conv [2] iters
+                   // [3] reorth_flag [4] reorth_count [5] breakdown [6] restarts
+  double* scal;    // [0] normb [1] beta [2] resid [3] scale [4] tol [5] eta^2 [6] ww
+  double *h, *h2, *y, *H, *s, *cs, *sn, *partial, *hist;
+  unsigned* ticket;
+  int m, hist_cap, partial_ld;
+};
+enum { F_CONV = 0, F_KCONV = 1, F_ITERS = 2, F_REORTH = 3, F_NREORTH = 4, F_BREAK = 5, F_RESTARTS = 6, F_COUNT = 8 };
+enum { S_NORMB = 0, S_BETA = 1, S_RESID = 2, S_SCALE = 3, S_TOL = 4, S_ETA2 = 5, S_WW = 6, S_COUNT = 8 };
+enum { FIN_NONE = 0, FIN_NORMB, FIN_BETA0, FIN_BETA, FIN_CGS1, FIN_CGS2, FIN_MGS_DOT, FIN_MGS_NORM };
+
+// ---- launchers (defined in the .cu files) --------------------------------------------------
+int launch_spmv(bg_context_t ctx, bg_matrix_t A, double alpha, const void* x, double beta, const void* b,
+                void* y, bool axpby, const int* skip_flag);
+// generic CSR y = A x with independent value/vector types (used for the warm-start U*x)
+int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci, const void* val, int val_dt,
+                          const void* x, void* y, int vec_dt, const int* skip_flag);
+
+// dots: partial[k] = V[:,k].w for k<j, partial[j] = w.w ; then finalize variant `fin`
+int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w,
+                const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth_flag);
+// out = (a + sgn * sum_k coef[k] V[:,k]) * (use_scale ? scal[S_SCALE] : 1)
+int launch_update(bg_context_t ctx, int dtype, int n, const void* a, const void* V, int64_t ld, int j,
+                  const double* coef, double sgn, void* out, const GmresDev& st, int use_scale, int force,
+                  int need_reorth_flag);
+int launch_solve_y(bg_context_t ctx, const GmresDev& st, int k, int force);
+int launch_state_reset(bg_context_t ctx, const GmresDev& st, double tol, double eta);
+
+int launch_trsv_level(bg_context_t ctx, const LevelStreamDev& S, int vec_dt, int fac_dt, bool unit,
+                      const void* in, void* xs, void* out, const TrsvXform& xf, const int* skip_flag);
+int launch_trsv_block(bg_context_t ctx, const BlockStreamDev& S, int vec_dt, int fac_dt, bool unit, bool tma,
+                      const void* in, void* out, const int* skip_flag);
+int launch_diag_scale(bg_context_t ctx, int dtype, int n, const void* in, const void* d, void* out,
+                      const int* skip_flag);
+// out[perm[i]] = in[i]*scale[i]  (warm-start scatter), out[i] = in[i]/scale[i]
+int launch_scatter_scale(bg_context_t ctx, int vec_dt, int n, const void* in, const void* scale, const int* perm,
+                         void* out_ct);
+int launch_divide_cast(bg_context_t ctx, int vec_dt, int n, const void* in_ct, const void* scale, void* out);
+int launch_copy(bg_context_t ctx, int dtype, int n, const void* in, void* out, const int* skip_flag);
+
+}  // namespace bg
+
+struct bg_precond_s {
+  bg_context_t ctx = nullptr;
+  int kind = BG_PRECOND_NONE, n = 0, dtype = BG_F64, factor_dtype = BG_F64, schedule = BG_TRSV_LEVEL;
+  bool unit_lower = true, use_tma = true;
+  int64_t nnzL = 0, nnzU = 0;
+  bg::DevBuf dinv;                                 // DIAG
+  bg::LevelStreamDev lsL, lsU;                     // BG_TRSV_LEVEL
+  bg::BlockStreamDev bsL, bsU;                     // BG_TRSV_BLOCK
+  bg::DevBuf xsL, xsU, tmp;                        // scratch vectors (compute type)
+  bg::DevBuf middle, lscale, rscale, permRow, permCol, invPermCol;  // SPLIT
+  bg::DevBuf u_rp, u_ci, u_val;                    // raw CSR U for the warm-start product
+  int ct_dtype() const { return (dtype == BG_F64 || factor_dtype == BG_F64) ? BG_F64 : BG_F32; }
+};
+
+struct bg_solver_s {
+  bg_context_t ctx = nullptr;
+  int n = 0, m = 0, dtype = BG_F64;
+  int64_t ld = 0;
+  bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb;
+  bg::GmresDev dev{};
+  void* pinned = nullptr;  // host mirror of flags+scal for polling
+  cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
+  std::vector<double> last_hist;
+  int last_hist_len = 0;
+};
+
+struct bg_factors_s {
+  int n = 0, dtype = BG_F64;
+  bg::Factors<float> f32;
+  bg::Factors<double> f64;
+};

@@ -1,0 +1,187 @@
+// spmv.cu -- y = A x (and y = alpha A x + beta b) for CSR and sliced-ELL storage, sm_100a.
+//
+// Replaces the reference's half-warp-per-row kernel (src/SpMV_kernel.cu:166-221: 16 lanes per row,
+// 32-bit scalar loads, shared-memory round trip, serial 16-term add by lane 0) and the
+// cusparseScsrmv calls (src/gmres.cu:2303,2351,2403).
+//
+//  * sliced ELL (stencil-like rows, chosen by the inspector): one thread owns RPT consecutive rows
+//    of a 32*RPT-row slice; entry k of those rows is contiguous, so values and column indices are
+//    fetched with 128-bit loads (RPT=4 for FP32, int4 + float4; RPT=2 for FP64, int2 + double2)
+//    and a warp reads 512 contiguous bytes per load.  No lane is idle on 5- or 7-point rows.
+//  * CSR vector: LANES (2..32, from the mean row length) lanes per row, shuffle reduction.
+// x is gathered through L1/L2 (it fits the 126 MB L2 for every single-GPU config of BASELINE.json).
+// HBM-bound: algorithmic bytes (s+4)*nnz + 4(n+1) + 2*s*n.
+#include "internal.h"
+
+namespace bg {
+
+template <class T> struct Vec;
+template <> struct Vec<float> { using v4 = float4; };
+template <> struct Vec<double> { using v2 = double2; };
+
+template <class VT, class MT, int LANES, bool AXPBY>
+__global__ void __launch_bounds__(256) spmv_csr_vector(int n, const int* __restrict__ rp, const int* __restrict__ ci,
+                                                        const MT* __restrict__ val, const VT* __restrict__ x,
+                                                        VT* __restrict__ y, double alpha, double beta,
+                                                        const VT* __restrict__ b, const int* skip) {
+  if (skip && *skip) return;
+  using CT = decltype(MT() * VT());
+  const int lane = threadIdx.x % LANES;
+  const int rows_per_block = blockDim.x / LANES;
+  for (int base = blockIdx.x * rows_per_block; base < n; base += gridDim.x * rows_per_block) {
+    const int row = base + threadIdx.x / LANES;  // loop bound is block-uniform: shuffles stay converged
+    const bool valid = row < n;
+    const int lb = valid ? rp[row] : 0, ub = valid ? rp[row + 1] : 0;
+    CT acc = 0;
+    for (int p = lb + lane; p < ub; p += LANES) acc += val[p] * x[ci[p]];
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+    if (valid && lane == 0) {
+      if (AXPBY) y[row] = (VT)(alpha * (double)acc + beta * (double)b[row]);
+      else y[row] = (VT)acc;
+    }
+  }
+}
+
+// sliced ELL, FP32: 4 rows per thread, slice height 128
+template <bool AXPBY>
+__global__ void __launch_bounds__(128) spmv_sell_f32(int n, int nslices, const int64_t* __restrict__ sp,
+                                                     const int* __restrict__ cols, const float* __restrict__ vals,
+                                                     const float* __restrict__ x, float* __restrict__ y, float alpha,
+                                                     float beta, const float* __restrict__ b, const int* skip) {
+  if (skip && *skip) return;
+  const int warps_per_block = blockDim.x / 32, lane = threadIdx.x & 31;
+  for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < nslices; s += gridDim.x * warps_per_block) {
+    const int64_t base = sp[s];
+    const int width = (int)((sp[s + 1] - base) >> 7);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int4* c4 = reinterpret_cast<const int4*>(cols + base) + lane;
+    const float4* v4 = reinterpret_cast<const float4*>(vals + base) + lane;
+#pragma unroll 4
+    for (int k = 0; k < width; ++k) {
+      const int4 c = __ldg(c4 + k * 32);
+      const float4 v = __ldg(v4 + k * 32);
+      a0 += v.x * x[c.x]; a1 += v.y * x[c.y]; a2 += v.z * x[c.z]; a3 += v.w * x[c.w];
+    }
+    const int row = s * 128 + lane * 4;
+    if (row + 3 < n) {
+      float4 o = make_float4(a0, a1, a2, a3);
+      if (AXPBY) {
+        const float4 bb = *reinterpret_cast<const float4*>(b + row);
+        o.x = alpha * o.x + beta * bb.x; o.y = alpha * o.y + beta * bb.y;
+        o.z = alpha * o.z + beta * bb.z; o.w = alpha * o.w + beta * bb.w;
+      }
+      *reinterpret_cast<float4*>(y + row) = o;
+    } else {
+      const float a[4] = {a0, a1, a2, a3};
+      for (int r = 0; r < 4; ++r)
+        if (row + r < n) y[row + r] = AXPBY ? alpha * a[r] + beta * b[row + r] : a[r];
+    }
+  }
+}
+
+// sliced ELL, FP64: 2 rows per thread, slice height 64
+template <bool AXPBY>
+__global__ void __launch_bounds__(128) spmv_sell_f64(int n, int nslices, const int64_t* __restrict__ sp,
+                                                     const int* __restrict__ cols, const double* __restrict__ vals,
+                                                     const double* __restrict__ x, double* __restrict__ y,
+                                                     double alpha, double beta, const double* __restrict__ b,
+                                                     const int* skip) {
+  if (skip && *skip) return;
+  const int warps_per_block = blockDim.x / 32, lane = threadIdx.x & 31;
+  for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < nslices; s += gridDim.x * warps_per_block) {
+    const int64_t base = sp[s];
+    const int width = (int)((sp[s + 1] - base) >> 6);
+    double a0 = 0.0, a1 = 0.0;
+    const int2* c2 = reinterpret_cast<const int2*>(cols + base) + lane;
+    const double2* v2 = reinterpret_cast<const double2*>(vals + base) + lane;
+#pragma unroll 4
+    for (int k = 0; k < width; ++k) {
+      const int2 c = __ldg(c2 + k * 32);
+      const double2 v = __ldg(v2 + k * 32);
+      a0 += v.x * x[c.x]; a1 += v.y * x[c.y];
+    }
+    const int row = s * 64 + lane * 2;
+    if (row + 1 < n) {
+      double2 o = make_double2(a0, a1);
+      if (AXPBY) {
+        const double2 bb = *reinterpret_cast<const double2*>(b + row);
+        o.x = alpha * o.x + beta * bb.x; o.y = alpha * o.y + beta * bb.y;
+      }
+      *reinterpret_cast<double2*>(y + row) = o;
+    } else if (row < n) {
+      y[row] = AXPBY ? alpha * a0 + beta * b[row] : a0;
+    }
+  }
+}
+
+template <class VT, class MT, int LANES>
+static void csr_launch(bg_context_t ctx, int n, const int* rp, const int* ci, const MT* val, const VT* x, VT* y,
+                       double alpha, double beta, const VT* b, bool axpby, const int* skip) {
+  const int rows_per_block = 256 / LANES;
+  int64_t blocks = ((int64_t)n + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)ctx->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (axpby) spmv_csr_vector<VT, MT, LANES, true><<<(int)blocks, 256, 0, ctx->stream>>>(n, rp, ci, val, x, y, alpha, beta, b, skip);
+  else spmv_csr_vector<VT, MT, LANES, false><<<(int)blocks, 256, 0, ctx->stream>>>(n, rp, ci, val, x, y, alpha, beta, b, skip);
+}
+
+template <class VT, class MT>
+static void csr_dispatch(bg_context_t ctx, int lanes, int n, const int* rp, const int* ci, const MT* val, const VT* x,
+                         VT* y, double alpha, double beta, const VT* b, bool axpby, const int* skip) {
+  switch (lanes) {
+    case 2: csr_launch<VT, MT, 2>(ctx, n, rp, ci, val, x, y, alpha, beta, b, axpby, skip); break;
+    case 4: csr_launch<VT, MT, 4>(ctx, n, rp, ci, val, x, y, alpha, beta, b, axpby, skip); break;
+    case 8: csr_launch<VT, MT, 8>(ctx, n, rp, ci, val, x, y, alpha, beta, b, axpby, skip); break;
+    case 16: csr_launch<VT, MT, 16>(ctx, n, rp, ci, val, x, y, alpha, beta, b, axpby, skip); break;
+    default: csr_launch<VT, MT, 32>(ctx, n, rp, ci, val, x, y, alpha, beta, b, axpby, skip); break;
+  }
+}
+
+int launch_spmv(bg_context_t ctx, bg_matrix_t A, double alpha, const void* x, double beta, const void* b, void* y,
+                bool axpby, const int* skip) {
+  const int n = A->n;
+  if (n == 0) return BG_OK;
+  if (A->format == BG_SPMV_SELL) {
+    const int wpb = 4;
+    int64_t blocks = ((int64_t)A->sell_slices + wpb - 1) / wpb;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (A->dtype == BG_F32) {
+      if (axpby) spmv_sell_f32<true><<<(int)blocks, 128, 0, ctx->stream>>>(n, A->sell_slices, A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.as<float>(), (const float*)x, (float*)y, (float)alpha, (float)beta, (const float*)b, skip);
+      else spmv_sell_f32<false><<<(int)blocks, 128, 0, ctx->stream>>>(n, A->sell_slices, A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.as<float>(), (const float*)x, (float*)y, 1.f, 0.f, nullptr, skip);
+    } else {
+      if (axpby) spmv_sell_f64<true><<<(int)blocks, 128, 0, ctx->stream>>>(n, A->sell_slices, A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.as<double>(), (const double*)x, (double*)y, alpha, beta, (const double*)b, skip);
+      else spmv_sell_f64<false><<<(int)blocks, 128, 0, ctx->stream>>>(n, A->sell_slices, A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.as<double>(), (const double*)x, (double*)y, 1.0, 0.0, nullptr, skip);
+    }
+  } else {
+    if (A->dtype == BG_F32)
+      csr_dispatch<float, float>(ctx, A->lanes, n, A->rp.as<int>(), A->ci.as<int>(), A->val.as<float>(), (const float*)x, (float*)y, alpha, beta, (const float*)b, axpby, skip);
+    else
+      csr_dispatch<double, double>(ctx, A->lanes, n, A->rp.as<int>(), A->ci.as<int>(), A->val.as<double>(), (const double*)x, (double*)y, alpha, beta, (const double*)b, axpby, skip);
+  }
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+
+int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci, const void* val, int val_dt,
+                          const void* x, void* y, int vec_dt, const int* skip) {
+  if (n == 0) return BG_OK;
+  if (val_dt == BG_F64 && vec_dt == BG_F64)
+    csr_dispatch<double, double>(ctx, 4, n, rp, ci, (const double*)val, (const double*)x, (double*)y, 1, 0, nullptr, false, skip);
+  else if (val_dt == BG_F32 && vec_dt == BG_F32)
+    csr_dispatch<float, float>(ctx, 4, n, rp, ci, (const float*)val, (const float*)x, (float*)y, 1, 0, nullptr, false, skip);
+  else if (val_dt == BG_F32 && vec_dt == BG_F64)
+    csr_dispatch<double, float>(ctx, 4, n, rp, ci, (const float*)val, (const double*)x, (double*)y, 1, 0, nullptr, false, skip);
+  else {
+    set_error("csr_spmv_mixed: FP64 values with FP32 vectors are staged through FP64 vectors");
+    return BG_ERR_UNSUPPORTED;
+  }
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+
+}  // namespace bg

@@ -1,0 +1,593 @@
+// host_algos.cpp -- see host_algos.h.  All routines are written from the behaviour documented in
+// SURVEY.md (appendix A) and cite the reference location whose integer artefacts they reproduce.
+#include "host_algos.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <set>
+#include <stdexcept>
+
+// METIS 5 as shipped inside the CUDA toolkit (libmetis_static.a, 64-bit idx_t, no header).
+extern "C" int METIS_SetDefaultOptions(int64_t* options);
+extern "C" int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj, int64_t* adjncy, int64_t* vwgt,
+                                   int64_t* vsize, int64_t* adjwgt, int64_t* nparts, float* tpwgts, float* ubvec,
+                                   int64_t* options, int64_t* edgecut, int64_t* part);
+
+namespace bg {
+
+// ------------------------------------------------------------------ level sets
+void factor_levels(int n, const int* rp, const int* ci, const float* v, int* level) {
+  std::fill(level, level + n, 0);
+  for (int r = 0; r < n; ++r) {
+    const int lr = level[r] + 1;
+    for (int p = rp[r]; p < rp[r + 1]; ++p) {
+      const int c = ci[p];
+      if (c > r && !is_zero(v[p]) && level[c] < lr) level[c] = lr;
+    }
+  }
+}
+
+template <class T>
+void trsv_levels(bool lower, int n, const int* rp, const int* ci, const T* v, int* level) {
+  std::fill(level, level + n, 0);
+  if (lower) {
+    for (int i = 1; i < n; ++i) {
+      int best = 0;
+      for (int p = rp[i]; p < rp[i + 1]; ++p) {
+        if (is_zero(v[p]) || ci[p] >= i) break;  // padding sits at the row end; row sorted by column
+        best = std::max(best, level[ci[p]] + 1);
+      }
+      level[i] = best;
+    }
+  } else {
+    for (int i = n - 2; i >= 0; --i) {
+      int best = 0;
+      for (int p = rp[i + 1] - 1; p >= rp[i]; --p) {
+        if (is_zero(v[p])) continue;
+        if (ci[p] <= i) break;
+        best = std::max(best, level[ci[p]] + 1);
+      }
+      level[i] = best;
+    }
+  }
+}
+template void trsv_levels<float>(bool, int, const int*, const int*, const float*, int*);
+template void trsv_levels<double>(bool, int, const int*, const int*, const double*, int*);
+
+int bucket_levels(int n, const int* level, std::vector<int>& levelPtr, std::vector<int>& nodes) {
+  int nl = 0;
+  for (int i = 0; i < n; ++i) nl = std::max(nl, level[i] + 1);
+  levelPtr.assign(nl + 1, 0);
+  nodes.resize(n);
+  for (int i = 0; i < n; ++i) levelPtr[level[i] + 1]++;
+  for (int l = 0; l < nl; ++l) levelPtr[l + 1] += levelPtr[l];
+  std::vector<int> cur(levelPtr.begin(), levelPtr.end() - (nl ? 1 : 0));
+  for (int i = 0; i < n; ++i) nodes[cur[level[i]]++] = i;
+  return nl;
+}
+
+// ------------------------------------------------------------------ ILU helpers
+namespace {
+// sorted (by column) working copy of the rows, optionally restricted to the block diagonal
+template <class T>
+void sorted_copy(int n, const int* rp, const int* ci, const T* v, const int* block, Csr<T>& W) {
+  W.n = n;
+  W.rp.assign(n + 1, 0);
+  W.ci.clear();
+  W.v.clear();
+  W.ci.reserve(rp[n]);
+  W.v.reserve(rp[n]);
+  std::vector<std::pair<int, T>> row;
+  for (int i = 0; i < n; ++i) {
+    row.clear();
+    bool sorted = true;
+    int prev = -1;
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+      if (block && block[ci[p]] != block[i]) continue;
+      if (ci[p] < prev) sorted = false;
+      prev = ci[p];
+      row.emplace_back(ci[p], v[p]);
+    }
+    if (!sorted)
+      std::stable_sort(row.begin(), row.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
+    for (auto& e : row) { W.ci.push_back(e.first); W.v.push_back(e.second); }
+    W.rp[i + 1] = (int)W.ci.size();
+  }
+}
+
+// split a factored CSR (columns ascending) into the reference's L / U layout,
+// dropping |v| < eps (splitLU_csr, src/leftILU.cu:481-541)
+template <class T> void split_lu(const Csr<T>& W, Factors<T>& F) {
+  const int n = W.n;
+  F.L.n = F.U.n = n;
+  F.L.rp.assign(n + 1, 0);
+  F.U.rp.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    int nl = 0, nu = 0;
+    for (int p = W.rp[i]; p < W.rp[i + 1]; ++p) {
+      if (is_zero(W.v[p])) continue;
+      (W.ci[p] < i ? nl : nu)++;
+    }
+    F.L.rp[i + 1] = F.L.rp[i] + nl + 1;
+    F.U.rp[i + 1] = F.U.rp[i] + nu;
+  }
+  F.L.ci.resize(F.L.rp[n]); F.L.v.resize(F.L.rp[n]);
+  F.U.ci.resize(F.U.rp[n]); F.U.v.resize(F.U.rp[n]);
+  for (int i = 0; i < n; ++i) {
+    int a = F.L.rp[i], b = F.U.rp[i];
+    for (int p = W.rp[i]; p < W.rp[i + 1]; ++p) {
+      if (is_zero(W.v[p])) continue;
+      if (W.ci[p] < i) { F.L.ci[a] = W.ci[p]; F.L.v[a++] = W.v[p]; }
+      else { F.U.ci[b] = W.ci[p]; F.U.v[b++] = W.v[p]; }
+    }
+    F.L.ci[a] = i;
+    F.L.v[a] = (T)1;
+  }
+  F.unit_lower = true;
+}
+}  // namespace
+
+template <class T>
+void ilu0(int n, const int* rp, const int* ci, const T* v, const int* block, Factors<T>& F) {
+  Csr<T> W;
+  sorted_copy(n, rp, ci, v, block, W);
+  std::vector<int> diag(n, -1), pos(n, -1);
+  F.zero_pivots = 0;
+  for (int i = 0; i < n; ++i) {
+    const int lb = W.rp[i], ub = W.rp[i + 1];
+    for (int p = lb; p < ub; ++p) {
+      pos[W.ci[p]] = p;
+      if (W.ci[p] == i) diag[i] = p;
+    }
+    for (int p = lb; p < ub; ++p) {
+      const int k = W.ci[p];
+      if (k >= i) break;
+      const T ukk = diag[k] >= 0 ? W.v[diag[k]] : (T)0;
+      // reference: L column of a vanishing pivot is zeroed (src/leftILU.cu:812-818)
+      const T lik = is_zero(ukk) ? (T)0 : W.v[p] / ukk;
+      W.v[p] = lik;
+      // a_ij -= l_ik * u_kj over the part of row k right of its diagonal that row i also stores
+      for (int q = (diag[k] >= 0 ? diag[k] + 1 : std::lower_bound(W.ci.begin() + W.rp[k], W.ci.begin() + W.rp[k + 1], k) - W.ci.begin());
+           q < W.rp[k + 1]; ++q) {
+        const int t = pos[W.ci[q]];
+        if (t >= 0) W.v[t] -= lik * W.v[q];
+      }
+    }
+    if (diag[i] < 0 || is_zero(W.v[diag[i]])) F.zero_pivots++;
+    for (int p = lb; p < ub; ++p) pos[W.ci[p]] = -1;
+  }
+  split_lu(W, F);
+}
+template void ilu0<float>(int, const int*, const int*, const float*, const int*, Factors<float>&);
+template void ilu0<double>(int, const int*, const int*, const double*, const int*, Factors<double>&);
+
+template <class T>
+void ilut(int n, const int* rp, const int* ci, const T* v, double tau, int lfil, const int* block,
+          Factors<T>& F) {
+  Csr<T> A;
+  sorted_copy(n, rp, ci, v, block, A);
+  // U rows are kept diagonal-first; L rows strict-lower ascending.
+  std::vector<std::vector<std::pair<int, T>>> Lr(n), Ur(n);
+  std::vector<T> w(n, (T)0);
+  std::vector<char> in_w(n, 0);
+  std::vector<int> idx;
+  std::set<int> lower;  // pending lower columns, ascending
+  F.zero_pivots = 0;
+  for (int i = 0; i < n; ++i) {
+    idx.clear();
+    lower.clear();
+    double nrm = 0;
+    for (int p = A.rp[i]; p < A.rp[i + 1]; ++p) {
+      const int c = A.ci[p];
+      w[c] = A.v[p];
+      in_w[c] = 1;
+      idx.push_back(c);
+      if (c < i) lower.insert(c);
+      nrm += (double)A.v[p] * (double)A.v[p];
+    }
+    const int row_nnz = A.rp[i + 1] - A.rp[i];
+    nrm = row_nnz ? std::sqrt(nrm / row_nnz) : 0.0;
+    const double drop = tau * nrm;
+    if (!in_w[i]) { in_w[i] = 1; w[i] = 0; idx.push_back(i); }
+    while (!lower.empty()) {
+      const int k = *lower.begin();
+      lower.erase(lower.begin());
+      const T ukk = Ur[k].empty() ? (T)0 : Ur[k][0].second;
+      T lik = is_zero(ukk) ? (T)0 : w[k] / ukk;
+      if (std::fabs((double)lik) < drop) lik = 0;
+      w[k] = lik;
+      if (lik == (T)0) continue;
+      for (size_t q = 1; q < Ur[k].size(); ++q) {
+        const int c = Ur[k][q].first;
+        if (!in_w[c]) {
+          in_w[c] = 1;
+          w[c] = 0;
+          idx.push_back(c);
+          if (c < i) lower.insert(c);
+        }
+        w[c] -= lik * Ur[k][q].second;
+      }
+    }
+    std::vector<std::pair<int, T>> lo, up;
+    T dii = w[i];
+    for (int c : idx) {
+      const T val = w[c];
+      if (c < i) { if (val != (T)0 && std::fabs((double)val) >= drop) lo.emplace_back(c, val); }
+      else if (c > i) { if (std::fabs((double)val) >= drop) up.emplace_back(c, val); }
+      w[c] = 0;
+      in_w[c] = 0;
+    }
+    auto keep_largest = [&](std::vector<std::pair<int, T>>& e) {
+      if ((int)e.size() > lfil) {
+        std::nth_element(e.begin(), e.begin() + lfil, e.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) {
+          return std::fabs((double)a.second) > std::fabs((double)b.second);
+        });
+        e.resize(lfil);
+      }
+      std::sort(e.begin(), e.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
+    };
+    keep_largest(lo);
+    keep_largest(up);
+    if (is_zero(dii)) {  // keep the factor usable: replace a vanishing pivot by the drop scale
+      F.zero_pivots++;
+      dii = (T)(nrm > 0 ? (tau > 0 ? tau * nrm : nrm) : 1.0);
+      if (is_zero(dii)) dii = (T)1;
+    }
+    Lr[i] = std::move(lo);
+    Ur[i].emplace_back(i, dii);
+    for (auto& e : up) Ur[i].push_back(e);
+  }
+  F.L.n = F.U.n = n;
+  F.L.rp.assign(n + 1, 0);
+  F.U.rp.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    F.L.rp[i + 1] = F.L.rp[i] + (int)Lr[i].size() + 1;
+    F.U.rp[i + 1] = F.U.rp[i] + (int)Ur[i].size();
+  }
+  F.L.ci.resize(F.L.rp[n]); F.L.v.resize(F.L.rp[n]);
+  F.U.ci.resize(F.U.rp[n]); F.U.v.resize(F.U.rp[n]);
+  for (int i = 0; i < n; ++i) {
+    int a = F.L.rp[i];
+    for (auto& e : Lr[i]) { F.L.ci[a] = e.first; F.L.v[a++] = e.second; }
+    F.L.ci[a] = i; F.L.v[a] = (T)1;
+    int b = F.U.rp[i];
+    for (auto& e : Ur[i]) { F.U.ci[b] = e.first; F.U.v[b++] = e.second; }
+  }
+  F.unit_lower = true;
+}
+template void ilut<float>(int, const int*, const int*, const float*, double, int, const int*, Factors<float>&);
+template void ilut<double>(int, const int*, const int*, const double*, double, int, const int*, Factors<double>&);
+
+// ------------------------------------------------------------------ partitioning
+namespace {
+void finish_partition(int64_t m, int npart, const int64_t* node_part, int64_t* part_size, int64_t* pinv,
+                      int64_t* q) {
+  for (int k = 0; k <= npart; ++k) part_size[k] = 0;
+  for (int64_t j = 0; j < m; ++j) part_size[node_part[j]]++;
+  std::vector<int64_t> next(npart + 1, 0);
+  for (int k = 1; k <= npart; ++k) next[k] = next[k - 1] + part_size[k - 1];
+  for (int64_t j = 0; j < m; ++j) {
+    const int64_t slot = next[node_part[j]]++;
+    pinv[j] = slot;
+    q[slot] = j;
+  }
+}
+}  // namespace
+
+void partition_ref(int64_t m, const int64_t* Ap, const int64_t* Ai, int npart, int64_t nNodes,
+                   int64_t* part_size, int64_t* node_part, int64_t* pinv, int64_t* q) {
+  // contiguous chunks of floor(nNodes/npart) rows, remainder to the last part (partition.cpp:31-45)
+  const int64_t avg = nNodes / npart;
+  for (int64_t i = 0; i < m; ++i) node_part[i] = -1;
+  int64_t cur = 0;
+  for (int64_t i = 0; i < nNodes; ++i) {
+    if (i >= (cur + 1) * avg) {
+      if (cur + 1 < npart) ++cur;
+      else if (cur + 1 > npart) { node_part[i] = 0; continue; }
+    }
+    node_part[i] = cur;
+  }
+  // single order-dependent sweep over the CSC entries (partition.cpp:54-69): unknowns beyond
+  // nNodes inherit the part of the first column touching them; of every cut edge the larger
+  // index goes to the separator part `npart`.
+  for (int64_t j = 0; j < m; ++j)
+    for (int64_t p = Ap[j]; p < Ap[j + 1]; ++p) {
+      const int64_t r = Ai[p];
+      if (node_part[r] == -1) { node_part[r] = node_part[j]; continue; }
+      if (node_part[r] == npart || node_part[j] == npart || node_part[r] == node_part[j]) continue;
+      if (j > r) node_part[j] = npart;
+      else node_part[r] = npart;
+    }
+  finish_partition(m, npart, node_part, part_size, pinv, q);
+}
+
+void partition3_post(int64_t m, const int64_t* Ap, const int64_t* Ai, int npart, const int64_t* part,
+                     int64_t* part_size, int64_t* node_part, int64_t* pinv, int64_t* q) {
+  for (int64_t j = 0; j < m; ++j) node_part[j] = part[j];
+  std::vector<char> sep(m, 0);  // both endpoints of every cut edge (partition3.cpp:79-90)
+  for (int64_t j = 0; j < m; ++j)
+    for (int64_t p = Ap[j]; p < Ap[j + 1]; ++p)
+      if (part[Ai[p]] != part[j]) sep[Ai[p]] = sep[j] = 1;
+  for (int64_t j = 0; j < m; ++j)
+    if (sep[j]) node_part[j] = npart;
+  finish_partition(m, npart, node_part, part_size, pinv, q);
+}
+
+int block_partition(int method, int n, const int* rp, const int* ci, int nblocks, const int* dims,
+                    int* block_of_row) {
+  if (nblocks < 1) nblocks = 1;
+  if (method == 2 || method == 3) {
+    const int nx = dims[0], ny = dims[1], nz = method == 3 ? dims[2] : 1;
+    const int tx = std::max(1, dims[3]), ty = std::max(1, dims[4]), tz = method == 3 ? std::max(1, dims[5]) : 1;
+    if ((int64_t)nx * ny * nz != n) throw std::invalid_argument("grid dims do not match n");
+    const int bx = (nx + tx - 1) / tx, by = (ny + ty - 1) / ty, bz = (nz + tz - 1) / tz;
+    for (int z = 0; z < nz; ++z)
+      for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x)
+          block_of_row[((int64_t)z * ny + y) * nx + x] = ((z / tz) * by + (y / ty)) * bx + (x / tx);
+    return bx * by * bz;
+  }
+  if (method == 1 && nblocks > 1) {
+    // symmetrised off-diagonal pattern -> METIS k-way
+    std::vector<int64_t> deg(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p)
+        if (ci[p] != i) { deg[i + 1]++; deg[ci[p] + 1]++; }
+    for (int i = 0; i < n; ++i) deg[i + 1] += deg[i];
+    std::vector<int64_t> adj(deg[n]), cur(deg.begin(), deg.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p)
+        if (ci[p] != i) { adj[cur[i]++] = ci[p]; adj[cur[ci[p]]++] = i; }
+    std::vector<int64_t> xadj(n + 1, 0);
+    int64_t w = 0;
+    for (int i = 0; i < n; ++i) {  // sort + unique each list
+      int64_t b = deg[i], e = deg[i + 1];
+      std::sort(adj.begin() + b, adj.begin() + e);
+      int64_t u = std::unique(adj.begin() + b, adj.begin() + e) - (adj.begin() + b);
+      std::copy(adj.begin() + b, adj.begin() + b + u, adj.begin() + w);
+      xadj[i] = w;
+      w += u;
+    }
+    xadj[n] = w;
+    int64_t nv = n, ncon = 1, np = nblocks, cut = 0, options[40];
+    METIS_SetDefaultOptions(options);
+    std::vector<int64_t> part(n, 0);
+    int rc = METIS_PartGraphKway(&nv, &ncon, xadj.data(), adj.data(), nullptr, nullptr, nullptr, &np, nullptr,
+                                 nullptr, options, &cut, part.data());
+    if (rc != 1) throw std::runtime_error("METIS_PartGraphKway failed");
+    for (int i = 0; i < n; ++i) block_of_row[i] = (int)part[i];
+    return nblocks;
+  }
+  // contiguous: floor(n/nblocks) rows per block, remainder into the last one (partition.cpp:31-45)
+  const int avg = std::max(1, n / nblocks);
+  for (int i = 0; i < n; ++i) block_of_row[i] = std::min(i / avg, nblocks - 1);
+  return nblocks;
+}
+
+// ------------------------------------------------------------------ packers
+template <class T>
+void pack_level_stream(bool lower, bool unit, const Csr<T>& M, int thin_rows, LevelStream<T>& out) {
+  const int n = M.n;
+  out.n = n;
+  out.level.resize(n);
+  trsv_levels(lower, n, M.rp.data(), M.ci.data(), M.v.data(), out.level.data());
+  out.n_levels = bucket_levels(n, out.level.data(), out.lev_ptr, out.rows);
+  const int nl = out.n_levels;
+  out.lev_K.assign(nl, 0);
+  out.lev_off.assign(nl + 1, 0);
+  out.max_level_rows = 0;
+  for (int l = 0; l < nl; ++l) {
+    int K = 0;
+    for (int s = out.lev_ptr[l]; s < out.lev_ptr[l + 1]; ++s) {
+      const int r = out.rows[s];
+      K = std::max(K, M.rp[r + 1] - M.rp[r] - 1);
+    }
+    out.lev_K[l] = K;
+    const int R = out.lev_ptr[l + 1] - out.lev_ptr[l];
+    out.max_level_rows = std::max(out.max_level_rows, R);
+    out.lev_off[l + 1] = out.lev_off[l] + (int64_t)K * R;
+  }
+  out.cols.assign(out.lev_off[nl], -1);
+  out.vals.assign(out.lev_off[nl], (T)0);
+  out.diag.assign(n, (T)1);
+  for (int l = 0; l < nl; ++l) {
+    const int R = out.lev_ptr[l + 1] - out.lev_ptr[l];
+    for (int t = 0; t < R; ++t) {
+      const int s = out.lev_ptr[l] + t, r = out.rows[s];
+      const int lb = M.rp[r], ub = M.rp[r + 1];
+      const int dpos = lower ? ub - 1 : lb;
+      if (!unit) out.diag[s] = M.v[dpos];
+      int k = 0;
+      for (int p = lb; p < ub; ++p) {
+        if (p == dpos) continue;
+        out.cols[out.lev_off[l] + (int64_t)k * R + t] = M.ci[p];
+        out.vals[out.lev_off[l] + (int64_t)k * R + t] = M.v[p];
+        ++k;
+      }
+    }
+  }
+  // launch plan
+  out.seg_begin.clear(); out.seg_end.clear(); out.seg_single.clear();
+  int l = 0;
+  while (l < nl) {
+    const int R = out.lev_ptr[l + 1] - out.lev_ptr[l];
+    if (R > thin_rows) {
+      out.seg_begin.push_back(l); out.seg_end.push_back(l + 1); out.seg_single.push_back(0);
+      ++l;
+    } else {
+      int e = l;
+      while (e < nl && out.lev_ptr[e + 1] - out.lev_ptr[e] <= thin_rows) ++e;
+      out.seg_begin.push_back(l); out.seg_end.push_back(e); out.seg_single.push_back(1);
+      l = e;
+    }
+  }
+}
+template void pack_level_stream<float>(bool, bool, const Csr<float>&, int, LevelStream<float>&);
+template void pack_level_stream<double>(bool, bool, const Csr<double>&, int, LevelStream<double>&);
+
+template <class T>
+void pack_block_stream(bool lower, bool unit, const Csr<T>& M, int nblocks, const int* block_of_row,
+                       int chunk_slots, BlockStream<T>& out) {
+  const int n = M.n;
+  out.n = n;
+  out.nblocks = nblocks;
+  out.CS = chunk_slots;
+  // rows grouped by block, ascending inside a block; local ids
+  out.blk_row_ptr.assign(nblocks + 1, 0);
+  for (int i = 0; i < n; ++i) out.blk_row_ptr[block_of_row[i] + 1]++;
+  for (int b = 0; b < nblocks; ++b) out.blk_row_ptr[b + 1] += out.blk_row_ptr[b];
+  out.grow.resize(n);
+  std::vector<int> local(n);
+  {
+    std::vector<int> cur(out.blk_row_ptr.begin(), out.blk_row_ptr.end() - 1);
+    for (int i = 0; i < n; ++i) {
+      const int b = block_of_row[i];
+      local[i] = cur[b] - out.blk_row_ptr[b];
+      out.grow[cur[b]++] = i;
+    }
+  }
+  int K = 0;
+  out.max_rows = 0;
+  for (int b = 0; b < nblocks; ++b) out.max_rows = std::max(out.max_rows, out.blk_row_ptr[b + 1] - out.blk_row_ptr[b]);
+  if (out.max_rows > 65534) throw std::invalid_argument("block too large for 16-bit local ids");
+  for (int i = 0; i < n; ++i) {
+    int k = 0;
+    const int dpos = lower ? M.rp[i + 1] - 1 : M.rp[i];
+    for (int p = M.rp[i]; p < M.rp[i + 1]; ++p) {
+      if (p == dpos) continue;
+      if (block_of_row[M.ci[p]] != block_of_row[i]) throw std::invalid_argument("factor couples two blocks");
+      ++k;
+    }
+    K = std::max(K, k);
+  }
+  out.K = K;
+  const int CS = chunk_slots;
+  out.chunk_bytes = (int64_t)CS * (2 + 2 * K + (int64_t)sizeof(T) * K + sizeof(T));
+  out.chunk_bytes = (out.chunk_bytes + 15) / 16 * 16;
+  // per-block levels
+  out.blk_lev_ptr.assign(nblocks + 1, 0);
+  out.blk_chunk_ptr.assign(nblocks + 1, 0);
+  out.lev_slot.clear();
+  std::vector<int> lvl(out.max_rows), order(out.max_rows);
+  std::vector<std::vector<int>> sched(nblocks);
+  out.max_levels = 0;
+  out.max_chunks = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    const int base = out.blk_row_ptr[b], nb = out.blk_row_ptr[b + 1] - base;
+    int nl = 0;
+    auto row_level = [&](int li) {
+      const int r = out.grow[base + li];
+      const int dpos = lower ? M.rp[r + 1] - 1 : M.rp[r];
+      int best = 0;
+      for (int p = M.rp[r]; p < M.rp[r + 1]; ++p)
+        if (p != dpos) best = std::max(best, lvl[local[M.ci[p]]] + 1);
+      lvl[li] = best;
+      nl = std::max(nl, best + 1);
+    };
+    if (lower) for (int li = 0; li < nb; ++li) row_level(li);
+    else for (int li = nb - 1; li >= 0; --li) row_level(li);
+    std::vector<int> cnt(nl + 1, 0);
+    for (int li = 0; li < nb; ++li) cnt[lvl[li] + 1]++;
+    for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
+    out.blk_lev_ptr[b + 1] = out.blk_lev_ptr[b] + nl + 1;
+    for (int l = 0; l <= nl; ++l) out.lev_slot.push_back(cnt[l]);
+    std::vector<int> cur(cnt.begin(), cnt.end() - (nl ? 1 : 0));
+    sched[b].resize(nb);
+    for (int li = 0; li < nb; ++li) sched[b][cur[lvl[li]]++] = li;
+    const int nch = (nb + CS - 1) / CS;
+    out.blk_chunk_ptr[b + 1] = out.blk_chunk_ptr[b] + nch;
+    out.max_levels = std::max(out.max_levels, nl);
+    out.max_chunks = std::max(out.max_chunks, nch);
+  }
+  out.stream.assign((size_t)out.blk_chunk_ptr[nblocks] * out.chunk_bytes, 0);
+  for (int b = 0; b < nblocks; ++b) {
+    const int base = out.blk_row_ptr[b], nb = out.blk_row_ptr[b + 1] - base;
+    for (int s = 0; s < (int)((nb + CS - 1) / CS) * CS; ++s) {
+      const int64_t ch = out.blk_chunk_ptr[b] + s / CS;
+      const int t = s % CS;
+      unsigned char* rec = out.stream.data() + ch * out.chunk_bytes;
+      uint16_t* sc = reinterpret_cast<uint16_t*>(rec);
+      uint16_t* cc = sc + CS;
+      T* vv = reinterpret_cast<T*>(rec + (size_t)CS * (2 + 2 * K));
+      T* dd = vv + (size_t)K * CS;
+      if (s >= nb) {
+        sc[t] = 0xFFFF;
+        for (int k = 0; k < K; ++k) { cc[k * CS + t] = 0; vv[(size_t)k * CS + t] = (T)0; }
+        dd[t] = (T)1;
+        continue;
+      }
+      const int li = sched[b][s], r = out.grow[base + li];
+      sc[t] = (uint16_t)li;
+      const int lb = M.rp[r], ub = M.rp[r + 1], dpos = lower ? ub - 1 : lb;
+      dd[t] = unit ? (T)1 : M.v[dpos];
+      int k = 0;
+      for (int p = lb; p < ub; ++p) {
+        if (p == dpos) continue;
+        cc[k * CS + t] = (uint16_t)local[M.ci[p]];
+        vv[(size_t)k * CS + t] = M.v[p];
+        ++k;
+      }
+      for (; k < K; ++k) { cc[k * CS + t] = (uint16_t)li; vv[(size_t)k * CS + t] = (T)0; }
+    }
+  }
+}
+template void pack_block_stream<float>(bool, bool, const Csr<float>&, int, const int*, int, BlockStream<float>&);
+template void pack_block_stream<double>(bool, bool, const Csr<double>&, int, const int*, int, BlockStream<double>&);
+
+// ------------------------------------------------------------------ SpMV inspector
+SpmvPlan inspect_rows(int n, const int* rp) {
+  SpmvPlan p;
+  int64_t padded = 0;
+  for (int s = 0; s < n; s += p.slice) {
+    int mx = 0;
+    for (int i = s; i < std::min(n, s + p.slice); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
+    padded += (int64_t)mx * p.slice;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int len = rp[i + 1] - rp[i];
+    p.max_row = std::max(p.max_row, len);
+    int b = len == 0 ? 0 : len <= 2 ? 1 : len <= 4 ? 2 : len <= 8 ? 3 : len <= 16 ? 4 : len <= 32 ? 5 : len <= 64 ? 6 : 7;
+    p.hist[b]++;
+  }
+  const int64_t nnz = n ? rp[n] : 0;
+  p.mean_row = n ? (double)nnz / n : 0.0;
+  p.sell_padded = padded;
+  // Short, regular rows (stencils): thread-per-row over sliced ELL wastes no lanes and reads
+  // values/columns fully coalesced.  Long or ragged rows: CSR with a sub-warp vector per row.
+  const bool regular = nnz > 0 && (double)padded <= 1.25 * (double)nnz && p.max_row <= 32;
+  p.format = regular ? 2 /*SELL*/ : (p.mean_row >= 24 ? 3 /*CSR warp*/ : 1 /*CSR vector*/);
+  return p;
+}
+
+template <class T>
+void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std::vector<int64_t>& slice_ptr,
+                std::vector<int>& cols, std::vector<T>& vals) {
+  const int ns = (n + slice - 1) / slice;
+  slice_ptr.assign(ns + 1, 0);
+  for (int s = 0; s < ns; ++s) {
+    int mx = 0;
+    for (int i = s * slice; i < std::min(n, (s + 1) * slice); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
+    slice_ptr[s + 1] = slice_ptr[s] + (int64_t)mx * slice;
+  }
+  cols.assign(slice_ptr[ns], 0);
+  vals.assign(slice_ptr[ns], (T)0);
+  for (int s = 0; s < ns; ++s)
+    for (int t = 0; t < slice; ++t) {
+      const int i = s * slice + t;
+      if (i >= n) continue;
+      int k = 0;
+      for (int p = rp[i]; p < rp[i + 1]; ++p, ++k) {
+        cols[slice_ptr[s] + (int64_t)k * slice + t] = ci[p];
+        vals[slice_ptr[s] + (int64_t)k * slice + t] = v[p];
+      }
+      // padding keeps column = own row (a valid, cached address) and value 0
+      const int64_t wid = (slice_ptr[s + 1] - slice_ptr[s]) / slice;
+      for (; k < wid; ++k) cols[slice_ptr[s] + (int64_t)k * slice + t] = i;
+    }
+}
+template void build_sell<float>(int, const int*, const int*, const float*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<float>&);
+template void build_sell<double>(int, const int*, const int*, const double*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<double>&);
+
+}  // namespace bg

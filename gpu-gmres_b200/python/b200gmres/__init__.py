@@ -1,6 +1,381 @@
 """ctypes binding of libb200gmres.so (the C ABI in include/b200gmres.h) plus synthetic workloads.
 
 Python is only the test/bench harness here; the product is the CUDA library and the C++ shim
-that mirrors the reference's solver API (gpu-gmres_b200/host).
+that mirrors the reference's solver API (gpu-gmres_b200/host/shim).  Nothing in this module
+computes: every call goes through the C ABI, and a missing library is a hard error.
 """
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
 from . import synth  # noqa: F401
+
+_PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # gpu-gmres_b200/
+LIB_PATH = os.path.join(_PKG, "libb200gmres.so")
+HEADER = os.path.join(os.path.dirname(_PKG), "include", "b200gmres.h")
+
+F32, F64 = 0, 1
+HOST, DEVICE = 0, 1
+SPMV_AUTO, SPMV_CSR_VECTOR, SPMV_SELL, SPMV_CSR_WARP = 0, 1, 2, 3
+PC_FULL, PC_LEFT, PC_RIGHT, PC_START, PC_RHS = 0, 1, 2, 3, 4
+ORTH_MGS, ORTH_CGS_ADAPTIVE, ORTH_CGS2 = 0, 1, 2
+TRSV_LEVEL, TRSV_BLOCK = 0, 1
+PART_CONTIGUOUS, PART_METIS, PART_GRID2D, PART_GRID3D = 0, 1, 2, 3
+ERR_NO_GPU = -3
+
+_NP = {F32: np.float32, F64: np.float64}
+
+
+def dtype_code(dt) -> int:
+    return F32 if np.dtype(dt) == np.float32 else F64
+
+
+class BgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200gmres error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile libb200gmres.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _PKG, "-j8"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class MatrixInfo(C.Structure):
+    _fields_ = [("n", C.c_int), ("nnz", C.c_int64), ("dtype", C.c_int), ("format", C.c_int),
+                ("max_row_nnz", C.c_int), ("mean_row_nnz", C.c_double), ("hist", C.c_int64 * 8),
+                ("sell_padded_nnz", C.c_int64), ("sell_slice", C.c_int), ("spmv_bytes", C.c_int64)]
+
+
+class FactorsInfo(C.Structure):
+    _fields_ = [("n", C.c_int), ("dtype", C.c_int), ("nnzL", C.c_int64), ("nnzU", C.c_int64), ("zero_pivots", C.c_int)]
+
+
+class PrecondOpts(C.Structure):
+    _fields_ = [("trsv_schedule", C.c_int), ("block_method", C.c_int), ("block_rows", C.c_int), ("dims", C.c_int * 6),
+                ("factor_dtype", C.c_int), ("use_tma", C.c_int), ("ilut_lfil", C.c_int), ("ilut_tau", C.c_double)]
+
+
+class PrecondInfo(C.Structure):
+    _fields_ = [("kind", C.c_int), ("n", C.c_int), ("dtype", C.c_int), ("factor_dtype", C.c_int), ("trsv_schedule", C.c_int),
+                ("nnzL", C.c_int64), ("nnzU", C.c_int64), ("levelsL", C.c_int), ("levelsU", C.c_int),
+                ("nblocks", C.c_int), ("max_block_rows", C.c_int), ("trsv_bytes", C.c_int64), ("stream_bytes", C.c_int64)]
+
+
+class GmresOpts(C.Structure):
+    _fields_ = [("m", C.c_int), ("max_iter", C.c_int), ("tol", C.c_double), ("orth", C.c_int), ("reorth_eta", C.c_double),
+                ("poll_chunk", C.c_int), ("use_graph", C.c_int), ("history_cap", C.c_int)]
+
+
+class GmresResult(C.Structure):
+    _fields_ = [("flag", C.c_int), ("iters", C.c_int), ("iters_done", C.c_int), ("resid", C.c_double),
+                ("restarts", C.c_int), ("reorths", C.c_int), ("launches", C.c_int64), ("solve_ms", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C ABI.  Raises if the library is missing (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built: run __graft_entry__.build() (make -C gpu-gmres_b200)")
+        L = C.CDLL(LIB_PATH)
+        L.bg_last_error.restype = C.c_char_p
+        L.bg_context_launch_count.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc < 0:
+        raise BgError(rc, lib().bg_last_error().decode())
+    return rc
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw device pointer
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def device_count() -> int:
+    return lib().bg_device_count()
+
+
+# ------------------------------------------------------------------ host-only artefacts
+def host_factor_levels(rowptr, col, val):
+    n = len(rowptr) - 1
+    level = np.zeros(n, np.int32)
+    _chk(lib().bg_host_factor_levels(n, _p(_i32(rowptr)), _p(_i32(col)), _p(np.ascontiguousarray(val, np.float32)), _p(level)))
+    return level
+
+
+def host_trsv_levels(is_lower, rowptr, col, val):
+    n = len(rowptr) - 1
+    val = np.ascontiguousarray(val)
+    level = np.zeros(n, np.int32)
+    _chk(lib().bg_host_trsv_levels(int(is_lower), n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), _p(level)))
+    return level
+
+
+def host_bucket_levels(level):
+    level = _i32(level)
+    n = len(level)
+    nl = C.c_int(0)
+    lp = np.zeros((int(level.max()) + 2) if n else 1, np.int32)
+    nodes = np.zeros(n, np.int32)
+    _chk(lib().bg_host_bucket_levels(n, _p(level), C.byref(nl), _p(lp), _p(nodes)))
+    return nl.value, lp, nodes
+
+
+def _factors_out(h):
+    info = FactorsInfo()
+    _chk(lib().bg_factors_get_info(h, C.byref(info)))
+    dt = _NP[info.dtype]
+    n = info.n
+    r = dict(lp=np.zeros(n + 1, np.int32), li=np.zeros(info.nnzL, np.int32), lv=np.zeros(info.nnzL, dt),
+             up=np.zeros(n + 1, np.int32), ui=np.zeros(info.nnzU, np.int32), uv=np.zeros(info.nnzU, dt),
+             zero_pivots=info.zero_pivots)
+    _chk(lib().bg_factors_get(h, _p(r["lp"]), _p(r["li"]), _p(r["lv"]), _p(r["up"]), _p(r["ui"]), _p(r["uv"])))
+    lib().bg_factors_destroy(h)
+    return r
+
+
+def host_ilu0(rowptr, col, val, block_of_row=None):
+    n = len(rowptr) - 1
+    val = np.ascontiguousarray(val)
+    h = C.c_void_p()
+    blk = None if block_of_row is None else _i32(block_of_row)
+    _chk(lib().bg_host_ilu0(n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), _p(blk), C.byref(h)))
+    return _factors_out(h)
+
+
+def host_ilut(rowptr, col, val, tau, lfil, block_of_row=None):
+    n = len(rowptr) - 1
+    val = np.ascontiguousarray(val)
+    h = C.c_void_p()
+    blk = None if block_of_row is None else _i32(block_of_row)
+    _chk(lib().bg_host_ilut(n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), C.c_double(tau), int(lfil),
+                            _p(blk), C.byref(h)))
+    return _factors_out(h)
+
+
+def host_partition(Ap, Ai, npart, n_nodes):
+    m = len(Ap) - 1
+    ps, npt, pinv, q = np.zeros(npart + 1, np.int64), np.zeros(m, np.int64), np.zeros(m, np.int64), np.zeros(m, np.int64)
+    _chk(lib().bg_host_partition(C.c_int64(m), _p(_i64(Ap)), _p(_i64(Ai)), npart, C.c_int64(n_nodes), _p(ps), _p(npt), _p(pinv), _p(q)))
+    return ps, npt, pinv, q
+
+
+def host_partition3_post(Ap, Ai, npart, part):
+    m = len(Ap) - 1
+    ps, npt, pinv, q = np.zeros(npart + 1, np.int64), np.zeros(m, np.int64), np.zeros(m, np.int64), np.zeros(m, np.int64)
+    _chk(lib().bg_host_partition3_post(C.c_int64(m), _p(_i64(Ap)), _p(_i64(Ai)), npart, _p(_i64(part)), _p(ps), _p(npt), _p(pinv), _p(q)))
+    return ps, npt, pinv, q
+
+
+def host_block_partition(method, rowptr, col, nblocks, dims=None):
+    n = len(rowptr) - 1
+    blk = np.zeros(n, np.int32)
+    d = None if dims is None else _i32(dims)
+    nb = _chk(lib().bg_host_block_partition(method, n, _p(_i32(rowptr)), _p(_i32(col)), nblocks, _p(d), _p(blk)))
+    return nb, blk
+
+
+# ------------------------------------------------------------------ device objects
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _chk(lib().bg_context_create(C.byref(self.h), device))
+        self.device = device
+
+    def sync(self):
+        _chk(lib().bg_context_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _chk(lib().bg_context_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def launches(self) -> int:
+        return lib().bg_context_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().bg_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Matrix:
+    def __init__(self, ctx, rowptr, col, val, dtype=F64, fmt=SPMV_AUTO):
+        self.ctx = ctx
+        rowptr, col = _i32(rowptr), _i32(col)
+        val = np.ascontiguousarray(val)
+        self.n = len(rowptr) - 1
+        self.dtype = dtype
+        self.h = C.c_void_p()
+        _chk(lib().bg_matrix_create_csr(ctx.h, self.n, C.c_int64(len(col)), _p(rowptr), _p(col), _p(val), dtype_code(val.dtype),
+                                        HOST, dtype, fmt, C.byref(self.h)))
+
+    def info(self) -> MatrixInfo:
+        i = MatrixInfo()
+        _chk(lib().bg_matrix_get_info(self.h, C.byref(i)))
+        return i
+
+    def spmv(self, d_x, d_y):
+        _chk(lib().bg_spmv(self.ctx.h, self.h, _p(d_x), _p(d_y)))
+
+    def spmv_axpby(self, alpha, d_x, beta, d_b, d_y):
+        _chk(lib().bg_spmv_axpby(self.ctx.h, self.h, C.c_double(alpha), _p(d_x), C.c_double(beta), _p(d_b), _p(d_y)))
+
+    def close(self):
+        if self.h:
+            lib().bg_matrix_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def precond_opts(**kw) -> PrecondOpts:
+    o = PrecondOpts()
+    lib().bg_precond_opts_default(C.byref(o))
+    for k, v in kw.items():
+        if k == "dims":
+            for i, d in enumerate(v):
+                o.dims[i] = int(d)
+        else:
+            setattr(o, k, v)
+    return o
+
+
+class Precond:
+    def __init__(self, ctx, h, n):
+        self.ctx, self.h, self.n = ctx, h, n
+
+    @classmethod
+    def none(cls, ctx, n, dtype=F64):
+        h = C.c_void_p()
+        _chk(lib().bg_precond_create_none(ctx.h, n, dtype, C.byref(h)))
+        return cls(ctx, h, n)
+
+    @classmethod
+    def diag(cls, ctx, rowptr, col, val, dtype=F64):
+        n = len(rowptr) - 1
+        val = np.ascontiguousarray(val)
+        h = C.c_void_p()
+        _chk(lib().bg_precond_create_diag(ctx.h, n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), dtype, C.byref(h)))
+        return cls(ctx, h, n)
+
+    @classmethod
+    def ilu0(cls, ctx, rowptr, col, val, dtype=F64, opts=None, ilut=False):
+        n = len(rowptr) - 1
+        val = np.ascontiguousarray(val)
+        h = C.c_void_p()
+        f = lib().bg_precond_create_ilut if ilut else lib().bg_precond_create_ilu0
+        _chk(f(ctx.h, n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), dtype,
+               C.byref(opts) if opts is not None else None, C.byref(h)))
+        return cls(ctx, h, n)
+
+    @classmethod
+    def lu(cls, ctx, lp, li, lv, up, ui, uv, dtype=F64, opts=None):
+        n = len(lp) - 1
+        lv = np.ascontiguousarray(lv)
+        uv = np.ascontiguousarray(uv, dtype=lv.dtype)
+        h = C.c_void_p()
+        _chk(lib().bg_precond_create_lu(ctx.h, n, _p(_i32(lp)), _p(_i32(li)), _p(lv), _p(_i32(up)), _p(_i32(ui)), _p(uv),
+                                        dtype_code(lv.dtype), dtype, C.byref(opts) if opts is not None else None, C.byref(h)))
+        return cls(ctx, h, n)
+
+    @classmethod
+    def split(cls, ctx, lp, li, lv, up, ui, uv, middle, lscale, rscale, permRow, permCol, dtype=F32, opts=None):
+        n = len(lp) - 1
+        lv = np.ascontiguousarray(lv)
+        uv = np.ascontiguousarray(uv, dtype=lv.dtype)
+        sd = np.float64
+        middle, lscale, rscale = (np.ascontiguousarray(a, dtype=sd) for a in (middle, lscale, rscale))
+        h = C.c_void_p()
+        _chk(lib().bg_precond_create_split(ctx.h, n, _p(_i32(lp)), _p(_i32(li)), _p(lv), _p(_i32(up)), _p(_i32(ui)), _p(uv),
+                                           dtype_code(lv.dtype), _p(middle), _p(lscale), _p(rscale), F64, _p(_i32(permRow)),
+                                           _p(_i32(permCol)), dtype, C.byref(opts) if opts is not None else None, C.byref(h)))
+        return cls(ctx, h, n)
+
+    def apply(self, which, d_in, d_out):
+        _chk(lib().bg_precond_apply(self.ctx.h, self.h, which, _p(d_in), _p(d_out)))
+
+    def info(self) -> PrecondInfo:
+        i = PrecondInfo()
+        _chk(lib().bg_precond_get_info(self.h, C.byref(i)))
+        return i
+
+    def levels(self, is_lower):
+        level = np.zeros(self.n, np.int32)
+        _chk(lib().bg_precond_get_levels(self.h, int(is_lower), _p(level)))
+        return level
+
+    def close(self):
+        if self.h:
+            lib().bg_precond_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def gmres_opts(**kw) -> GmresOpts:
+    o = GmresOpts()
+    lib().bg_gmres_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Solver:
+    def __init__(self, ctx, n, m=32, dtype=F64):
+        self.ctx, self.n, self.m, self.dtype = ctx, n, m, dtype
+        self.h = C.c_void_p()
+        _chk(lib().bg_solver_create(ctx.h, n, m, dtype, C.byref(self.h)))
+
+    def solve(self, A, M, d_b, d_x, opts=None, host=False):
+        """GMRES_GPU / GMRESilu_GPU through the C ABI.  d_b/d_x: device pointers (ints or torch
+        data_ptr) unless host=True, in which case they are numpy arrays (x updated in place)."""
+        o = opts if opts is not None else gmres_opts(m=self.m)
+        r = GmresResult()
+        f = lib().bg_gmres_solve_host if host else lib().bg_gmres_solve
+        _chk(f(self.ctx.h, self.h, A.h, M.h, _p(d_b), _p(d_x), C.byref(o), C.byref(r)))
+        return r
+
+    def history(self):
+        n = C.c_int(0)
+        _chk(lib().bg_solver_get_history(self.h, None, 0, C.byref(n)))
+        h = np.zeros(max(n.value, 1))
+        _chk(lib().bg_solver_get_history(self.h, _p(h), n.value, C.byref(n)))
+        return h[: n.value]
+
+    def hessenberg(self):
+        m = self.m
+        H, s, cs, sn = np.zeros((m, m + 1)), np.zeros(m + 1), np.zeros(m + 1), np.zeros(m + 1)
+        _chk(lib().bg_solver_get_hessenberg(self.h, _p(H), _p(s), _p(cs), _p(sn)))
+        return H.T.copy(), s, cs, sn  # H[k, i]
+
+    def bench_orth(self, j):
+        _chk(lib().bg_solver_bench_orth(self.ctx.h, self.h, j))
+
+    def close(self):
+        if self.h:
+            lib().bg_solver_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,247 @@
+/* b200gmres.h -- C ABI of the B200-native restarted-GMRES(m) + ILU hot path.
+ *
+ * This is the drop-in boundary for the hot path of sheldonucr/GPU-GMRES: every entry point
+ * names the reference interface (file:line under the reference tree) it replaces.  Signatures use
+ * plain pointers, sizes and opaque handles only -- no CUDA, torch or C++ types.  The C++ shim in
+ * gpu-gmres_b200/host/shim/ re-creates the reference's own headers (gmres.h, preconditioner.h,
+ * gmres_interface_pg.h, SpMV.h, leftILU.h) on top of these calls; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - return value: BG_OK (0) on success, BG_NOT_CONVERGED (1) only from the solve calls (the
+ *    reference's 0/1 convention, src/gmres.cu:2393,2445), negative BG_ERR_* on failure;
+ *    bg_last_error() gives the message.  Nothing here calls exit()/abort().
+ *  - "d_" pointers are device pointers on the context's GPU, "h_" are host pointers.
+ *  - vectors are dense arrays of the context-independent value type given per object
+ *    (BG_F32 = the reference's REAL, BG_F64 = the 1e-8 parity mode).
+ *  - there is NO CPU fallback: every compute entry point fails with BG_ERR_NO_GPU when no
+ *    CUDA device is usable.  Functions prefixed bg_host_ are pure host integer/setup work.
+ */
+#ifndef B200GMRES_H_
+#define B200GMRES_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_API __attribute__((visibility("default")))
+
+typedef struct bg_context_s* bg_context_t; /* device + stream + scratch                     */
+typedef struct bg_matrix_s* bg_matrix_t;   /* CSR matrix resident in HBM (+ sliced-ELL copy) */
+typedef struct bg_precond_s* bg_precond_t; /* ≙ class Preconditioner, preconditioner.h:34-84 */
+typedef struct bg_solver_s* bg_solver_t;   /* ≙ GMRES_GPU_Data, gmres.h:82-112               */
+typedef struct bg_factors_s* bg_factors_t; /* host L/U factors + level sets                  */
+typedef struct bg_dist_s* bg_dist_t;       /* row-partitioned (multi-GPU) problem            */
+
+enum { BG_OK = 0, BG_NOT_CONVERGED = 1, BG_ERR_ARG = -1, BG_ERR_CUDA = -2, BG_ERR_NO_GPU = -3,
+       BG_ERR_ALLOC = -4, BG_ERR_ZERO_PIVOT = -5, BG_ERR_UNSUPPORTED = -6, BG_ERR_COMM = -7 };
+enum { BG_F32 = 0, BG_F64 = 1 };
+enum { BG_HOST = 0, BG_DEVICE = 1 };
+/* SpMV storage chosen by the inspector (≙ SpMV_inspect.cpp:38-456 deciding the kernel variant) */
+enum { BG_SPMV_AUTO = 0, BG_SPMV_CSR_VECTOR = 1, BG_SPMV_SELL = 2, BG_SPMV_CSR_WARP = 3 };
+/* which half of the preconditioner to apply (≙ DevPrecond / DevPrecond_left / _right / _rhs /
+   _starting_value, preconditioner.h:53-80) */
+enum { BG_PC_FULL = 0, BG_PC_LEFT = 1, BG_PC_RIGHT = 2, BG_PC_START = 3, BG_PC_RHS = 4 };
+enum { BG_PRECOND_NONE = 0, BG_PRECOND_DIAG = 1, BG_PRECOND_LU = 2, BG_PRECOND_SPLIT = 3 };
+/* Arnoldi orthogonalisation: strict MGS (the reference, gmres.cu:2356-2359) or one-reduction
+   classical GS with DGKS-style re-orthogonalisation */
+enum { BG_ORTH_MGS = 0, BG_ORTH_CGS_ADAPTIVE = 1, BG_ORTH_CGS2 = 2 };
+/* triangular-solve schedule */
+enum { BG_TRSV_LEVEL = 0,  /* global level sets, bit-exact with getLevel (gmres.cu:1033-1077)      */
+       BG_TRSV_BLOCK = 1 };/* block-Jacobi: each block solved by one warp out of shared memory      */
+/* row-block partitioners for BG_TRSV_BLOCK and for the multi-GPU row partition */
+enum { BG_PART_CONTIGUOUS = 0, /* src/partition.cpp:22-45 contiguous nNodes/npart chunks            */
+       BG_PART_METIS = 1,      /* src/partition3.cpp:49-64 graph from the off-diagonal pattern       */
+       BG_PART_GRID2D = 2, BG_PART_GRID3D = 3 /* structured tiles when the caller knows the grid     */ };
+
+BG_API const char* bg_last_error(void);
+BG_API int bg_version(void);
+/* number of usable CUDA devices (0 without a GPU; never fails) */
+BG_API int bg_device_count(void);
+
+/* ---- context: replaces setGPUdevice (src/setGPUdevice.cu:4-29) and the implicit legacy
+        cuBLAS/cuSPARSE global state (gmres.cu:2260-2274) ---- */
+BG_API int bg_context_create(bg_context_t* ctx, int device);
+BG_API int bg_context_destroy(bg_context_t ctx);
+BG_API int bg_context_synchronize(bg_context_t ctx);
+BG_API int bg_context_stream(bg_context_t ctx, void** cuda_stream);
+/* kernels launched through this context since creation (bench.py's gpu_launches) */
+BG_API int64_t bg_context_launch_count(bg_context_t ctx);
+
+/* ---- matrix: replaces gpuMallocCpyCSR / allocateSparseMatrixGPU (src/SpMV_alloc.cu:16-162),
+        MySpMatrix::Initilize (src/mySpMatrix.cu:11-39) and setPrecondPG's upload
+        (src/gmres_interface_pg.cu:42-47).  The caller keeps ownership of its arrays. ---- */
+BG_API int bg_matrix_create_csr(bg_context_t ctx, int n, int64_t nnz, const int* rowptr, const int* col,
+                                const void* val, int val_dtype, int mem, int compute_dtype, int spmv_format,
+                                bg_matrix_t* A);
+BG_API int bg_matrix_destroy(bg_matrix_t A);
+typedef struct {
+  int n; int64_t nnz; int dtype; int format;     /* format actually chosen                        */
+  int max_row_nnz; double mean_row_nnz;          /* row-length histogram summary                  */
+  int64_t hist[8];                               /* rows with nnz in [0],[1-2],[3-4],[5-8],[9-16],[17-32],[33-64],[65+] */
+  int64_t sell_padded_nnz; int sell_slice;       /* sliced-ELL storage (0 when not built)         */
+  int64_t spmv_bytes;                            /* algorithmic bytes of one y=Ax, SURVEY 8d      */
+} bg_matrix_info;
+BG_API int bg_matrix_get_info(bg_matrix_t A, bg_matrix_info* info);
+/* y = A x: replaces the SpMV kernel (src/SpMV_kernel.cu:12-18,166-221) and cusparseScsrmv
+   (src/gmres.cu:2351-2353) */
+BG_API int bg_spmv(bg_context_t ctx, bg_matrix_t A, const void* d_x, void* d_y);
+/* y = alpha*A*x + beta*b: replaces sgemv_GPU (src/gmres.cu:1010-1030) and the copy+csrmv pair at
+   src/gmres.cu:2302-2305 */
+BG_API int bg_spmv_axpby(bg_context_t ctx, bg_matrix_t A, double alpha, const void* d_x, double beta,
+                         const void* d_b, void* d_y);
+
+/* ---- host-side integer artefacts (no GPU needed; bit-exact with the reference) ---- */
+/* factorisation level sets: generateLevel (src/leftILU.cu:339-368) on float values */
+BG_API int bg_host_factor_levels(int n, const int* rowptr, const int* col, const float* val, int* level);
+/* triangular-solve level sets: getLevel (src/gmres.cu:1033-1077) */
+BG_API int bg_host_trsv_levels(int is_lower, int n, const int* rowptr, const int* col, const void* val,
+                               int val_dtype, int* level);
+/* bucket rows by level, ascending row id inside a level (src/leftILU.cu:41-49,188-192);
+   levelPtr has max(level)+2 entries; returns the number of levels through *n_levels */
+BG_API int bg_host_bucket_levels(int n, const int* level, int* n_levels, int* levelPtr, int* nodes);
+/* ILU(0) with leftILU's CPU semantics (src/leftILU.cu:27-336,769-825) and its L/U layout
+   (splitLU_csr, src/leftILU.cu:481-541: L = strict lower + unit diagonal LAST, U = diagonal FIRST).
+   block_of_row (may be NULL) restricts the factorisation to the block-diagonal part of A. */
+BG_API int bg_host_ilu0(int n, const int* rowptr, const int* col, const void* val, int val_dtype,
+                        const int* block_of_row, bg_factors_t* F);
+/* ILUT(tau, lfil) on the host (dual threshold, row-wise); same L/U layout as bg_host_ilu0.
+   SURVEY 8(f) N2; the reference obtains its threshold-dropped factors from ILU++ instead
+   (src/mna_solve_gpu_gmres.cpp:316-344) and hands them to bg_precond_create_split. */
+BG_API int bg_host_ilut(int n, const int* rowptr, const int* col, const void* val, int val_dtype,
+                        double tau, int lfil, const int* block_of_row, bg_factors_t* F);
+typedef struct { int n; int dtype; int64_t nnzL, nnzU; int zero_pivots; } bg_factors_info;
+BG_API int bg_factors_get_info(bg_factors_t F, bg_factors_info* info);
+/* copy out; any pointer may be NULL */
+BG_API int bg_factors_get(bg_factors_t F, int* l_rowptr, int* l_col, void* l_val, int* u_rowptr, int* u_col,
+                          void* u_val);
+BG_API int bg_factors_destroy(bg_factors_t F);
+/* row partition with the reference's semantics: partition (src/partition.cpp:22-99) on a CSC
+   pattern with 64-bit indices; outputs part_size[npart+1], node_part[m], pinv[m], q[m] */
+BG_API int bg_host_partition(int64_t m, const int64_t* Ap, const int64_t* Ai, int npart, int64_t n_nodes,
+                             int64_t* part_size, int64_t* node_part, int64_t* pinv, int64_t* q);
+/* separator post-processing of partition3 (src/partition3.cpp:68-117) for a given part[] */
+BG_API int bg_host_partition3_post(int64_t m, const int64_t* Ap, const int64_t* Ai, int npart,
+                                   const int64_t* part, int64_t* part_size, int64_t* node_part,
+                                   int64_t* pinv, int64_t* q);
+/* assign every row to exactly one of nblocks blocks (no separator): block_of_row[n].
+   dims = {nx,ny,nz,tile_x,tile_y,tile_z} for the GRID methods, ignored otherwise. */
+BG_API int bg_host_block_partition(int method, int n, const int* rowptr, const int* col, int nblocks,
+                                   const int* dims, int* block_of_row);
+
+/* ---- preconditioners ---- */
+typedef struct {
+  int trsv_schedule;   /* BG_TRSV_LEVEL (default) or BG_TRSV_BLOCK                               */
+  int block_method;    /* BG_PART_* for BG_TRSV_BLOCK                                              */
+  int block_rows;      /* target rows per block (default 1024)                                     */
+  int dims[6];         /* grid description for BG_PART_GRID*                                       */
+  int factor_dtype;    /* storage type of L/U values on the device: -1 = same as the factors given */
+  int use_tma;         /* 1 (default): bulk-async staged factor streams; 0: plain loads            */
+  int ilut_lfil; double ilut_tau; /* used by bg_precond_create_ilut                                */
+} bg_precond_opts;
+BG_API void bg_precond_opts_default(bg_precond_opts* o);
+/* MyNONE (preconditioner.h) */
+BG_API int bg_precond_create_none(bg_context_t ctx, int n, int dtype, bg_precond_t* M);
+/* MyDIAG::Initilize (src/preconditioner.cu:500-540): entry nearest the diagonal, inverted */
+BG_API int bg_precond_create_diag(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
+                                  const void* h_val, int val_dtype, int dtype, bg_precond_t* M);
+/* MyILU0::Initilize (src/preconditioner.cu:288-362): leftILU on the host, upload, level analysis */
+BG_API int bg_precond_create_ilu0(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
+                                  const void* h_val, int val_dtype, int dtype, const bg_precond_opts* o,
+                                  bg_precond_t* M);
+BG_API int bg_precond_create_ilut(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
+                                  const void* h_val, int val_dtype, int dtype, const bg_precond_opts* o,
+                                  bg_precond_t* M);
+/* M^-1 = U^-1 L^-1 from caller-supplied CSR factors in the reference's ILU0 layout (unit-lower L
+   with its diagonal stored last, U with the diagonal first): what MyILU0/MyILUK::DevPrecond
+   consume (src/preconditioner.cu:253-285) */
+BG_API int bg_precond_create_lu(bg_context_t ctx, int n, const int* l_rowptr, const int* l_col,
+                                const void* l_val, const int* u_rowptr, const int* u_col, const void* u_val,
+                                int factor_val_dtype, int dtype, const bg_precond_opts* o, bg_precond_t* M);
+/* MyILUPPfloat::Initilize (src/preconditioner.cu:1205-1334): split preconditioner from ILU++
+   factors.  L lower NON-unit (diagonal last in row), U upper non-unit (diagonal first in row);
+   middle / lscale / rscale are length-n vectors of type scale_dtype; permRow / permCol length-n. */
+BG_API int bg_precond_create_split(bg_context_t ctx, int n, const int* l_rowptr, const int* l_col,
+                                   const void* l_val, const int* u_rowptr, const int* u_col, const void* u_val,
+                                   int factor_val_dtype, const void* middle, const void* lscale,
+                                   const void* rscale, int scale_dtype, const int* permRow, const int* permCol,
+                                   int dtype, const bg_precond_opts* o, bg_precond_t* M);
+/* DevPrecond / DevPrecond_left / _right / _rhs / _starting_value (preconditioner.h:53-80;
+   src/preconditioner.cu:253-285, 1561-1657) */
+BG_API int bg_precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* d_in, void* d_out);
+typedef struct {
+  int kind, n, dtype, factor_dtype, trsv_schedule;
+  int64_t nnzL, nnzU;
+  int levelsL, levelsU;        /* global level counts (BG_TRSV_LEVEL) or max per-block levels    */
+  int nblocks, max_block_rows;
+  int64_t trsv_bytes;          /* algorithmic bytes of one full application, SURVEY 8d           */
+  int64_t stream_bytes;        /* bytes of the packed factor streams actually read per apply     */
+} bg_precond_info;
+BG_API int bg_precond_get_info(bg_precond_t M, bg_precond_info* info);
+/* level sets the device schedule was built from (BG_TRSV_LEVEL only), for parity tests */
+BG_API int bg_precond_get_levels(bg_precond_t M, int is_lower, int* level);
+BG_API int bg_precond_destroy(bg_precond_t M);
+
+/* ---- GMRES(m) ---- */
+typedef struct {
+  int m;               /* restart (reference default 32, src/defs.h:11)                           */
+  int max_iter;        /* in: cap on inner iterations                                             */
+  double tol;          /* in: relative residual target, metric of src/gmres.cu:2294-2296,2372     */
+  int orth;            /* BG_ORTH_*                                                               */
+  double reorth_eta;   /* CGS_ADAPTIVE: re-orthogonalise when ||w'|| < eta*||w|| (default 0.7071) */
+  int poll_chunk;      /* inner iterations enqueued between host polls (default 8)                */
+  int use_graph;       /* capture restart cycles into CUDA graphs                                 */
+  int history_cap;     /* residual-history slots to record (0 = none)                             */
+} bg_gmres_opts;
+typedef struct {
+  int flag;            /* 0 converged / 1 not converged                                           */
+  int iters;           /* value the reference returns through *max_iter               */
+  int iters_done;      /* inner iterations actually performed                                     */
+  double resid;        /* value the reference returns through *tol                    */
+  int restarts; int reorths; int64_t launches;
+  double solve_ms;     /* device time of the solve, CUDA events on the context stream             */
+} bg_gmres_result;
+BG_API void bg_gmres_opts_default(bg_gmres_opts* o);
+/* workspace: replaces GMRES_GPU_Data::Initilize (src/gmres.h:89-105) and the workspace the PG
+   path hides inside the Preconditioner (src/preconditioner.cu:1318-1331) */
+BG_API int bg_solver_create(bg_context_t ctx, int n, int m, int dtype, bg_solver_t* S);
+BG_API int bg_solver_destroy(bg_solver_t S);
+/* GMRES_GPU / GMRES_GPU_tran / GMRESilu_GPU (src/gmres.cu:2567-2732, 2736-2827, 2254-2446).
+   M of kind SPLIT selects the GMRESilu_GPU algebra, anything else the left-preconditioned one.
+   d_x is the initial guess on entry and the solution on return. */
+BG_API int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b,
+                          void* d_x, const bg_gmres_opts* o, bg_gmres_result* r);
+/* same with HOST vectors: gmresInterfacePGfloat::GMRES_dev_PG (src/gmres_interface_pg.cu:110-139):
+   H2D of x and rhs, solve, D2H of x */
+BG_API int bg_gmres_solve_host(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* h_b,
+                               void* h_x, const bg_gmres_opts* o, bg_gmres_result* r);
+BG_API int bg_solver_get_history(bg_solver_t S, double* hist, int cap, int* len);
+/* Hessenberg / Givens state of the last cycle (H col-major ld=m+1, s, cs, sn) */
+BG_API int bg_solver_get_hessenberg(bg_solver_t S, double* H, double* s, double* cs, double* sn);
+/* diagnostic: one fused orthogonalisation step (dots + update) against j basis columns on the
+   solver's own workspace; used by bench.py to time the dominant kernel pair in isolation */
+BG_API int bg_solver_bench_orth(bg_context_t ctx, bg_solver_t S, int j);
+/* per-phase device time and algorithmic bytes of the last solve (≙ SUB_TIMER, gmres.h:64-80) */
+typedef struct {
+  double spmv_ms, trsv_ms, orth_ms, other_ms;
+  int64_t spmv_bytes, trsv_bytes, orth_bytes, other_bytes;
+  int64_t spmv_calls, trsv_calls, orth_calls;
+} bg_phase_stats;
+BG_API int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b,
+                             void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st);
+
+/* ---- device vector helpers for hosts without a CUDA runtime binding ---- */
+BG_API int bg_device_malloc(bg_context_t ctx, size_t bytes, void** d_ptr);
+BG_API int bg_device_free(bg_context_t ctx, void* d_ptr);
+BG_API int bg_memcpy_h2d(bg_context_t ctx, void* d_dst, const void* h_src, size_t bytes);
+BG_API int bg_memcpy_d2h(bg_context_t ctx, void* h_dst, const void* d_src, size_t bytes);
+BG_API int bg_host_alloc_pinned(size_t bytes, void** h_ptr);
+BG_API int bg_host_free_pinned(void* h_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GMRES_H_ */
