@@ -152,6 +152,7 @@ struct bg_solver_s {
   bg::GmresDev dev{};
   void* pinned = nullptr;  // host mirror of flags+scal for polling
   cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
+  std::vector<cudaEvent_t> prof_events;
   std::vector<double> last_hist;
   int last_hist_len = 0;
 };

@@ -692,30 +692,54 @@ namespace {
 struct Status { int flags[F_COUNT]; double scal[S_COUNT]; };
 static_assert(sizeof(Status) <= 128, "status slot");
 
+// optional per-phase timing (bg_solver_profile): event pairs around kernel groups
+struct Prof {
+  std::vector<cudaEvent_t>* pool = nullptr;
+  std::vector<std::pair<int, int>> spans[4];  // event index pairs per phase
+  int64_t calls[4] = {0, 0, 0, 0};
+  size_t used = 0;
+  cudaStream_t stream = nullptr;
+  int mark() {
+    if (used == pool->size()) { cudaEvent_t e; cudaEventCreate(&e); pool->push_back(e); }
+    cudaEventRecord((*pool)[used], stream);
+    return (int)used++;
+  }
+};
+enum { PH_SPMV = 0, PH_TRSV = 1, PH_ORTH = 2, PH_OTHER = 3 };
+
 struct Driver {
   bg_context_t ctx; bg_solver_t S; bg_matrix_t A; bg_precond_t M; const bg_gmres_opts& o;
   const void* b; void* x;
   int n, m; int64_t ld; size_t es; bool split; const int* skip; GmresDev st;
+  Prof* prof = nullptr;
   char* col(int k) const { return S->V.as<char>() + (size_t)k * ld * es; }
+  struct Span {
+    Prof* p; int ph, a;
+    Span(Prof* p_, int ph_) : p(p_), ph(ph_), a(p_ ? p_->mark() : 0) {}
+    ~Span() { if (p) { p->spans[ph].emplace_back(a, p->mark()); p->calls[ph]++; } }
+  };
 
   int apply_left(const void* in, void* out, const int* sk) { return precond_apply(ctx, M, split ? BG_PC_LEFT : BG_PC_FULL, in, out, sk); }
 
   // r = M_L^-1 (b - A x); beta, convergence test, v0 = r/beta
   int residual(int fin) {
-    BG_TRY(launch_spmv(ctx, A, -1.0, x, 1.0, b, S->rr.p, true, skip));
-    BG_TRY(apply_left(S->rr.p, S->r.p, skip));
+    { Span sp(prof, PH_SPMV); BG_TRY(launch_spmv(ctx, A, -1.0, x, 1.0, b, S->rr.p, true, skip)); }
+    { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->rr.p, S->r.p, skip)); }
+    Span sp(prof, PH_OTHER);
     BG_TRY(launch_dots(ctx, S->dtype, n, nullptr, ld, 0, S->r.p, st, fin, 0, 0, o.orth, 0));
     return launch_update(ctx, S->dtype, n, S->r.p, nullptr, ld, 0, nullptr, 0.0, col(0), st, 1, 0, 0);
   }
   int iteration(int i) {
     // w = M_L^-1 A M_R^-1 v_i   (gmres.cu:2350-2354 / 2637-2640)
     if (split) {
-      BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, col(i), S->w.p, skip));
-      BG_TRY(launch_spmv(ctx, A, 1.0, S->w.p, 0.0, nullptr, S->ww.p, false, skip));
+      { Span sp(prof, PH_TRSV); BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, col(i), S->w.p, skip)); }
+      { Span sp(prof, PH_SPMV); BG_TRY(launch_spmv(ctx, A, 1.0, S->w.p, 0.0, nullptr, S->ww.p, false, skip)); }
     } else {
+      Span sp(prof, PH_SPMV);
       BG_TRY(launch_spmv(ctx, A, 1.0, col(i), 0.0, nullptr, S->ww.p, false, skip));
     }
-    BG_TRY(apply_left(S->ww.p, S->w.p, skip));
+    { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->ww.p, S->w.p, skip)); }
+    Span sp(prof, PH_ORTH);
     if (o.orth == BG_ORTH_MGS) {
       for (int k = 0; k <= i; ++k) {
         BG_TRY(launch_dots(ctx, S->dtype, n, col(k), ld, 1, S->w.p, st, FIN_MGS_DOT, i, k, o.orth, 0));
@@ -732,6 +756,7 @@ struct Driver {
   }
   // x += V[:,0..k] y  (split: y-vector += V y ; x = M_R^-1 y-vector)   gmres.cu:2399-2400
   int apply_update(int k, int force) {
+    Span sp(prof, PH_OTHER);
     const int* sk = force ? nullptr : skip;
     BG_TRY(launch_solve_y(ctx, st, k, force));
     void* tgt = split ? S->yv.p : x;
@@ -755,8 +780,8 @@ struct Driver {
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
-                              const bg_gmres_opts* opts, bg_gmres_result* res) {
+static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                            const bg_gmres_opts* opts, bg_gmres_result* res, Prof* prof) {
   if (!ctx || !S || !A || !M || !d_b || !d_x || !opts) { set_error("bg_gmres_solve: null argument"); return BG_ERR_ARG; }
   const bg_gmres_opts& o = *opts;
   if (A->n != S->n || M->n != S->n || A->dtype != S->dtype || M->dtype != S->dtype) { set_error("matrix / preconditioner / solver shapes or dtypes differ"); return BG_ERR_ARG; }
@@ -770,7 +795,7 @@ extern "C" int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg
   GmresDev st = S->dev;
   st.m = m;  // H leading dimension follows the active restart length
   st.hist_cap = std::min(std::max(o.history_cap, 0), kHistCap);
-  Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st};
+  Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof};
   const int chunk = std::max(1, o.poll_chunk);
 
   BG_CUDA(cudaEventRecord(S->t0, ctx->stream));
@@ -841,6 +866,11 @@ extern "C" int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg
   return conv ? BG_OK : BG_NOT_CONVERGED;
 }
 
+extern "C" int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                              const bg_gmres_opts* opts, bg_gmres_result* res) {
+  return gmres_solve_impl(ctx, S, A, M, d_b, d_x, opts, res, nullptr);
+}
+
 extern "C" int bg_gmres_solve_host(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* h_b,
                                    void* h_x, const bg_gmres_opts* o, bg_gmres_result* r) {
   if (!ctx || !S || !h_b || !h_x) return BG_ERR_ARG;
@@ -883,8 +913,40 @@ extern "C" BG_API int bg_solver_bench_orth(bg_context_t ctx, bg_solver_t S, int 
   return launch_update(ctx, S->dtype, S->n, S->w.p, S->V.p, S->ld, j, st.h, -1.0, S->V.as<char>() + (size_t)j * S->ld * dtype_size(S->dtype), st, 1, 0, 0);
 }
 
-extern "C" int bg_solver_profile(bg_context_t, bg_solver_t, bg_matrix_t, bg_precond_t, const void*, void*, const bg_gmres_opts*,
-                                 bg_gmres_result*, bg_phase_stats*) {
-  set_error("bg_solver_profile: not implemented yet");
-  return BG_ERR_UNSUPPORTED;
+extern "C" int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                                 const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* out) {
+  if (!ctx || !S || !A || !M || !out) return BG_ERR_ARG;
+  Prof prof;
+  prof.pool = &S->prof_events;
+  prof.stream = ctx->stream;
+  bg_gmres_result rr;
+  std::memset(&rr, 0, sizeof(rr));
+  int rc = gmres_solve_impl(ctx, S, A, M, d_b, d_x, o, &rr, &prof);
+  if (rc < 0) return rc;
+  if (r) *r = rr;
+  double ms[4] = {0, 0, 0, 0};
+  for (int ph = 0; ph < 4; ++ph)
+    for (auto& sp : prof.spans[ph]) {
+      float t = 0;
+      cudaEventElapsedTime(&t, S->prof_events[sp.first], S->prof_events[sp.second]);
+      ms[ph] += t;
+    }
+  std::memset(out, 0, sizeof(*out));
+  out->spmv_ms = ms[PH_SPMV]; out->trsv_ms = ms[PH_TRSV]; out->orth_ms = ms[PH_ORTH]; out->other_ms = ms[PH_OTHER];
+  out->spmv_calls = prof.calls[PH_SPMV]; out->trsv_calls = prof.calls[PH_TRSV]; out->orth_calls = prof.calls[PH_ORTH];
+  // algorithmic bytes of the work actually performed (iters_done inner iterations)
+  bg_matrix_info mi; bg_precond_info pi;
+  bg_matrix_get_info(A, &mi); bg_precond_get_info(M, &pi);
+  const int64_t s = dtype_size(S->dtype), n = S->n, it = rr.iters_done, m = o->m;
+  const bool split = M->kind == BG_PRECOND_SPLIT;
+  const int64_t nres = 1 + rr.restarts + (rr.flag == 0 && rr.iters != rr.iters_done ? 1 : 0);  // residual evaluations
+  out->spmv_bytes = (it + nres) * mi.spmv_bytes;
+  // a left-only application runs both factors; the split one runs L and U in separate calls
+  out->trsv_bytes = (it + nres + 1) * pi.trsv_bytes + (split ? 0 : 0);
+  int64_t orth = 0;
+  for (int64_t t = 0; t < it; ++t) { const int64_t j = t % m + 1; orth += 2 * j * s * n + 5 * s * n; }  // SURVEY 8d B_orth(j)
+  orth += (int64_t)rr.reorths * 0;  // second passes are reported through `reorths`, not counted as algorithmic bytes
+  out->orth_bytes = orth;
+  out->other_bytes = nres * (3 * s * n) + (rr.restarts + 1) * (s * n * m + 2 * s * n);
+  return rc;
 }

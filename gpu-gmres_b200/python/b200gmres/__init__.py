@@ -78,6 +78,12 @@ class GmresResult(C.Structure):
                 ("restarts", C.c_int), ("reorths", C.c_int), ("launches", C.c_int64), ("solve_ms", C.c_double)]
 
 
+class PhaseStats(C.Structure):
+    _fields_ = [("spmv_ms", C.c_double), ("trsv_ms", C.c_double), ("orth_ms", C.c_double), ("other_ms", C.c_double),
+                ("spmv_bytes", C.c_int64), ("trsv_bytes", C.c_int64), ("orth_bytes", C.c_int64), ("other_bytes", C.c_int64),
+                ("spmv_calls", C.c_int64), ("trsv_calls", C.c_int64), ("orth_calls", C.c_int64)]
+
+
 _lib = None
 
 
@@ -358,6 +364,13 @@ class Solver:
         f = lib().bg_gmres_solve_host if host else lib().bg_gmres_solve
         _chk(f(self.ctx.h, self.h, A.h, M.h, _p(d_b), _p(d_x), C.byref(o), C.byref(r)))
         return r
+
+    def profile(self, A, M, d_b, d_x, opts=None):
+        """Same solve with CUDA-event pairs around every SpMV / SpTRSV / orthogonalisation group."""
+        o = opts if opts is not None else gmres_opts(m=self.m)
+        r, st = GmresResult(), PhaseStats()
+        _chk(lib().bg_solver_profile(self.ctx.h, self.h, A.h, M.h, _p(d_b), _p(d_x), C.byref(o), C.byref(r), C.byref(st)))
+        return r, st
 
     def history(self):
         n = C.c_int(0)
