@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- time-to-solution of the GMRES(m)+ILU hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA library through the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 5 ...  # the reference's CPU path (ILU++ GMRES)
+
+One "step" is one complete DC solve (relative residual 1e-8, GMRES(32)) of the synthetic
+ibmpg6-sized 2-D power grid (BASELINE.json configs[1]; n = 1304^2 = 1 700 416 unknowns) with the
+factorisation done once outside the timed region, exactly like the reference drivers reuse their
+preconditioner across solves (src/mna_solve_gpu_gmres.cpp:518-531, 608-621).
+
+Printed JSON (one line, rank 0): the contract keys plus
+  roofline      dominant kernel group (from CUDA-event pairs around every launch group of a
+                profiled solve, bg_solver_profile) against MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref/libilupp.so = vendored ILU++
+                GMRES, kind "reference") or the oracle port, timed on this box's host cores
+  e2e           the same solve through the host-buffer entry point (bg_gmres_solve_host ≙
+                gmresInterfacePGfloat::GMRES_dev_PG): H2D of x and rhs, solve, D2H of x in the
+                timed region.
+Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gpu-gmres_b200", "python"))
+
+METRIC = "time_to_solve_relres_1e-8"
+UNIT = "ms"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=1304, help="grid edge; n = nx*nx (1304 = ibmpg6-sized)")
+    ap.add_argument("--precond", default="ilu0", choices=["ilu0", "ilut"])
+    ap.add_argument("--schedule", default="block", choices=["block", "level"])
+    ap.add_argument("--blocks", default="grid", choices=["grid", "metis"])
+    ap.add_argument("--tile", type=int, default=32)
+    ap.add_argument("--factor-dtype", default="f64", choices=["f32", "f64"])
+    ap.add_argument("--orth", default="cgs", choices=["mgs", "cgs", "cgs2"])
+    ap.add_argument("--eta", type=float, default=0.70710678)
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-nx", type=int, default=652, help="grid edge of the bounded CPU sample (0 = same as --nx); 652^2 = n/4")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({nm for r in self.rows if len(r) >= 9 for nm, c in zip(names, r[5:9]) if c.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def workload(nx):
+    from b200gmres import synth
+
+    rp, ci, v, b = synth.pg2d(nx, nx, seed=synth.SEED_BASE + 2)
+    return rp, ci, v, b
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(nx_full, nx_cpu, steps, warmup, tol):
+    """The reference's CPU implementation of the path, timed on the host cores of this box.
+
+    kind "reference": iluplusplus::gmres with the ILUCDP preconditioner, the `-gmres -ilu` driver
+    path (src/mna_solve_gpu_gmres.cpp:1896-2276), from the vendored ILU++ compiled unchanged into
+    oracle/_ref/libilupp.so.  Single-threaded, as in the reference.  Falls back to the oracle port
+    of GMRES + ILU(0) (kind "port") when that library is absent."""
+    import scipy.sparse as sp
+
+    from oracle import pyoracle as O
+
+    nx = nx_cpu or nx_full
+    rp, ci, v, b = workload(nx)
+    n = len(rp) - 1
+    scale = (nx_full * nx_full) / float(n)
+    times, iters, kind, setup_s = [], None, "port", 0.0
+    if O.ilupp() is not None:
+        kind = "reference"
+        A = sp.csr_matrix((v, ci, rp), shape=(n, n)).tocsc()
+        A.sort_indices()
+        t0 = time.perf_counter()
+        fac = O.ilupp_factor(n, A.indptr, A.indices, A.data, threshold=1.2, mem_factor=1.0)
+        setup_s = time.perf_counter() - t0
+        # restart = 100 is the reference driver's own setting for this path (mna_solve_gpu_gmres.cpp:2063);
+        # with restart 32 the locally patched ILU++ gmres never recomputes r at a restart
+        # and stagnates.  ILU++ ANDs a relative and an absolute test (both -log10 exponents): the
+        # absolute one is switched off so the stopping rule is the metric's relative residual.
+        ex = -np.log10(tol)
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            x, iters, rt, at = O.ilupp_gmres(fac, b, restart=100, max_iter=1000, rel_tol=ex, abs_tol=-30.0)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+        O.ilupp_free(fac)
+        what = f"ILU++ ILUCDP(threshold 1.2) + iluplusplus::gmres(restart 100) double, {iters} iterations, reached 1e-{rt:.2f}"
+    else:
+        O.build()
+        t0 = time.perf_counter()
+        f = O.ilu0(rp, ci, v, "f64")
+        setup_s = time.perf_counter() - t0
+        pc = O.Precond(O.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            flag, x, iters, res, _ = O.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, tol, pc)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+        what = f"oracle port of GMRES(32)+ILU(0) (gmres.cu:1904-2066) double, {iters} iterations"
+    ms = 1e3 * float(np.mean(times)) * scale
+    sample = f"{what}; full DC solve on the {nx}x{nx} grid (n={n})" + (
+        f", time scaled by n_full/n = {scale:.2f} (iteration count is size-independent for this recipe)" if scale != 1.0 else "")
+    return {"value": ms, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "setup_s": setup_s, "iters": int(iters),
+            "host_cores_online": os.cpu_count()}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cb = cpu_reference(args.nx, args.cpu_nx, args.steps, args.warmup, args.tol)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"pg2d {args.nx}x{args.nx} DC solve, GMRES(32), rel. residual {args.tol:g}", "n": args.nx * args.nx},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import b200gmres as bg
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    rp, ci, v, b = workload(args.nx)
+    n = len(rp) - 1
+    ctx = bg.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    A = bg.Matrix(ctx, rp, ci, v, dtype=bg.F64)
+    fdt = bg.F32 if args.factor_dtype == "f32" else bg.F64
+    t_setup = time.perf_counter()
+    if args.schedule == "block":
+        o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile, factor_dtype=fdt,
+                            block_method=bg.PART_GRID2D if args.blocks == "grid" else bg.PART_METIS,
+                            dims=[args.nx, args.nx, 1, args.tile, args.tile, 1], ilut_tau=1e-3, ilut_lfil=10)
+    else:
+        o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=1e-3, ilut_lfil=10)
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(args.precond == "ilut"))
+    t_setup = time.perf_counter() - t_setup
+    S = bg.Solver(ctx, n, 32, dtype=bg.F64)
+    orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[args.orth]
+    opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
+
+    db = torch.from_numpy(b).cuda()
+    dx = torch.zeros(n, dtype=torch.float64, device="cuda")
+    hb = torch.from_numpy(b).pin_memory()
+    hx = torch.zeros(n, dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_device():
+        with torch.cuda.stream(stream):
+            dx.zero_()  # DC solve starts from x = 0 (mna_solve_gpu_gmres.cpp:525-527)
+        return S.solve(A, M, db.data_ptr(), dx.data_ptr(), opts)
+
+    def step_host():
+        hx.zero_()
+        return S.solve(A, M, hb.numpy(), hx.numpy(), opts, host=True)
+
+    def timed(fn, k):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record(stream)
+        for _ in range(k):
+            r = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, r, ctx.launches - l0
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, r, launches = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_host()
+    ms_e2e, r_e2e, _ = timed(step_host, args.steps)
+
+    # profiled solve: CUDA-event pairs around every launch group, on the launching stream
+    with torch.cuda.stream(stream):
+        dx.zero_()
+    rprof, st = S.profile(A, M, db.data_ptr(), dx.data_ptr(), opts)
+    x = dx.cpu().numpy()
+    true_rel = float(np.linalg.norm(b - _spmv_host(rp, ci, v, x)) / np.linalg.norm(b))
+
+    if rank == 0:
+        peak, which = peaks()
+        info, pinfo = A.info(), M.info()
+        phases = {
+            "spmv": (st.spmv_ms, st.spmv_bytes, st.spmv_calls),
+            "trsv": (st.trsv_ms, st.trsv_bytes, st.trsv_calls),
+            "orth": (st.orth_ms, st.orth_bytes, st.orth_calls),
+        }
+        tot_ms = st.spmv_ms + st.trsv_ms + st.orth_ms + st.other_ms
+        dom = max(phases, key=lambda k: phases[k][0])
+        kernel_names = {"orth": "dots_kernel+update_kernel (fused Arnoldi CGS step)",
+                        "trsv": "trsv_block_kernel x2 (L and U solve)" if args.schedule == "block" else "trsv_level_walk/_wide (L and U solve)",
+                        "spmv": "spmv_sell_f64"}
+        dms, dbytes, dcalls = phases[dom]
+        ach = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": which,
+                    "bytes_per_launch_group": dbytes / max(dcalls, 1), "ms_per_launch_group": dms / max(dcalls, 1),
+                    "share_of_step": dms / tot_ms if tot_ms else None}
+        all_bytes = st.spmv_bytes + st.trsv_bytes + st.orth_bytes + st.other_bytes
+        per_phase = {k: {"ms": p[0], "GBps": (p[1] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0), "frac": (p[1] / (p[0] * 1e-3) / 1e9 / peak if p[0] > 0 else 0.0),
+                         "share": p[0] / tot_ms if tot_ms else None} for k, p in phases.items()}
+        step_ms = ms / args.steps
+        line = {
+            "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong" if world == 1 else "replicas",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"pg2d {args.nx}x{args.nx} (ibmpg6-sized, BASELINE configs[1]) DC solve, GMRES(32), rel. residual {args.tol:g}",
+                       "n": n, "nnz": int(info.nnz), "precond": args.precond, "trsv_schedule": args.schedule,
+                       "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "factor_dtype": args.factor_dtype,
+                       "orth": args.orth, "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
+                       "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
+            "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
+            "ms_per_iteration": step_ms / max(r.iters_done, 1),
+            "iteration_roofline": {"bytes_per_iteration": all_bytes / max(rprof.iters_done, 1), "achieved_GBps": all_bytes / (step_ms * 1e-3) / 1e9,
+                                   "frac": all_bytes / (step_ms * 1e-3) / 1e9 / peak},
+            "phases": per_phase, "setup_s": t_setup,
+            "roofline": roofline,
+            "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_reference(args.nx, args.cpu_nx, 1, 0, args.tol)
+        print(json.dumps(line))
+    S.close(); M.close(); A.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _spmv_host(rp, ci, v, x):
+    import scipy.sparse as sp
+
+    return sp.csr_matrix((v, ci, rp), shape=(len(rp) - 1, len(rp) - 1)) @ x
+
+
+if __name__ == "__main__":
+    main()

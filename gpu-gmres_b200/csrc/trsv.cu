@@ -297,7 +297,11 @@ static int block_run(bg_context_t ctx, const BlockStreamDev& S, bool tma, const 
     return BG_ERR_UNSUPPORTED;
   }
   auto kern = tma ? trsv_block_kernel<VT, FT, CT, UNIT, true> : trsv_block_kernel<VT, FT, CT, UNIT, false>;
-  BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set[2] = {false, false};  // per template instantiation and TMA variant
+  if (!attr_set[tma ? 1 : 0]) {
+    BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    attr_set[tma ? 1 : 0] = true;
+  }
   int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin + 1024) / (smem + 1024)));
   int blocks = std::min((S.nblocks + warps - 1) / warps, ctx->sm_count * ctas_per_sm);
   kern<<<blocks, warps * 32, smem, ctx->stream>>>(a, (const VT*)in, (VT*)out, skip);

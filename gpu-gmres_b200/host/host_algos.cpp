@@ -433,7 +433,6 @@ void pack_block_stream(bool lower, bool unit, const Csr<T>& M, int nblocks, cons
   const int n = M.n;
   out.n = n;
   out.nblocks = nblocks;
-  out.CS = chunk_slots;
   // rows grouped by block, ascending inside a block; local ids
   out.blk_row_ptr.assign(nblocks + 1, 0);
   for (int i = 0; i < n; ++i) out.blk_row_ptr[block_of_row[i] + 1]++;
@@ -463,7 +462,14 @@ void pack_block_stream(bool lower, bool unit, const Csr<T>& M, int nblocks, cons
     K = std::max(K, k);
   }
   out.K = K;
-  const int CS = chunk_slots;
+  // chunk = one bulk copy: keep it around 4-6 KB whatever the row width (CS stays a multiple of 8
+  // so the value array inside the record is 8-byte aligned and the record size a multiple of 16)
+  int CS = chunk_slots > 0 ? chunk_slots : 128;
+  {
+    const int64_t bps = 2 + 2 * K + (int64_t)sizeof(T) * (K + 1);
+    while (CS > 8 && CS * bps > 6144) CS /= 2;
+  }
+  out.CS = CS;
   out.chunk_bytes = (int64_t)CS * (2 + 2 * K + (int64_t)sizeof(T) * K + sizeof(T));
   out.chunk_bytes = (out.chunk_bytes + 15) / 16 * 16;
   // per-block levels

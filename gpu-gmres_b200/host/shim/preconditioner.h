@@ -1,0 +1,61 @@
+// preconditioner.h (B200 shim) -- the reference's Preconditioner hierarchy (src/preconditioner.h:34-357)
+// with the same class names, public data members the drivers poke, and virtual interface; device
+// work is forwarded to bg_precond_* (include/b200gmres.h).  The legacy cuSPARSE/cusp members are gone.
+// HostPrecond* (the CPU twins) are intentionally not provided: this build has no CPU path.
+#ifndef PRECONDITIONER_H_
+#define PRECONDITIONER_H_
+#include "SpMV.h"
+#include "defs.h"
+
+class Preconditioner {
+ public:
+  typedef int IndexType;
+  typedef float ValueType;
+  int numRows;
+  // GMRES workspace the PG path used to keep inside the preconditioner (preconditioner.h:47-50).
+  // Kept for source compatibility; the B200 solver owns its workspace (bg_solver_t), these stay NULL.
+  float *d_r, *d_rr, *d_bb, *d_y;
+  float *s, *cs, *sn, *H;
+  float *d_v, *d_w, *d_ww;
+  void* bg_handle;  // bg_precond_t
+
+  Preconditioner();
+  virtual void HostPrecond(const ValueType* i_data, ValueType* o_data);
+  virtual void DevPrecond(const ValueType* i_data, ValueType* o_data);
+  virtual void Initilize(const MySpMatrix& mySpM) = 0;
+  virtual void HostPrecond_rhs(const ValueType* i, ValueType* o);
+  virtual void HostPrecond_right(const ValueType* i, ValueType* o);
+  virtual void HostPrecond_left(const ValueType* i, ValueType* o);
+  virtual void HostPrecond_starting_value(const ValueType* i, ValueType* o);
+  virtual void DevPrecond_rhs(float* i_data, float* o_data);
+  virtual void DevPrecond_right(float* i_data, float* o_data);
+  virtual void DevPrecond_left(float* i_data, float* o_data);
+  virtual void DevPrecond_starting_value(float* i_data, float* o_data);
+  virtual ~Preconditioner();
+};
+
+class MyNONE : public Preconditioner { public: void Initilize(const MySpMatrix& mySpM); };
+class MyDIAG : public Preconditioner { public: void Initilize(const MySpMatrix& mySpM); };
+// ILU(0) through leftILU semantics on the host, level-scheduled solves on the device
+// (MyILU0::Initilize / DevPrecond, src/preconditioner.cu:253-362)
+class MyILU0 : public Preconditioner {
+ public:
+  ValueType *l_val, *u_val;
+  IndexType *l_rowIndices, *l_indices, *u_rowIndices, *u_indices;
+  MyILU0();
+  void Initilize(const MySpMatrix& mySpM);
+  ~MyILU0();
+};
+// the reference's MyILUK / MyILUPP(MySpMatrix) run ITSOL ilukC and then ignore it, using leftILU
+// factors: they behave like MyILU0.
+class MyILUK : public MyILU0 {};
+// split preconditioner from ILU++ factors, FP64 factors / FP32 vectors
+// (MyILUPPfloat::Initilize, src/preconditioner.cu:1205-1334)
+class MyILUPPfloat : public Preconditioner {
+ public:
+  void Initilize(const MySpMatrix& mySpM);
+  void Initilize(const MySpMatrixDouble& PrLeft, const MySpMatrixDouble& PrRight, const MySpMatrix& PrMiddle,
+                 const MySpMatrix& PrPermRow, const MySpMatrix& PrPermCol, const MySpMatrix& PrLscale,
+                 const MySpMatrix& PrRscale, int restart);
+};
+#endif

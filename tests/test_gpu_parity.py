@@ -258,7 +258,13 @@ def test_gmres_ilu0_f32_reference_precision(bg, ctx, name):
     M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=0)
     r, x, _ = run_gpu(bg, ctx, rp, ci, v, b, np.zeros(n), M, 0, tol=tol, max_iter=2000, orth=0)
     assert r.flag == 0 and r.resid < tol
-    assert abs(r.iters - int(it)) <= max(3, int(0.15 * it))   # FP32 round-off moves the stopping iteration
+    # FP32 round-off can only delay the stopping iteration relative to exact arithmetic: the FP32
+    # oracle (float accumulators, like cublasSdot) may stagnate just above tol until the next restart
+    # while the device dots accumulate in FP64.  So: no earlier than the FP64 trajectory crosses
+    # tol, no later than the FP32 oracle (each with a small slack).
+    first64 = int(np.argmax(g["f64_hist"] < tol)) + 1
+    slack = max(3, int(0.15 * it))
+    assert first64 - slack <= r.iters <= int(it) + slack
     assert np.linalg.norm(x - g["f64_x"]) <= 5e-4 * np.linalg.norm(g["f64_x"])
     M.close()
 
