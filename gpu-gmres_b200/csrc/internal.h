@@ -59,6 +59,14 @@ struct bg_matrix_s {
   bg::DevBuf rp, ci, val;            // CSR
   bg::DevBuf s_ptr, s_col, s_val;    // sliced ELL
   int sell_rpt = 1, sell_height = 32, sell_slices = 0;
+  // host CSR (compute dtype) kept so that a symmetrically permuted copy P A P^T can be built when a
+  // preconditioner asks for its own row order; one cached copy per ordering serial
+  std::vector<int> h_rp, h_ci;
+  std::vector<unsigned char> h_val;
+  int requested_format = BG_SPMV_AUTO;
+  bg_matrix_s* permuted = nullptr;
+  uint64_t permuted_serial = 0;
+  ~bg_matrix_s() { delete permuted; }
 };
 
 // ---- device-side argument bundles --------------------------------------------------------
@@ -80,10 +88,14 @@ struct LevelStreamDev {
   int64_t bytes = 0;
 };
 
-struct BlockStreamDev {
-  int n = 0, nblocks = 0, K = 0, CS = 0, max_rows = 0, max_levels = 0;
-  int64_t chunk_bytes = 0, bytes = 0;
-  DevBuf grow, blk_row_ptr, blk_lev_ptr, lev_slot, blk_chunk_ptr, stream;
+// device copy of host_algos.h FusedBlockStream (block-Jacobi L+U solve, trsv_block.cu)
+struct FusedBlockDev {
+  int n = 0, nblocks = 0, max_rows = 0, max_levels_L = 0, max_levels_U = 0, max_chunk_bytes = 0, max_chunks = 0;
+  int stages = 4, warps_per_cta = 4;
+  int64_t bytes = 0, total_steps = 0;
+  DevBuf perm, iperm, dinv, blk, chunk_off, stream;
+  std::vector<int> h_perm;  // new -> old, kept for permuting matrices on the host
+  uint64_t serial = 0;      // identifies this ordering (matrix copies are cached per serial)
 };
 
 // state shared by the orthogonalisation / Givens kernels (all double, device memory)
@@ -118,8 +130,13 @@ int launch_state_reset(bg_context_t ctx, const GmresDev& st, double tol, double 
 
 int launch_trsv_level(bg_context_t ctx, const LevelStreamDev& S, int vec_dt, int fac_dt, bool unit,
                       const void* in, void* xs, void* out, const TrsvXform& xf, const int* skip_flag);
-int launch_trsv_block(bg_context_t ctx, const BlockStreamDev& S, int vec_dt, int fac_dt, bool unit, bool tma,
+// z = U^-1 L^-1 r per diagonal block.  gather = vectors are in the ORIGINAL row order (the kernel
+// goes through perm); otherwise they are in the block-major order of the stream.
+int launch_trsv_block(bg_context_t ctx, const FusedBlockDev& S, int vec_dt, int fac_dt, bool gather,
                       const void* in, void* out, const int* skip_flag);
+// out[i] = in[perm[i]]  /  out[perm[i]] = in[i]
+int launch_gather(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out);
+int launch_scatter(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out);
 int launch_diag_scale(bg_context_t ctx, int dtype, int n, const void* in, const void* d, void* out,
                       const int* skip_flag);
 // out[perm[i]] = in[i]*scale[i]  (warm-start scatter), out[i] = in[i]/scale[i]
@@ -134,10 +151,11 @@ struct bg_precond_s {
   bg_context_t ctx = nullptr;
   int kind = BG_PRECOND_NONE, n = 0, dtype = BG_F64, factor_dtype = BG_F64, schedule = BG_TRSV_LEVEL;
   bool unit_lower = true, use_tma = true;
+  int fb_chunk_bytes = 2048;
   int64_t nnzL = 0, nnzU = 0;
   bg::DevBuf dinv;                                 // DIAG
   bg::LevelStreamDev lsL, lsU;                     // BG_TRSV_LEVEL
-  bg::BlockStreamDev bsL, bsU;                     // BG_TRSV_BLOCK
+  bg::FusedBlockDev fb;                            // BG_TRSV_BLOCK
   bg::DevBuf xsL, xsU, tmp;                        // scratch vectors (compute type)
   bg::DevBuf middle, lscale, rscale, permRow, permCol, invPermCol;  // SPLIT
   bg::DevBuf u_rp, u_ci, u_val;                    // raw CSR U for the warm-start product
@@ -148,7 +166,7 @@ struct bg_solver_s {
   bg_context_t ctx = nullptr;
   int n = 0, m = 0, dtype = BG_F64;
   int64_t ld = 0;
-  bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb;
+  bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb, bp, xp;
   bg::GmresDev dev{};
   void* pinned = nullptr;  // host mirror of flags+scal for polling
   cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;

@@ -13,6 +13,9 @@
 //  * update_kernel<VT,J>: out = (a + sgn * V[:,0..j) c) * scale in one pass (the MGS/CGS axpy
 //    sweep fused with the normalisation cublasScopy+cublasSscal of the reference).
 // HBM-bound: (2j+3)*s*n bytes per inner iteration (SURVEY 8d B_orth lower bound).
+#include <algorithm>
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace bg {
@@ -49,10 +52,48 @@ __device__ inline void rot_gen(double dx, double dy, double& cs, double& sn) {
   else if (fabs(dy) > fabs(dx)) { const double t = dx / dy; sn = 1.0 / sqrt(1.0 + t * t); cs = t * sn; }
   else { const double t = dy / dx; cs = 1.0 / sqrt(1.0 + t * t); sn = t * cs; }
 }
+// Scratch of the finalizing block: the previous rotations and the first-pass coefficients are
+// fetched by many threads at once, so the serial rotation sweep of thread 0 runs out of shared
+// memory instead of paying one L2 round trip per dependent global load.
+constexpr int kFinMax = 32;  // restart lengths up to this use the scratch; longer ones read global memory
+struct FinScratch {
+  double cs[kFinMax + 1], sn[kFinMax + 1], h1[kFinMax + 1], col[kFinMax + 2];
+  double s_i, normb, tol, eta2;
+  int iters;
+};
+__device__ __forceinline__ void fin_prefetch(const GmresDev& st, FinScratch& f, int i, int tid) {
+  if (st.m > kFinMax) return;
+  if (tid < i) { f.cs[tid] = st.cs[tid]; f.sn[tid] = st.sn[tid]; }
+  if (tid >= 32 && tid - 32 <= i) f.h1[tid - 32] = st.h[tid - 32];
+  if (tid == 64) f.s_i = st.s[i];
+  if (tid == 65) f.normb = st.scal[S_NORMB];
+  if (tid == 66) f.tol = st.scal[S_TOL];
+  if (tid == 67) f.eta2 = st.scal[S_ETA2];
+  if (tid == 68) f.iters = st.flags[F_ITERS];
+}
 // column i of H is complete: rotate, update s, residual estimate, convergence (gmres.cu:2365-2372)
-__device__ void givens_column(const GmresDev& st, int i) {
+__device__ void givens_column(const GmresDev& st, int i, FinScratch* f) {
   const int ld = st.m + 1;
   double* Hc = st.H + (size_t)i * ld;
+  if (f && st.m <= kFinMax) {
+    // f->col holds the new column (entries 0..i+1); all operands are on chip
+    double* c = f->col;
+    for (int k = 0; k < i; ++k) rot_apply(c[k], c[k + 1], f->cs[k], f->sn[k]);
+    double csi, sni;
+    rot_gen(c[i], c[i + 1], csi, sni);
+    rot_apply(c[i], c[i + 1], csi, sni);
+    double si = f->s_i, si1 = 0.0;  // s[i+1] is zero before this rotation (gmres.cu:2344-2346)
+    rot_apply(si, si1, csi, sni);
+    for (int k = 0; k <= i + 1; ++k) Hc[k] = c[k];
+    st.cs[i] = csi; st.sn[i] = sni; st.s[i] = si; st.s[i + 1] = si1;
+    const double resid = fabs(si1) / f->normb;
+    st.scal[S_RESID] = resid;
+    const int it = f->iters;
+    if (st.hist && it < st.hist_cap) st.hist[it] = resid;
+    st.flags[F_ITERS] = it + 1;
+    if (resid < f->tol) { st.flags[F_CONV] = 1; st.flags[F_KCONV] = i; }
+    return;
+  }
   for (int k = 0; k < i; ++k) rot_apply(Hc[k], Hc[k + 1], st.cs[k], st.sn[k]);
   rot_gen(Hc[i], Hc[i + 1], st.cs[i], st.sn[i]);
   rot_apply(Hc[i], Hc[i + 1], st.cs[i], st.sn[i]);
@@ -65,9 +106,11 @@ __device__ void givens_column(const GmresDev& st, int i) {
   if (resid < st.scal[S_TOL]) { st.flags[F_CONV] = 1; st.flags[F_KCONV] = i; }
 }
 
-__device__ void finalize(const GmresDev& st, int fin, int i, int mgs_k, int orth_mode, const double* red, int j) {
+__device__ void finalize(const GmresDev& st, int fin, int i, int mgs_k, int orth_mode, const double* red, int j,
+                         FinScratch* f) {
   const int ld = st.m + 1;
   const double ww = red[j];
+  const bool fast = f && st.m <= kFinMax;
   switch (fin) {
     case FIN_NORMB: {  // normb = ||M_L^-1 b||, zero -> 1 (gmres.cu:2294-2296)
       double nb = sqrt(ww);
@@ -93,30 +136,31 @@ __device__ void finalize(const GmresDev& st, int fin, int i, int mgs_k, int orth
       for (int k = 0; k < j; ++k) { st.h[k] = red[k]; sum += red[k] * red[k]; }
       const double hn2 = ww - sum;
       st.scal[S_WW] = ww;
-      if (orth_mode == BG_ORTH_CGS2 || !(hn2 >= st.scal[S_ETA2] * ww)) {
+      const double eta2 = fast ? f->eta2 : st.scal[S_ETA2];
+      if (orth_mode == BG_ORTH_CGS2 || !(hn2 >= eta2 * ww)) {
         st.flags[F_REORTH] = 1;   // second pass decides the column
         st.scal[S_SCALE] = 1.0;
       } else {
         st.flags[F_REORTH] = 0;
-        double* Hc = st.H + (size_t)i * ld;
+        double* Hc = fast ? f->col : st.H + (size_t)i * ld;
         for (int k = 0; k < j; ++k) Hc[k] = red[k];
         const double hn = sqrt(hn2);
         Hc[i + 1] = hn;
         if (hn > 0.0) st.scal[S_SCALE] = 1.0 / hn; else { st.scal[S_SCALE] = 0.0; st.flags[F_BREAK] = 1; }
-        givens_column(st, i);
+        givens_column(st, i, f);
       }
     } break;
     case FIN_CGS2: {
       double sum = 0.0;
-      double* Hc = st.H + (size_t)i * ld;
-      for (int k = 0; k < j; ++k) { st.h2[k] = red[k]; sum += red[k] * red[k]; Hc[k] = st.h[k] + red[k]; }
+      double* Hc = fast ? f->col : st.H + (size_t)i * ld;
+      for (int k = 0; k < j; ++k) { st.h2[k] = red[k]; sum += red[k] * red[k]; Hc[k] = (fast ? f->h1[k] : st.h[k]) + red[k]; }
       double hn2 = ww - sum;
       if (hn2 < 0.0) hn2 = 0.0;
       const double hn = sqrt(hn2);
       Hc[i + 1] = hn;
       if (hn > 0.0) st.scal[S_SCALE] = 1.0 / hn; else { st.scal[S_SCALE] = 0.0; st.flags[F_BREAK] = 1; }
       st.flags[F_NREORTH]++;
-      givens_column(st, i);
+      givens_column(st, i, f);
     } break;
     case FIN_MGS_DOT: {  // H(k,i) = <w, v_k>  (gmres.cu:2357)
       st.H[(size_t)i * ld + mgs_k] = red[0];
@@ -126,65 +170,148 @@ __device__ void finalize(const GmresDev& st, int fin, int i, int mgs_k, int orth
       const double hn = sqrt(ww);
       st.H[(size_t)i * ld + i + 1] = hn;
       if (hn > 0.0) st.scal[S_SCALE] = 1.0 / hn; else { st.scal[S_SCALE] = 0.0; st.flags[F_BREAK] = 1; }
-      givens_column(st, i);
+      givens_column(st, i, nullptr);  // the MGS dots wrote H(0..i,i) to global memory one by one
     } break;
     default: break;
   }
 }
 
+// ---------------------------------------------------------------------------- TMA pipeline
+// Both hot kernels stream a tall-skinny tile of the Krylov basis (R rows x all active columns)
+// through a ring of shared-memory stages filled by the TMA unit (cp.async.bulk, one bulk copy per
+// column segment, completion counted on an mbarrier), so the bytes in flight per SM are set by
+// the ring (~190 KB) and not by how many loads a thread can keep in registers.  One persistent
+// CTA per SM: warp 8 produces, warps 0-7 consume.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a pipeline bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kConsumerWarps = 8;
+constexpr int kPipeThreads = (kConsumerWarps + 1) * 32;
+
+struct Pipe {          // geometry chosen on the host per launch
+  int R;               // rows per stage (multiple of 32)
+  int stages;
+  uint32_t stage_bytes;
+};
+
+// producer warp: tiles t = first, first+step, ... ; column c < ncols of a tile comes from
+// (c < j ? V + c*ld : extra) + t*R.  `reverse` walks the tiles from the last one down.
+template <class VT>
+__device__ __forceinline__ void pipe_produce(const Pipe& pp, unsigned char* ring, uint64_t* full, uint64_t* empty, int n,
+                                             const VT* V, int64_t ld, int j, const VT* extra, bool reverse) {
+  const int lane = threadIdx.x & 31;
+  const int ntiles = (n + pp.R - 1) / pp.R;
+  const int ncols = j + (extra ? 1 : 0);
+  int it = 0;
+  for (int t0 = blockIdx.x; t0 < ntiles; t0 += gridDim.x, ++it) {
+    const int t = reverse ? ntiles - 1 - t0 : t0;
+    const int s = it % pp.stages;
+    const uint32_t use = (uint32_t)(it / pp.stages);
+    if (use > 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+    const int rows = min(pp.R, n - t * pp.R);
+    const uint32_t col_bytes = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;  // V columns and work vectors are padded to ld
+    if (lane == 0) mbar_expect_tx(&full[s], col_bytes * (uint32_t)ncols);
+    __syncwarp();
+    unsigned char* tile = ring + (size_t)s * pp.stage_bytes;
+    for (int c = lane; c < ncols; c += 32) {
+      const VT* src = (c < j ? V + (size_t)c * ld : extra) + (size_t)t * pp.R;
+      bulk_g2s(tile + (size_t)c * pp.R * sizeof(VT), src, col_bytes, &full[s]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- dots
-template <class VT, int J>
-__global__ void __launch_bounds__(256) dots_kernel(int n, const VT* __restrict__ V, int64_t ld, int j,
-                                                   const VT* __restrict__ w, GmresDev st, int fin, int inner_i,
-                                                   int mgs_k, int orth_mode, int need_reorth) {
+// partial[k] = V[:,k].w (k<j), partial[j] = w.w ; the last CTA reduces and runs finalize().
+template <class VT>
+__global__ void __launch_bounds__(kPipeThreads, 1) dots_kernel(int n, const VT* __restrict__ V, int64_t ld, int j,
+                                                                const VT* __restrict__ w, GmresDev st, int fin,
+                                                                int inner_i, int mgs_k, int orth_mode, int need_reorth,
+                                                                Pipe pp) {
   if (st.flags[F_CONV]) return;
   if (need_reorth && !st.flags[F_REORTH]) return;
-  constexpr int W = VecIO<VT>::W;
-  using VV = typename VecIO<VT>::V;
-  double acc[J + 1];
-#pragma unroll
-  for (int k = 0; k <= J; ++k) acc[k] = 0.0;
-  const int64_t nvec = n / W;
-  const VV* w4 = reinterpret_cast<const VV*>(w);
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nvec; c += (int64_t)gridDim.x * blockDim.x) {
-    double wv[W];
-    VecIO<VT>::unpack(w4[c], wv);
-#pragma unroll
-    for (int e = 0; e < W; ++e) acc[J] += wv[e] * wv[e];
-#pragma unroll
-    for (int k = 0; k < J; ++k) {
-      if (k < j) {
-        double vv[W];
-        VecIO<VT>::unpack(*reinterpret_cast<const VV*>(V + (size_t)k * ld + c * W), vv);
-#pragma unroll
-        for (int e = 0; e < W; ++e) acc[k] += vv[e] * wv[e];
-      }
-    }
-  }
-  if (blockIdx.x == 0) {  // scalar tail (n not a multiple of the vector width)
-    for (int64_t r = nvec * W + threadIdx.x; r < n; r += blockDim.x) {
-      const double wr = (double)w[r];
-      acc[J] += wr * wr;
-#pragma unroll
-      for (int k = 0; k < J; ++k)
-        if (k < j) acc[k] += (double)V[(size_t)k * ld + r] * wr;
-    }
-  }
-  __shared__ double sm[8][J + 1];
+  extern __shared__ __align__(128) unsigned char dyn[];
+  unsigned char* ring = dyn;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dyn + (size_t)pp.stages * pp.stage_bytes);
+  uint64_t* empty = full + pp.stages;
+  __shared__ double red_w[kConsumerWarps][5];
+  __shared__ double red[kFinMax + 2];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k <= J; ++k) {
-    const double v = warp_sum(acc[k]);
-    if (lane == 0) sm[wid][k] = v;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pp.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // slot j of the partial row carries w.w ; slots [0,j) the projections
-  if (threadIdx.x <= j) {
-    const int src = threadIdx.x == j ? J : threadIdx.x;
-    double v = 0.0;
+  const int ncols = j + 1;
+  // column groups x row groups over the 8 consumer warps; at most 5 columns per warp
+  const int CW = ncols > 20 ? 8 : ncols > 10 ? 4 : ncols > 5 ? 2 : 1, RW = kConsumerWarps / CW;
+  if (wid == kConsumerWarps) {
+    pipe_produce<VT>(pp, ring, full, empty, n, V, ld, j, w, false);
+  } else {
+    const int cg = wid % CW, rg = wid / CW;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int ntiles = (n + pp.R - 1) / pp.R;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % pp.stages;
+      mbar_wait(&full[s], (uint32_t)(it / pp.stages) & 1u);
+      const VT* tile = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes);
+      const VT* tw = tile + (size_t)j * pp.R;
+      const int rows = min(pp.R, n - t * pp.R);
+#pragma unroll 4
+      for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
+        const double wv = (double)tw[r];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v += sm[q][src];
+        for (int a = 0; a < 5; ++a) {
+          const int c = cg + a * CW;
+          if (c < ncols) acc[a] += (double)tile[(size_t)c * pp.R + r] * wv;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const double v = warp_sum(acc[a]);
+      if (lane == 0) red_w[wid][a] = v;
+    }
+  }
+  __syncthreads();
+  // slot k of the partial row: column k = cg + a*CW, summed over the row groups
+  if (threadIdx.x <= j) {
+    const int cg = threadIdx.x % CW, a = threadIdx.x / CW;
+    double v = 0.0;
+    for (int rg = 0; rg < RW; ++rg) v += red_w[cg + CW * rg][a];
     st.partial[(size_t)blockIdx.x * st.partial_ld + threadIdx.x] = v;
   }
   __threadfence();
@@ -193,68 +320,124 @@ __global__ void __launch_bounds__(256) dots_kernel(int n, const VT* __restrict__
   __syncthreads();
   if (!last) return;
   __threadfence();
-  // deterministic final reduction: warp q owns slots q, q+8, ...; lanes stride over blocks
-  __shared__ double red[J + 2];
-  for (int k = wid; k <= j; k += 8) {
+  // deterministic final reduction: warp q owns slots q, q+9, ...; lanes stride over CTAs
+  for (int k = wid; k <= j; k += kConsumerWarps + 1) {
     double v = 0.0;
     for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&st.partial[(size_t)b * st.partial_ld + k]);
     v = warp_sum(v);
     if (lane == 0) red[k] = v;
   }
+  __shared__ FinScratch fs;
+  const bool column_fin = fin == FIN_CGS1 || fin == FIN_CGS2;
+  if (column_fin) fin_prefetch(st, fs, inner_i, threadIdx.x);
   __syncthreads();
   if (threadIdx.x == 0) {
-    finalize(st, fin, inner_i, mgs_k, orth_mode, red, j);
+    finalize(st, fin, inner_i, mgs_k, orth_mode, red, j, column_fin ? &fs : nullptr);
     *st.ticket = 0u;
   }
 }
 
 // ---------------------------------------------------------------------------- update
-template <class VT, int J>
-__global__ void __launch_bounds__(256) update_kernel(int n, const VT* a, const VT* __restrict__ V,
-                                                     int64_t ld, int j, const double* __restrict__ coef, double sgn,
-                                                     VT* out, GmresDev st, int use_scale, int force,
-                                                     int need_reorth) {
+// out = (a + sgn * V[:,0..j) c) * scale, j >= 1 (the MGS/CGS axpy sweep fused with the
+// normalisation cublasScopy+cublasSscal of the reference, and Update_GPU's x += V y).
+template <class VT>
+__global__ void __launch_bounds__(kPipeThreads, 1) update_kernel(int n, const VT* a, const VT* __restrict__ V, int64_t ld,
+                                                                  int j, const double* __restrict__ coef, double sgn,
+                                                                  VT* out, GmresDev st, int use_scale, int force,
+                                                                  int need_reorth, Pipe pp) {
   if (!force && st.flags[F_CONV]) return;
   if (need_reorth && !st.flags[F_REORTH]) return;
-  constexpr int W = VecIO<VT>::W;
-  using VV = typename VecIO<VT>::V;
-  double c[J > 0 ? J : 1];
-#pragma unroll
-  for (int k = 0; k < J; ++k) c[k] = k < j ? sgn * coef[k] : 0.0;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  unsigned char* ring = dyn;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dyn + (size_t)pp.stages * pp.stage_bytes);
+  uint64_t* empty = full + pp.stages;
+  __shared__ double cs[kFinMax];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pp.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < j) cs[threadIdx.x] = sgn * coef[threadIdx.x];
+  __syncthreads();
+  if (wid == kConsumerWarps) {
+    // rows are walked from the END: the dots kernel that ran just before finished on the high rows
+    // of every basis column, so those are the lines still resident in the 126 MB L2
+    pipe_produce<VT>(pp, ring, full, empty, n, V, ld, j, (const VT*)nullptr, true);
+    return;
+  }
   const double scale = use_scale ? st.scal[S_SCALE] : 1.0;
-  const int64_t nvec = n / W;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += (int64_t)gridDim.x * blockDim.x) {
-    double av[W];
-    VecIO<VT>::unpack(*reinterpret_cast<const VV*>(a + q * W), av);
+  const int ntiles = (n + pp.R - 1) / pp.R;
+  int it = 0;
+  for (int t0 = blockIdx.x; t0 < ntiles; t0 += gridDim.x, ++it) {
+    const int t = ntiles - 1 - t0;
+    const int s = it % pp.stages;
+    const int rows = min(pp.R, n - t * pp.R);
+    const size_t base = (size_t)t * pp.R;
+    // the addend comes straight from global memory (it may be a caller-owned, unpadded vector);
+    // its loads are issued before the wait so they overlap the bulk copies
+    double av[4];
 #pragma unroll
-    for (int k = 0; k < J; ++k) {
-      if (k < j) {
-        double vv[W];
-        VecIO<VT>::unpack(*reinterpret_cast<const VV*>(V + (size_t)k * ld + q * W), vv);
+    for (int u = 0; u < 4; ++u) {
+      const int r = threadIdx.x + 256 * u;
+      av[u] = r < rows ? (double)a[base + r] : 0.0;
+    }
+    mbar_wait(&full[s], (uint32_t)(it / pp.stages) & 1u);
+    const VT* tile = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes);
+    for (int r0 = 0; r0 < rows; r0 += 1024) {
+      if (r0 > 0) {
 #pragma unroll
-        for (int e = 0; e < W; ++e) av[e] += c[k] * vv[e];
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + threadIdx.x + 256 * u;
+          av[u] = r < rows ? (double)a[base + r] : 0.0;
+        }
+      }
+      for (int k = 0; k < j; ++k) {
+        const double c = cs[k];
+        const VT* col = tile + (size_t)k * pp.R + r0 + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (r0 + (int)threadIdx.x + 256 * u < rows) av[u] += c * (double)col[256 * u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + threadIdx.x + 256 * u;
+        if (r < rows) out[base + r] = (VT)(av[u] * scale);
       }
     }
-#pragma unroll
-    for (int e = 0; e < W; ++e) av[e] *= scale;
-    *reinterpret_cast<VV*>(out + q * W) = VecIO<VT>::pack(av);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
-  if (blockIdx.x == 0) {
-    for (int64_t r = nvec * W + threadIdx.x; r < n; r += blockDim.x) {
-      double v = (double)a[r];
-#pragma unroll
-      for (int k = 0; k < J; ++k)
-        if (k < j) v += c[k] * (double)V[(size_t)k * ld + r];
-      out[r] = (VT)(v * scale);
-    }
-  }
+}
+
+// out = a * scale (no basis columns: v0 = r/beta, gmres.cu:2342-2343)
+template <class VT>
+__global__ void __launch_bounds__(256) scale_copy_kernel(int n, const VT* a, VT* out, GmresDev st, int use_scale, int force) {
+  if (!force && st.flags[F_CONV]) return;
+  const double scale = use_scale ? st.scal[S_SCALE] : 1.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (VT)((double)a[i] * scale);
 }
 
 // back-substitution H y = s on one thread (Update, src/gmres.cu:92-105 / Update_GPU :172-181)
 __global__ void solve_y_kernel(GmresDev st, int k, int force) {
   if (!force && st.flags[F_CONV]) return;
-  if (threadIdx.x != 0) return;
   const int ld = st.m + 1;
+  if (st.m <= kFinMax) {  // whole triangle on chip: parallel fetch, serial solve out of shared memory
+    __shared__ double Hs[(kFinMax + 1) * kFinMax], ys[kFinMax + 1];
+    for (int t = threadIdx.x; t < ld * (k + 1); t += blockDim.x) Hs[t] = st.H[t];
+    for (int t = threadIdx.x; t <= k; t += blockDim.x) ys[t] = st.s[t];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = k; i >= 0; --i) {
+        ys[i] /= Hs[i * ld + i];
+        for (int q = i - 1; q >= 0; --q) ys[q] -= Hs[i * ld + q] * ys[i];
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t <= k; t += blockDim.x) st.y[t] = ys[t];
+    return;
+  }
+  if (threadIdx.x != 0) return;
   for (int i = 0; i <= k; ++i) st.y[i] = st.s[i];
   for (int i = k; i >= 0; --i) {
     st.y[i] /= st.H[(size_t)i * ld + i];
@@ -305,31 +488,56 @@ __global__ void divide_cast_kernel(int n, const CT* __restrict__ in, const VT* _
     out[i] = (VT)(in[i] / scale[i]);
 }
 
+// block-major renumbering of the solver's vectors (trsv_block.cu): out[i] = in[perm[i]] / out[perm[i]] = in[i]
+template <class VT>
+__global__ void gather_kernel(int n, const int* __restrict__ perm, const VT* __restrict__ in, VT* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[perm[i]];
+}
+template <class VT>
+__global__ void scatter_kernel(int n, const int* __restrict__ perm, const VT* __restrict__ in, VT* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[perm[i]] = in[i];
+}
+
 // ---------------------------------------------------------------------------- launchers
-static int vec_grid(bg_context_t ctx, int64_t n, int per_thread) {
+static int vec_grid(bg_context_t ctx, int64_t n, int per_thread, int ctas_per_sm = 4) {
   int64_t blocks = (n / per_thread + 255) / 256;
-  const int64_t cap = (int64_t)ctx->sm_count * 4;
+  const int64_t cap = (int64_t)ctx->sm_count * ctas_per_sm;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }
-static int round_j(int j) { return j == 0 ? 0 : j == 1 ? 1 : j <= 4 ? 4 : j <= 8 ? 8 : j <= 16 ? 16 : j <= 24 ? 24 : j <= 32 ? 32 : -1; }
+
+// ring geometry: `stages` stages of about `stage_kb` KB each, R rows x ncols columns per stage
+static Pipe pipe_geometry(int ncols, size_t elem) {
+  static const int stage_kb = [] { const char* e = getenv("BG_ORTH_STAGE_KB"); int v = e ? atoi(e) : 0; return v >= 4 && v <= 96 ? v : 48; }();
+  static const int stages = [] { const char* e = getenv("BG_ORTH_STAGES"); int v = e ? atoi(e) : 0; return v >= 2 && v <= 8 ? v : 4; }();
+  Pipe p;
+  int R = (int)((size_t)stage_kb * 1024 / ((size_t)std::max(1, ncols) * elem)) / 32 * 32;
+  p.R = std::max(32, std::min(R, 4096));
+  p.stages = stages;
+  p.stage_bytes = (uint32_t)(((size_t)std::max(1, ncols) * p.R * elem + 127) / 128 * 128);
+  return p;
+}
+template <class K> static int pipe_smem_attr(K kernel, bg_context_t ctx) {
+  static bool done = false;  // per kernel instantiation
+  if (!done) {
+    BG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 8192));
+    done = true;
+  }
+  return BG_OK;
+}
 
 template <class VT>
 static int dots_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int j, const VT* w, const GmresDev& st,
                          int fin, int i, int mk, int om, int nr) {
-  const int g = vec_grid(ctx, n, VecIO<VT>::W);
-#define BG_D(JJ) dots_kernel<VT, JJ><<<g, 256, 0, ctx->stream>>>(n, V, ld, j, w, st, fin, i, mk, om, nr)
-  switch (round_j(j)) {
-    case 0: BG_D(0); break;
-    case 1: BG_D(1); break;
-    case 4: BG_D(4); break;
-    case 8: BG_D(8); break;
-    case 16: BG_D(16); break;
-    case 24: BG_D(24); break;
-    case 32: BG_D(32); break;
-    default: set_error("dots: j=%d exceeds one pass (max 32 columns)", j); return BG_ERR_ARG;
-  }
-#undef BG_D
+  if (j < 0 || j > kFinMax) { set_error("dots: j=%d exceeds one pass (max %d columns)", j, kFinMax); return BG_ERR_ARG; }
+  const Pipe pp = pipe_geometry(j + 1, sizeof(VT));
+  const size_t smem = (size_t)pp.stages * pp.stage_bytes + 2 * sizeof(uint64_t) * pp.stages;
+  BG_TRY(pipe_smem_attr(dots_kernel<VT>, ctx));
+  const int ntiles = (n + pp.R - 1) / pp.R;
+  const int g = std::max(1, std::min(ntiles, ctx->sm_count));
+  dots_kernel<VT><<<g, kPipeThreads, smem, ctx->stream>>>(n, V, ld, j, w, st, fin, i, mk, om, nr, pp);
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
@@ -344,19 +552,17 @@ int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, i
 template <class VT>
 static int update_dispatch(bg_context_t ctx, int n, const VT* a, const VT* V, int64_t ld, int j, const double* coef,
                            double sgn, VT* out, const GmresDev& st, int us, int force, int nr) {
-  const int g = vec_grid(ctx, n, VecIO<VT>::W);
-#define BG_U(JJ) update_kernel<VT, JJ><<<g, 256, 0, ctx->stream>>>(n, a, V, ld, j, coef, sgn, out, st, us, force, nr)
-  switch (round_j(j)) {
-    case 0: BG_U(0); break;
-    case 1: BG_U(1); break;
-    case 4: BG_U(4); break;
-    case 8: BG_U(8); break;
-    case 16: BG_U(16); break;
-    case 24: BG_U(24); break;
-    case 32: BG_U(32); break;
-    default: set_error("update: j=%d exceeds one pass (max 32 columns)", j); return BG_ERR_ARG;
+  if (j < 0 || j > kFinMax) { set_error("update: j=%d exceeds one pass (max %d columns)", j, kFinMax); return BG_ERR_ARG; }
+  if (j == 0) {
+    scale_copy_kernel<VT><<<vec_grid(ctx, n, 1, 8), 256, 0, ctx->stream>>>(n, a, out, st, us, force);
+  } else {
+    const Pipe pp = pipe_geometry(j, sizeof(VT));
+    const size_t smem = (size_t)pp.stages * pp.stage_bytes + 2 * sizeof(uint64_t) * pp.stages;
+    BG_TRY(pipe_smem_attr(update_kernel<VT>, ctx));
+    const int ntiles = (n + pp.R - 1) / pp.R;
+    const int g = std::max(1, std::min(ntiles, ctx->sm_count));
+    update_kernel<VT><<<g, kPipeThreads, smem, ctx->stream>>>(n, a, V, ld, j, coef, sgn, out, st, us, force, nr, pp);
   }
-#undef BG_U
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
@@ -370,7 +576,7 @@ int launch_update(bg_context_t ctx, int dtype, int n, const void* a, const void*
 }
 
 int launch_solve_y(bg_context_t ctx, const GmresDev& st, int k, int force) {
-  solve_y_kernel<<<1, 32, 0, ctx->stream>>>(st, k, force);
+  solve_y_kernel<<<1, 256, 0, ctx->stream>>>(st, k, force);
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
@@ -393,6 +599,22 @@ int launch_copy(bg_context_t ctx, int dtype, int n, const void* in, void* out, c
   const int g = vec_grid(ctx, n, 1);
   if (dtype == BG_F32) copy_kernel<float><<<g, 256, 0, ctx->stream>>>(n, (const float*)in, (float*)out, skip);
   else copy_kernel<double><<<g, 256, 0, ctx->stream>>>(n, (const double*)in, (double*)out, skip);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+int launch_gather(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out) {
+  const int g = vec_grid(ctx, n, 1);
+  if (dtype == BG_F32) gather_kernel<float><<<g, 256, 0, ctx->stream>>>(n, perm, (const float*)in, (float*)out);
+  else gather_kernel<double><<<g, 256, 0, ctx->stream>>>(n, perm, (const double*)in, (double*)out);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+int launch_scatter(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out) {
+  const int g = vec_grid(ctx, n, 1);
+  if (dtype == BG_F32) scatter_kernel<float><<<g, 256, 0, ctx->stream>>>(n, perm, (const float*)in, (float*)out);
+  else scatter_kernel<double><<<g, 256, 0, ctx->stream>>>(n, perm, (const double*)in, (double*)out);
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;

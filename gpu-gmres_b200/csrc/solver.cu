@@ -158,6 +158,11 @@ template <class T>
 static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::vector<int>& ci, const std::vector<T>& v,
                         int format) {
   cudaStream_t s = A->ctx->stream;
+  A->requested_format = format;
+  A->h_rp = rp;
+  A->h_ci = ci;
+  A->h_val.resize(v.size() * sizeof(T));
+  if (!v.empty()) std::memcpy(A->h_val.data(), v.data(), A->h_val.size());
   A->plan = inspect_rows(A->n, rp.data());
   if (format == BG_SPMV_AUTO) format = A->plan.format;
   A->format = format;
@@ -331,6 +336,9 @@ extern "C" void bg_precond_opts_default(bg_precond_opts* o) {
   o->use_tma = 1;
   o->ilut_lfil = 10;
   o->ilut_tau = 1e-3;
+  o->chunk_bytes = 2048;
+  o->stages = 4;
+  o->warps_per_cta = 4;
 }
 
 template <class T> static int upload_level_stream(bg_context_t ctx, const LevelStream<T>& h, LevelStreamDev& d) {
@@ -344,14 +352,21 @@ template <class T> static int upload_level_stream(bg_context_t ctx, const LevelS
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }
-template <class T> static int upload_block_stream(bg_context_t ctx, const BlockStream<T>& h, BlockStreamDev& d) {
+static uint64_t g_order_serial = 0;
+template <class T> static int upload_fused_stream(bg_context_t ctx, const FusedBlockStream<T>& h, FusedBlockDev& d) {
   cudaStream_t s = ctx->stream;
-  d.n = h.n; d.nblocks = h.nblocks; d.K = h.K; d.CS = h.CS; d.max_rows = h.max_rows; d.max_levels = h.max_levels;
-  d.chunk_bytes = h.chunk_bytes;
-  BG_TRY(upload_vec(d.grow, h.grow, s)); BG_TRY(upload_vec(d.blk_row_ptr, h.blk_row_ptr, s));
-  BG_TRY(upload_vec(d.blk_lev_ptr, h.blk_lev_ptr, s)); BG_TRY(upload_vec(d.lev_slot, h.lev_slot, s));
-  BG_TRY(upload_vec(d.blk_chunk_ptr, h.blk_chunk_ptr, s)); BG_TRY(upload_vec(d.stream, h.stream, s));
-  d.bytes = (int64_t)h.stream.size() + (int64_t)h.grow.size() * 4;
+  d.n = h.n; d.nblocks = h.nblocks; d.max_rows = h.max_rows; d.max_levels_L = h.max_levels_L; d.max_levels_U = h.max_levels_U;
+  d.max_chunk_bytes = h.max_chunk_bytes; d.max_chunks = h.max_chunks; d.total_steps = h.total_steps;
+  d.h_perm = h.perm;
+  d.serial = ++g_order_serial;
+  std::vector<int> inv(h.n);
+  for (int i = 0; i < h.n; ++i) inv[h.perm[i]] = i;
+  BG_TRY(upload_vec(d.perm, h.perm, s)); BG_TRY(upload_vec(d.iperm, inv, s));
+  BG_TRY(d.blk.upload(h.blk.data(), h.blk.size() * sizeof(BlockDesc), s));
+  BG_TRY(upload_vec(d.chunk_off, h.chunk_off, s)); BG_TRY(upload_vec(d.stream, h.stream, s));
+  BG_TRY(upload_vec(d.dinv, h.dinv, s));
+  d.bytes = (int64_t)h.stream.size() + (int64_t)h.blk.size() * sizeof(BlockDesc) + (int64_t)h.chunk_off.size() * 4 +
+            (int64_t)h.dinv.size() * sizeof(T);
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }
@@ -365,11 +380,9 @@ static int precond_install(bg_precond_t M, const Csr<FH>& L, const Csr<FH>& U, b
   M->unit_lower = unit_lower;
   try {
     if (M->schedule == BG_TRSV_BLOCK) {
-      BlockStream<FT> bl, bu;
-      pack_block_stream<FT>(true, unit_lower, Lf, nblocks, block_of_row, 128, bl);
-      pack_block_stream<FT>(false, false, Uf, nblocks, block_of_row, 128, bu);
-      BG_TRY(upload_block_stream(M->ctx, bl, M->bsL));
-      BG_TRY(upload_block_stream(M->ctx, bu, M->bsU));
+      FusedBlockStream<FT> fs;
+      pack_fused_block_stream<FT>(unit_lower, Lf, Uf, nblocks, block_of_row, M->fb_chunk_bytes, fs);
+      BG_TRY(upload_fused_stream(M->ctx, fs, M->fb));
     } else {
       LevelStream<FT> ll, lu;
       pack_level_stream<FT>(true, unit_lower, Lf, 2048, ll);
@@ -453,6 +466,9 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
   M->schedule = o.trsv_schedule;
   M->factor_dtype = o.factor_dtype < 0 ? dtype : o.factor_dtype;
   M->use_tma = o.use_tma != 0;
+  M->fb_chunk_bytes = o.chunk_bytes > 0 ? o.chunk_bytes : 2048;
+  M->fb.stages = std::min(16, std::max(2, o.stages > 0 ? o.stages : 4));
+  M->fb.warps_per_cta = std::min(16, std::max(1, o.warps_per_cta > 0 ? o.warps_per_cta : 4));
   int rc = precond_install_dt<T>(M, F.L, F.U, true, block ? blk.data() : nullptr, nb);
   if (rc < 0) { delete M; return rc; }
   *out = M;
@@ -561,7 +577,7 @@ extern "C" int bg_precond_create_split(bg_context_t ctx, int n, const int* lp, c
 
 namespace bg {
 // internal apply with the solver's skip flag
-int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, void* out, const int* skip) {
+int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, void* out, const int* skip, bool permuted) {
   const int n = M->n;
   switch (M->kind) {
     case BG_PRECOND_NONE: return launch_copy(ctx, M->dtype, n, in, out, skip);
@@ -570,10 +586,8 @@ int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, v
       return launch_diag_scale(ctx, M->dtype, n, in, M->dinv.p, out, skip);
     case BG_PRECOND_LU: {
       if (which == BG_PC_RIGHT || which == BG_PC_START) return launch_copy(ctx, M->dtype, n, in, out, skip);
-      if (M->schedule == BG_TRSV_BLOCK) {
-        BG_TRY(launch_trsv_block(ctx, M->bsL, M->dtype, M->factor_dtype, M->unit_lower, M->use_tma, in, M->tmp.p, skip));
-        return launch_trsv_block(ctx, M->bsU, M->dtype, M->factor_dtype, false, M->use_tma, M->tmp.p, out, skip);
-      }
+      if (M->schedule == BG_TRSV_BLOCK)  // `permuted`: vectors already in the block-major order of the stream
+        return launch_trsv_block(ctx, M->fb, M->dtype, M->factor_dtype, !permuted, in, out, skip);
       TrsvXform xf;
       const bool same = M->ct_dtype() == M->dtype;
       BG_TRY(launch_trsv_level(ctx, M->lsL, M->dtype, M->factor_dtype, M->unit_lower, in, M->xsL.p, same ? nullptr : M->tmp.p, xf, skip));
@@ -605,7 +619,7 @@ int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, v
 
 extern "C" int bg_precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, void* out) {
   if (!ctx || !M || !in || !out) return BG_ERR_ARG;
-  return precond_apply(ctx, M, which, in, out, nullptr);
+  return precond_apply(ctx, M, which, in, out, nullptr, false);
 }
 extern "C" int bg_precond_get_info(bg_precond_t M, bg_precond_info* o) {
   if (!M || !o) return BG_ERR_ARG;
@@ -615,8 +629,8 @@ extern "C" int bg_precond_get_info(bg_precond_t M, bg_precond_info* o) {
   const int64_t s = dtype_size(M->dtype), sf = dtype_size(M->factor_dtype), n = M->n;
   if (M->kind == BG_PRECOND_LU || M->kind == BG_PRECOND_SPLIT) {
     if (M->schedule == BG_TRSV_BLOCK) {
-      o->levelsL = M->bsL.max_levels; o->levelsU = M->bsU.max_levels; o->nblocks = M->bsL.nblocks; o->max_block_rows = M->bsL.max_rows;
-      o->stream_bytes = M->bsL.bytes + M->bsU.bytes;
+      o->levelsL = M->fb.max_levels_L; o->levelsU = M->fb.max_levels_U; o->nblocks = M->fb.nblocks; o->max_block_rows = M->fb.max_rows;
+      o->stream_bytes = M->fb.bytes;
     } else {
       o->levelsL = M->lsL.n_levels; o->levelsU = M->lsU.n_levels; o->nblocks = 1; o->max_block_rows = M->n;
       o->stream_bytes = M->lsL.bytes + M->lsU.bytes;
@@ -657,7 +671,7 @@ extern "C" int bg_solver_create(bg_context_t ctx, int n, int m, int dtype, bg_so
   for (DevBuf* b : {&S->w, &S->ww, &S->r, &S->rr, &S->bb, &S->yv})
     if (rc >= 0) rc = b->alloc((size_t)S->ld * s);
   // state block: flags | scal | h | h2 | y | H | s | cs | sn | ticket | hist | partial
-  const int pl = m + 2, nblk = ctx->sm_count * 4;
+  const int pl = m + 2, nblk = ctx->sm_count * 8;  // dots grids never exceed 8 resident CTAs per SM
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
   const size_t o_flags = take(F_COUNT * sizeof(int)), o_scal = take(S_COUNT * 8), o_h = take(pl * 8), o_h2 = take(pl * 8),
@@ -712,6 +726,7 @@ struct Driver {
   const void* b; void* x;
   int n, m; int64_t ld; size_t es; bool split; const int* skip; GmresDev st;
   Prof* prof = nullptr;
+  bool permuted = false;  // A, b, x and all work vectors are in the preconditioner's block-major row order
   char* col(int k) const { return S->V.as<char>() + (size_t)k * ld * es; }
   struct Span {
     Prof* p; int ph, a;
@@ -719,7 +734,7 @@ struct Driver {
     ~Span() { if (p) { p->spans[ph].emplace_back(a, p->mark()); p->calls[ph]++; } }
   };
 
-  int apply_left(const void* in, void* out, const int* sk) { return precond_apply(ctx, M, split ? BG_PC_LEFT : BG_PC_FULL, in, out, sk); }
+  int apply_left(const void* in, void* out, const int* sk) { return precond_apply(ctx, M, split ? BG_PC_LEFT : BG_PC_FULL, in, out, sk, permuted); }
 
   // r = M_L^-1 (b - A x); beta, convergence test, v0 = r/beta
   int residual(int fin) {
@@ -732,7 +747,7 @@ struct Driver {
   int iteration(int i) {
     // w = M_L^-1 A M_R^-1 v_i   (gmres.cu:2350-2354 / 2637-2640)
     if (split) {
-      { Span sp(prof, PH_TRSV); BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, col(i), S->w.p, skip)); }
+      { Span sp(prof, PH_TRSV); BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, col(i), S->w.p, skip, false)); }
       { Span sp(prof, PH_SPMV); BG_TRY(launch_spmv(ctx, A, 1.0, S->w.p, 0.0, nullptr, S->ww.p, false, skip)); }
     } else {
       Span sp(prof, PH_SPMV);
@@ -761,7 +776,7 @@ struct Driver {
     BG_TRY(launch_solve_y(ctx, st, k, force));
     void* tgt = split ? S->yv.p : x;
     BG_TRY(launch_update(ctx, S->dtype, n, tgt, col(0), ld, k + 1, st.y, 1.0, tgt, st, 0, force, 0));
-    if (split) BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, S->yv.p, x, sk));
+    if (split) BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, S->yv.p, x, sk, false));
     return BG_OK;
   }
   int poll_async(int slot) {
@@ -780,6 +795,45 @@ struct Driver {
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
+// P A P^T for the block-major order of a block-Jacobi preconditioner (new row i = old row perm[i]);
+// built once per ordering and cached inside A.
+template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev& fb) {
+  const int n = A->n;
+  const std::vector<int>& perm = fb.h_perm;
+  std::vector<int> inv(n);
+  for (int i = 0; i < n; ++i) inv[perm[i]] = i;
+  const T* v = reinterpret_cast<const T*>(A->h_val.data());
+  std::vector<int> rp(n + 1, 0), ci(A->h_ci.size());
+  std::vector<T> vv(A->h_ci.size());
+  for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (A->h_rp[perm[i] + 1] - A->h_rp[perm[i]]);
+  std::vector<std::pair<int, T>> row;
+  for (int i = 0; i < n; ++i) {
+    const int o = perm[i];
+    row.clear();
+    for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) row.emplace_back(inv[A->h_ci[p]], v[p]);
+    std::sort(row.begin(), row.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
+    int q = rp[i];
+    for (auto& e : row) { ci[q] = e.first; vv[q++] = e.second; }
+  }
+  bg_matrix_t P = new bg_matrix_s;
+  P->ctx = A->ctx; P->n = n; P->nnz = A->nnz; P->dtype = A->dtype;
+  int rc = matrix_build<T>(P, rp, ci, vv, A->requested_format);
+  if (rc < 0) { delete P; return rc; }
+  P->h_rp.clear(); P->h_rp.shrink_to_fit(); P->h_ci.clear(); P->h_ci.shrink_to_fit(); P->h_val.clear(); P->h_val.shrink_to_fit();
+  delete A->permuted;
+  A->permuted = P;
+  A->permuted_serial = fb.serial;
+  return BG_OK;
+}
+static int permuted_matrix(bg_matrix_t A, const FusedBlockDev& fb, bg_matrix_t* out) {
+  if (!A->permuted || A->permuted_serial != fb.serial) {
+    if ((int)fb.h_perm.size() != A->n) { set_error("preconditioner ordering does not match the matrix"); return BG_ERR_ARG; }
+    BG_TRY(A->dtype == BG_F32 ? build_permuted<float>(A, fb) : build_permuted<double>(A, fb));
+  }
+  *out = A->permuted;
+  return BG_OK;
+}
+
 static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
                             const bg_gmres_opts* opts, bg_gmres_result* res, Prof* prof) {
   if (!ctx || !S || !A || !M || !d_b || !d_x || !opts) { set_error("bg_gmres_solve: null argument"); return BG_ERR_ARG; }
@@ -792,18 +846,33 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
   BG_CUDA(cudaSetDevice(ctx->device));
   const int64_t launches0 = ctx->launches;
   const int n = S->n, m = o.m;
+  // block-Jacobi preconditioners solve in their own block-major row order: run the whole iteration
+  // on P A P^T, P b, P x (residual norms and the Hessenberg matrix are permutation invariant)
+  const bool permuted = M->kind == BG_PRECOND_LU && M->schedule == BG_TRSV_BLOCK;
+  void* const d_x_user = d_x;
+  if (permuted) {
+    BG_TRY(permuted_matrix(A, M->fb, &A));
+    const size_t bytes = (size_t)S->ld * dtype_size(S->dtype);
+    if (S->bp.bytes < bytes) { BG_TRY(S->bp.alloc(bytes)); BG_TRY(S->xp.alloc(bytes)); }
+  }
   GmresDev st = S->dev;
   st.m = m;  // H leading dimension follows the active restart length
   st.hist_cap = std::min(std::max(o.history_cap, 0), kHistCap);
-  Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof};
   const int chunk = std::max(1, o.poll_chunk);
 
   BG_CUDA(cudaEventRecord(S->t0, ctx->stream));
+  if (permuted) {
+    BG_TRY(launch_gather(ctx, S->dtype, n, M->fb.perm.as<int>(), d_b, S->bp.p));
+    BG_TRY(launch_gather(ctx, S->dtype, n, M->fb.perm.as<int>(), d_x, S->xp.p));
+    d_b = S->bp.p;
+    d_x = S->xp.p;
+  }
+  Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof, permuted};
   BG_TRY(launch_state_reset(ctx, st, o.tol, o.reorth_eta));
   // normb = || M_L^-1 b ||   (gmres.cu:2294-2296)
   BG_TRY(D.apply_left(d_b, S->bb.p, nullptr));
   BG_TRY(launch_dots(ctx, S->dtype, n, nullptr, S->ld, 0, S->bb.p, st, FIN_NORMB, 0, 0, o.orth, 0));
-  if (D.split) BG_TRY(precond_apply(ctx, M, BG_PC_START, d_x, S->yv.p, nullptr));  // gmres.cu:2300
+  if (D.split) BG_TRY(precond_apply(ctx, M, BG_PC_START, d_x, S->yv.p, nullptr, false));  // gmres.cu:2300
   BG_TRY(D.residual(FIN_BETA0));
 
   Status stt;
@@ -842,6 +911,7 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
     // in-cycle convergence at inner index k_conv: the update was skipped by the flag, do it now
     BG_TRY(D.apply_update(stt.flags[F_KCONV], 1));
   }
+  if (permuted) BG_TRY(launch_scatter(ctx, S->dtype, n, M->fb.perm.as<int>(), d_x, d_x_user));
   BG_CUDA(cudaEventRecord(S->t1, ctx->stream));
   BG_CUDA(cudaStreamSynchronize(ctx->stream));
   S->last_hist_len = std::min(stt.flags[F_ITERS], st.hist_cap);

@@ -1,0 +1,257 @@
+// trsv_block.cu -- fused forward+backward sparse triangular solve of a block-Jacobi ILU, sm_100a.
+//
+// Performance-mode replacement of the two cusparse?csrsv_solve calls per preconditioner
+// application (src/preconditioner.cu:263,273 / 1612,1637).  The global level schedule of the
+// reference's factors (trsv.cu) has thousands of dependent levels on grid matrices and is bound
+// by that chain, not by HBM; here the factors are block-diagonal (the north-star's per-partition
+// block-Jacobi ILU applied inside one GPU as well), so every block is an independent problem:
+//
+//  * ONE warp solves one block: z = U_b^-1 L_b^-1 r_b, both solves back to back with the
+//    intermediate vector never leaving shared memory (one kernel instead of two, no temporary
+//    vector in HBM).
+//  * rows are renumbered block-major on the host, so r_b and z_b are contiguous in HBM
+//    (coalesced 8 KB reads/writes); the public entry point offers a gather/scatter variant for
+//    callers whose vectors are in the original order.
+//  * the factor stream of a block (schedule, 16-bit local columns, values, reciprocal diagonal;
+//    packed step by step on the host, host_algos.h FusedBlockStream) is staged by bulk-async copies
+//    (cp.async.bulk.shared::cluster.global + mbarrier complete_tx, SASS UBLKCP) into a per-warp
+//    ring of `stages` slots, so HBM reads are large and sequential and run ahead of the dependent
+//    FMA chain.  Every piece of per-step metadata lives in shared memory; the metadata of step s+1
+//    is fetched into registers before the warp barrier of step s.
+//  * 12 resident warps per SM (3 CTAs x 4 warps) give 1776 concurrent block solves on 148 SMs.
+//
+//  * both factors are rescaled on the host (Lh = D^-1 L D, Ut = D^-1 U, D = diag U) so that the
+//    device performs two UNIT solves on d .* r: no division and no per-row diagonal in the stream.
+//
+// Bytes per row (5-point ILU(0), FP64): L 24 B + U 24 B + 1/diag 8 B + rhs 8 B + result 8 B.
+#include "internal.h"
+
+namespace bg {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a scheduling bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 24)) __trap();
+}
+// global -> shared bulk-async copy completing on an mbarrier (TMA unit, SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct FbArgs {
+  const BlockDesc* blk;
+  const uint32_t* chunk_off;
+  const unsigned char* stream;
+  const int* perm;
+  const void* dinv;     // FT[n], block-major
+  int nblocks, max_rows, stages, max_chunks;
+  uint32_t slot_bytes;  // ring slot stride (multiple of 128)
+  uint32_t warp_smem;   // bytes of shared memory per warp (multiple of 128)
+};
+
+template <class FT> struct PairOf;
+template <> struct PairOf<float> { using type = float2; };
+template <> struct PairOf<double> { using type = double2; };
+
+// metadata of one slot (row id + K <= 3 local columns in one 8-byte quad, K values)
+template <class FT, class CT, int K>
+__device__ __forceinline__ void load_slot(int t, int nsA, const uint2* quads, const FT* vals, uint2& q, CT* v) {
+  q = quads[t];
+  using P = typename PairOf<FT>::type;
+#pragma unroll
+  for (int p = 0; p < K / 2; ++p) {
+    const P pr = reinterpret_cast<const P*>(vals)[(size_t)p * nsA + t];
+    v[2 * p] = (CT)pr.x;
+    v[2 * p + 1] = (CT)pr.y;
+  }
+  if (K & 1) v[K - 1] = (CT)vals[(size_t)(K / 2) * 2 * nsA + t];
+}
+
+// all steps of one chunk whose rows have at most K <= 3 off-diagonals: the slot of step s+1 is
+// fetched into registers before the warp barrier of step s
+template <class FT, class CT, int K>
+__device__ __forceinline__ void run_steps_fast(int lane, int nst, int nsA, const unsigned char* cnts, const uint2* quads,
+                                               const FT* vals, CT* xl) {
+  uint2 qn = make_uint2(0u, 0u);
+  CT vn[K > 0 ? K : 1];
+  int s0 = 0, cnt = cnts[0];
+  if (lane < cnt) load_slot<FT, CT, K>(lane, nsA, quads, vals, qn, vn);
+  for (int s = 0; s < nst; ++s) {
+    const uint2 q = qn;
+    CT v[K > 0 ? K : 1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = vn[k];
+    const bool act = lane < cnt;
+    s0 += cnt;
+    const int cnt2 = s + 1 < nst ? (int)cnts[s + 1] : 0;
+    if (lane < cnt2) load_slot<FT, CT, K>(s0 + lane, nsA, quads, vals, qn, vn);
+    if (act) {
+      const uint32_t li = q.x & 0xffffu;
+      CT acc = xl[li];
+      if (K > 0) acc -= v[0] * xl[q.x >> 16];
+      if (K > 1) acc -= v[1] * xl[q.y & 0xffffu];
+      if (K > 2) acc -= v[2] * xl[q.y >> 16];
+      xl[li] = acc;  // rows of one step never read each other
+    }
+    __syncwarp();  // orders this step's writes before the next step's reads
+    cnt = cnt2;
+  }
+}
+
+// any K: no register prefetch (wide ILUT rows)
+template <class FT, class CT>
+__device__ __forceinline__ void run_steps_generic(int lane, int K, int nst, int nsA, const unsigned char* cnts,
+                                                  const uint2* quads, const FT* vals, CT* xl) {
+  const uint16_t* q16 = reinterpret_cast<const uint16_t*>(quads);
+  int s0 = 0;
+  for (int s = 0; s < nst; ++s) {
+    const int cnt = cnts[s];
+    if (lane < cnt) {
+      const int t = s0 + lane;
+      const uint32_t li = q16[(size_t)t * 4];
+      CT acc = xl[li];
+      for (int k = 0; k < K; ++k) {
+        const int e = k + 1;
+        const uint32_t c = q16[((size_t)(e >> 2) * nsA + t) * 4 + (e & 3)];
+        const FT v = (k == K - 1 && (K & 1)) ? vals[(size_t)(K / 2) * 2 * nsA + t] : vals[((size_t)(k >> 1) * nsA + t) * 2 + (k & 1)];
+        acc -= (CT)v * xl[c];
+      }
+      xl[li] = acc;
+    }
+    __syncwarp();
+    s0 += cnt;
+  }
+}
+
+template <class VT, class FT, class CT, bool GATHER>
+__global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __restrict__ in, VT* __restrict__ out,
+                                                        const int* skip) {
+  if (skip && *skip) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned char* mine = smem + (size_t)wid * a.warp_smem;
+  CT* xl = reinterpret_cast<CT*>(mine);
+  const uint32_t xl_bytes = ((uint32_t)a.max_rows * sizeof(CT) + 127u) & ~127u;
+  uint32_t* coff = reinterpret_cast<uint32_t*>(mine + xl_bytes);
+  const uint32_t coff_bytes = ((uint32_t)(a.max_chunks + 1) * 4u + 127u) & ~127u;
+  unsigned char* ring = mine + xl_bytes + coff_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * a.slot_bytes);
+  const FT* dinv = reinterpret_cast<const FT*>(a.dinv);
+  if (lane == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t g0 = 0;  // ring-global index of the current block's first chunk (monotone per warp)
+  for (int b = blockIdx.x * nw + wid; b < a.nblocks; b += gridDim.x * nw) {
+    const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.blk + b));
+    const int row0 = d0.x, nb = d0.y, chunk0 = d0.z, nch = d0.w;
+    for (int i = lane; i <= nch; i += 32) coff[i] = __ldg(a.chunk_off + chunk0 + i);
+    __syncwarp();
+    auto issue = [&](int c) {  // lane 0 only
+      const uint32_t st = (g0 + (uint32_t)c) % (uint32_t)a.stages;
+      const uint32_t o0 = coff[c], bytes = (coff[c + 1] - o0) * 16u;
+      mbar_expect_tx(&bars[st], bytes);
+      bulk_g2s(ring + (size_t)st * a.slot_bytes, a.stream + (size_t)o0 * 16u, bytes, &bars[st]);
+    };
+    if (lane == 0)
+      for (int c = 0; c < nch && c < a.stages; ++c) issue(c);
+    // d .* r of the block -> shared memory (contiguous in the block-major numbering)
+    for (int i = lane; i < nb; i += 32)
+      xl[i] = (CT)in[GATHER ? __ldg(a.perm + row0 + i) : row0 + i] * (CT)__ldg(dinv + row0 + i);
+    __syncwarp();
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t g = g0 + (uint32_t)c, st = g % (uint32_t)a.stages;
+      mbar_wait(&bars[st], (g / (uint32_t)a.stages) & 1u);
+      const unsigned char* rec = ring + (size_t)st * a.slot_bytes;
+      const uint2 h = *reinterpret_cast<const uint2*>(rec);
+      const int K = (int)(h.x >> 16), nst = (int)(h.y & 0xffffu), nsA = (int)(h.y >> 16);
+      const unsigned char* cnts = rec + 16;
+      const int stA = (nst + 15) & ~15;
+      const uint2* quads = reinterpret_cast<const uint2*>(rec + 16 + stA);
+      const FT* vals = reinterpret_cast<const FT*>(rec + 16 + stA + 8 * (size_t)((K + 4) >> 2) * nsA);
+      switch (K) {  // uniform per chunk
+        case 0: run_steps_fast<FT, CT, 0>(lane, nst, nsA, cnts, quads, vals, xl); break;
+        case 1: run_steps_fast<FT, CT, 1>(lane, nst, nsA, cnts, quads, vals, xl); break;
+        case 2: run_steps_fast<FT, CT, 2>(lane, nst, nsA, cnts, quads, vals, xl); break;
+        case 3: run_steps_fast<FT, CT, 3>(lane, nst, nsA, cnts, quads, vals, xl); break;
+        default: run_steps_generic<FT, CT>(lane, K, nst, nsA, cnts, quads, vals, xl); break;
+      }
+      // every lane is past its last read of this ring slot: refill it
+      if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
+    }
+    for (int i = lane; i < nb; i += 32) out[GATHER ? __ldg(a.perm + row0 + i) : row0 + i] = (VT)xl[i];
+    __syncwarp();
+    g0 += (uint32_t)nch;
+  }
+}
+
+template <class VT, class FT>
+int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void* in, void* out, const int* skip) {
+  using CT = decltype(VT() * FT());
+  FbArgs a{};
+  a.blk = S.blk.as<BlockDesc>(); a.chunk_off = S.chunk_off.as<uint32_t>(); a.stream = S.stream.as<unsigned char>();
+  a.perm = S.perm.as<int>();
+  a.dinv = S.dinv.p;
+  a.nblocks = S.nblocks; a.max_rows = S.max_rows; a.stages = S.stages; a.max_chunks = S.max_chunks;
+  a.slot_bytes = ((uint32_t)S.max_chunk_bytes + 127u) & ~127u;
+  const uint32_t xl_bytes = ((uint32_t)S.max_rows * sizeof(CT) + 127u) & ~127u;
+  const uint32_t coff_bytes = ((uint32_t)(S.max_chunks + 1) * 4u + 127u) & ~127u;
+  a.warp_smem = xl_bytes + coff_bytes + (uint32_t)a.stages * a.slot_bytes + 128u;
+  const int warps = S.warps_per_cta;
+  const size_t smem = (size_t)warps * a.warp_smem;
+  if (smem > ctx->smem_optin) {
+    set_error("block TRSV needs %zu bytes of shared memory per CTA (limit %zu): use smaller blocks", smem, ctx->smem_optin);
+    return BG_ERR_UNSUPPORTED;
+  }
+  auto kern = gather ? trsv_block_fused<VT, FT, CT, true> : trsv_block_fused<VT, FT, CT, false>;
+  static size_t attr_set[2] = {0, 0};  // per template instantiation
+  if (attr_set[gather ? 1 : 0] < smem) {
+    BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    attr_set[gather ? 1 : 0] = ctx->smem_optin;
+  }
+  // resident CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
+  int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(228 * 1024) / (smem + 1024)));
+  ctas_per_sm = std::min(ctas_per_sm, 2048 / (warps * 32));
+  const int blocks = std::max(1, std::min((S.nblocks + warps - 1) / warps, ctx->sm_count * ctas_per_sm));
+  kern<<<blocks, warps * 32, smem, ctx->stream>>>(a, (const VT*)in, (VT*)out, skip);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+
+}  // namespace
+
+int launch_trsv_block(bg_context_t ctx, const FusedBlockDev& S, int vec_dt, int fac_dt, bool gather, const void* in,
+                      void* out, const int* skip) {
+  if (S.n == 0) return BG_OK;
+  if (vec_dt == BG_F32 && fac_dt == BG_F32) return fused_run<float, float>(ctx, S, gather, in, out, skip);
+  if (vec_dt == BG_F32 && fac_dt == BG_F64) return fused_run<float, double>(ctx, S, gather, in, out, skip);
+  if (vec_dt == BG_F64 && fac_dt == BG_F32) return fused_run<double, float>(ctx, S, gather, in, out, skip);
+  return fused_run<double, double>(ctx, S, gather, in, out, skip);
+}
+
+}  // namespace bg

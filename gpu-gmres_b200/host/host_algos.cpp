@@ -428,119 +428,164 @@ template void pack_level_stream<float>(bool, bool, const Csr<float>&, int, Level
 template void pack_level_stream<double>(bool, bool, const Csr<double>&, int, LevelStream<double>&);
 
 template <class T>
-void pack_block_stream(bool lower, bool unit, const Csr<T>& M, int nblocks, const int* block_of_row,
-                       int chunk_slots, BlockStream<T>& out) {
-  const int n = M.n;
+void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, int nblocks, const int* block_of_row,
+                             int chunk_target, FusedBlockStream<T>& out) {
+  if (!unit_lower) throw std::invalid_argument("the block schedule needs a unit lower factor");
+  const int n = L.n;
   out.n = n;
   out.nblocks = nblocks;
-  // rows grouped by block, ascending inside a block; local ids
-  out.blk_row_ptr.assign(nblocks + 1, 0);
-  for (int i = 0; i < n; ++i) out.blk_row_ptr[block_of_row[i] + 1]++;
-  for (int b = 0; b < nblocks; ++b) out.blk_row_ptr[b + 1] += out.blk_row_ptr[b];
-  out.grow.resize(n);
+  // block-major renumbering, ascending old id inside a block
+  std::vector<int> bptr(nblocks + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (block_of_row[i] < 0 || block_of_row[i] >= nblocks) throw std::invalid_argument("block id out of range");
+    bptr[block_of_row[i] + 1]++;
+  }
+  for (int b = 0; b < nblocks; ++b) bptr[b + 1] += bptr[b];
+  out.perm.resize(n);
   std::vector<int> local(n);
   {
-    std::vector<int> cur(out.blk_row_ptr.begin(), out.blk_row_ptr.end() - 1);
+    std::vector<int> cur(bptr.begin(), bptr.end() - 1);
     for (int i = 0; i < n; ++i) {
       const int b = block_of_row[i];
-      local[i] = cur[b] - out.blk_row_ptr[b];
-      out.grow[cur[b]++] = i;
+      local[i] = cur[b] - bptr[b];
+      out.perm[cur[b]++] = i;
     }
   }
-  int K = 0;
   out.max_rows = 0;
-  for (int b = 0; b < nblocks; ++b) out.max_rows = std::max(out.max_rows, out.blk_row_ptr[b + 1] - out.blk_row_ptr[b]);
-  if (out.max_rows > 65534) throw std::invalid_argument("block too large for 16-bit local ids");
+  for (int b = 0; b < nblocks; ++b) out.max_rows = std::max(out.max_rows, bptr[b + 1] - bptr[b]);
+  if (out.max_rows > 65535) throw std::invalid_argument("block too large for 16-bit local ids");
+  if (chunk_target < 512) chunk_target = 512;
+  // reciprocal pivots (old numbering for the rescaling below, block-major for the device)
+  std::vector<double> d(n), di(n);
   for (int i = 0; i < n; ++i) {
-    int k = 0;
-    const int dpos = lower ? M.rp[i + 1] - 1 : M.rp[i];
-    for (int p = M.rp[i]; p < M.rp[i + 1]; ++p) {
-      if (p == dpos) continue;
-      if (block_of_row[M.ci[p]] != block_of_row[i]) throw std::invalid_argument("factor couples two blocks");
-      ++k;
-    }
-    K = std::max(K, k);
+    d[i] = (double)U.v[U.rp[i]];
+    di[i] = 1.0 / d[i];
   }
-  out.K = K;
-  // chunk = one bulk copy: keep it around 4-6 KB whatever the row width (CS stays a multiple of 8
-  // so the value array inside the record is 8-byte aligned and the record size a multiple of 16)
-  int CS = chunk_slots > 0 ? chunk_slots : 128;
-  {
-    const int64_t bps = 2 + 2 * K + (int64_t)sizeof(T) * (K + 1);
-    while (CS > 8 && CS * bps > 6144) CS /= 2;
-  }
-  out.CS = CS;
-  out.chunk_bytes = (int64_t)CS * (2 + 2 * K + (int64_t)sizeof(T) * K + sizeof(T));
-  out.chunk_bytes = (out.chunk_bytes + 15) / 16 * 16;
-  // per-block levels
-  out.blk_lev_ptr.assign(nblocks + 1, 0);
-  out.blk_chunk_ptr.assign(nblocks + 1, 0);
-  out.lev_slot.clear();
-  std::vector<int> lvl(out.max_rows), order(out.max_rows);
-  std::vector<std::vector<int>> sched(nblocks);
-  out.max_levels = 0;
-  out.max_chunks = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    const int base = out.blk_row_ptr[b], nb = out.blk_row_ptr[b + 1] - base;
+  out.dinv.resize(n);
+  for (int i = 0; i < n; ++i) out.dinv[i] = (T)di[out.perm[i]];
+  out.blk.assign(nblocks, BlockDesc{0, 0, 0, 0, 0, 0, 0, 0});
+  out.chunk_off.assign(1, 0u);
+  out.stream.clear();
+  out.max_levels_L = out.max_levels_U = out.max_chunk_bytes = out.max_chunks = 0;
+  out.total_steps = out.total_slots = 0;
+
+  std::vector<int> lvl(out.max_rows), order;
+  std::vector<int> cnt;
+  struct Step { int first, count; };  // into `order`
+  std::vector<Step> steps;
+  auto chunk_bytes = [](int ns, int K, int nsteps) {
+    const int nsA = (ns + 7) / 8 * 8, stA = (nsteps + 15) / 16 * 16, KQ = (K + 4) / 4;
+    return 16 + stA + 8 * KQ * nsA + (int)sizeof(T) * K * nsA;
+  };
+  // emits the chunks of one factor of one block
+  auto emit_factor = [&](const Csr<T>& M, bool lower, int base, int nb, int* n_levels) {
     int nl = 0;
     auto row_level = [&](int li) {
-      const int r = out.grow[base + li];
+      const int r = out.perm[base + li];
       const int dpos = lower ? M.rp[r + 1] - 1 : M.rp[r];
       int best = 0;
-      for (int p = M.rp[r]; p < M.rp[r + 1]; ++p)
-        if (p != dpos) best = std::max(best, lvl[local[M.ci[p]]] + 1);
+      for (int p = M.rp[r]; p < M.rp[r + 1]; ++p) {
+        if (p == dpos) continue;
+        const int c = M.ci[p];
+        if (block_of_row[c] != block_of_row[r]) throw std::invalid_argument("factor couples two blocks");
+        best = std::max(best, lvl[local[c]] + 1);
+      }
       lvl[li] = best;
       nl = std::max(nl, best + 1);
     };
     if (lower) for (int li = 0; li < nb; ++li) row_level(li);
     else for (int li = nb - 1; li >= 0; --li) row_level(li);
-    std::vector<int> cnt(nl + 1, 0);
+    *n_levels = nl;
+    cnt.assign(nl + 1, 0);
     for (int li = 0; li < nb; ++li) cnt[lvl[li] + 1]++;
     for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
-    out.blk_lev_ptr[b + 1] = out.blk_lev_ptr[b] + nl + 1;
-    for (int l = 0; l <= nl; ++l) out.lev_slot.push_back(cnt[l]);
-    std::vector<int> cur(cnt.begin(), cnt.end() - (nl ? 1 : 0));
-    sched[b].resize(nb);
-    for (int li = 0; li < nb; ++li) sched[b][cur[lvl[li]]++] = li;
-    const int nch = (nb + CS - 1) / CS;
-    out.blk_chunk_ptr[b + 1] = out.blk_chunk_ptr[b] + nch;
-    out.max_levels = std::max(out.max_levels, nl);
-    out.max_chunks = std::max(out.max_chunks, nch);
-  }
-  out.stream.assign((size_t)out.blk_chunk_ptr[nblocks] * out.chunk_bytes, 0);
-  for (int b = 0; b < nblocks; ++b) {
-    const int base = out.blk_row_ptr[b], nb = out.blk_row_ptr[b + 1] - base;
-    for (int s = 0; s < (int)((nb + CS - 1) / CS) * CS; ++s) {
-      const int64_t ch = out.blk_chunk_ptr[b] + s / CS;
-      const int t = s % CS;
-      unsigned char* rec = out.stream.data() + ch * out.chunk_bytes;
-      uint16_t* sc = reinterpret_cast<uint16_t*>(rec);
-      uint16_t* cc = sc + CS;
-      T* vv = reinterpret_cast<T*>(rec + (size_t)CS * (2 + 2 * K));
-      T* dd = vv + (size_t)K * CS;
-      if (s >= nb) {
-        sc[t] = 0xFFFF;
-        for (int k = 0; k < K; ++k) { cc[k * CS + t] = 0; vv[(size_t)k * CS + t] = (T)0; }
-        dd[t] = (T)1;
-        continue;
-      }
-      const int li = sched[b][s], r = out.grow[base + li];
-      sc[t] = (uint16_t)li;
-      const int lb = M.rp[r], ub = M.rp[r + 1], dpos = lower ? ub - 1 : lb;
-      dd[t] = unit ? (T)1 : M.v[dpos];
-      int k = 0;
-      for (int p = lb; p < ub; ++p) {
-        if (p == dpos) continue;
-        cc[k * CS + t] = (uint16_t)local[M.ci[p]];
-        vv[(size_t)k * CS + t] = M.v[p];
-        ++k;
-      }
-      for (; k < K; ++k) { cc[k * CS + t] = (uint16_t)li; vv[(size_t)k * CS + t] = (T)0; }
+    order.resize(nb);
+    {
+      std::vector<int> cur(cnt.begin(), cnt.end() - (nl ? 1 : 0));
+      for (int li = 0; li < nb; ++li) order[cur[lvl[li]]++] = li;
     }
+    steps.clear();
+    for (int l = 0; l < nl; ++l)
+      for (int s = cnt[l]; s < cnt[l + 1]; s += 32) steps.push_back(Step{s, std::min(32, cnt[l + 1] - s)});
+    auto row_K = [&](int li) {
+      const int r = out.perm[base + li];
+      return M.rp[r + 1] - M.rp[r] - 1;
+    };
+    size_t si = 0;
+    while (si < steps.size()) {
+      // greedy: whole steps while the record stays within the target (always at least one step)
+      int ns = 0, K = 0, nst = 0;
+      size_t sj = si;
+      while (sj < steps.size() && nst < 255) {
+        int K2 = K;
+        for (int q = 0; q < steps[sj].count; ++q) K2 = std::max(K2, row_K(order[steps[sj].first + q]));
+        if (nst > 0 && chunk_bytes(ns + steps[sj].count, K2, nst + 1) > chunk_target) break;
+        ns += steps[sj].count; K = K2; ++nst; ++sj;
+      }
+      const int nsA = (ns + 7) / 8 * 8, stA = (nst + 15) / 16 * 16, KQ = (K + 4) / 4;
+      const int bytes = (chunk_bytes(ns, K, nst) + 15) / 16 * 16;
+      const size_t off = out.stream.size();
+      out.stream.resize(off + bytes, 0);
+      unsigned char* rec = out.stream.data() + off;
+      uint16_t* hdr = reinterpret_cast<uint16_t*>(rec);
+      hdr[0] = (uint16_t)ns; hdr[1] = (uint16_t)K; hdr[2] = (uint16_t)nst; hdr[3] = (uint16_t)nsA;
+      unsigned char* sc8 = rec + 16;
+      uint16_t* quads = reinterpret_cast<uint16_t*>(rec + 16 + stA);          // [KQ][nsA][4]
+      T* vals = reinterpret_cast<T*>(rec + 16 + stA + 8 * (size_t)KQ * nsA);  // pairs then the odd one
+      auto col_slot = [&](int k, int t) -> uint16_t& {  // k-th off-diagonal column of slot t
+        const int e = k + 1;                             // element 0 of quad 0 is the row id
+        return quads[((size_t)(e / 4) * nsA + t) * 4 + e % 4];
+      };
+      auto val_slot = [&](int k, int t) -> T& {
+        if (k == K - 1 && (K & 1)) return vals[(size_t)(K / 2) * 2 * nsA + t];
+        return vals[((size_t)(k / 2) * nsA + t) * 2 + k % 2];
+      };
+      int t = 0;
+      for (size_t s = si; s < sj; ++s) {
+        sc8[s - si] = (unsigned char)steps[s].count;
+        for (int q = 0; q < steps[s].count; ++q, ++t) {
+          const int li = order[steps[s].first + q], r = out.perm[base + li];
+          const int lb = M.rp[r], ub = M.rp[r + 1], dpos = lower ? ub - 1 : lb;
+          quads[(size_t)t * 4] = (uint16_t)li;
+          int k = 0;
+          for (int p = lb; p < ub; ++p) {
+            if (p == dpos) continue;
+            const int c = M.ci[p];
+            col_slot(k, t) = (uint16_t)local[c];
+            // Lh = D^-1 L D, Ut = D^-1 U
+            val_slot(k, t) = (T)(lower ? (double)M.v[p] * di[r] * d[c] : (double)M.v[p] * di[r]);
+            ++k;
+          }
+          for (; k < 4 * KQ - 1; ++k) {
+            col_slot(k, t) = (uint16_t)li;
+            if (k < K) val_slot(k, t) = (T)0;
+          }
+        }
+      }
+      out.chunk_off.push_back((uint32_t)(out.stream.size() / 16));
+      out.max_chunk_bytes = std::max(out.max_chunk_bytes, bytes);
+      out.total_steps += nst;
+      out.total_slots += ns;
+      si = sj;
+    }
+  };
+  for (int b = 0; b < nblocks; ++b) {
+    const int base = bptr[b], nb = bptr[b + 1] - base;
+    BlockDesc& dsc = out.blk[b];
+    dsc.row0 = base; dsc.nrows = nb;
+    dsc.chunk0 = (int)out.chunk_off.size() - 1;
+    emit_factor(L, true, base, nb, &dsc.levelsL);
+    emit_factor(U, false, base, nb, &dsc.levelsU);
+    dsc.nchunks = (int)out.chunk_off.size() - 1 - dsc.chunk0;
+    out.max_levels_L = std::max(out.max_levels_L, dsc.levelsL);
+    out.max_levels_U = std::max(out.max_levels_U, dsc.levelsU);
+    out.max_chunks = std::max(out.max_chunks, dsc.nchunks);
+    if (out.stream.size() / 16 > 0xFFFFFFF0ull) throw std::invalid_argument("factor stream exceeds 64 GB");
   }
+  out.stream.resize(out.stream.size() + 16, 0);  // a readable tail for 16-byte granularity
 }
-template void pack_block_stream<float>(bool, bool, const Csr<float>&, int, const int*, int, BlockStream<float>&);
-template void pack_block_stream<double>(bool, bool, const Csr<double>&, int, const int*, int, BlockStream<double>&);
+template void pack_fused_block_stream<float>(bool, const Csr<float>&, const Csr<float>&, int, const int*, int, FusedBlockStream<float>&);
+template void pack_fused_block_stream<double>(bool, const Csr<double>&, const Csr<double>&, int, const int*, int, FusedBlockStream<double>&);
 
 // ------------------------------------------------------------------ SpMV inspector
 SpmvPlan inspect_rows(int n, const int* rp) {

@@ -75,26 +75,44 @@ template <class T> struct LevelStream {
 template <class T>
 void pack_level_stream(bool lower, bool unit, const Csr<T>& M, int thin_rows, LevelStream<T>& out);
 
-// Block stream (BG_TRSV_BLOCK): every block is solved by one warp out of shared memory.
-// Block b owns rows grow[blk_row_ptr[b] .. blk_row_ptr[b+1]) (ascending); local id = position.
-// Its schedule lists local ids level by level; the packed stream is cut into chunks of CS slots,
-// each chunk one contiguous, 16-byte aligned record
-//     [ sched : CS x u16 ][ cols : K x CS x u16 ][ vals : K x CS x T ][ diag : CS x T ]
-// so one bulk-async copy stages a chunk.  Padding slots have sched = 0xFFFF; padding entries have
-// val = 0 and col = the slot's own local id.
-template <class T> struct BlockStream {
-  int n = 0, nblocks = 0, K = 0, CS = 0, max_rows = 0, max_levels = 0, max_chunks = 0;
-  int64_t chunk_bytes = 0;
-  std::vector<int> grow;            // n, rows grouped by block, ascending inside a block
-  std::vector<int> blk_row_ptr;     // nblocks+1
-  std::vector<int> blk_lev_ptr;     // nblocks+1 -> into lev_slot
-  std::vector<int> lev_slot;        // per block: n_levels+1 slot boundaries (0-based inside block)
-  std::vector<int64_t> blk_chunk_ptr;  // nblocks+1 -> chunk index of the block's first chunk
-  std::vector<unsigned char> stream;   // all chunks
+// Fused block stream (BG_TRSV_BLOCK): every diagonal block's forward AND backward solve is done
+// by one warp out of shared memory in one kernel.  Rows are renumbered block-major
+// (new row i = old row perm[i]; a block owns the contiguous new rows [blk[b].row0, +nrows)), so the
+// right-hand side and the result of a block are contiguous in HBM.
+// A block's work is a sequence of STEPS (<= 32 mutually independent rows = one level, or a 32-row
+// slice of a wide level), L steps first, then U steps.  Both factors are rescaled on the host so that
+// the device only ever performs UNIT triangular solves:  with D = diag(U), d = 1/D,
+//     z = U^-1 L^-1 r  =  Ut^-1 Lh^-1 (d .* r),   Lh = D^-1 L D (unit lower),  Ut = D^-1 U (unit upper)
+// and the kernel multiplies by dinv (block-major, n entries) while it loads r.
+// Steps are packed, whole, into CHUNKS of <= chunk_target bytes; one chunk = one bulk-async copy:
+//     [ u16 ns, K, nsteps, nsA, pad[4] ]                               16 B header
+//     [ u8  step_cnt[nstepsA] ]          nstepsA = nsteps rounded up to 16
+//     [ u16x4 quad[KQ][nsA] ]            quad 0 = (row, c0, c1, c2), quad q>0 = (c[4q-1] .. c[4q+2]);
+//                                        KQ = (K+4)/4, local ids; padding columns = the row itself
+//     [ T x2  pair[K/2][nsA] ]           values (v0,v1), (v2,v3), ...
+//     [ T     last[nsA] ]                only when K is odd
+// nsA = ns rounded up to 8.  Chunk c of the whole stream starts at byte 16*chunk_off[c].
+struct BlockDesc {      // 32 bytes, read by the kernel with two 16-byte loads
+  int row0, nrows;      // new-order row range
+  int chunk0, nchunks;  // into chunk_off (L chunks followed by U chunks)
+  int levelsL, levelsU; // informational
+  int pad0, pad1;
 };
+template <class T> struct FusedBlockStream {
+  int n = 0, nblocks = 0, max_rows = 0, max_levels_L = 0, max_levels_U = 0;
+  int max_chunk_bytes = 0, max_chunks = 0;
+  int64_t total_steps = 0, total_slots = 0;
+  std::vector<int> perm;             // n: new -> old
+  std::vector<T> dinv;               // n, block-major: 1 / diag(U)
+  std::vector<BlockDesc> blk;        // nblocks
+  std::vector<uint32_t> chunk_off;   // total chunks + 1, in units of 16 bytes
+  std::vector<unsigned char> stream;
+};
+// L: unit lower, diagonal LAST in each row (value ignored); U: diagonal FIRST.  Every off-diagonal
+// of a row must lie in the row's own block (block-Jacobi factors).
 template <class T>
-void pack_block_stream(bool lower, bool unit, const Csr<T>& M, int nblocks, const int* block_of_row,
-                       int chunk_slots, BlockStream<T>& out);
+void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, int nblocks, const int* block_of_row,
+                             int chunk_target, FusedBlockStream<T>& out);
 
 // Row-length histogram -> SpMV format (role of SpMV_inspect.cpp:38-456)
 struct SpmvPlan {

@@ -59,7 +59,8 @@ class FactorsInfo(C.Structure):
 
 class PrecondOpts(C.Structure):
     _fields_ = [("trsv_schedule", C.c_int), ("block_method", C.c_int), ("block_rows", C.c_int), ("dims", C.c_int * 6),
-                ("factor_dtype", C.c_int), ("use_tma", C.c_int), ("ilut_lfil", C.c_int), ("ilut_tau", C.c_double)]
+                ("factor_dtype", C.c_int), ("use_tma", C.c_int), ("ilut_lfil", C.c_int), ("ilut_tau", C.c_double),
+                ("chunk_bytes", C.c_int), ("stages", C.c_int), ("warps_per_cta", C.c_int)]
 
 
 class PrecondInfo(C.Structure):

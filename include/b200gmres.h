@@ -51,7 +51,8 @@ enum { BG_PRECOND_NONE = 0, BG_PRECOND_DIAG = 1, BG_PRECOND_LU = 2, BG_PRECOND_S
 enum { BG_ORTH_MGS = 0, BG_ORTH_CGS_ADAPTIVE = 1, BG_ORTH_CGS2 = 2 };
 /* triangular-solve schedule */
 enum { BG_TRSV_LEVEL = 0,  /* global level sets, bit-exact with getLevel (gmres.cu:1033-1077)      */
-       BG_TRSV_BLOCK = 1 };/* block-Jacobi: each block solved by one warp out of shared memory      */
+       BG_TRSV_BLOCK = 1 };/* block-Jacobi: each block's L and U solve by one warp out of shared
+                              memory, rows renumbered block-major (the solver permutes A, b, x)   */
 /* row-block partitioners for BG_TRSV_BLOCK and for the multi-GPU row partition */
 enum { BG_PART_CONTIGUOUS = 0, /* src/partition.cpp:22-45 contiguous nNodes/npart chunks            */
        BG_PART_METIS = 1,      /* src/partition3.cpp:49-64 graph from the off-diagonal pattern       */
@@ -141,6 +142,9 @@ typedef struct {
   int factor_dtype;    /* storage type of L/U values on the device: -1 = same as the factors given */
   int use_tma;         /* 1 (default): bulk-async staged factor streams; 0: plain loads            */
   int ilut_lfil; double ilut_tau; /* used by bg_precond_create_ilut                                */
+  int chunk_bytes;     /* BG_TRSV_BLOCK: target size of one bulk copy of the factor stream (2048) */
+  int stages;          /* BG_TRSV_BLOCK: ring slots per warp (4)                                  */
+  int warps_per_cta;   /* BG_TRSV_BLOCK: block solves per CTA (4)                                 */
 } bg_precond_opts;
 BG_API void bg_precond_opts_default(bg_precond_opts* o);
 /* MyNONE (preconditioner.h) */

@@ -2,6 +2,7 @@
 bit-exact with the oracle and the golden fixtures; the C ABI library loads and exports every
 symbol include/b200gmres.h declares; compute entry points fail loudly without a device."""
 import ctypes as C
+import os
 import re
 
 import numpy as np
@@ -140,3 +141,17 @@ def test_ilut_reduces_to_ilu_and_improves(bg, oracle):
     pc = oracle.Precond(oracle.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
     it_ilut = oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 500, 1e-8, pc)[2]
     assert it_ilut < g["f64_meta"][1]
+
+
+def test_fused_block_stream_packer(tmp_path):
+    """The packed factor stream of the block-Jacobi solve, interpreted on the host step by step the
+    way trsv_block_fused consumes it, reproduces a plain CSR forward/backward solve."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pack_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "pack_check.cpp"),
+                           os.path.join(root, "gpu-gmres_b200", "host", "host_algos.cpp"),
+                           "/usr/local/cuda/lib64/libmetis_static.a", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

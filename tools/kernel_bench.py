@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--js", default="1,4,8,16,24,32")
     ap.add_argument("--tma", default="1")
     ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--etas", default="0.70710678")
+    ap.add_argument("--chunks", default="2048")
+    ap.add_argument("--stages", default="4")
+    ap.add_argument("--warps", default="4")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -105,23 +109,28 @@ def main():
     for sched in args.schedules.split(","):
         for tile in [int(t) for t in args.tiles.split(",")]:
             for fd in args.factor_dtypes.split(","):
-                for tma in [int(t) for t in args.tma.split(",")]:
+                import itertools
+                for tma, chunk, stages, warps in itertools.product([int(t) for t in args.tma.split(",")], [int(t) for t in args.chunks.split(",")],
+                                                                   [int(t) for t in args.stages.split(",")], [int(t) for t in args.warps.split(",")]):
                     fdt = bg.F32 if fd == "f32" else bg.F64
                     if sched == "block":
                         o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=tile * tile, factor_dtype=fdt, use_tma=tma,
+                                            chunk_bytes=chunk, stages=stages, warps_per_cta=warps,
                                             block_method=bg.PART_GRID2D, dims=[args.nx, args.nx, 1, tile, tile, 1])
                     else:
                         o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt)
                     M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=dtc, opts=o, ilut=(args.precond == "ilut"))
                     pi = M.info()
-                    tag = dict(schedule=sched, tile=tile, factor=fd, tma=tma, blocks=pi.nblocks, levels=(pi.levelsL, pi.levelsU))
+                    tag = dict(schedule=sched, tile=tile, factor=fd, chunk=chunk, stages=stages, warps=warps, blocks=pi.nblocks, levels=(pi.levelsL, pi.levelsU))
                     reps = args.reps if sched == "block" else 3
                     for fl in (False, True):
                         ms = timeit(lambda: M.apply(bg.PC_FULL, db.data_ptr(), dy.data_ptr()), reps, fl)
                         report("trsv(L+U)", ms, pi.trsv_bytes, l2_flushed=fl, stream_MB=round(pi.stream_bytes / 1e6, 1), **tag)
-                    for orth in args.orths.split(","):
+                    for orth, eta in itertools.product(args.orths.split(","), [float(t) for t in args.etas.split(",")]):
+                        if orth != "cgs" and eta != float(args.etas.split(",")[0]):
+                            continue
                         oc = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[orth]
-                        opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=3000, orth=oc, use_graph=args.graph)
+                        opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=3000, orth=oc, use_graph=args.graph, reorth_eta=eta)
                         for _ in range(2):
                             with torch.cuda.stream(stream):
                                 dx.zero_()
@@ -130,7 +139,7 @@ def main():
                             dx.zero_()
                         rp_, st = S.profile(A, M, db.data_ptr(), dx.data_ptr(), opts)
                         tot = st.spmv_bytes + st.trsv_bytes + st.orth_bytes + st.other_bytes
-                        row = dict(kernel="solve", orth=orth, iters=r.iters, reorths=r.reorths, solve_ms=round(r.solve_ms, 3),
+                        row = dict(kernel="solve", orth=orth, eta=eta, resid=float(r.resid), iters=r.iters, reorths=r.reorths, solve_ms=round(r.solve_ms, 3),
                                    us_per_iter=round(1e3 * r.solve_ms / max(r.iters_done, 1), 1), launches=int(r.launches),
                                    GBps=round(tot / (r.solve_ms * 1e-3) / 1e9, 1), frac=round(tot / (r.solve_ms * 1e-3) / 1e9 / peak, 3),
                                    profiled_ms=dict(spmv=round(st.spmv_ms, 3), trsv=round(st.trsv_ms, 3), orth=round(st.orth_ms, 3),
