@@ -42,7 +42,7 @@ UNIT = "ms"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=1304, help="grid edge; n = nx*nx (1304 = ibmpg6-sized)")
@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--tile", type=int, default=32)
     ap.add_argument("--factor-dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--orth", default="cgs", choices=["mgs", "cgs", "cgs2"])
-    ap.add_argument("--eta", type=float, default=0.70710678)
+    ap.add_argument("--eta", type=float, default=0.1, help="CGS re-orthogonalisation threshold (DGKS): second pass when ||w'|| < eta ||w||")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-nx", type=int, default=652, help="grid edge of the bounded CPU sample (0 = same as --nx); 652^2 = n/4")
@@ -76,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -84,21 +84,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.monotonic()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        return time.monotonic()
+
+    def stop(self, t0=None, t1=None):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if len(r) >= 10]
+        window = [r[1:] for r in self.rows if len(r) >= 10 and t0 is not None and t0 <= r[0] <= t1 + 0.05]
+        scope = "timed region"
+        if len(window) < 2:  # region shorter than two sampling periods: use everything sampled under load
+            window, scope = rows, "warm-up + timed region"
+        sm = [float(r[1]) for r in window if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in window if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({nm for r in self.rows if len(r) >= 9 for nm, c in zip(names, r[5:9]) if c.lower().startswith("active")})
+        reasons = sorted({nm for r in window for nm, c in zip(names, r[5:9]) if c.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "scope": scope}
 
 
 def workload(nx):
@@ -254,13 +262,16 @@ def main():
             ms = float(t.item())
         return ms, r, ctx.launches - l0
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(1.0)  # nvidia-smi needs a moment before its first sample
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    tc0 = sampler.mark()
     ms, r, launches = timed(step_device, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    tc1 = sampler.mark()
+    clocks = sampler.stop(tc0, tc1) if rank == 0 else None
     for _ in range(2):
         step_host()
     ms_e2e, r_e2e, _ = timed(step_host, args.steps)
@@ -275,25 +286,30 @@ def main():
     if rank == 0:
         peak, which = peaks()
         info, pinfo = A.info(), M.info()
-        phases = {
-            "spmv": (st.spmv_ms, st.spmv_bytes, st.spmv_calls),
-            "trsv": (st.trsv_ms, st.trsv_bytes, st.trsv_calls),
-            "orth": (st.orth_ms, st.orth_bytes, st.orth_calls),
+        trsv_kernel = "trsv_block_fused (L and U solve of every diagonal block, one launch)" if args.schedule == "block" else "trsv_level_walk/_wide (L and U solve)"
+        kernels = {
+            "spmv_sell_f64": (st.spmv_ms, st.spmv_bytes, st.spmv_calls),
+            trsv_kernel: (st.trsv_ms, st.trsv_bytes, st.trsv_calls),
+            "dots_kernel (V^T w and w.w, TMA-staged tiles)": (st.dots_ms, st.dots_bytes, st.dots_calls),
+            "update_kernel (w - V h, normalised, TMA-staged tiles)": (st.update_ms, st.update_bytes, st.update_calls),
         }
+        if args.orth == "mgs":
+            kernels = {k: v for k, v in kernels.items() if v[2] > 0}
+            kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls)
         tot_ms = st.spmv_ms + st.trsv_ms + st.orth_ms + st.other_ms
-        dom = max(phases, key=lambda k: phases[k][0])
-        kernel_names = {"orth": "dots_kernel+update_kernel (fused Arnoldi CGS step)",
-                        "trsv": "trsv_block_kernel x2 (L and U solve)" if args.schedule == "block" else "trsv_level_walk/_wide (L and U solve)",
-                        "spmv": "spmv_sell_f64"}
-        dms, dbytes, dcalls = phases[dom]
+        dom = max(kernels, key=lambda k: kernels[k][0])
+        dms, dbytes, dcalls = kernels[dom]
         ach = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": which,
-                    "bytes_per_launch_group": dbytes / max(dcalls, 1), "ms_per_launch_group": dms / max(dcalls, 1),
-                    "share_of_step": dms / tot_ms if tot_ms else None}
+        traffic = ncu_traffic(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic.get("bytes") if traffic else None, "traffic_launch": traffic,
+                    "peak_source": which, "bytes_per_launch": dbytes / max(dcalls, 1), "us_per_launch": 1e3 * dms / max(dcalls, 1),
+                    "launches_timed": int(dcalls), "share_of_step": dms / tot_ms if tot_ms else None,
+                    "how": "CUDA-event pairs on the library stream around every launch of the profiled solve (bg_solver_profile)"}
         all_bytes = st.spmv_bytes + st.trsv_bytes + st.orth_bytes + st.other_bytes
-        per_phase = {k: {"ms": p[0], "GBps": (p[1] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0), "frac": (p[1] / (p[0] * 1e-3) / 1e9 / peak if p[0] > 0 else 0.0),
-                         "share": p[0] / tot_ms if tot_ms else None} for k, p in phases.items()}
+        per_kernel = {k: {"ms": p[0], "launches": int(p[2]), "GBps": (p[1] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0),
+                          "frac": (p[1] / (p[0] * 1e-3) / 1e9 / peak if p[0] > 0 else 0.0), "share": p[0] / tot_ms if tot_ms else None}
+                      for k, p in kernels.items()}
         step_ms = ms / args.steps
         line = {
             "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -302,13 +318,14 @@ def main():
             "config": {"workload": f"pg2d {args.nx}x{args.nx} (ibmpg6-sized, BASELINE configs[1]) DC solve, GMRES(32), rel. residual {args.tol:g}",
                        "n": n, "nnz": int(info.nnz), "precond": args.precond, "trsv_schedule": args.schedule,
                        "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "factor_dtype": args.factor_dtype,
-                       "orth": args.orth, "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
+                       "orth": args.orth, "reorth_eta": args.eta, "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
                        "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
             "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
             "ms_per_iteration": step_ms / max(r.iters_done, 1),
             "iteration_roofline": {"bytes_per_iteration": all_bytes / max(rprof.iters_done, 1), "achieved_GBps": all_bytes / (step_ms * 1e-3) / 1e9,
-                                   "frac": all_bytes / (step_ms * 1e-3) / 1e9 / peak},
-            "phases": per_phase, "setup_s": t_setup,
+                                   "frac": all_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                                   "bytes": "SURVEY.md 8(d): B_spmv + B_trsv + B_orth(j) per inner iteration, restart terms per cycle"},
+            "kernels": per_kernel, "setup_s": t_setup,
             "roofline": roofline,
             "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
             "gpu_launches": int(launches), "clocks": clocks,
@@ -319,6 +336,18 @@ def main():
     S.close(); M.close(); A.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes of one captured launch of the dominant kernel (ncu --set full, read offline into
+    profiles/ncu_traffic.json by tools/ncu_summary.py --traffic); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    for key, val in json.load(open(p)).items():
+        if kernel.startswith(key):
+            return val
+    return None
 
 
 def _spmv_host(rp, ci, v, x):

@@ -91,10 +91,11 @@ struct LevelStreamDev {
 // device copy of host_algos.h FusedBlockStream (block-Jacobi L+U solve, trsv_block.cu)
 struct FusedBlockDev {
   int n = 0, nblocks = 0, max_rows = 0, max_levels_L = 0, max_levels_U = 0, max_chunk_bytes = 0, max_chunks = 0;
-  int stages = 4, warps_per_cta = 4;
+  int stages = 4, warps_per_cta = 4, tab_stride = 0;
   int64_t bytes = 0, total_steps = 0;
-  DevBuf perm, iperm, dinv, blk, chunk_off, stream;
-  std::vector<int> h_perm;  // new -> old, kept for permuting matrices on the host
+  DevBuf perm, iperm, dinv, blk, chunk_tab, stream;
+  std::vector<int> h_perm;     // new -> old, kept for permuting matrices on the host
+  std::vector<double> h_dinv;  // block-major 1/diag(U): the solver folds it into its copy of A and into b
   uint64_t serial = 0;      // identifies this ordering (matrix copies are cached per serial)
 };
 
@@ -134,8 +135,9 @@ int launch_trsv_level(bg_context_t ctx, const LevelStreamDev& S, int vec_dt, int
 // goes through perm); otherwise they are in the block-major order of the stream.
 int launch_trsv_block(bg_context_t ctx, const FusedBlockDev& S, int vec_dt, int fac_dt, bool gather,
                       const void* in, void* out, const int* skip_flag);
-// out[i] = in[perm[i]]  /  out[perm[i]] = in[i]
-int launch_gather(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out);
+// out[i] = in[perm[i]] (* scale[i] when scale != null, scale in the factor dtype)  /  out[perm[i]] = in[i]
+int launch_gather(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out, const void* scale = nullptr,
+                  int scale_dt = BG_F64);
 int launch_scatter(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out);
 int launch_diag_scale(bg_context_t ctx, int dtype, int n, const void* in, const void* d, void* out,
                       const int* skip_flag);

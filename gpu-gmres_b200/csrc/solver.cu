@@ -336,8 +336,8 @@ extern "C" void bg_precond_opts_default(bg_precond_opts* o) {
   o->use_tma = 1;
   o->ilut_lfil = 10;
   o->ilut_tau = 1e-3;
-  o->chunk_bytes = 2048;
-  o->stages = 4;
+  o->chunk_bytes = 4096;
+  o->stages = 2;
   o->warps_per_cta = 4;
 }
 
@@ -363,10 +363,15 @@ template <class T> static int upload_fused_stream(bg_context_t ctx, const FusedB
   for (int i = 0; i < h.n; ++i) inv[h.perm[i]] = i;
   BG_TRY(upload_vec(d.perm, h.perm, s)); BG_TRY(upload_vec(d.iperm, inv, s));
   BG_TRY(d.blk.upload(h.blk.data(), h.blk.size() * sizeof(BlockDesc), s));
-  BG_TRY(upload_vec(d.chunk_off, h.chunk_off, s)); BG_TRY(upload_vec(d.stream, h.stream, s));
+  // fixed-stride chunk table so that a block's descriptor and chunk offsets are independent loads
+  d.tab_stride = (h.max_chunks + 1 + 3) / 4 * 4;
+  std::vector<uint32_t> tab((size_t)h.nblocks * d.tab_stride, 0u);
+  for (int b = 0; b < h.nblocks; ++b)
+    for (int c = 0; c <= h.blk[b].nchunks; ++c) tab[(size_t)b * d.tab_stride + c] = h.chunk_off[h.blk[b].chunk0 + c];
+  BG_TRY(upload_vec(d.chunk_tab, tab, s)); BG_TRY(upload_vec(d.stream, h.stream, s));
   BG_TRY(upload_vec(d.dinv, h.dinv, s));
-  d.bytes = (int64_t)h.stream.size() + (int64_t)h.blk.size() * sizeof(BlockDesc) + (int64_t)h.chunk_off.size() * 4 +
-            (int64_t)h.dinv.size() * sizeof(T);
+  d.h_dinv.assign(h.dinv.begin(), h.dinv.end());
+  d.bytes = (int64_t)h.stream.size() + (int64_t)h.blk.size() * sizeof(BlockDesc) + (int64_t)tab.size() * 4;
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }
@@ -466,8 +471,8 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
   M->schedule = o.trsv_schedule;
   M->factor_dtype = o.factor_dtype < 0 ? dtype : o.factor_dtype;
   M->use_tma = o.use_tma != 0;
-  M->fb_chunk_bytes = o.chunk_bytes > 0 ? o.chunk_bytes : 2048;
-  M->fb.stages = std::min(16, std::max(2, o.stages > 0 ? o.stages : 4));
+  M->fb_chunk_bytes = o.chunk_bytes > 0 ? o.chunk_bytes : 4096;
+  M->fb.stages = std::min(8, std::max(2, o.stages > 0 ? o.stages : 2));
   M->fb.warps_per_cta = std::min(16, std::max(1, o.warps_per_cta > 0 ? o.warps_per_cta : 4));
   int rc = precond_install_dt<T>(M, F.L, F.U, true, block ? blk.data() : nullptr, nb);
   if (rc < 0) { delete M; return rc; }
@@ -709,8 +714,8 @@ static_assert(sizeof(Status) <= 128, "status slot");
 // optional per-phase timing (bg_solver_profile): event pairs around kernel groups
 struct Prof {
   std::vector<cudaEvent_t>* pool = nullptr;
-  std::vector<std::pair<int, int>> spans[4];  // event index pairs per phase
-  int64_t calls[4] = {0, 0, 0, 0};
+  std::vector<std::pair<int, int>> spans[6];  // event index pairs per phase
+  int64_t calls[6] = {0, 0, 0, 0, 0, 0};
   size_t used = 0;
   cudaStream_t stream = nullptr;
   int mark() {
@@ -719,7 +724,7 @@ struct Prof {
     return (int)used++;
   }
 };
-enum { PH_SPMV = 0, PH_TRSV = 1, PH_ORTH = 2, PH_OTHER = 3 };
+enum { PH_SPMV = 0, PH_TRSV = 1, PH_ORTH = 2, PH_OTHER = 3, PH_DOTS = 4, PH_UPDATE = 5 };
 
 struct Driver {
   bg_context_t ctx; bg_solver_t S; bg_matrix_t A; bg_precond_t M; const bg_gmres_opts& o;
@@ -764,8 +769,8 @@ struct Driver {
       return launch_update(ctx, S->dtype, n, S->w.p, nullptr, ld, 0, nullptr, 0.0, col(i + 1), st, 1, 0, 0);
     }
     const int j = i + 1;
-    BG_TRY(launch_dots(ctx, S->dtype, n, col(0), ld, j, S->w.p, st, FIN_CGS1, i, 0, o.orth, 0));
-    BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(0), ld, j, st.h, -1.0, col(j), st, 1, 0, 0));
+    { Span sd(prof, PH_DOTS); BG_TRY(launch_dots(ctx, S->dtype, n, col(0), ld, j, S->w.p, st, FIN_CGS1, i, 0, o.orth, 0)); }
+    { Span su(prof, PH_UPDATE); BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(0), ld, j, st.h, -1.0, col(j), st, 1, 0, 0)); }
     BG_TRY(launch_dots(ctx, S->dtype, n, col(0), ld, j, col(j), st, FIN_CGS2, i, 0, o.orth, 1));
     return launch_update(ctx, S->dtype, n, col(j), col(0), ld, j, st.h2, -1.0, col(j), st, 1, 0, 1);
   }
@@ -795,8 +800,10 @@ struct Driver {
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-// P A P^T for the block-major order of a block-Jacobi preconditioner (new row i = old row perm[i]);
-// built once per ordering and cached inside A.
+// D^-1 P A P^T for the block-major order of a block-Jacobi preconditioner (new row i = old row
+// perm[i], D = diag(U) in that order); built once per ordering and cached inside A.  With b scaled
+// the same way the left-preconditioned operator M^-1 A and M^-1 b are unchanged, but the device
+// triangular solves become unit solves (trsv_block.cu).
 template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev& fb) {
   const int n = A->n;
   const std::vector<int>& perm = fb.h_perm;
@@ -810,7 +817,8 @@ template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev&
   for (int i = 0; i < n; ++i) {
     const int o = perm[i];
     row.clear();
-    for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) row.emplace_back(inv[A->h_ci[p]], v[p]);
+    const double di = fb.h_dinv[i];  // row scaling D^-1 (D = diag U): the device solves are unit solves
+    for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) row.emplace_back(inv[A->h_ci[p]], (T)((double)v[p] * di));
     std::sort(row.begin(), row.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
     int q = rp[i];
     for (auto& e : row) { ci[q] = e.first; vv[q++] = e.second; }
@@ -862,7 +870,7 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
 
   BG_CUDA(cudaEventRecord(S->t0, ctx->stream));
   if (permuted) {
-    BG_TRY(launch_gather(ctx, S->dtype, n, M->fb.perm.as<int>(), d_b, S->bp.p));
+    BG_TRY(launch_gather(ctx, S->dtype, n, M->fb.perm.as<int>(), d_b, S->bp.p, M->fb.dinv.p, M->factor_dtype));
     BG_TRY(launch_gather(ctx, S->dtype, n, M->fb.perm.as<int>(), d_x, S->xp.p));
     d_b = S->bp.p;
     d_x = S->xp.p;
@@ -994,8 +1002,8 @@ extern "C" int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A,
   int rc = gmres_solve_impl(ctx, S, A, M, d_b, d_x, o, &rr, &prof);
   if (rc < 0) return rc;
   if (r) *r = rr;
-  double ms[4] = {0, 0, 0, 0};
-  for (int ph = 0; ph < 4; ++ph)
+  double ms[6] = {0, 0, 0, 0, 0, 0};
+  for (int ph = 0; ph < 6; ++ph)
     for (auto& sp : prof.spans[ph]) {
       float t = 0;
       cudaEventElapsedTime(&t, S->prof_events[sp.first], S->prof_events[sp.second]);
@@ -1004,6 +1012,8 @@ extern "C" int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A,
   std::memset(out, 0, sizeof(*out));
   out->spmv_ms = ms[PH_SPMV]; out->trsv_ms = ms[PH_TRSV]; out->orth_ms = ms[PH_ORTH]; out->other_ms = ms[PH_OTHER];
   out->spmv_calls = prof.calls[PH_SPMV]; out->trsv_calls = prof.calls[PH_TRSV]; out->orth_calls = prof.calls[PH_ORTH];
+  out->dots_ms = ms[PH_DOTS]; out->update_ms = ms[PH_UPDATE];
+  out->dots_calls = prof.calls[PH_DOTS]; out->update_calls = prof.calls[PH_UPDATE];
   // algorithmic bytes of the work actually performed (iters_done inner iterations)
   bg_matrix_info mi; bg_precond_info pi;
   bg_matrix_get_info(A, &mi); bg_precond_get_info(M, &pi);
@@ -1017,6 +1027,10 @@ extern "C" int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A,
   for (int64_t t = 0; t < it; ++t) { const int64_t j = t % m + 1; orth += 2 * j * s * n + 5 * s * n; }  // SURVEY 8d B_orth(j)
   orth += (int64_t)rr.reorths * 0;  // second passes are reported through `reorths`, not counted as algorithmic bytes
   out->orth_bytes = orth;
+  // first-pass kernels alone, with the bytes each launch cannot avoid: dots reads j basis columns + w,
+  // update reads them again + w and writes v_j (CGS modes only; zero under strict MGS)
+  if (o->orth != BG_ORTH_MGS)
+    for (int64_t t = 0; t < it; ++t) { const int64_t j = t % m + 1; out->dots_bytes += (j + 1) * s * n; out->update_bytes += (j + 2) * s * n; }
   out->other_bytes = nres * (3 * s * n) + (rr.restarts + 1) * (s * n * m + 2 * s * n);
   return rc;
 }

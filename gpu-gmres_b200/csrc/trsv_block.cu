@@ -63,11 +63,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 struct FbArgs {
   const BlockDesc* blk;
-  const uint32_t* chunk_off;
+  const uint32_t* chunk_tab;  // [nblocks][tab_stride]: chunk start offsets (16-byte units) of a block + end
   const unsigned char* stream;
   const int* perm;
-  const void* dinv;     // FT[n], block-major
-  int nblocks, max_rows, stages, max_chunks;
+  const void* dinv;     // FT[n], block-major (gather variant only: the solver folds it into A and b)
+  int nblocks, max_rows, stages, tab_stride;
   uint32_t slot_bytes;  // ring slot stride (multiple of 128)
   uint32_t warp_smem;   // bytes of shared memory per warp (multiple of 128)
 };
@@ -76,10 +76,11 @@ template <class FT> struct PairOf;
 template <> struct PairOf<float> { using type = float2; };
 template <> struct PairOf<double> { using type = double2; };
 
-// metadata of one slot (row id + K <= 3 local columns in one 8-byte quad, K values)
+// metadata of one slot: row id + K <= 7 local columns in one or two 8-byte quads, K values
 template <class FT, class CT, int K>
-__device__ __forceinline__ void load_slot(int t, int nsA, const uint2* quads, const FT* vals, uint2& q, CT* v) {
-  q = quads[t];
+__device__ __forceinline__ void load_slot(int t, int nsA, const uint2* quads, const FT* vals, uint2& q0, uint2& q1, CT* v) {
+  q0 = quads[t];
+  if (K > 3) q1 = quads[nsA + t];
   using P = typename PairOf<FT>::type;
 #pragma unroll
   for (int p = 0; p < K / 2; ++p) {
@@ -90,34 +91,37 @@ __device__ __forceinline__ void load_slot(int t, int nsA, const uint2* quads, co
   if (K & 1) v[K - 1] = (CT)vals[(size_t)(K / 2) * 2 * nsA + t];
 }
 
-// all steps of one chunk whose rows have at most K <= 3 off-diagonals: the slot of step s+1 is
-// fetched into registers before the warp barrier of step s
+// all steps of one chunk whose rows have at most K <= 7 off-diagonals.  Branch-free: lanes beyond the
+// step's row count read a (clamped) later slot and only their store is predicated off; the slot of
+// step s+1 is fetched into registers before the warp barrier of step s.
 template <class FT, class CT, int K>
-__device__ __forceinline__ void run_steps_fast(int lane, int nst, int nsA, const unsigned char* cnts, const uint2* quads,
-                                               const FT* vals, CT* xl) {
-  uint2 qn = make_uint2(0u, 0u);
+__device__ __forceinline__ void run_steps_fast(int lane, int ns, int nst, int nsA, const unsigned char* cnts,
+                                               const uint2* quads, const FT* vals, CT* xl) {
+  uint2 qn0, qn1 = make_uint2(0u, 0u);
   CT vn[K > 0 ? K : 1];
+  const int last = ns - 1;
   int s0 = 0, cnt = cnts[0];
-  if (lane < cnt) load_slot<FT, CT, K>(lane, nsA, quads, vals, qn, vn);
+  load_slot<FT, CT, K>(min(lane, last), nsA, quads, vals, qn0, qn1, vn);
   for (int s = 0; s < nst; ++s) {
-    const uint2 q = qn;
+    const uint2 q0 = qn0, q1 = qn1;
     CT v[K > 0 ? K : 1];
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = vn[k];
     const bool act = lane < cnt;
     s0 += cnt;
-    const int cnt2 = s + 1 < nst ? (int)cnts[s + 1] : 0;
-    if (lane < cnt2) load_slot<FT, CT, K>(s0 + lane, nsA, quads, vals, qn, vn);
-    if (act) {
-      const uint32_t li = q.x & 0xffffu;
-      CT acc = xl[li];
-      if (K > 0) acc -= v[0] * xl[q.x >> 16];
-      if (K > 1) acc -= v[1] * xl[q.y & 0xffffu];
-      if (K > 2) acc -= v[2] * xl[q.y >> 16];
-      xl[li] = acc;  // rows of one step never read each other
-    }
-    __syncwarp();  // orders this step's writes before the next step's reads
-    cnt = cnt2;
+    cnt = cnts[s + 1];  // one readable byte past the last count (alignment padding)
+    load_slot<FT, CT, K>(min(s0 + lane, last), nsA, quads, vals, qn0, qn1, vn);
+    const uint32_t li = q0.x & 0xffffu;
+    CT acc = xl[li];
+    if (K > 0) acc -= v[0] * xl[q0.x >> 16];
+    if (K > 1) acc -= v[1] * xl[q0.y & 0xffffu];
+    if (K > 2) acc -= v[2] * xl[q0.y >> 16];
+    if (K > 3) acc -= v[3] * xl[q1.x & 0xffffu];
+    if (K > 4) acc -= v[4] * xl[q1.x >> 16];
+    if (K > 5) acc -= v[5] * xl[q1.y & 0xffffu];
+    if (K > 6) acc -= v[6] * xl[q1.y >> 16];
+    if (act) xl[li] = acc;  // rows of one step never read each other
+    __syncwarp();           // orders this step's writes before the next step's reads
   }
 }
 
@@ -146,6 +150,9 @@ __device__ __forceinline__ void run_steps_generic(int lane, int K, int nst, int 
   }
 }
 
+// GATHER: vectors in the caller's original row order, r scaled by 1/diag(U) while loading.
+// !GATHER: vectors in block-major order and already row-scaled (the solver runs on D^-1 P A P^T,
+//          D^-1 P b), so a block's right-hand side / result is one bulk copy each way.
 template <class VT, class FT, class CT, bool GATHER>
 __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __restrict__ in, VT* __restrict__ out,
                                                         const int* skip) {
@@ -156,20 +163,24 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
   CT* xl = reinterpret_cast<CT*>(mine);
   const uint32_t xl_bytes = ((uint32_t)a.max_rows * sizeof(CT) + 127u) & ~127u;
   uint32_t* coff = reinterpret_cast<uint32_t*>(mine + xl_bytes);
-  const uint32_t coff_bytes = ((uint32_t)(a.max_chunks + 1) * 4u + 127u) & ~127u;
+  const uint32_t coff_bytes = ((uint32_t)a.tab_stride * 4u + 127u) & ~127u;
   unsigned char* ring = mine + xl_bytes + coff_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * a.slot_bytes);
+  uint64_t* bar_in = bars + a.stages;
   const FT* dinv = reinterpret_cast<const FT*>(a.dinv);
+  constexpr bool kBulkVec = !GATHER && sizeof(VT) == sizeof(CT);  // rhs/result move as bulk copies
   if (lane == 0) {
-    for (int s = 0; s < a.stages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s <= a.stages; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t g0 = 0;  // ring-global index of the current block's first chunk (monotone per warp)
+  uint32_t g0 = 0;   // ring-global index of the current block's first chunk (monotone per warp)
+  uint32_t nin = 0;  // bulk loads of a right-hand side so far (phase of bar_in)
   for (int b = blockIdx.x * nw + wid; b < a.nblocks; b += gridDim.x * nw) {
+    // descriptor and chunk table are fetched in one round trip (the table has a fixed stride)
     const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.blk + b));
-    const int row0 = d0.x, nb = d0.y, chunk0 = d0.z, nch = d0.w;
-    for (int i = lane; i <= nch; i += 32) coff[i] = __ldg(a.chunk_off + chunk0 + i);
+    for (int i = lane; i < a.tab_stride; i += 32) coff[i] = __ldg(a.chunk_tab + (size_t)b * a.tab_stride + i);
+    const int row0 = d0.x, nb = d0.y, nch = d0.w;
     __syncwarp();
     auto issue = [&](int c) {  // lane 0 only
       const uint32_t st = (g0 + (uint32_t)c) % (uint32_t)a.stages;
@@ -177,49 +188,79 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
       mbar_expect_tx(&bars[st], bytes);
       bulk_g2s(ring + (size_t)st * a.slot_bytes, a.stream + (size_t)o0 * 16u, bytes, &bars[st]);
     };
-    if (lane == 0)
+    const bool bulk_vec = kBulkVec && (((uint32_t)row0 * sizeof(VT)) & 15u) == 0 && (((uint32_t)nb * sizeof(VT)) & 15u) == 0 && nb > 0;
+    if (lane == 0) {
+      if (kBulkVec) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous result has left xl
+      if (bulk_vec) {
+        mbar_expect_tx(bar_in, (uint32_t)nb * sizeof(VT));
+        bulk_g2s(xl, in + row0, (uint32_t)nb * sizeof(VT), bar_in);
+      }
       for (int c = 0; c < nch && c < a.stages; ++c) issue(c);
-    // d .* r of the block -> shared memory (contiguous in the block-major numbering)
-    for (int i = lane; i < nb; i += 32)
-      xl[i] = (CT)in[GATHER ? __ldg(a.perm + row0 + i) : row0 + i] * (CT)__ldg(dinv + row0 + i);
+    }
     __syncwarp();
+    if (bulk_vec) {
+      mbar_wait(bar_in, nin & 1u);
+      ++nin;
+    } else {
+      for (int i = lane; i < nb; i += 32) {
+        if (GATHER) xl[i] = (CT)in[__ldg(a.perm + row0 + i)] * (CT)__ldg(dinv + row0 + i);
+        else xl[i] = (CT)in[row0 + i];
+      }
+      __syncwarp();
+    }
     for (int c = 0; c < nch; ++c) {
       const uint32_t g = g0 + (uint32_t)c, st = g % (uint32_t)a.stages;
       mbar_wait(&bars[st], (g / (uint32_t)a.stages) & 1u);
       const unsigned char* rec = ring + (size_t)st * a.slot_bytes;
       const uint2 h = *reinterpret_cast<const uint2*>(rec);
-      const int K = (int)(h.x >> 16), nst = (int)(h.y & 0xffffu), nsA = (int)(h.y >> 16);
+      const int ns = (int)(h.x & 0xffffu), K = (int)(h.x >> 16), nst = (int)(h.y & 0xffffu), nsA = (int)(h.y >> 16);
       const unsigned char* cnts = rec + 16;
-      const int stA = (nst + 15) & ~15;
+      const int stA = (nst + 16) & ~15;
       const uint2* quads = reinterpret_cast<const uint2*>(rec + 16 + stA);
       const FT* vals = reinterpret_cast<const FT*>(rec + 16 + stA + 8 * (size_t)((K + 4) >> 2) * nsA);
       switch (K) {  // uniform per chunk
-        case 0: run_steps_fast<FT, CT, 0>(lane, nst, nsA, cnts, quads, vals, xl); break;
-        case 1: run_steps_fast<FT, CT, 1>(lane, nst, nsA, cnts, quads, vals, xl); break;
-        case 2: run_steps_fast<FT, CT, 2>(lane, nst, nsA, cnts, quads, vals, xl); break;
-        case 3: run_steps_fast<FT, CT, 3>(lane, nst, nsA, cnts, quads, vals, xl); break;
+        case 0: run_steps_fast<FT, CT, 0>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 1: run_steps_fast<FT, CT, 1>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 2: run_steps_fast<FT, CT, 2>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 3: run_steps_fast<FT, CT, 3>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 4: run_steps_fast<FT, CT, 4>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 5: run_steps_fast<FT, CT, 5>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 6: run_steps_fast<FT, CT, 6>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
+        case 7: run_steps_fast<FT, CT, 7>(lane, ns, nst, nsA, cnts, quads, vals, xl); break;
         default: run_steps_generic<FT, CT>(lane, K, nst, nsA, cnts, quads, vals, xl); break;
       }
       // every lane is past its last read of this ring slot: refill it
       if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
     }
-    for (int i = lane; i < nb; i += 32) out[GATHER ? __ldg(a.perm + row0 + i) : row0 + i] = (VT)xl[i];
+    if (bulk_vec) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of xl -> async proxy
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + row0), "r"(smem_u32(xl)),
+                     "r"((uint32_t)nb * (uint32_t)sizeof(VT))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      for (int i = lane; i < nb; i += 32) out[GATHER ? __ldg(a.perm + row0 + i) : row0 + i] = (VT)xl[i];
+    }
     __syncwarp();
     g0 += (uint32_t)nch;
   }
+  if (kBulkVec && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // results are in HBM before exit
 }
 
 template <class VT, class FT>
 int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void* in, void* out, const int* skip) {
   using CT = decltype(VT() * FT());
   FbArgs a{};
-  a.blk = S.blk.as<BlockDesc>(); a.chunk_off = S.chunk_off.as<uint32_t>(); a.stream = S.stream.as<unsigned char>();
+  a.blk = S.blk.as<BlockDesc>(); a.chunk_tab = S.chunk_tab.as<uint32_t>(); a.stream = S.stream.as<unsigned char>();
   a.perm = S.perm.as<int>();
   a.dinv = S.dinv.p;
-  a.nblocks = S.nblocks; a.max_rows = S.max_rows; a.stages = S.stages; a.max_chunks = S.max_chunks;
+  a.nblocks = S.nblocks; a.max_rows = S.max_rows; a.stages = S.stages; a.tab_stride = S.tab_stride;
   a.slot_bytes = ((uint32_t)S.max_chunk_bytes + 127u) & ~127u;
   const uint32_t xl_bytes = ((uint32_t)S.max_rows * sizeof(CT) + 127u) & ~127u;
-  const uint32_t coff_bytes = ((uint32_t)(S.max_chunks + 1) * 4u + 127u) & ~127u;
+  const uint32_t coff_bytes = ((uint32_t)S.tab_stride * 4u + 127u) & ~127u;
   a.warp_smem = xl_bytes + coff_bytes + (uint32_t)a.stages * a.slot_bytes + 128u;
   const int warps = S.warps_per_cta;
   const size_t smem = (size_t)warps * a.warp_smem;

@@ -474,7 +474,7 @@ void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, 
   struct Step { int first, count; };  // into `order`
   std::vector<Step> steps;
   auto chunk_bytes = [](int ns, int K, int nsteps) {
-    const int nsA = (ns + 7) / 8 * 8, stA = (nsteps + 15) / 16 * 16, KQ = (K + 4) / 4;
+    const int nsA = (ns + 7) / 8 * 8, stA = (nsteps + 16) / 16 * 16, KQ = (K + 4) / 4;
     return 16 + stA + 8 * KQ * nsA + (int)sizeof(T) * K * nsA;
   };
   // emits the chunks of one factor of one block
@@ -522,7 +522,7 @@ void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, 
         if (nst > 0 && chunk_bytes(ns + steps[sj].count, K2, nst + 1) > chunk_target) break;
         ns += steps[sj].count; K = K2; ++nst; ++sj;
       }
-      const int nsA = (ns + 7) / 8 * 8, stA = (nst + 15) / 16 * 16, KQ = (K + 4) / 4;
+      const int nsA = (ns + 7) / 8 * 8, stA = (nst + 16) / 16 * 16, KQ = (K + 4) / 4;
       const int bytes = (chunk_bytes(ns, K, nst) + 15) / 16 * 16;
       const size_t off = out.stream.size();
       out.stream.resize(off + bytes, 0);

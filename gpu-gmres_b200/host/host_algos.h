@@ -86,7 +86,7 @@ void pack_level_stream(bool lower, bool unit, const Csr<T>& M, int thin_rows, Le
 // and the kernel multiplies by dinv (block-major, n entries) while it loads r.
 // Steps are packed, whole, into CHUNKS of <= chunk_target bytes; one chunk = one bulk-async copy:
 //     [ u16 ns, K, nsteps, nsA, pad[4] ]                               16 B header
-//     [ u8  step_cnt[nstepsA] ]          nstepsA = nsteps rounded up to 16
+//     [ u8  step_cnt[nstepsA] ]          nstepsA = nsteps+1 rounded up to 16 (one readable byte past the end)
 //     [ u16x4 quad[KQ][nsA] ]            quad 0 = (row, c0, c1, c2), quad q>0 = (c[4q-1] .. c[4q+2]);
 //                                        KQ = (K+4)/4, local ids; padding columns = the row itself
 //     [ T x2  pair[K/2][nsA] ]           values (v0,v1), (v2,v3), ...

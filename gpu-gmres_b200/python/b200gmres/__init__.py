@@ -82,7 +82,9 @@ class GmresResult(C.Structure):
 class PhaseStats(C.Structure):
     _fields_ = [("spmv_ms", C.c_double), ("trsv_ms", C.c_double), ("orth_ms", C.c_double), ("other_ms", C.c_double),
                 ("spmv_bytes", C.c_int64), ("trsv_bytes", C.c_int64), ("orth_bytes", C.c_int64), ("other_bytes", C.c_int64),
-                ("spmv_calls", C.c_int64), ("trsv_calls", C.c_int64), ("orth_calls", C.c_int64)]
+                ("spmv_calls", C.c_int64), ("trsv_calls", C.c_int64), ("orth_calls", C.c_int64),
+                ("dots_ms", C.c_double), ("update_ms", C.c_double), ("dots_bytes", C.c_int64), ("update_bytes", C.c_int64),
+                ("dots_calls", C.c_int64), ("update_calls", C.c_int64)]
 
 
 _lib = None

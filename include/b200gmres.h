@@ -142,8 +142,8 @@ typedef struct {
   int factor_dtype;    /* storage type of L/U values on the device: -1 = same as the factors given */
   int use_tma;         /* 1 (default): bulk-async staged factor streams; 0: plain loads            */
   int ilut_lfil; double ilut_tau; /* used by bg_precond_create_ilut                                */
-  int chunk_bytes;     /* BG_TRSV_BLOCK: target size of one bulk copy of the factor stream (2048) */
-  int stages;          /* BG_TRSV_BLOCK: ring slots per warp (4)                                  */
+  int chunk_bytes;     /* BG_TRSV_BLOCK: target size of one bulk copy of the factor stream (4096) */
+  int stages;          /* BG_TRSV_BLOCK: ring slots per warp (2)                                  */
   int warps_per_cta;   /* BG_TRSV_BLOCK: block solves per CTA (4)                                 */
 } bg_precond_opts;
 BG_API void bg_precond_opts_default(bg_precond_opts* o);
@@ -233,6 +233,9 @@ typedef struct {
   double spmv_ms, trsv_ms, orth_ms, other_ms;
   int64_t spmv_bytes, trsv_bytes, orth_bytes, other_bytes;
   int64_t spmv_calls, trsv_calls, orth_calls;
+  /* the two kernels of the fused orthogonalisation step on their own (first pass only) */
+  double dots_ms, update_ms;
+  int64_t dots_bytes, update_bytes, dots_calls, update_calls;
 } bg_phase_stats;
 BG_API int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b,
                              void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st);

@@ -80,7 +80,7 @@ static int run_case(int n, int nblocks, int max_off, int chunk_target, unsigned 
       const unsigned char* rec = S.stream.data() + off;
       const uint16_t* hdr = reinterpret_cast<const uint16_t*>(rec);
       const int ns = hdr[0], K = hdr[1], nst = hdr[2], nsA = hdr[3];
-      const int stA = (nst + 15) / 16 * 16, KQ = (K + 4) / 4;
+      const int stA = (nst + 16) / 16 * 16, KQ = (K + 4) / 4;
       const unsigned char* cnts = rec + 16;
       const uint16_t* quads = reinterpret_cast<const uint16_t*>(rec + 16 + stA);
       const T* vals = reinterpret_cast<const T*>(rec + 16 + stA + 8 * (size_t)KQ * nsA);

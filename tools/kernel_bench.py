@@ -35,9 +35,9 @@ def main():
     ap.add_argument("--js", default="1,4,8,16,24,32")
     ap.add_argument("--tma", default="1")
     ap.add_argument("--graph", type=int, default=0)
-    ap.add_argument("--etas", default="0.70710678")
-    ap.add_argument("--chunks", default="2048")
-    ap.add_argument("--stages", default="4")
+    ap.add_argument("--etas", default="0.1")
+    ap.add_argument("--chunks", default="4096")
+    ap.add_argument("--stages", default="2")
     ap.add_argument("--warps", default="4")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
