@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--schedule", default="block", choices=["block", "level"])
     ap.add_argument("--blocks", default="grid", choices=["grid", "metis"])
     ap.add_argument("--tile", type=int, default=32)
+    ap.add_argument("--ilut-tau", type=float, default=1e-2)
+    ap.add_argument("--ilut-lfil", type=int, default=5)
     ap.add_argument("--factor-dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--orth", default="cgs", choices=["mgs", "cgs", "cgs2"])
     ap.add_argument("--eta", type=float, default=0.1, help="CGS re-orthogonalisation threshold (DGKS): second pass when ||w'|| < eta ||w||")
@@ -210,6 +212,9 @@ def main():
         if world > 1:
             dist.barrier()
 
+    if world > 1:
+        run_dist(args, rank, world, local)
+        return
     rp, ci, v, b = workload(args.nx)
     n = len(rp) - 1
     ctx = bg.Context(local)
@@ -220,9 +225,9 @@ def main():
     if args.schedule == "block":
         o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile, factor_dtype=fdt,
                             block_method=bg.PART_GRID2D if args.blocks == "grid" else bg.PART_METIS,
-                            dims=[args.nx, args.nx, 1, args.tile, args.tile, 1], ilut_tau=1e-3, ilut_lfil=10)
+                            dims=[args.nx, args.nx, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     else:
-        o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=1e-3, ilut_lfil=10)
+        o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(args.precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
     S = bg.Solver(ctx, n, 32, dtype=bg.F64)
@@ -336,6 +341,129 @@ def main():
     S.close(); M.close(); A.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_dist(args, rank, world, local):
+    """N > 1: the same DC solve, row-partitioned into `world` horizontal strips of the grid (contiguous
+    row blocks, src/partition.cpp's initial assignment), one process per GPU: NCCL halo exchange per
+    SpMV, one NCCL allreduce per orthogonalisation step, per-rank block-Jacobi ILU (dist.cu)."""
+    import torch
+    import torch.distributed as dist
+
+    import b200gmres as bg
+
+    dev = torch.device("cuda", local)
+    rp, ci, v, b = workload(args.nx)
+    n, nx = len(rp) - 1, args.nx
+    # strips of whole grid rows, heights as equal as possible
+    ys = [(r * nx) // world for r in range(world + 1)]
+    part = np.repeat(np.arange(world, dtype=np.int32), np.diff(ys) * nx)
+    t_setup = time.perf_counter()
+    plan = bg.DistPlan(rp, ci, v, world, rank, part)
+    ids = [bg.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx = bg.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    fdt = bg.F32 if args.factor_dtype == "f32" else bg.F64
+    ny_local = ys[rank + 1] - ys[rank]
+    o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile, factor_dtype=fdt, block_method=bg.PART_GRID2D,
+                        dims=[nx, ny_local, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
+    D = bg.Dist(ctx, plan, ids[0], dtype=bg.F64, m=32, opts=o, ilut=(args.precond == "ilut"))
+    t_setup = time.perf_counter() - t_setup
+    a = plan.arrays()
+    nl = plan.info.n_local
+    orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[args.orth]
+    opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
+    bl = np.ascontiguousarray(b[a["l2g"]])
+    db = torch.from_numpy(bl).to(dev)
+    dx = torch.zeros(nl, dtype=torch.float64, device=dev)
+    hb = torch.from_numpy(bl).pin_memory()
+    hx = torch.zeros(nl, dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_device():
+        with torch.cuda.stream(stream):
+            dx.zero_()
+        return D.solve(db.data_ptr(), dx.data_ptr(), opts)
+
+    def step_host():
+        hx.zero_()
+        return D.solve(hb.numpy(), hx.numpy(), opts, host=True)
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record(stream)
+        for _ in range(k):
+            r = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        return float(t.item()), r, ctx.launches - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(1.0)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    tc0 = sampler.mark()
+    ms, r, launches = timed(step_device, args.steps)
+    tc1 = sampler.mark()
+    clocks = sampler.stop(tc0, tc1) if rank == 0 else None
+    for _ in range(2):
+        step_host()
+    ms_e2e, _, _ = timed(step_host, args.steps)
+    # true residual of the assembled solution (gathered on rank 0)
+    step_device()
+    torch.cuda.synchronize()
+    sizes = [int((part == q).sum()) for q in range(world)]
+    pieces = []
+    for q in range(world):
+        t = dx.clone() if q == rank else torch.zeros(sizes[q], dtype=torch.float64, device=dev)
+        dist.broadcast(t, src=q)
+        pieces.append(t)
+    info = D.info()
+    if rank == 0:
+        x = np.concatenate([p.cpu().numpy() for p in pieces])
+        true_rel = float(np.linalg.norm(b - _spmv_host(rp, ci, v, x)) / np.linalg.norm(b))
+        peak, which = peaks()
+        step_ms = ms / args.steps
+        s8 = 8
+        nnz = len(ci)
+        # SURVEY 8(d) bytes per inner iteration summed over all ranks (the halo adds nothing to HBM traffic worth counting)
+        it = max(r.iters_done, 1)
+        orth_b = sum((2 * (t % 32 + 1) + 5) * s8 * n for t in range(it))
+        spmv_b = ((s8 + 4) * nnz + 4 * (n + 1) + 2 * s8 * n) * it
+        trsv_b = ((s8 + 4) * (info.precond.nnzL + info.precond.nnzU) * world + 8 * (n + 1) + 4 * s8 * n) * it  # nnz of rank 0 x world
+        all_b = orth_b + spmv_b + trsv_b
+        line = {
+            "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"pg2d {nx}x{nx} (ibmpg6-sized, BASELINE configs[1]) DC solve, GMRES(32), rel. residual {args.tol:g}",
+                       "n": n, "nnz": nnz, "precond": args.precond, "trsv_schedule": "block",
+                       "partition": f"{world} horizontal strips (contiguous rows), per-rank block-Jacobi ILU, tiles {args.tile}x{args.tile}",
+                       "orth": args.orth, "reorth_eta": args.eta,
+                       "l2_policy": "per-rank Krylov basis 33 x n/N x 8 B = %.0f MB" % (33 * n * 8 / 1e6 / world)},
+            "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
+            "ms_per_iteration": step_ms / it,
+            "iteration_roofline": {"bytes_per_iteration": all_b / it, "achieved_GBps": all_b / (step_ms * 1e-3) / 1e9,
+                                   "frac": all_b / (step_ms * 1e-3) / 1e9 / (peak * world), "peak": peak * world,
+                                   "bytes": "SURVEY.md 8(d) per inner iteration, all ranks; peak = N x measured HBM copy bandwidth"},
+            "comm": {"halo_bytes_per_exchange_rank0": int(info.halo_bytes_per_exchange), "neighbors_rank0": int(info.n_neighbors),
+                     "allreduce_doubles_max": 34, "backend": "NCCL send/recv + allreduce on the solver stream"},
+            "roofline": None, "setup_s": t_setup,
+            "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    D.close(); plan.close(); ctx.close()
+    dist.destroy_process_group()
 
 
 def ncu_traffic(kernel):

@@ -54,6 +54,7 @@ struct bg_context_s {
 struct bg_matrix_s {
   bg_context_t ctx = nullptr;
   int n = 0, dtype = BG_F64, format = BG_SPMV_CSR_VECTOR, lanes = 4;
+  int ncols = 0;  // > n for the local rows of a row-partitioned matrix (own columns, then halo slots)
   int64_t nnz = 0;
   bg::SpmvPlan plan;
   bg::DevBuf rp, ci, val;            // CSR
@@ -120,8 +121,14 @@ int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci,
                           const void* x, void* y, int vec_dt, const int* skip_flag);
 
 // dots: partial[k] = V[:,k].w for k<j, partial[j] = w.w ; then finalize variant `fin`
+// red_out != null (row-partitioned run): write this rank's sums there and skip the finalize; the caller
+// allreduces them and runs launch_finalize
 int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w,
-                const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth_flag);
+                const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth_flag,
+                double* red_out = nullptr);
+int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth,
+                    int j, const double* red_in);
+int launch_pack(bg_context_t ctx, int dtype, int cnt, const int* idx, const void* v, void* buf, const int* skip);
 // out = (a + sgn * sum_k coef[k] V[:,k]) * (use_scale ? scal[S_SCALE] : 1)
 int launch_update(bg_context_t ctx, int dtype, int n, const void* a, const void* V, int64_t ld, int j,
                   const double* coef, double sgn, void* out, const GmresDev& st, int use_scale, int force,
@@ -168,7 +175,7 @@ struct bg_solver_s {
   bg_context_t ctx = nullptr;
   int n = 0, m = 0, dtype = BG_F64;
   int64_t ld = 0;
-  bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb, bp, xp;
+  bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb, bp, xp, red;
   bg::GmresDev dev{};
   void* pinned = nullptr;  // host mirror of flags+scal for polling
   cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
@@ -176,6 +183,20 @@ struct bg_solver_s {
   std::vector<double> last_hist;
   int last_hist_len = 0;
 };
+
+// communication hooks of a row-partitioned solve (dist.cu); null for a single GPU
+namespace bg {
+struct DistHooks {
+  virtual int exchange(void* vec, const int* skip) = 0;  // fill vec[n_local .. n_local+n_halo) from the neighbours
+  virtual int allreduce(double* buf, int count) = 0;     // sum over ranks, in place, on the context stream
+  virtual ~DistHooks() {}
+};
+int gmres_solve_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                     const bg_gmres_opts* opts, bg_gmres_result* res, DistHooks* dh);
+int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
+                           const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out);
+int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out);
+}  // namespace bg
 
 struct bg_factors_s {
   int n = 0, dtype = BG_F64;

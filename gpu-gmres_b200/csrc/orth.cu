@@ -256,7 +256,7 @@ template <class VT>
 __global__ void __launch_bounds__(kPipeThreads, 1) dots_kernel(int n, const VT* __restrict__ V, int64_t ld, int j,
                                                                 const VT* __restrict__ w, GmresDev st, int fin,
                                                                 int inner_i, int mgs_k, int orth_mode, int need_reorth,
-                                                                Pipe pp) {
+                                                                Pipe pp, double* red_out) {
   if (st.flags[F_CONV]) return;
   if (need_reorth && !st.flags[F_REORTH]) return;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -337,6 +337,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) dots_kernel(int n, const VT* 
       if (k <= j && lane == 0) red[k] = r;
     }
   }
+  if (red_out) {
+    // row-partitioned run: these are one rank's sums; the host allreduces red_out over the ranks
+    // (NCCL) and finalize_kernel runs the scalar epilogue on the global values
+    __syncthreads();
+    if (threadIdx.x <= j) red_out[threadIdx.x] = red[threadIdx.x];
+    if (threadIdx.x == 0) *st.ticket = 0u;
+    return;
+  }
   __shared__ FinScratch fs;
   const bool column_fin = fin == FIN_CGS1 || fin == FIN_CGS2;
   if (column_fin) fin_prefetch(st, fs, inner_i, threadIdx.x);
@@ -345,6 +353,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) dots_kernel(int n, const VT* 
     finalize(st, fin, inner_i, mgs_k, orth_mode, red, j, column_fin ? &fs : nullptr);
     *st.ticket = 0u;
   }
+}
+
+// scalar epilogue of a row-partitioned dots step, after the allreduce of the per-rank sums
+__global__ void finalize_kernel(GmresDev st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth, int j,
+                                const double* __restrict__ red_in) {
+  if (st.flags[F_CONV]) return;
+  if (need_reorth && !st.flags[F_REORTH]) return;
+  __shared__ double red[kFinMax + 2];
+  __shared__ FinScratch fs;
+  if (threadIdx.x <= j) red[threadIdx.x] = red_in[threadIdx.x];
+  const bool column_fin = fin == FIN_CGS1 || fin == FIN_CGS2;
+  if (column_fin) fin_prefetch(st, fs, inner_i, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x == 0) finalize(st, fin, inner_i, mgs_k, orth_mode, red, j, column_fin ? &fs : nullptr);
+}
+
+// boundary values of a vector packed for the halo exchange: buf[k] = v[idx[k]]
+template <class VT>
+__global__ void pack_kernel(int cnt, const int* __restrict__ idx, const VT* __restrict__ v, VT* __restrict__ buf, const int* skip) {
+  if (skip && *skip) return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) buf[k] = v[idx[k]];
 }
 
 // ---------------------------------------------------------------------------- update
@@ -541,23 +570,39 @@ template <class K> static int pipe_smem_attr(K kernel, bg_context_t ctx) {
 
 template <class VT>
 static int dots_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int j, const VT* w, const GmresDev& st,
-                         int fin, int i, int mk, int om, int nr) {
+                         int fin, int i, int mk, int om, int nr, double* red_out) {
   if (j < 0 || j > kFinMax) { set_error("dots: j=%d exceeds one pass (max %d columns)", j, kFinMax); return BG_ERR_ARG; }
   const Pipe pp = pipe_geometry(j + 1, sizeof(VT));
   const size_t smem = (size_t)pp.stages * pp.stage_bytes + 2 * sizeof(uint64_t) * pp.stages;
   BG_TRY(pipe_smem_attr(dots_kernel<VT>, ctx));
   const int ntiles = (n + pp.R - 1) / pp.R;
   const int g = std::max(1, std::min(ntiles, ctx->sm_count));
-  dots_kernel<VT><<<g, kPipeThreads, smem, ctx->stream>>>(n, V, ld, j, w, st, fin, i, mk, om, nr, pp);
+  dots_kernel<VT><<<g, kPipeThreads, smem, ctx->stream>>>(n, V, ld, j, w, st, fin, i, mk, om, nr, pp, red_out);
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
 }
 
 int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, const GmresDev& st,
-                int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth) {
-  if (dtype == BG_F32) return dots_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth);
-  return dots_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth);
+                int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth, double* red_out) {
+  if (dtype == BG_F32) return dots_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out);
+  return dots_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out);
+}
+int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth, int j,
+                    const double* red_in) {
+  finalize_kernel<<<1, 128, 0, ctx->stream>>>(st, fin, inner_i, mgs_k, orth_mode, need_reorth, j, red_in);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+int launch_pack(bg_context_t ctx, int dtype, int cnt, const int* idx, const void* v, void* buf, const int* skip) {
+  if (cnt <= 0) return BG_OK;
+  const int g = std::max(1, std::min((cnt + 255) / 256, ctx->sm_count * 4));
+  if (dtype == BG_F32) pack_kernel<float><<<g, 256, 0, ctx->stream>>>(cnt, idx, (const float*)v, (float*)buf, skip);
+  else pack_kernel<double><<<g, 256, 0, ctx->stream>>>(cnt, idx, (const double*)v, (double*)buf, skip);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
 }
 
 template <class VT>

@@ -163,6 +163,7 @@ static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::ve
   A->h_ci = ci;
   A->h_val.resize(v.size() * sizeof(T));
   if (!v.empty()) std::memcpy(A->h_val.data(), v.data(), A->h_val.size());
+  if (A->ncols < A->n) A->ncols = A->n;
   A->plan = inspect_rows(A->n, rp.data());
   if (format == BG_SPMV_AUTO) format = A->plan.format;
   A->format = format;
@@ -206,16 +207,23 @@ extern "C" int bg_matrix_create_csr(bg_context_t ctx, int n, int64_t nnz, const 
     if (nnz) { std::memcpy(ci.data(), col, sizeof(int) * nnz); std::memcpy(hv.data(), val, hv.size()); }
   }
   if (n && (rp[0] != 0 || rp[n] != nnz)) { set_error("rowptr[0] must be 0 and rowptr[n] == nnz"); return BG_ERR_ARG; }
+  return matrix_create_internal(ctx, n, n, rp, ci, hv.data(), val_dtype, compute_dtype, spmv_format, out);
+}
+namespace bg {
+int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
+                           const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out) {
+  const int64_t nnz = (int64_t)ci.size();
   for (int64_t p = 0; p < nnz; ++p)
-    if (ci[p] < 0 || ci[p] >= n) { set_error("column index out of range at entry %lld", (long long)p); return BG_ERR_ARG; }
+    if (ci[p] < 0 || ci[p] >= ncols) { set_error("column index out of range at entry %lld", (long long)p); return BG_ERR_ARG; }
   bg_matrix_t A = new bg_matrix_s;
-  A->ctx = ctx; A->n = n; A->nnz = nnz; A->dtype = compute_dtype;
-  int rc = compute_dtype == BG_F32 ? matrix_build<float>(A, rp, ci, to_vec<float>(hv.data(), val_dtype, nnz), spmv_format)
-                                   : matrix_build<double>(A, rp, ci, to_vec<double>(hv.data(), val_dtype, nnz), spmv_format);
+  A->ctx = ctx; A->n = n; A->ncols = ncols; A->nnz = nnz; A->dtype = compute_dtype;
+  int rc = compute_dtype == BG_F32 ? matrix_build<float>(A, rp, ci, to_vec<float>(val, val_dtype, nnz), spmv_format)
+                                   : matrix_build<double>(A, rp, ci, to_vec<double>(val, val_dtype, nnz), spmv_format);
   if (rc < 0) { delete A; return rc; }
   *out = A;
   return BG_OK;
 }
+}  // namespace bg
 extern "C" int bg_matrix_destroy(bg_matrix_t A) { delete A; return BG_OK; }
 extern "C" int bg_matrix_get_info(bg_matrix_t A, bg_matrix_info* o) {
   if (!A || !o) return BG_ERR_ARG;
@@ -666,11 +674,15 @@ extern "C" void bg_gmres_opts_default(bg_gmres_opts* o) {
 static const int kHistCap = 1 << 16;
 
 extern "C" int bg_solver_create(bg_context_t ctx, int n, int m, int dtype, bg_solver_t* out) {
-  if (!ctx || !out || n < 0 || m < 1 || m > 1024) return BG_ERR_ARG;
+  return solver_create_internal(ctx, n, m, dtype, 0, out);
+}
+int bg::solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out) {
+  if (!ctx || !out || n < 0 || m < 1 || m > 1024 || extra_rows < 0) return BG_ERR_ARG;
   BG_CUDA(cudaSetDevice(ctx->device));
   bg_solver_t S = new bg_solver_s;
   S->ctx = ctx; S->n = n; S->m = m; S->dtype = dtype;
-  S->ld = ((int64_t)n + 31) / 32 * 32;
+  // every vector has room for `extra_rows` halo values behind its n own entries (row-partitioned runs)
+  S->ld = ((int64_t)n + extra_rows + 31) / 32 * 32;
   const size_t s = dtype_size(dtype);
   int rc = S->V.alloc((size_t)S->ld * (m + 1) * s);
   for (DevBuf* b : {&S->w, &S->ww, &S->r, &S->rr, &S->bb, &S->yv})
@@ -683,6 +695,7 @@ extern "C" int bg_solver_create(bg_context_t ctx, int n, int m, int dtype, bg_so
                o_y = take((m + 1) * 8), o_H = take((size_t)(m + 1) * m * 8), o_s = take((m + 1) * 8), o_cs = take((m + 1) * 8),
                o_sn = take((m + 1) * 8), o_t = take(16), o_hist = take((size_t)kHistCap * 8), o_p = take((size_t)nblk * pl * 8);
   if (rc >= 0) rc = S->state.alloc(off);
+  if (rc >= 0) rc = S->red.alloc(sizeof(double) * (size_t)(m + 8));
   if (rc < 0) { delete S; return rc; }
   cudaMemset(S->state.p, 0, off);
   unsigned char* b = S->state.as<unsigned char>();
@@ -732,6 +745,19 @@ struct Driver {
   int n, m; int64_t ld; size_t es; bool split; const int* skip; GmresDev st;
   Prof* prof = nullptr;
   bool permuted = false;  // A, b, x and all work vectors are in the preconditioner's block-major row order
+  DistHooks* dh = nullptr;  // row-partitioned run: halo exchange before every SpMV, allreduce inside every dots step
+  // y = alpha A x (+ beta b): x must have room for the halo behind its n entries when dh is set
+  int spmv(double alpha, void* xv, double beta, const void* bv, void* y, bool axpby) {
+    if (dh) BG_TRY(dh->exchange(xv, skip));
+    return launch_spmv(ctx, A, alpha, xv, beta, bv, y, axpby, skip);
+  }
+  int dots(const void* Vp, int j, const void* w, int fin, int i, int mk, int nr) {
+    if (!dh) return launch_dots(ctx, S->dtype, n, Vp, ld, j, w, st, fin, i, mk, o.orth, nr);
+    double* red = S->red.as<double>();
+    BG_TRY(launch_dots(ctx, S->dtype, n, Vp, ld, j, w, st, fin, i, mk, o.orth, nr, red));
+    BG_TRY(dh->allreduce(red, j + 1));
+    return launch_finalize(ctx, st, fin, i, mk, o.orth, nr, j, red);
+  }
   char* col(int k) const { return S->V.as<char>() + (size_t)k * ld * es; }
   struct Span {
     Prof* p; int ph, a;
@@ -743,35 +769,35 @@ struct Driver {
 
   // r = M_L^-1 (b - A x); beta, convergence test, v0 = r/beta
   int residual(int fin) {
-    { Span sp(prof, PH_SPMV); BG_TRY(launch_spmv(ctx, A, -1.0, x, 1.0, b, S->rr.p, true, skip)); }
+    { Span sp(prof, PH_SPMV); BG_TRY(spmv(-1.0, x, 1.0, b, S->rr.p, true)); }
     { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->rr.p, S->r.p, skip)); }
     Span sp(prof, PH_OTHER);
-    BG_TRY(launch_dots(ctx, S->dtype, n, nullptr, ld, 0, S->r.p, st, fin, 0, 0, o.orth, 0));
+    BG_TRY(dots(nullptr, 0, S->r.p, fin, 0, 0, 0));
     return launch_update(ctx, S->dtype, n, S->r.p, nullptr, ld, 0, nullptr, 0.0, col(0), st, 1, 0, 0);
   }
   int iteration(int i) {
     // w = M_L^-1 A M_R^-1 v_i   (gmres.cu:2350-2354 / 2637-2640)
     if (split) {
       { Span sp(prof, PH_TRSV); BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, col(i), S->w.p, skip, false)); }
-      { Span sp(prof, PH_SPMV); BG_TRY(launch_spmv(ctx, A, 1.0, S->w.p, 0.0, nullptr, S->ww.p, false, skip)); }
+      { Span sp(prof, PH_SPMV); BG_TRY(spmv(1.0, S->w.p, 0.0, nullptr, S->ww.p, false)); }
     } else {
       Span sp(prof, PH_SPMV);
-      BG_TRY(launch_spmv(ctx, A, 1.0, col(i), 0.0, nullptr, S->ww.p, false, skip));
+      BG_TRY(spmv(1.0, col(i), 0.0, nullptr, S->ww.p, false));
     }
     { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->ww.p, S->w.p, skip)); }
     Span sp(prof, PH_ORTH);
     if (o.orth == BG_ORTH_MGS) {
       for (int k = 0; k <= i; ++k) {
-        BG_TRY(launch_dots(ctx, S->dtype, n, col(k), ld, 1, S->w.p, st, FIN_MGS_DOT, i, k, o.orth, 0));
+        BG_TRY(dots(col(k), 1, S->w.p, FIN_MGS_DOT, i, k, 0));
         BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(k), ld, 1, st.h, -1.0, S->w.p, st, 0, 0, 0));
       }
-      BG_TRY(launch_dots(ctx, S->dtype, n, nullptr, ld, 0, S->w.p, st, FIN_MGS_NORM, i, 0, o.orth, 0));
+      BG_TRY(dots(nullptr, 0, S->w.p, FIN_MGS_NORM, i, 0, 0));
       return launch_update(ctx, S->dtype, n, S->w.p, nullptr, ld, 0, nullptr, 0.0, col(i + 1), st, 1, 0, 0);
     }
     const int j = i + 1;
-    { Span sd(prof, PH_DOTS); BG_TRY(launch_dots(ctx, S->dtype, n, col(0), ld, j, S->w.p, st, FIN_CGS1, i, 0, o.orth, 0)); }
+    { Span sd(prof, PH_DOTS); BG_TRY(dots(col(0), j, S->w.p, FIN_CGS1, i, 0, 0)); }
     { Span su(prof, PH_UPDATE); BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(0), ld, j, st.h, -1.0, col(j), st, 1, 0, 0)); }
-    BG_TRY(launch_dots(ctx, S->dtype, n, col(0), ld, j, col(j), st, FIN_CGS2, i, 0, o.orth, 1));
+    BG_TRY(dots(col(0), j, col(j), FIN_CGS2, i, 0, 1));
     return launch_update(ctx, S->dtype, n, col(j), col(0), ld, j, st.h2, -1.0, col(j), st, 1, 0, 1);
   }
   // x += V[:,0..k] y  (split: y-vector += V y ; x = M_R^-1 y-vector)   gmres.cu:2399-2400
@@ -818,13 +844,16 @@ template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev&
     const int o = perm[i];
     row.clear();
     const double di = fb.h_dinv[i];  // row scaling D^-1 (D = diag U): the device solves are unit solves
-    for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) row.emplace_back(inv[A->h_ci[p]], (T)((double)v[p] * di));
+    for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) {
+      const int c = A->h_ci[p];  // halo columns (>= n, row-partitioned matrices) keep their slot
+      row.emplace_back(c < n ? inv[c] : c, (T)((double)v[p] * di));
+    }
     std::sort(row.begin(), row.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
     int q = rp[i];
     for (auto& e : row) { ci[q] = e.first; vv[q++] = e.second; }
   }
   bg_matrix_t P = new bg_matrix_s;
-  P->ctx = A->ctx; P->n = n; P->nnz = A->nnz; P->dtype = A->dtype;
+  P->ctx = A->ctx; P->n = n; P->ncols = A->ncols; P->nnz = A->nnz; P->dtype = A->dtype;
   int rc = matrix_build<T>(P, rp, ci, vv, A->requested_format);
   if (rc < 0) { delete P; return rc; }
   P->h_rp.clear(); P->h_rp.shrink_to_fit(); P->h_ci.clear(); P->h_ci.shrink_to_fit(); P->h_val.clear(); P->h_val.shrink_to_fit();
@@ -843,7 +872,7 @@ static int permuted_matrix(bg_matrix_t A, const FusedBlockDev& fb, bg_matrix_t* 
 }
 
 static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
-                            const bg_gmres_opts* opts, bg_gmres_result* res, Prof* prof) {
+                            const bg_gmres_opts* opts, bg_gmres_result* res, Prof* prof, DistHooks* dh = nullptr) {
   if (!ctx || !S || !A || !M || !d_b || !d_x || !opts) { set_error("bg_gmres_solve: null argument"); return BG_ERR_ARG; }
   const bg_gmres_opts& o = *opts;
   if (A->n != S->n || M->n != S->n || A->dtype != S->dtype || M->dtype != S->dtype) { set_error("matrix / preconditioner / solver shapes or dtypes differ"); return BG_ERR_ARG; }
@@ -875,11 +904,12 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
     d_b = S->bp.p;
     d_x = S->xp.p;
   }
-  Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof, permuted};
+  if (dh && !permuted) { set_error("a row-partitioned solve needs a block-Jacobi (BG_TRSV_BLOCK) ILU preconditioner"); return BG_ERR_UNSUPPORTED; }
+  Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof, permuted, dh};
   BG_TRY(launch_state_reset(ctx, st, o.tol, o.reorth_eta));
   // normb = || M_L^-1 b ||   (gmres.cu:2294-2296)
   BG_TRY(D.apply_left(d_b, S->bb.p, nullptr));
-  BG_TRY(launch_dots(ctx, S->dtype, n, nullptr, S->ld, 0, S->bb.p, st, FIN_NORMB, 0, 0, o.orth, 0));
+  BG_TRY(D.dots(nullptr, 0, S->bb.p, FIN_NORMB, 0, 0, 0));
   if (D.split) BG_TRY(precond_apply(ctx, M, BG_PC_START, d_x, S->yv.p, nullptr, false));  // gmres.cu:2300
   BG_TRY(D.residual(FIN_BETA0));
 
@@ -942,6 +972,11 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
     res->solve_ms = ms;
   }
   return conv ? BG_OK : BG_NOT_CONVERGED;
+}
+
+int bg::gmres_solve_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                         const bg_gmres_opts* opts, bg_gmres_result* res, DistHooks* dh) {
+  return gmres_solve_impl(ctx, S, A, M, d_b, d_x, opts, res, nullptr, dh);
 }
 
 extern "C" int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,

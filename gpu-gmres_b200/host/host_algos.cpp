@@ -587,6 +587,60 @@ void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, 
 template void pack_fused_block_stream<float>(bool, const Csr<float>&, const Csr<float>&, int, const int*, int, FusedBlockStream<float>&);
 template void pack_fused_block_stream<double>(bool, const Csr<double>&, const Csr<double>&, int, const int*, int, FusedBlockStream<double>&);
 
+// ------------------------------------------------------------------ multi-GPU row partition
+template <class T>
+void build_dist_plan(int n, const int* rp, const int* ci, const T* v, int nranks, int rank, const int* part,
+                     DistPlan<T>& out) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("bad rank");
+  out.nranks = nranks; out.rank = rank; out.n_global = n;
+  out.l2g.clear();
+  std::vector<int> g2l(n, -1);
+  for (int i = 0; i < n; ++i) {
+    if (part[i] < 0 || part[i] >= nranks) throw std::invalid_argument("part id out of range");
+    if (part[i] == rank) { g2l[i] = (int)out.l2g.size(); out.l2g.push_back(i); }
+  }
+  out.n_local = (int)out.l2g.size();
+  // one pass over the global pattern: what I need from others (halo) and what others need from me
+  std::vector<std::vector<int>> need(nranks), give(nranks);
+  for (int i = 0; i < n; ++i) {
+    const int pi = part[i];
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+      const int c = ci[p], pc = part[c];
+      if (pc == pi) continue;
+      if (pi == rank) need[pc].push_back(c);
+      else if (pc == rank) give[pi].push_back(c);
+    }
+  }
+  auto uniq = [](std::vector<int>& a) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); };
+  out.nbr.clear(); out.recv_ptr.assign(1, 0); out.send_ptr.assign(1, 0); out.send_idx.clear(); out.h2g.clear();
+  std::vector<int> halo_slot(n, -1);
+  for (int q = 0; q < nranks; ++q) {
+    uniq(need[q]); uniq(give[q]);
+    if (need[q].empty() && give[q].empty()) continue;
+    out.nbr.push_back(q);
+    for (int g : need[q]) { halo_slot[g] = (int)out.h2g.size(); out.h2g.push_back(g); }
+    out.recv_ptr.push_back((int)out.h2g.size());
+    for (int g : give[q]) out.send_idx.push_back(g2l[g]);
+    out.send_ptr.push_back((int)out.send_idx.size());
+  }
+  out.n_halo = (int)out.h2g.size();
+  Csr<T>& A = out.A;
+  A.n = out.n_local;
+  A.rp.assign(out.n_local + 1, 0);
+  A.ci.clear(); A.v.clear();
+  for (int li = 0; li < out.n_local; ++li) {
+    const int i = out.l2g[li];
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+      const int c = ci[p];
+      A.ci.push_back(part[c] == rank ? g2l[c] : out.n_local + halo_slot[c]);
+      A.v.push_back(v[p]);
+    }
+    A.rp[li + 1] = (int)A.ci.size();
+  }
+}
+template void build_dist_plan<float>(int, const int*, const int*, const float*, int, int, const int*, DistPlan<float>&);
+template void build_dist_plan<double>(int, const int*, const int*, const double*, int, int, const int*, DistPlan<double>&);
+
 // ------------------------------------------------------------------ SpMV inspector
 SpmvPlan inspect_rows(int n, const int* rp) {
   SpmvPlan p;

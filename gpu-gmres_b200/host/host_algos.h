@@ -114,6 +114,28 @@ template <class T>
 void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, int nblocks, const int* block_of_row,
                              int chunk_target, FusedBlockStream<T>& out);
 
+// ------------------------------------------------------------------ multi-GPU row partition
+// One rank's share of a row-partitioned system: rank p owns the rows with part[i] == p
+// (kept in ascending global order), every column it references that another rank owns becomes a
+// HALO slot behind its own n_local entries.  Built independently on every rank from the global
+// pattern, so both sides of an exchange agree without any communication:
+//   local CSR column c < n_local  -> own row l2g[c];  c >= n_local -> halo slot c - n_local = global h2g[...]
+//   halo slots are grouped by owner rank (ascending), ascending global id inside a group
+//   neighbour k = rank nbr[k]: receives halo slots [recv_ptr[k], recv_ptr[k+1]) and is sent the own
+//   rows send_idx[send_ptr[k] .. send_ptr[k+1]) (local ids, ascending global id = the order in which
+//   that neighbour stores them in ITS halo)
+template <class T> struct DistPlan {
+  int nranks = 1, rank = 0;
+  int64_t n_global = 0;
+  int n_local = 0, n_halo = 0;
+  std::vector<int> l2g, h2g;
+  Csr<T> A;                       // n_local rows, columns in [0, n_local + n_halo)
+  std::vector<int> nbr, recv_ptr, send_ptr, send_idx;
+};
+template <class T>
+void build_dist_plan(int n, const int* rp, const int* ci, const T* v, int nranks, int rank, const int* part,
+                     DistPlan<T>& out);
+
 // Row-length histogram -> SpMV format (role of SpMV_inspect.cpp:38-456)
 struct SpmvPlan {
   int format = 0, max_row = 0, slice = 32;

@@ -395,3 +395,78 @@ class Solver:
         if self.h:
             lib().bg_solver_destroy(self.h)
             self.h = C.c_void_p()
+
+
+# ------------------------------------------------------------------ row-partitioned (multi-GPU) solve
+class DistPlanInfo(C.Structure):
+    _fields_ = [("nranks", C.c_int), ("rank", C.c_int), ("n_global", C.c_int64), ("n_local", C.c_int), ("n_halo", C.c_int),
+                ("nnz_local", C.c_int64), ("n_neighbors", C.c_int), ("send_count", C.c_int64)]
+
+
+class DistInfo(C.Structure):
+    _fields_ = [("nranks", C.c_int), ("rank", C.c_int), ("n_global", C.c_int64), ("n_local", C.c_int), ("n_halo", C.c_int),
+                ("n_neighbors", C.c_int), ("halo_messages", C.c_int64), ("allreduces", C.c_int64),
+                ("halo_bytes_per_exchange", C.c_int64), ("precond", PrecondInfo)]
+
+
+DIST_ID_BYTES = 128
+
+
+class DistPlan:
+    """One rank's share of a row-partitioned system (host only, no GPU needed)."""
+
+    def __init__(self, rowptr, col, val, nranks, rank, part):
+        n = len(rowptr) - 1
+        val = np.ascontiguousarray(val)
+        self.h = C.c_void_p()
+        _chk(lib().bg_host_dist_plan(n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), nranks, rank,
+                                     _p(_i32(part)), C.byref(self.h)))
+        self.info = DistPlanInfo()
+        _chk(lib().bg_dist_plan_get_info(self.h, C.byref(self.info)))
+
+    def arrays(self):
+        i = self.info
+        r = dict(l2g=np.zeros(i.n_local, np.int32), h2g=np.zeros(i.n_halo, np.int32), rowptr=np.zeros(i.n_local + 1, np.int32),
+                 col=np.zeros(i.nnz_local, np.int32), val=np.zeros(i.nnz_local), nbr=np.zeros(i.n_neighbors, np.int32),
+                 recv_ptr=np.zeros(i.n_neighbors + 1, np.int32), send_ptr=np.zeros(i.n_neighbors + 1, np.int32),
+                 send_idx=np.zeros(i.send_count, np.int32))
+        _chk(lib().bg_dist_plan_get(self.h, _p(r["l2g"]), _p(r["h2g"]), _p(r["rowptr"]), _p(r["col"]), _p(r["val"]), _p(r["nbr"]),
+                                    _p(r["recv_ptr"]), _p(r["send_ptr"]), _p(r["send_idx"])))
+        return r
+
+    def close(self):
+        if self.h:
+            lib().bg_dist_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def dist_unique_id() -> bytes:
+    buf = C.create_string_buffer(DIST_ID_BYTES)
+    _chk(lib().bg_dist_unique_id(buf))
+    return buf.raw
+
+
+class Dist:
+    """Communicator + local matrix + per-rank block-Jacobi ILU + workspace (collective constructor)."""
+
+    def __init__(self, ctx, plan, uid, dtype=F64, m=32, opts=None, ilut=False):
+        self.ctx, self.h = ctx, C.c_void_p()
+        idbuf = C.create_string_buffer(uid, DIST_ID_BYTES) if uid is not None else None
+        _chk(lib().bg_dist_create(ctx.h, plan.h, idbuf, dtype, m, C.byref(opts) if opts is not None else None, int(ilut), C.byref(self.h)))
+        self.n_local = plan.info.n_local
+
+    def solve(self, d_b, d_x, opts, host=False):
+        r = GmresResult()
+        f = lib().bg_dist_gmres_solve_host if host else lib().bg_dist_gmres_solve
+        _chk(f(self.h, _p(d_b), _p(d_x), C.byref(opts), C.byref(r)))
+        return r
+
+    def info(self) -> DistInfo:
+        i = DistInfo()
+        _chk(lib().bg_dist_get_info(self.h, C.byref(i)))
+        return i
+
+    def close(self):
+        if self.h:
+            lib().bg_dist_destroy(self.h)
+            self.h = C.c_void_p()

@@ -240,6 +240,45 @@ typedef struct {
 BG_API int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b,
                              void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st);
 
+/* ---- row-partitioned solve across the GPUs of one box (the reference is single-GPU) ----
+   One process per GPU.  Every rank builds its own plan from the GLOBAL CSR pattern and the row ->
+   rank map `part` (bg_host_block_partition with nblocks = nranks, or any map of the caller, e.g. from
+   src/partition3.cpp's METIS graph); plans of different ranks agree without communication.
+   Local vectors hold the rank's rows in ascending global order (l2g). */
+typedef struct bg_dist_plan_s* bg_dist_plan_t;
+typedef struct {
+  int nranks, rank; int64_t n_global; int n_local, n_halo; int64_t nnz_local; int n_neighbors; int64_t send_count;
+} bg_dist_plan_info;
+BG_API int bg_host_dist_plan(int n, const int* rowptr, const int* col, const void* val, int val_dtype, int nranks,
+                             int rank, const int* part, bg_dist_plan_t* plan);
+BG_API int bg_dist_plan_get_info(bg_dist_plan_t plan, bg_dist_plan_info* info);
+/* copy out (any pointer may be NULL): l2g[n_local], h2g[n_halo], local CSR (columns >= n_local are halo
+   slots), nbr[n_neighbors], recv_ptr/send_ptr[n_neighbors+1], send_idx[send_count] (local row ids) */
+BG_API int bg_dist_plan_get(bg_dist_plan_t plan, int* l2g, int* h2g, int* local_rowptr, int* local_col, double* local_val,
+                            int* nbr, int* recv_ptr, int* send_ptr, int* send_idx);
+BG_API int bg_dist_plan_destroy(bg_dist_plan_t plan);
+#define BG_DIST_ID_BYTES 128
+/* rank 0 creates the NCCL rendezvous id; the host framework (MPI, torch.distributed, a file) hands the
+   128 bytes to the other ranks */
+BG_API int bg_dist_unique_id(void* id128);
+/* communicator + local matrix + block-Jacobi ILU(0)/ILUT of the own diagonal block + workspace.
+   `o` carries the intra-GPU block description (block_method / block_rows / dims of the LOCAL rows). */
+BG_API int bg_dist_create(bg_context_t ctx, bg_dist_plan_t plan, const void* id128, int dtype, int m,
+                          const bg_precond_opts* o, int use_ilut, bg_dist_t* D);
+BG_API int bg_dist_destroy(bg_dist_t D);
+/* collective over all ranks: same options everywhere; b and x are the rank's LOCAL rows */
+BG_API int bg_dist_gmres_solve(bg_dist_t D, const void* d_b_local, void* d_x_local, const bg_gmres_opts* o,
+                               bg_gmres_result* r);
+BG_API int bg_dist_gmres_solve_host(bg_dist_t D, const void* h_b_local, void* h_x_local, const bg_gmres_opts* o,
+                                    bg_gmres_result* r);
+typedef struct {
+  int nranks, rank; int64_t n_global; int n_local, n_halo, n_neighbors;
+  int64_t halo_messages, allreduces;      /* issued so far */
+  int64_t halo_bytes_per_exchange;        /* bytes this rank sends per SpMV */
+  bg_precond_info precond;
+} bg_dist_info;
+BG_API int bg_dist_get_info(bg_dist_t D, bg_dist_info* info);
+
 /* ---- device vector helpers for hosts without a CUDA runtime binding ---- */
 BG_API int bg_device_malloc(bg_context_t ctx, size_t bytes, void** d_ptr);
 BG_API int bg_device_free(bg_context_t ctx, void* d_ptr);
