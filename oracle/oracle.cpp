@@ -15,7 +15,7 @@
 // Parity pinning: the reference ships no golden vectors for this path
 // (SURVEY.md 8c).  This restatement is pinned against the reference's own CPU
 // translation units compiled unchanged into oracle/_ref (computeSpMV,
-// LUSolve_ignoreZero, coo2csr_in, partition) by tests/test_oracle_vs_ref.py,
+// LUSolve_ignoreZero, coo2csr_in, partition) by tests/test_oracle_golden.py,
 // and against committed fixtures in tests/golden/ generated from it.
 // The host GMRES/ILU0 loops live in .cu files that do not compile under CUDA
 // 12.9, so for those the pin is "restated, cross-checked against scipy and
