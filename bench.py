@@ -45,7 +45,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nx", type=int, default=1304, help="grid edge; n = nx*nx (1304 = ibmpg6-sized)")
+    ap.add_argument("--workload", default="pg10m", choices=["pg10m", "ibmpg6"],
+                    help="pg10m: the 10M-node power grid BASELINE.json's north_star quotes the target on (3162^2); "
+                         "ibmpg6: BASELINE configs[1] (1304^2 = 1.7M nodes)")
+    ap.add_argument("--nx", type=int, default=0, help="grid edge, overrides --workload; n = nx*nx")
+    ap.add_argument("--no-configs1", action="store_true", help="N=1: skip the secondary BASELINE configs[1] solve (ibmpg6-sized, ILUT)")
     ap.add_argument("--precond", default="ilu0", choices=["ilu0", "ilut"])
     ap.add_argument("--schedule", default="block", choices=["block", "level"])
     ap.add_argument("--blocks", default="grid", choices=["grid", "metis"])
@@ -57,8 +61,20 @@ def parse():
     ap.add_argument("--eta", type=float, default=0.1, help="CGS re-orthogonalisation threshold (DGKS): second pass when ||w'|| < eta ||w||")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1: peer-memory kernels over NVLink (default) or the NCCL baseline")
     ap.add_argument("--cpu-nx", type=int, default=652, help="grid edge of the bounded CPU sample (0 = same as --nx); 652^2 = n/4")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.nx <= 0:
+        a.nx = 3162 if a.workload == "pg10m" else 1304
+    return a
+
+
+def workload_name(nx):
+    if nx == 3162:
+        return "pg2d 3162x3162 = synthetic 10M-node power grid (the workload BASELINE.json's north_star states the target on)"
+    if nx == 1304:
+        return "pg2d 1304x1304 (ibmpg6-sized, BASELINE configs[1])"
+    return f"pg2d {nx}x{nx}"
 
 
 def peaks():
@@ -182,7 +198,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"pg2d {args.nx}x{args.nx} DC solve, GMRES(32), rel. residual {args.tol:g}", "n": args.nx * args.nx},
+            "config": {"workload": f"{workload_name(args.nx)} DC solve, GMRES(32), rel. residual {args.tol:g}", "n": args.nx * args.nx},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -215,7 +231,28 @@ def main():
     if world > 1:
         run_dist(args, rank, world, local)
         return
-    rp, ci, v, b = workload(args.nx)
+    line = run_single(args, local, args.nx, args.precond, args.steps, headline=True)
+    if not args.no_configs1 and args.nx != 1304:
+        # BASELINE configs[1] next to the headline: ibmpg6-sized grid, GMRES(32)+ILUT on 1 B200
+        sec = run_single(args, local, 1304, "ilut", min(args.steps, 10), headline=False)
+        line["configs1"] = {k: sec[k] for k in ("value", "unit", "iters", "ms_per_iteration", "true_rel_residual", "iteration_roofline", "kernels", "e2e", "setup_s")}
+        line["configs1"]["config"] = sec["config"]
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(args.nx, args.cpu_nx, 1, 0, args.tol)
+    print(json.dumps(line))
+
+
+def run_single(args, local, nx, precond, steps, headline):
+    import torch
+
+    import b200gmres as bg
+
+    rank, world = 0, 1
+
+    def barrier():
+        pass
+
+    rp, ci, v, b = workload(nx)
     n = len(rp) - 1
     ctx = bg.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
@@ -225,10 +262,10 @@ def main():
     if args.schedule == "block":
         o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile, factor_dtype=fdt,
                             block_method=bg.PART_GRID2D if args.blocks == "grid" else bg.PART_METIS,
-                            dims=[args.nx, args.nx, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
+                            dims=[nx, nx, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     else:
         o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
-    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(args.precond == "ilut"))
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
     S = bg.Solver(ctx, n, 32, dtype=bg.F64)
     orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[args.orth]
@@ -268,18 +305,18 @@ def main():
         return ms, r, ctx.launches - l0
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if headline:
         sampler.start()
         time.sleep(1.0)  # nvidia-smi needs a moment before its first sample
     for _ in range(max(args.warmup, 3)):
         step_device()
     tc0 = sampler.mark()
-    ms, r, launches = timed(step_device, args.steps)
+    ms, r, launches = timed(step_device, steps)
     tc1 = sampler.mark()
-    clocks = sampler.stop(tc0, tc1) if rank == 0 else None
+    clocks = sampler.stop(tc0, tc1) if headline else None
     for _ in range(2):
         step_host()
-    ms_e2e, r_e2e, _ = timed(step_host, args.steps)
+    ms_e2e, r_e2e, _ = timed(step_host, steps)
 
     # profiled solve: CUDA-event pairs around every launch group, on the launching stream
     with torch.cuda.stream(stream):
@@ -307,7 +344,8 @@ def main():
         ach = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
         traffic = ncu_traffic(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic.get("bytes") if traffic else None, "traffic_launch": traffic,
+                    "frac": ach / peak, "frac_of_nominal_7700": ach / 7700.0,
+                    "traffic": traffic.get("bytes") if traffic else None, "traffic_launch": traffic,
                     "peak_source": which, "bytes_per_launch": dbytes / max(dcalls, 1), "us_per_launch": 1e3 * dms / max(dcalls, 1),
                     "launches_timed": int(dcalls), "share_of_step": dms / tot_ms if tot_ms else None,
                     "how": "CUDA-event pairs on the library stream around every launch of the profiled solve (bg_solver_profile)"}
@@ -315,13 +353,13 @@ def main():
         per_kernel = {k: {"ms": p[0], "launches": int(p[2]), "GBps": (p[1] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0),
                           "frac": (p[1] / (p[0] * 1e-3) / 1e9 / peak if p[0] > 0 else 0.0), "share": p[0] / tot_ms if tot_ms else None}
                       for k, p in kernels.items()}
-        step_ms = ms / args.steps
+        step_ms = ms / steps
         line = {
-            "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong" if world == 1 else "replicas",
+            "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"pg2d {args.nx}x{args.nx} (ibmpg6-sized, BASELINE configs[1]) DC solve, GMRES(32), rel. residual {args.tol:g}",
-                       "n": n, "nnz": int(info.nnz), "precond": args.precond, "trsv_schedule": args.schedule,
+            "config": {"workload": f"{workload_name(nx)} DC solve, GMRES(32), rel. residual {args.tol:g}",
+                       "n": n, "nnz": int(info.nnz), "precond": precond, "trsv_schedule": args.schedule,
                        "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "factor_dtype": args.factor_dtype,
                        "orth": args.orth, "reorth_eta": args.eta, "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
                        "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
@@ -329,18 +367,19 @@ def main():
             "ms_per_iteration": step_ms / max(r.iters_done, 1),
             "iteration_roofline": {"bytes_per_iteration": all_bytes / max(rprof.iters_done, 1), "achieved_GBps": all_bytes / (step_ms * 1e-3) / 1e9,
                                    "frac": all_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                                   "bytes": "SURVEY.md 8(d): B_spmv + B_trsv + B_orth(j) per inner iteration, restart terms per cycle"},
+                                   "frac_of_nominal_7700": all_bytes / (step_ms * 1e-3) / 1e9 / 7700.0,
+                                   "bytes": "SURVEY.md 8(d): B_spmv + B_trsv + B_orth(j) per inner iteration, restart terms per cycle",
+                                   "note": "peak = measured COPY bandwidth (read+write); read-dominated kernels can exceed it, and the "
+                                           "triangular solve moves fewer bytes than the algorithmic count (16-bit local column ids), so frac may pass 1"},
             "kernels": per_kernel, "setup_s": t_setup,
             "roofline": roofline,
-            "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
+            "e2e": {"value": ms_e2e / steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference(args.nx, args.cpu_nx, 1, 0, args.tol)
-        print(json.dumps(line))
     S.close(); M.close(); A.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del db, dx, hb, hx
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_dist(args, rank, world, local):
@@ -370,6 +409,8 @@ def run_dist(args, rank, world, local):
                         dims=[nx, ny_local, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     D = bg.Dist(ctx, plan, ids[0], dtype=bg.F64, m=32, opts=o, ilut=(args.precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
+    if args.transport == "nccl" or not D.info().p2p_available:
+        D.set_transport(bg.TRANSPORT_NCCL)
     a = plan.arrays()
     nl = plan.info.n_local
     orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[args.orth]
@@ -419,6 +460,16 @@ def run_dist(args, rank, world, local):
     for _ in range(2):
         step_host()
     ms_e2e, _, _ = timed(step_host, args.steps)
+    # per-phase device time of one more collective solve (event pairs on every rank's stream; rank 0 reports)
+    with torch.cuda.stream(stream):
+        dx.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+    rprof, ph = D.profile(db.data_ptr(), dx.data_ptr(), opts)
+    itp = max(rprof.iters_done, 1)
+    phases = {"us_per_iteration": {"halo+spmv": 1e3 * ph.spmv_ms / itp, "trsv": 1e3 * ph.trsv_ms / itp, "dots(+allreduce+givens)": 1e3 * ph.dots_ms / itp,
+                                   "update": 1e3 * ph.update_ms / itp, "orth_total": 1e3 * ph.orth_ms / itp, "restart_terms": 1e3 * ph.other_ms / itp},
+              "note": "rank 0, CUDA-event pairs around every launch group of a separate profiled solve (adds event gaps)"}
     # true residual of the assembled solution (gathered on rank 0)
     step_device()
     torch.cuda.synchronize()
@@ -445,7 +496,7 @@ def run_dist(args, rank, world, local):
         line = {
             "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"pg2d {nx}x{nx} (ibmpg6-sized, BASELINE configs[1]) DC solve, GMRES(32), rel. residual {args.tol:g}",
+            "config": {"workload": f"{workload_name(nx)} DC solve, GMRES(32), rel. residual {args.tol:g}",
                        "n": n, "nnz": nnz, "precond": args.precond, "trsv_schedule": "block",
                        "partition": f"{world} horizontal strips (contiguous rows), per-rank block-Jacobi ILU, tiles {args.tile}x{args.tile}",
                        "orth": args.orth, "reorth_eta": args.eta,
@@ -456,7 +507,10 @@ def run_dist(args, rank, world, local):
                                    "frac": all_b / (step_ms * 1e-3) / 1e9 / (peak * world), "peak": peak * world,
                                    "bytes": "SURVEY.md 8(d) per inner iteration, all ranks; peak = N x measured HBM copy bandwidth"},
             "comm": {"halo_bytes_per_exchange_rank0": int(info.halo_bytes_per_exchange), "neighbors_rank0": int(info.n_neighbors),
-                     "allreduce_doubles_max": 34, "backend": "NCCL send/recv + allreduce on the solver stream"},
+                     "allreduce_doubles_max": 34,
+                     "backend": ("peer-memory kernels over NVLink (CUDA IPC windows): all-reduce fused into dots_kernel, halo = one gather+peer-store kernel"
+                                 if info.transport == bg.TRANSPORT_P2P else "NCCL send/recv + allreduce on the solver stream")},
+            "phases_rank0": phases,
             "roofline": None, "setup_s": t_setup,
             "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -14,6 +14,17 @@
 // host never waits for a collective; stopping is decided from the allreduced (rank-identical)
 // values, which keeps every rank's enqueue sequence identical.
 //
+// Two transports carry those two exchanges:
+//   BG_TRANSPORT_P2P (default when CUDA IPC between the ranks works): our own kernels over NVLink /
+//     NVSwitch peer memory.  Each rank exports a small window plus its Krylov basis through
+//     cudaIpcGetMemHandle (the handles travel in one ncclAllGather at creation).  The all-reduce is
+//     FUSED INTO dots_kernel: its last CTA stores the rank's partial sums into every rank's inbox, waits
+//     for the others' flags, sums in rank order and runs the Givens epilogue -- no collective call, no
+//     extra launch.  The halo exchange is one kernel that gathers the boundary entries and stores them
+//     straight into the halo slots behind the same vector on the neighbour (orth.cu halo_push_kernel).
+//   BG_TRANSPORT_NCCL: pack kernel + grouped ncclSend/ncclRecv, ncclAllReduce + finalize kernel (the
+//     baseline the P2P path is measured against; also the fallback when IPC is unavailable).
+//
 // NCCL is resolved with dlopen at first use (libnccl.so.2, the copy the host framework already
 // loaded if any), so single-GPU users need no NCCL at all.
 #include <dlfcn.h>
@@ -34,6 +45,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,10 +60,10 @@ NcclApi& nccl() {
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!h) { set_error("NCCL not found (libnccl.so.2): %s", dlerror()); return api; }
 #define BG_SYM(name) *(void**)(&api.name) = dlsym(h, "nccl" #name)
-  BG_SYM(GetUniqueId); BG_SYM(CommInitRank); BG_SYM(CommDestroy); BG_SYM(Send); BG_SYM(Recv); BG_SYM(AllReduce);
+  BG_SYM(GetUniqueId); BG_SYM(CommInitRank); BG_SYM(CommDestroy); BG_SYM(Send); BG_SYM(Recv); BG_SYM(AllReduce); BG_SYM(AllGather);
   BG_SYM(GroupStart); BG_SYM(GroupEnd); BG_SYM(GetErrorString);
 #undef BG_SYM
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.GroupStart &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.AllGather && api.GroupStart &&
            api.GroupEnd && api.GetErrorString;
   if (!api.ok) set_error("libnccl.so.2 lacks a required entry point");
   return api;
@@ -79,10 +91,31 @@ struct bg_dist_s : DistHooks {
   std::vector<int> nbr, recv_ptr, send_ptr;
   DevBuf send_idx, sendbuf;
   int64_t halo_msgs = 0, allreduces = 0;
+  // peer-memory transport
+  int transport = BG_TRANSPORT_NCCL;
+  bool p2p_ready = false;
+  DevBuf window, d_par, d_ph;
+  std::vector<void*> ipc_open;   // mappings of the other ranks' memory, closed in the destructor
+  int send_count = 0;
+
+  const PeerAR* peer_ar() override { return transport == BG_TRANSPORT_P2P && nranks > 1 ? d_par.as<PeerAR>() : nullptr; }
 
   int exchange(void* vec, const int* skip) override {
     if (nranks == 1 || nbr.empty()) return BG_OK;
     const size_t es = dtype_size(dtype);
+    if (transport == BG_TRANSPORT_P2P) {
+      // the destination is the same vector on the neighbour: a basis column or the solution buffer
+      const char* V0 = S->V.as<char>();
+      const size_t colb = (size_t)S->ld * es;
+      int which = -1, col = 0;
+      if (vec == S->xp.p) which = 1;
+      else if ((const char*)vec >= V0 && (const char*)vec < V0 + colb * (S->m + 1) && ((const char*)vec - V0) % colb == 0) { which = 0; col = (int)(((const char*)vec - V0) / colb); }
+      if (which >= 0) {
+        halo_msgs += (int64_t)nbr.size();
+        return launch_halo_push(ctx, dtype, d_ph.as<PeerHalo>(), send_count, which, col, send_idx.as<int>(), vec, skip);
+      }
+      // any other vector takes the NCCL route below (every rank takes the same branch)
+    }
     const ncclDataType_t dt = dtype == BG_F32 ? ncclFloat32 : ncclFloat64;
     BG_TRY(launch_pack(ctx, dtype, send_ptr.back(), send_idx.as<int>(), vec, sendbuf.p, skip));
     NcclApi& N = nccl();
@@ -151,6 +184,119 @@ extern "C" int bg_dist_unique_id(void* id) {
   return BG_OK;
 }
 
+namespace {
+// what every rank tells every other rank at creation (one ncclAllGather)
+struct PeerRecord {
+  cudaIpcMemHandle_t win, V, x;
+  long long ld;
+  int n_local, n_nbr, ok;
+  int nbr[kMaxPeers], recv_ptr[kMaxPeers + 1];
+};
+struct WindowLayout {
+  size_t ar_data, ar_flag, halo_flag, counters, bytes;
+  explicit WindowLayout(int R) {
+    ar_data = 0;
+    ar_flag = ar_data + sizeof(double) * 2 * R * kArLd;
+    halo_flag = ar_flag + (sizeof(unsigned) * 2 * R + 15) / 16 * 16;
+    counters = halo_flag + sizeof(unsigned) * kMaxPeers;
+    bytes = counters + 64;
+  }
+};
+
+// Map the other ranks' windows / Krylov bases and build the device-side descriptors.  Collective.
+// Returns BG_OK with D->p2p_ready = false when peer memory is unavailable on ANY rank (all ranks agree).
+int setup_p2p(bg_dist_t D) {
+  NcclApi& N = nccl();
+  bg_context_t ctx = D->ctx;
+  cudaStream_t st = ctx->stream;
+  const int R = D->nranks, me = D->rank, nn = (int)D->nbr.size();
+  const size_t es = dtype_size(D->dtype);
+  bg_solver_t S = D->S;
+  PeerRecord mine;
+  std::memset(&mine, 0, sizeof(mine));
+  bool ok = R <= kMaxPeers && nn <= kMaxPeers;
+  const char* env = getenv("B200GMRES_DIST_TRANSPORT");
+  if (env && std::strcmp(env, "nccl") == 0) ok = false;
+  const WindowLayout wl(R);
+  // the solution buffer of the block-major order must exist (and keep its address) before it is exported
+  const size_t vbytes = (size_t)S->ld * es;
+  if (S->bp.bytes < vbytes) { BG_TRY(S->bp.alloc(vbytes)); BG_TRY(S->xp.alloc(vbytes)); }
+  BG_TRY(D->window.alloc(wl.bytes));
+  BG_CUDA(cudaMemsetAsync(D->window.p, 0, wl.bytes, st));
+  if (ok) {
+    ok = cudaIpcGetMemHandle(&mine.win, D->window.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.V, S->V.p) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.x, S->xp.p) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
+  mine.ld = S->ld; mine.n_local = D->n_local; mine.n_nbr = nn; mine.ok = ok ? 1 : 0;
+  for (int k = 0; k < nn && k < kMaxPeers; ++k) { mine.nbr[k] = D->nbr[k]; mine.recv_ptr[k] = D->recv_ptr[k]; }
+  if (nn <= kMaxPeers) mine.recv_ptr[nn] = D->recv_ptr[nn];
+  // exchange the records
+  DevBuf sb, rb;
+  BG_TRY(sb.upload(&mine, sizeof(mine), st));
+  BG_TRY(rb.alloc(sizeof(PeerRecord) * R));
+  BG_NCCL(N.AllGather(sb.p, rb.p, sizeof(PeerRecord), ncclInt8, D->comm, st));
+  std::vector<PeerRecord> all(R);
+  BG_CUDA(cudaMemcpyAsync(all.data(), rb.p, sizeof(PeerRecord) * R, cudaMemcpyDeviceToHost, st));
+  BG_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < R; ++r) ok = ok && all[r].ok;
+  // open what this rank needs: every window, and the vectors of its neighbours
+  std::vector<char*> win(R, nullptr), pV(R, nullptr), pX(R, nullptr);
+  auto open = [&](const cudaIpcMemHandle_t& h, char** out) {
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+    D->ipc_open.push_back(p);
+    *out = (char*)p;
+    return true;
+  };
+  if (ok) {
+    win[me] = D->window.as<char>();
+    for (int r = 0; r < R && ok; ++r) if (r != me) ok = open(all[r].win, &win[r]);
+    for (int k = 0; k < nn && ok; ++k) { const int q = D->nbr[k]; ok = open(all[q].V, &pV[q]) && open(all[q].x, &pX[q]); }
+  }
+  // agree on the outcome (a rank whose open failed must not leave the others spinning on its flags)
+  int flag = ok ? 1 : 0;
+  BG_TRY(sb.upload(&flag, sizeof(int), st));
+  BG_NCCL(N.AllReduce(sb.p, sb.p, 1, ncclInt32, ncclMin, D->comm, st));
+  BG_CUDA(cudaMemcpyAsync(&flag, sb.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BG_CUDA(cudaStreamSynchronize(st));
+  if (!flag) {
+    for (void* p : D->ipc_open) cudaIpcCloseMemHandle(p);
+    D->ipc_open.clear();
+    cudaGetLastError();
+    return BG_OK;
+  }
+  PeerAR par;
+  std::memset(&par, 0, sizeof(par));
+  par.nranks = R; par.rank = me;
+  unsigned* counters = (unsigned*)(D->window.as<char>() + wl.counters);
+  par.seq = counters + 0;
+  for (int r = 0; r < R; ++r) { par.inbox[r] = (double*)(win[r] + wl.ar_data); par.flag[r] = (unsigned*)(win[r] + wl.ar_flag); }
+  PeerHalo ph;
+  std::memset(&ph, 0, sizeof(ph));
+  ph.n_nbr = nn; ph.seq = counters + 4; ph.ticket = counters + 8;
+  ph.my_flag = (unsigned*)(D->window.as<char>() + wl.halo_flag);
+  for (int k = 0; k <= nn; ++k) ph.send_ptr[k] = D->send_ptr[k];
+  for (int k = 0; k < nn; ++k) {
+    const int q = D->nbr[k];
+    const PeerRecord& pr = all[q];
+    int slot = -1;  // my position in q's neighbour list
+    for (int t = 0; t < pr.n_nbr; ++t) if (pr.nbr[t] == me) slot = t;
+    if (slot < 0) { set_error("neighbour lists of ranks %d and %d disagree", me, q); return BG_ERR_COMM; }
+    if (pr.recv_ptr[slot + 1] - pr.recv_ptr[slot] != D->send_ptr[k + 1] - D->send_ptr[k]) { set_error("halo sizes of ranks %d and %d disagree", me, q); return BG_ERR_COMM; }
+    ph.peer_V[k] = pV[q]; ph.peer_x[k] = pX[q]; ph.peer_ld[k] = pr.ld;
+    ph.peer_off[k] = (long long)pr.n_local + pr.recv_ptr[slot];
+    ph.peer_flag[k] = (unsigned*)(win[q] + wl.halo_flag) + slot;
+  }
+  BG_TRY(D->d_par.upload(&par, sizeof(par), st));
+  BG_TRY(D->d_ph.upload(&ph, sizeof(ph), st));
+  BG_CUDA(cudaStreamSynchronize(st));
+  D->p2p_ready = true;
+  D->transport = BG_TRANSPORT_P2P;
+  return BG_OK;
+}
+}  // namespace
+
 extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id, int dtype, int m, const bg_precond_opts* po,
                               int use_ilut, bg_dist_t* out) {
   if (!ctx || !P || !out || (P->p.nranks > 1 && !id)) return BG_ERR_ARG;
@@ -198,7 +344,9 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
     if (rc < 0) break;
     rc = D->sendbuf.alloc(dtype_size(dtype) * (sidx.size() + 2));
     if (rc < 0) break;
+    D->send_count = (int)sidx.size();
     cudaStreamSynchronize(ctx->stream);
+    if (p.nranks > 1) { rc = setup_p2p(D); if (rc < 0) break; }
   } while (false);
   if (rc < 0) { bg_dist_destroy(D); return rc; }
   *out = D;
@@ -208,6 +356,8 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
 extern "C" int bg_dist_destroy(bg_dist_t D) {
   if (!D) return BG_OK;
   if (D->ctx) cudaStreamSynchronize(D->ctx->stream);
+  for (void* p : D->ipc_open) cudaIpcCloseMemHandle(p);
+  D->ipc_open.clear();
   if (D->S) bg_solver_destroy(D->S);
   if (D->M) bg_precond_destroy(D->M);
   if (D->A) bg_matrix_destroy(D->A);
@@ -219,6 +369,11 @@ extern "C" int bg_dist_destroy(bg_dist_t D) {
 extern "C" int bg_dist_gmres_solve(bg_dist_t D, const void* d_b, void* d_x, const bg_gmres_opts* o, bg_gmres_result* r) {
   if (!D || !d_b || !d_x || !o) return BG_ERR_ARG;
   return gmres_solve_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, D);
+}
+
+extern "C" int bg_dist_profile(bg_dist_t D, const void* d_b, void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st) {
+  if (!D || !d_b || !d_x || !o || !st) return BG_ERR_ARG;
+  return gmres_profile_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, st, D);
 }
 
 extern "C" int bg_dist_gmres_solve_host(bg_dist_t D, const void* h_b, void* h_x, const bg_gmres_opts* o, bg_gmres_result* r) {
@@ -242,5 +397,14 @@ extern "C" int bg_dist_get_info(bg_dist_t D, bg_dist_info* o) {
   o->n_neighbors = (int)D->nbr.size(); o->halo_messages = D->halo_msgs; o->allreduces = D->allreduces;
   o->halo_bytes_per_exchange = (int64_t)D->send_ptr.back() * (int64_t)dtype_size(D->dtype);
   bg_precond_get_info(D->M, &o->precond);
+  o->transport = D->transport;
+  o->p2p_available = D->p2p_ready ? 1 : 0;
+  return BG_OK;
+}
+
+extern "C" int bg_dist_set_transport(bg_dist_t D, int transport) {
+  if (!D || (transport != BG_TRANSPORT_NCCL && transport != BG_TRANSPORT_P2P)) return BG_ERR_ARG;
+  if (transport == BG_TRANSPORT_P2P && D->nranks > 1 && !D->p2p_ready) { set_error("peer-memory transport is not available (CUDA IPC between the ranks failed at creation)"); return BG_ERR_UNSUPPORTED; }
+  D->transport = transport;
   return BG_OK;
 }

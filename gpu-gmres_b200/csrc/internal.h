@@ -113,6 +113,37 @@ enum { F_CONV = 0, F_KCONV = 1, F_ITERS = 2, F_REORTH = 3, F_NREORTH = 4, F_BREA
 enum { S_NORMB = 0, S_BETA = 1, S_RESID = 2, S_SCALE = 3, S_TOL = 4, S_ETA2 = 5, S_WW = 6, S_COUNT = 8 };
 enum { FIN_NONE = 0, FIN_NORMB, FIN_BETA0, FIN_BETA, FIN_CGS1, FIN_CGS2, FIN_MGS_DOT, FIN_MGS_NORM };
 
+// ---- peer-memory transport of a row-partitioned solve (dist.cu; kernels in orth.cu) ----------
+// Every rank owns a small "window" allocation that all other ranks of the box map through CUDA IPC
+// (NVLink / NVSwitch peer stores).  Both structs live in DEVICE memory of the owning rank.
+constexpr int kMaxPeers = 16;   // ranks of one box
+constexpr int kArLd = 40;       // doubles per rank and slot of the all-reduce inbox (>= kFinMax + 2)
+// All-reduce fused into the last CTA of dots_kernel: every rank stores its j+1 partial sums into the
+// inbox of every rank (slot = parity of a device-side sequence number, row = sender), raises the
+// sender's flag there, waits for all flags in its own inbox and sums the rows in rank order -- the
+// same bits on every rank, so stopping decisions stay identical without any further exchange.
+struct PeerAR {
+  int nranks, rank;
+  unsigned* seq;                 // local counter of executed all-reduces
+  double* inbox[kMaxPeers];      // inbox[r]: rank r's [2][nranks][kArLd] doubles (peer-mapped for r != rank)
+  unsigned* flag[kMaxPeers];     // flag[r]:  rank r's [2][nranks] arrival flags
+};
+// Halo exchange: the boundary entries of the vector entering the SpMV are stored straight into the
+// halo slots BEHIND THE SAME VECTOR on the neighbour (its Krylov basis / solution buffers are peer-mapped
+// too), followed by a per-neighbour sequence flag; the pushing kernel then waits for its own neighbours.
+struct PeerHalo {
+  int n_nbr;
+  unsigned* seq;                 // local counter of executed exchanges
+  unsigned* ticket;              // CTA arrival counter of the push kernel
+  int send_ptr[kMaxPeers + 1];   // entries [send_ptr[k], send_ptr[k+1]) of send_idx go to neighbour k
+  char* peer_V[kMaxPeers];       // neighbour's Krylov basis (column-major, leading dimension peer_ld)
+  char* peer_x[kMaxPeers];       // neighbour's block-major solution buffer
+  long long peer_ld[kMaxPeers];
+  long long peer_off[kMaxPeers]; // first halo element written on the neighbour: its n_local + its recv_ptr[me]
+  unsigned* peer_flag[kMaxPeers];// my slot in the neighbour's halo flag array
+  unsigned* my_flag;             // [n_nbr] local flags, slot k raised by neighbour k
+};
+
 // ---- launchers (defined in the .cu files) --------------------------------------------------
 int launch_spmv(bg_context_t ctx, bg_matrix_t A, double alpha, const void* x, double beta, const void* b,
                 void* y, bool axpby, const int* skip_flag);
@@ -125,7 +156,10 @@ int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci,
 // allreduces them and runs launch_finalize
 int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w,
                 const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth_flag,
-                double* red_out = nullptr);
+                double* red_out = nullptr, const PeerAR* peer = nullptr);
+// pack + peer-store + flag + wait of one halo exchange (which: 0 = column `col` of the basis, 1 = solution buffer)
+int launch_halo_push(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int n_send, int which, int col, const int* idx,
+                     const void* v, const int* skip);
 int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth,
                     int j, const double* red_in);
 int launch_pack(bg_context_t ctx, int dtype, int cnt, const int* idx, const void* v, void* buf, const int* skip);
@@ -189,10 +223,13 @@ namespace bg {
 struct DistHooks {
   virtual int exchange(void* vec, const int* skip) = 0;  // fill vec[n_local .. n_local+n_halo) from the neighbours
   virtual int allreduce(double* buf, int count) = 0;     // sum over ranks, in place, on the context stream
+  virtual const PeerAR* peer_ar() { return nullptr; }    // non-null: dots_kernel all-reduces through peer memory itself
   virtual ~DistHooks() {}
 };
 int gmres_solve_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
                      const bg_gmres_opts* opts, bg_gmres_result* res, DistHooks* dh);
+int gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                       const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* out, DistHooks* dh);
 int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
                            const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out);
 int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out);

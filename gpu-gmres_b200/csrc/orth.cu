@@ -250,13 +250,100 @@ __device__ __forceinline__ void pipe_produce(const Pipe& pp, unsigned char* ring
   }
 }
 
+// ---------------------------------------------------------------------------- peer memory (multi-GPU)
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *flag has reached seq; a peer that never arrives (crashed rank) must trap, not hang the GPU
+__device__ __forceinline__ void peer_wait(const unsigned* flag, unsigned seq) {
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+    __nanosleep(20);
+    if (global_ns() - t0 > 30000000000ull) __trap();
+  }
+}
+// red[0..cnt) <- sum over the ranks, in rank order (identical bits everywhere).  Called by ALL threads
+// of one CTA per rank.  Slots alternate with the parity of the sequence number: a rank can run at most
+// one all-reduce ahead of the slowest one, because finishing number s needs everybody's values of s.
+__device__ void peer_allreduce(const PeerAR* __restrict__ P, double* red, int cnt) {
+  __shared__ unsigned s_seq;
+  const int R = P->nranks, me = P->rank;
+  if (threadIdx.x == 0) { s_seq = *P->seq + 1u; *P->seq = s_seq; }
+  __syncthreads();
+  const unsigned seq = s_seq;
+  const size_t slot = (size_t)(seq & 1u) * R;
+  for (int t = threadIdx.x; t < R * cnt; t += blockDim.x) {
+    const int r = t / cnt, k = t - r * cnt;
+    P->inbox[r][(slot + me) * kArLd + k] = red[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < R) {
+    st_release_sys(&P->flag[threadIdx.x][slot + me], seq);
+    peer_wait(&P->flag[me][slot + threadIdx.x], seq);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < cnt) {
+    double v = 0.0;
+    for (int r = 0; r < R; ++r) v += ld_relaxed_sys(&P->inbox[me][(slot + r) * kArLd + threadIdx.x]);
+    red[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// One halo exchange in one kernel: gather the boundary entries, store them into the neighbours' halo
+// slots of the SAME vector over NVLink, publish a sequence flag per neighbour, then wait for the
+// neighbours' flags -- when the kernel retires, this rank's halo is complete and the SpMV can follow.
+template <class VT>
+__global__ void __launch_bounds__(512) halo_push_kernel(const PeerHalo* __restrict__ H, int which, int col,
+                                                         const int* __restrict__ idx, const VT* __restrict__ v,
+                                                         const int* skip) {
+  if (skip && *skip) return;
+  const int nn = H->n_nbr, total = H->send_ptr[nn];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int k = 0;
+    while (e >= H->send_ptr[k + 1]) ++k;
+    VT* dst = reinterpret_cast<VT*>(which == 0 ? H->peer_V[k] + (size_t)col * H->peer_ld[k] * sizeof(VT) : H->peer_x[k]) + H->peer_off[k];
+    dst[e - H->send_ptr[k]] = v[idx[e]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  __shared__ unsigned s_seq;
+  if (threadIdx.x == 0) last = atomicAdd(H->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) { s_seq = *H->seq + 1u; *H->seq = s_seq; *H->ticket = 0u; }
+  __syncthreads();
+  if ((int)threadIdx.x < nn) {
+    st_release_sys(H->peer_flag[threadIdx.x], s_seq);
+    peer_wait(&H->my_flag[threadIdx.x], s_seq);
+  }
+}
+
 // ---------------------------------------------------------------------------- dots
 // partial[k] = V[:,k].w (k<j), partial[j] = w.w ; the last CTA reduces and runs finalize().
 template <class VT>
 __global__ void __launch_bounds__(kPipeThreads, 1) dots_kernel(int n, const VT* __restrict__ V, int64_t ld, int j,
                                                                 const VT* __restrict__ w, GmresDev st, int fin,
                                                                 int inner_i, int mgs_k, int orth_mode, int need_reorth,
-                                                                Pipe pp, double* red_out) {
+                                                                Pipe pp, double* red_out, const PeerAR* peer) {
   if (st.flags[F_CONV]) return;
   if (need_reorth && !st.flags[F_REORTH]) return;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -348,6 +435,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) dots_kernel(int n, const VT* 
   __shared__ FinScratch fs;
   const bool column_fin = fin == FIN_CGS1 || fin == FIN_CGS2;
   if (column_fin) fin_prefetch(st, fs, inner_i, threadIdx.x);
+  if (peer) {
+    // row-partitioned run: sum the per-rank values over the GPUs of the box through peer memory,
+    // inside this same CTA (no NCCL call, no extra launch); the scalar epilogue then runs on
+    // rank-identical numbers
+    __syncthreads();
+    peer_allreduce(peer, red, j + 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     finalize(st, fin, inner_i, mgs_k, orth_mode, red, j, column_fin ? &fs : nullptr);
@@ -570,23 +664,32 @@ template <class K> static int pipe_smem_attr(K kernel, bg_context_t ctx) {
 
 template <class VT>
 static int dots_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int j, const VT* w, const GmresDev& st,
-                         int fin, int i, int mk, int om, int nr, double* red_out) {
+                         int fin, int i, int mk, int om, int nr, double* red_out, const PeerAR* peer) {
   if (j < 0 || j > kFinMax) { set_error("dots: j=%d exceeds one pass (max %d columns)", j, kFinMax); return BG_ERR_ARG; }
   const Pipe pp = pipe_geometry(j + 1, sizeof(VT));
   const size_t smem = (size_t)pp.stages * pp.stage_bytes + 2 * sizeof(uint64_t) * pp.stages;
   BG_TRY(pipe_smem_attr(dots_kernel<VT>, ctx));
   const int ntiles = (n + pp.R - 1) / pp.R;
   const int g = std::max(1, std::min(ntiles, ctx->sm_count));
-  dots_kernel<VT><<<g, kPipeThreads, smem, ctx->stream>>>(n, V, ld, j, w, st, fin, i, mk, om, nr, pp, red_out);
+  dots_kernel<VT><<<g, kPipeThreads, smem, ctx->stream>>>(n, V, ld, j, w, st, fin, i, mk, om, nr, pp, red_out, peer);
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
 }
 
 int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, const GmresDev& st,
-                int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth, double* red_out) {
-  if (dtype == BG_F32) return dots_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out);
-  return dots_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out);
+                int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth, double* red_out, const PeerAR* peer) {
+  if (dtype == BG_F32) return dots_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out, peer);
+  return dots_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out, peer);
+}
+int launch_halo_push(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int n_send, int which, int col, const int* idx,
+                     const void* v, const int* skip) {
+  const int g = std::max(1, std::min((n_send + 511) / 512, 32));
+  if (dtype == BG_F32) halo_push_kernel<float><<<g, 512, 0, ctx->stream>>>(d_ph, which, col, idx, (const float*)v, skip);
+  else halo_push_kernel<double><<<g, 512, 0, ctx->stream>>>(d_ph, which, col, idx, (const double*)v, skip);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
 }
 int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth, int j,
                     const double* red_in) {

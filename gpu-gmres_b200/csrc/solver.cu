@@ -753,6 +753,8 @@ struct Driver {
   }
   int dots(const void* Vp, int j, const void* w, int fin, int i, int mk, int nr) {
     if (!dh) return launch_dots(ctx, S->dtype, n, Vp, ld, j, w, st, fin, i, mk, o.orth, nr);
+    // peer-memory transport: the all-reduce and the scalar epilogue run inside the dots kernel
+    if (const PeerAR* par = dh->peer_ar()) return launch_dots(ctx, S->dtype, n, Vp, ld, j, w, st, fin, i, mk, o.orth, nr, nullptr, par);
     double* red = S->red.as<double>();
     BG_TRY(launch_dots(ctx, S->dtype, n, Vp, ld, j, w, st, fin, i, mk, o.orth, nr, red));
     BG_TRY(dh->allreduce(red, j + 1));
@@ -1028,13 +1030,17 @@ extern "C" BG_API int bg_solver_bench_orth(bg_context_t ctx, bg_solver_t S, int 
 
 extern "C" int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
                                  const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* out) {
+  return gmres_profile_dist(ctx, S, A, M, d_b, d_x, o, r, out, nullptr);
+}
+int bg::gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
+                           const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* out, DistHooks* dh) {
   if (!ctx || !S || !A || !M || !out) return BG_ERR_ARG;
   Prof prof;
   prof.pool = &S->prof_events;
   prof.stream = ctx->stream;
   bg_gmres_result rr;
   std::memset(&rr, 0, sizeof(rr));
-  int rc = gmres_solve_impl(ctx, S, A, M, d_b, d_x, o, &rr, &prof);
+  int rc = gmres_solve_impl(ctx, S, A, M, d_b, d_x, o, &rr, &prof, dh);
   if (rc < 0) return rc;
   if (r) *r = rr;
   double ms[6] = {0, 0, 0, 0, 0, 0};

@@ -406,7 +406,10 @@ class DistPlanInfo(C.Structure):
 class DistInfo(C.Structure):
     _fields_ = [("nranks", C.c_int), ("rank", C.c_int), ("n_global", C.c_int64), ("n_local", C.c_int), ("n_halo", C.c_int),
                 ("n_neighbors", C.c_int), ("halo_messages", C.c_int64), ("allreduces", C.c_int64),
-                ("halo_bytes_per_exchange", C.c_int64), ("precond", PrecondInfo)]
+                ("halo_bytes_per_exchange", C.c_int64), ("precond", PrecondInfo), ("transport", C.c_int), ("p2p_available", C.c_int)]
+
+
+TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1
 
 
 DIST_ID_BYTES = 128
@@ -465,6 +468,15 @@ class Dist:
         i = DistInfo()
         _chk(lib().bg_dist_get_info(self.h, C.byref(i)))
         return i
+
+    def profile(self, d_b, d_x, opts):
+        r, st = GmresResult(), PhaseStats()
+        _chk(lib().bg_dist_profile(self.h, _p(d_b), _p(d_x), C.byref(opts), C.byref(r), C.byref(st)))
+        return r, st
+
+    def set_transport(self, transport):
+        """TRANSPORT_P2P (peer-memory kernels over NVLink) or TRANSPORT_NCCL; same choice on every rank."""
+        _chk(lib().bg_dist_set_transport(self.h, int(transport)))
 
     def close(self):
         if self.h:

@@ -271,13 +271,26 @@ BG_API int bg_dist_gmres_solve(bg_dist_t D, const void* d_b_local, void* d_x_loc
                                bg_gmres_result* r);
 BG_API int bg_dist_gmres_solve_host(bg_dist_t D, const void* h_b_local, void* h_x_local, const bg_gmres_opts* o,
                                     bg_gmres_result* r);
+/* per-phase device time of one collective solve on THIS rank (event pairs on its stream; the halo kernel is
+   counted under spmv, waiting for slower ranks shows up in the dots / halo phases) */
+BG_API int bg_dist_profile(bg_dist_t D, const void* d_b_local, void* d_x_local, const bg_gmres_opts* o,
+                           bg_gmres_result* r, bg_phase_stats* st);
 typedef struct {
   int nranks, rank; int64_t n_global; int n_local, n_halo, n_neighbors;
   int64_t halo_messages, allreduces;      /* issued so far */
   int64_t halo_bytes_per_exchange;        /* bytes this rank sends per SpMV */
   bg_precond_info precond;
+  int transport;                          /* BG_TRANSPORT_* in use */
+  int p2p_available;                      /* CUDA IPC mappings between all ranks succeeded */
 } bg_dist_info;
 BG_API int bg_dist_get_info(bg_dist_t D, bg_dist_info* info);
+/* how the halo exchange and the all-reduce travel between the GPUs of the box:
+   BG_TRANSPORT_P2P  our own kernels over NVLink peer memory (CUDA IPC windows): the all-reduce is fused
+                     into the dots kernel, the halo is one gather+peer-store kernel (default when available)
+   BG_TRANSPORT_NCCL ncclSend/ncclRecv + ncclAllReduce (baseline / fallback).
+   Collective in spirit: every rank must select the same transport before the next solve. */
+enum { BG_TRANSPORT_NCCL = 0, BG_TRANSPORT_P2P = 1 };
+BG_API int bg_dist_set_transport(bg_dist_t D, int transport);
 
 /* ---- device vector helpers for hosts without a CUDA runtime binding ---- */
 BG_API int bg_device_malloc(bg_context_t ctx, size_t bytes, void** d_ptr);

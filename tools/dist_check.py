@@ -51,8 +51,20 @@ def main():
         dx = torch.zeros(plan.info.n_local, dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
         opts = bg.gmres_opts(m=32, tol=1e-8, max_iter=3000, reorth_eta=0.1)
-        r = D.solve(db.data_ptr(), dx.data_ptr(), opts)
-        ctx.sync()
+        # both transports: our peer-memory kernels (default) and the NCCL baseline; second solve of each is the warm time
+        per_transport = {}
+        avail = bool(D.info().p2p_available)
+        for tname, tr in (("nccl", bg.TRANSPORT_NCCL), ("p2p", bg.TRANSPORT_P2P)):
+            if tr == bg.TRANSPORT_P2P and not avail:
+                continue
+            D.set_transport(tr)
+            for rep in range(2):
+                dx.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                r = D.solve(db.data_ptr(), dx.data_ptr(), opts)
+                ctx.sync()
+            per_transport[tname] = dict(iters=int(r.iters), solve_ms=round(r.solve_ms, 3), resid=float(r.resid))
         x = np.zeros(n)
         for q in range(world):
             sz = int((part == q).sum())
@@ -77,11 +89,12 @@ def main():
             d1x = torch.zeros(n, dtype=torch.float64, device=dev)
             torch.cuda.synchronize()
             r1 = S1.solve(A1, M1, d1b.data_ptr(), d1x.data_ptr(), opts)
-            good = r.flag == 0 and err < 1e-6 and res < 1e-7
+            good = r.flag == 0 and err < 1e-6 and res < 1e-7 and len({t["iters"] for t in per_transport.values()}) == 1
             ok = ok and good
             print(json.dumps(dict(case=f"pg2d {nx}x{ny} {method}", ranks=world, flag=r.flag, iters=r.iters, iters_1gpu=r1.iters, resid=r.resid,
                                   true_rel_residual=res, x_err_vs_direct=err, halo_bytes=int(info.halo_bytes_per_exchange),
-                                  neighbors=int(info.n_neighbors), allreduces=int(info.allreduces), solve_ms=round(r.solve_ms, 3),
+                                  neighbors=int(info.n_neighbors), transport=("p2p" if info.transport == bg.TRANSPORT_P2P else "nccl"), transports=per_transport,
+                                  solve_ms=round(r.solve_ms, 3),
                                   solve_ms_1gpu=round(r1.solve_ms, 3), ok=bool(good))), flush=True)
             S1.close(); M1.close(); A1.close(); c1.close()
         D.close(); plan.close(); ctx.close()
