@@ -335,6 +335,11 @@ def run_single(args, local, nx, precond, steps, headline):
             "dots_kernel (V^T w and w.w, TMA-staged tiles)": (st.dots_ms, st.dots_bytes, st.dots_calls),
             "update_kernel (w - V h, normalised, TMA-staged tiles)": (st.update_ms, st.update_bytes, st.update_calls),
         }
+        if args.orth != "mgs" and st.dots_calls == 0:
+            # fused step: one cooperative launch per inner iteration (projections + Givens epilogue + v_j)
+            kernels = {k: v for k, v in kernels.items() if v[2] > 0}
+            kernels["orth_kernel (fused: V^T w, w.w, Givens, v_j = (w - V h)/||.||; TMA-staged tiles reused from shared memory / L2)"] = (
+                st.orth_ms, st.dots_bytes + st.update_bytes, st.orth_calls)
         if args.orth == "mgs":
             kernels = {k: v for k, v in kernels.items() if v[2] > 0}
             kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls)
@@ -467,9 +472,11 @@ def run_dist(args, rank, world, local):
     dist.barrier()
     rprof, ph = D.profile(db.data_ptr(), dx.data_ptr(), opts)
     itp = max(rprof.iters_done, 1)
-    phases = {"us_per_iteration": {"halo+spmv": 1e3 * ph.spmv_ms / itp, "trsv": 1e3 * ph.trsv_ms / itp, "dots(+allreduce+givens)": 1e3 * ph.dots_ms / itp,
-                                   "update": 1e3 * ph.update_ms / itp, "orth_total": 1e3 * ph.orth_ms / itp, "restart_terms": 1e3 * ph.other_ms / itp},
+    phases = {"us_per_iteration": {"halo": 1e3 * ph.halo_ms / itp, "halo+spmv": 1e3 * ph.spmv_ms / itp, "trsv": 1e3 * ph.trsv_ms / itp, "dots(+allreduce+givens)": 1e3 * ph.dots_ms / itp,
+                                   "update": 1e3 * ph.update_ms / itp, "orth_total(fused kernel when dots=0)": 1e3 * ph.orth_ms / itp, "restart_terms": 1e3 * ph.other_ms / itp},
               "note": "rank 0, CUDA-event pairs around every launch group of a separate profiled solve (adds event gaps)"}
+    dist.barrier()
+    comm_us = {"halo_exchange": D.bench_comm(0), "allreduce_33_doubles_in_dots_kernel": D.bench_comm(1, 33)}
     # true residual of the assembled solution (gathered on rank 0)
     step_device()
     torch.cuda.synchronize()
@@ -510,7 +517,7 @@ def run_dist(args, rank, world, local):
                      "allreduce_doubles_max": 34,
                      "backend": ("peer-memory kernels over NVLink (CUDA IPC windows): all-reduce fused into dots_kernel, halo = one gather+peer-store kernel"
                                  if info.transport == bg.TRANSPORT_P2P else "NCCL send/recv + allreduce on the solver stream")},
-            "phases_rank0": phases,
+            "phases_rank0": phases, "comm_us_per_op_rank0": comm_us,
             "roofline": None, "setup_s": t_setup,
             "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -16,12 +16,13 @@
 //
 // Two transports carry those two exchanges:
 //   BG_TRANSPORT_P2P (default when CUDA IPC between the ranks works): our own kernels over NVLink /
-//     NVSwitch peer memory.  Each rank exports a small window plus its Krylov basis through
-//     cudaIpcGetMemHandle (the handles travel in one ncclAllGather at creation).  The all-reduce is
-//     FUSED INTO dots_kernel: its last CTA stores the rank's partial sums into every rank's inbox, waits
-//     for the others' flags, sums in rank order and runs the Givens epilogue -- no collective call, no
-//     extra launch.  The halo exchange is one kernel that gathers the boundary entries and stores them
-//     straight into the halo slots behind the same vector on the neighbour (orth.cu halo_push_kernel).
+//     NVSwitch peer memory.  Each rank exports a small window through cudaIpcGetMemHandle (the handles
+//     travel in one ncclAllGather at creation).  Messages are flag-in-data 16-byte elements (value +
+//     sequence number, internal.h LL16), so no fence and no separate flag round trip is needed.  The
+//     all-reduce is FUSED INTO the dots / orth kernels: the last CTA stores the rank's partial sums into
+//     every rank's inbox, polls its own, sums in rank order and runs the Givens epilogue -- no collective
+//     call, no extra launch.  The halo exchange is one kernel that gathers the boundary entries, stores
+//     them into the neighbours' inboxes and unpacks its own arrivals (orth.cu halo_exchange_kernel).
 //   BG_TRANSPORT_NCCL: pack kernel + grouped ncclSend/ncclRecv, ncclAllReduce + finalize kernel (the
 //     baseline the P2P path is measured against; also the fallback when IPC is unavailable).
 //
@@ -97,6 +98,7 @@ struct bg_dist_s : DistHooks {
   DevBuf window, d_par, d_ph;
   std::vector<void*> ipc_open;   // mappings of the other ranks' memory, closed in the destructor
   int send_count = 0;
+  uint32_t solve_index = 0, exchange_in_solve = 0;
 
   const PeerAR* peer_ar() override { return transport == BG_TRANSPORT_P2P && nranks > 1 ? d_par.as<PeerAR>() : nullptr; }
 
@@ -104,17 +106,12 @@ struct bg_dist_s : DistHooks {
     if (nranks == 1 || nbr.empty()) return BG_OK;
     const size_t es = dtype_size(dtype);
     if (transport == BG_TRANSPORT_P2P) {
-      // the destination is the same vector on the neighbour: a basis column or the solution buffer
-      const char* V0 = S->V.as<char>();
-      const size_t colb = (size_t)S->ld * es;
-      int which = -1, col = 0;
-      if (vec == S->xp.p) which = 1;
-      else if ((const char*)vec >= V0 && (const char*)vec < V0 + colb * (S->m + 1) && ((const char*)vec - V0) % colb == 0) { which = 0; col = (int)(((const char*)vec - V0) / colb); }
-      if (which >= 0) {
-        halo_msgs += (int64_t)nbr.size();
-        return launch_halo_push(ctx, dtype, d_ph.as<PeerHalo>(), send_count, which, col, send_idx.as<int>(), vec, skip);
-      }
-      // any other vector takes the NCCL route below (every rank takes the same branch)
+      // sequence number of this exchange: (solve, launch within the solve) -- identical on both sides
+      // because every rank enqueues the same sequence until convergence (later launches are skipped)
+      const unsigned seq = (unsigned)(((uint64_t)solve_index << 20) + (uint64_t)(++exchange_in_solve));
+      halo_msgs += (int64_t)nbr.size();
+      return launch_halo_exchange(ctx, dtype, d_ph.as<PeerHalo>(), send_count, n_halo, send_idx.as<int>(), vec,
+                                  (char*)vec + (size_t)n_local * es, seq, skip);
     }
     const ncclDataType_t dt = dtype == BG_F32 ? ncclFloat32 : ncclFloat64;
     BG_TRY(launch_pack(ctx, dtype, send_ptr.back(), send_idx.as<int>(), vec, sendbuf.p, skip));
@@ -187,51 +184,44 @@ extern "C" int bg_dist_unique_id(void* id) {
 namespace {
 // what every rank tells every other rank at creation (one ncclAllGather)
 struct PeerRecord {
-  cudaIpcMemHandle_t win, V, x;
-  long long ld;
-  int n_local, n_nbr, ok;
+  cudaIpcMemHandle_t win;
+  int n_halo, n_nbr, ok, pad;
   int nbr[kMaxPeers], recv_ptr[kMaxPeers + 1];
 };
 struct WindowLayout {
-  size_t ar_data, ar_flag, halo_flag, counters, bytes;
-  explicit WindowLayout(int R) {
-    ar_data = 0;
-    ar_flag = ar_data + sizeof(double) * 2 * R * kArLd;
-    halo_flag = ar_flag + (sizeof(unsigned) * 2 * R + 15) / 16 * 16;
-    counters = halo_flag + sizeof(unsigned) * kMaxPeers;
-    bytes = counters + 64;
+  size_t ar_inbox, counters, halo_inbox, bytes;
+  WindowLayout(int R, int n_halo) {
+    ar_inbox = 0;
+    counters = ar_inbox + sizeof(LL16) * 2 * R * kArLd;
+    halo_inbox = counters + 64;
+    bytes = halo_inbox + sizeof(LL16) * (size_t)std::max(n_halo, 1);
   }
 };
 
-// Map the other ranks' windows / Krylov bases and build the device-side descriptors.  Collective.
+// Map the other ranks' windows and build the device-side descriptors.  Collective.
 // Returns BG_OK with D->p2p_ready = false when peer memory is unavailable on ANY rank (all ranks agree).
 int setup_p2p(bg_dist_t D) {
   NcclApi& N = nccl();
   bg_context_t ctx = D->ctx;
   cudaStream_t st = ctx->stream;
   const int R = D->nranks, me = D->rank, nn = (int)D->nbr.size();
-  const size_t es = dtype_size(D->dtype);
-  bg_solver_t S = D->S;
   PeerRecord mine;
   std::memset(&mine, 0, sizeof(mine));
   bool ok = R <= kMaxPeers && nn <= kMaxPeers;
   const char* env = getenv("B200GMRES_DIST_TRANSPORT");
   if (env && std::strcmp(env, "nccl") == 0) ok = false;
-  const WindowLayout wl(R);
-  // the solution buffer of the block-major order must exist (and keep its address) before it is exported
-  const size_t vbytes = (size_t)S->ld * es;
-  if (S->bp.bytes < vbytes) { BG_TRY(S->bp.alloc(vbytes)); BG_TRY(S->xp.alloc(vbytes)); }
+  const WindowLayout wl(R, D->n_halo);
   BG_TRY(D->window.alloc(wl.bytes));
-  BG_CUDA(cudaMemsetAsync(D->window.p, 0, wl.bytes, st));
+  BG_CUDA(cudaMemsetAsync(D->window.p, 0, wl.bytes, st));  // sequence numbers start at 1: zero never matches
   if (ok) {
-    ok = cudaIpcGetMemHandle(&mine.win, D->window.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.V, S->V.p) == cudaSuccess &&
-         cudaIpcGetMemHandle(&mine.x, S->xp.p) == cudaSuccess;
+    ok = cudaIpcGetMemHandle(&mine.win, D->window.p) == cudaSuccess;
     if (!ok) cudaGetLastError();
   }
-  mine.ld = S->ld; mine.n_local = D->n_local; mine.n_nbr = nn; mine.ok = ok ? 1 : 0;
+  mine.n_halo = D->n_halo; mine.n_nbr = nn; mine.ok = ok ? 1 : 0;
   for (int k = 0; k < nn && k < kMaxPeers; ++k) { mine.nbr[k] = D->nbr[k]; mine.recv_ptr[k] = D->recv_ptr[k]; }
   if (nn <= kMaxPeers) mine.recv_ptr[nn] = D->recv_ptr[nn];
-  // exchange the records
+  // exchange the records (the memset above precedes the all-gather in stream order on every rank, so
+  // nobody can store into a window that is not cleared yet)
   DevBuf sb, rb;
   BG_TRY(sb.upload(&mine, sizeof(mine), st));
   BG_TRY(rb.alloc(sizeof(PeerRecord) * R));
@@ -240,21 +230,18 @@ int setup_p2p(bg_dist_t D) {
   BG_CUDA(cudaMemcpyAsync(all.data(), rb.p, sizeof(PeerRecord) * R, cudaMemcpyDeviceToHost, st));
   BG_CUDA(cudaStreamSynchronize(st));
   for (int r = 0; r < R; ++r) ok = ok && all[r].ok;
-  // open what this rank needs: every window, and the vectors of its neighbours
-  std::vector<char*> win(R, nullptr), pV(R, nullptr), pX(R, nullptr);
-  auto open = [&](const cudaIpcMemHandle_t& h, char** out) {
-    void* p = nullptr;
-    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
-    D->ipc_open.push_back(p);
-    *out = (char*)p;
-    return true;
-  };
+  std::vector<char*> win(R, nullptr);
   if (ok) {
     win[me] = D->window.as<char>();
-    for (int r = 0; r < R && ok; ++r) if (r != me) ok = open(all[r].win, &win[r]);
-    for (int k = 0; k < nn && ok; ++k) { const int q = D->nbr[k]; ok = open(all[q].V, &pV[q]) && open(all[q].x, &pX[q]); }
+    for (int r = 0; r < R && ok; ++r) {
+      if (r == me) continue;
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].win, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      D->ipc_open.push_back(p);
+      win[r] = (char*)p;
+    }
   }
-  // agree on the outcome (a rank whose open failed must not leave the others spinning on its flags)
+  // agree on the outcome (a rank whose open failed must not leave the others polling its window)
   int flag = ok ? 1 : 0;
   BG_TRY(sb.upload(&flag, sizeof(int), st));
   BG_NCCL(N.AllReduce(sb.p, sb.p, 1, ncclInt32, ncclMin, D->comm, st));
@@ -269,13 +256,12 @@ int setup_p2p(bg_dist_t D) {
   PeerAR par;
   std::memset(&par, 0, sizeof(par));
   par.nranks = R; par.rank = me;
-  unsigned* counters = (unsigned*)(D->window.as<char>() + wl.counters);
-  par.seq = counters + 0;
-  for (int r = 0; r < R; ++r) { par.inbox[r] = (double*)(win[r] + wl.ar_data); par.flag[r] = (unsigned*)(win[r] + wl.ar_flag); }
+  par.seq = (unsigned*)(D->window.as<char>() + wl.counters);
+  for (int r = 0; r < R; ++r) par.inbox[r] = (LL16*)(win[r] + WindowLayout(R, all[r].n_halo).ar_inbox);
   PeerHalo ph;
   std::memset(&ph, 0, sizeof(ph));
-  ph.n_nbr = nn; ph.seq = counters + 4; ph.ticket = counters + 8;
-  ph.my_flag = (unsigned*)(D->window.as<char>() + wl.halo_flag);
+  ph.n_nbr = nn; ph.n_halo = D->n_halo;
+  ph.my_inbox = (LL16*)(D->window.as<char>() + wl.halo_inbox);
   for (int k = 0; k <= nn; ++k) ph.send_ptr[k] = D->send_ptr[k];
   for (int k = 0; k < nn; ++k) {
     const int q = D->nbr[k];
@@ -284,9 +270,7 @@ int setup_p2p(bg_dist_t D) {
     for (int t = 0; t < pr.n_nbr; ++t) if (pr.nbr[t] == me) slot = t;
     if (slot < 0) { set_error("neighbour lists of ranks %d and %d disagree", me, q); return BG_ERR_COMM; }
     if (pr.recv_ptr[slot + 1] - pr.recv_ptr[slot] != D->send_ptr[k + 1] - D->send_ptr[k]) { set_error("halo sizes of ranks %d and %d disagree", me, q); return BG_ERR_COMM; }
-    ph.peer_V[k] = pV[q]; ph.peer_x[k] = pX[q]; ph.peer_ld[k] = pr.ld;
-    ph.peer_off[k] = (long long)pr.n_local + pr.recv_ptr[slot];
-    ph.peer_flag[k] = (unsigned*)(win[q] + wl.halo_flag) + slot;
+    ph.peer_inbox[k] = (LL16*)(win[q] + WindowLayout(R, pr.n_halo).halo_inbox) + pr.recv_ptr[slot];
   }
   BG_TRY(D->d_par.upload(&par, sizeof(par), st));
   BG_TRY(D->d_ph.upload(&ph, sizeof(ph), st));
@@ -368,12 +352,44 @@ extern "C" int bg_dist_destroy(bg_dist_t D) {
 
 extern "C" int bg_dist_gmres_solve(bg_dist_t D, const void* d_b, void* d_x, const bg_gmres_opts* o, bg_gmres_result* r) {
   if (!D || !d_b || !d_x || !o) return BG_ERR_ARG;
+  D->solve_index++; D->exchange_in_solve = 0;
   return gmres_solve_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, D);
 }
 
 extern "C" int bg_dist_profile(bg_dist_t D, const void* d_b, void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st) {
   if (!D || !d_b || !d_x || !o || !st) return BG_ERR_ARG;
+  D->solve_index++; D->exchange_in_solve = 0;
   return gmres_profile_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, st, D);
+}
+
+extern "C" int bg_dist_bench_comm(bg_dist_t D, int what, int count, int reps, double* us) {
+  if (!D || !us || reps < 1 || count < 1 || count > 33) return BG_ERR_ARG;
+  bg_solver_t S = D->S;
+  bg_context_t ctx = D->ctx;
+  GmresDev st = S->dev;
+  D->solve_index++; D->exchange_in_solve = 0;
+  BG_TRY(launch_state_reset(ctx, st, 0.0, 0.1));
+  BG_CUDA(cudaMemsetAsync(S->w.p, 0, (size_t)S->ld * dtype_size(S->dtype), ctx->stream));
+  BG_CUDA(cudaMemsetAsync(S->V.p, 0, (size_t)S->ld * dtype_size(S->dtype) * (S->m + 1), ctx->stream));
+  double* red = S->red.as<double>();
+  auto op = [&]() -> int {
+    if (what == 0) return D->exchange(S->V.p, nullptr);
+    // an all-reduce of `count` values carried by a dots step over 32 rows (j = count - 1 basis columns)
+    const int rows = std::min(32, S->n);
+    if (D->peer_ar()) return launch_dots(ctx, S->dtype, rows, S->V.p, S->ld, count - 1, S->w.p, st, FIN_NONE, 0, 0, BG_ORTH_CGS_ADAPTIVE, 0, nullptr, D->peer_ar());
+    BG_TRY(launch_dots(ctx, S->dtype, rows, S->V.p, S->ld, count - 1, S->w.p, st, FIN_NONE, 0, 0, BG_ORTH_CGS_ADAPTIVE, 0, red));
+    BG_TRY(D->allreduce(red, count));
+    return launch_finalize(ctx, st, FIN_NONE, 0, 0, BG_ORTH_CGS_ADAPTIVE, 0, count - 1, red);
+  };
+  for (int i = 0; i < 20; ++i) BG_TRY(op());
+  BG_CUDA(cudaEventRecord(S->t0, ctx->stream));
+  for (int i = 0; i < reps; ++i) BG_TRY(op());
+  BG_CUDA(cudaEventRecord(S->t1, ctx->stream));
+  BG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, S->t0, S->t1);
+  *us = 1e3 * ms / reps;
+  return BG_OK;
 }
 
 extern "C" int bg_dist_gmres_solve_host(bg_dist_t D, const void* h_b, void* h_x, const bg_gmres_opts* o, bg_gmres_result* r) {

@@ -115,33 +115,29 @@ enum { FIN_NONE = 0, FIN_NORMB, FIN_BETA0, FIN_BETA, FIN_CGS1, FIN_CGS2, FIN_MGS
 
 // ---- peer-memory transport of a row-partitioned solve (dist.cu; kernels in orth.cu) ----------
 // Every rank owns a small "window" allocation that all other ranks of the box map through CUDA IPC
-// (NVLink / NVSwitch peer stores).  Both structs live in DEVICE memory of the owning rank.
+// (NVLink / NVSwitch peer stores).  Messages use a low-latency flag-in-data format: a double travels
+// as ONE 16-byte store {lo32, seq, hi32, seq}; the receiver polls the element itself until both
+// sequence words match, so no memory fence, no separate flag and no second round trip are needed.
+// Both structs live in DEVICE memory of the owning rank.
 constexpr int kMaxPeers = 16;   // ranks of one box
-constexpr int kArLd = 40;       // doubles per rank and slot of the all-reduce inbox (>= kFinMax + 2)
-// All-reduce fused into the last CTA of dots_kernel: every rank stores its j+1 partial sums into the
-// inbox of every rank (slot = parity of a device-side sequence number, row = sender), raises the
-// sender's flag there, waits for all flags in its own inbox and sums the rows in rank order -- the
-// same bits on every rank, so stopping decisions stay identical without any further exchange.
+constexpr int kArLd = 40;       // elements per rank and slot of the all-reduce inbox (>= kFinMax + 2)
+struct __align__(16) LL16 { unsigned lo, f0, hi, f1; };
+// All-reduce fused into the last CTA of the dots / orth kernels: every rank stores its j+1 partial sums
+// into the inbox of every rank (slot = parity of a device-side sequence number, row = sender), polls its
+// own inbox and sums the rows in rank order -- the same bits on every rank, so stopping decisions stay
+// identical without any further exchange.
 struct PeerAR {
   int nranks, rank;
   unsigned* seq;                 // local counter of executed all-reduces
-  double* inbox[kMaxPeers];      // inbox[r]: rank r's [2][nranks][kArLd] doubles (peer-mapped for r != rank)
-  unsigned* flag[kMaxPeers];     // flag[r]:  rank r's [2][nranks] arrival flags
+  LL16* inbox[kMaxPeers];        // inbox[r]: rank r's [2][nranks][kArLd] elements (peer-mapped for r != rank)
 };
-// Halo exchange: the boundary entries of the vector entering the SpMV are stored straight into the
-// halo slots BEHIND THE SAME VECTOR on the neighbour (its Krylov basis / solution buffers are peer-mapped
-// too), followed by a per-neighbour sequence flag; the pushing kernel then waits for its own neighbours.
+// Halo exchange: one kernel stores the boundary entries of the vector entering the SpMV into the
+// neighbours' halo inboxes and copies its own arrived inbox into the halo slots behind the local vector.
 struct PeerHalo {
-  int n_nbr;
-  unsigned* seq;                 // local counter of executed exchanges
-  unsigned* ticket;              // CTA arrival counter of the push kernel
+  int n_nbr, n_halo;
   int send_ptr[kMaxPeers + 1];   // entries [send_ptr[k], send_ptr[k+1]) of send_idx go to neighbour k
-  char* peer_V[kMaxPeers];       // neighbour's Krylov basis (column-major, leading dimension peer_ld)
-  char* peer_x[kMaxPeers];       // neighbour's block-major solution buffer
-  long long peer_ld[kMaxPeers];
-  long long peer_off[kMaxPeers]; // first halo element written on the neighbour: its n_local + its recv_ptr[me]
-  unsigned* peer_flag[kMaxPeers];// my slot in the neighbour's halo flag array
-  unsigned* my_flag;             // [n_nbr] local flags, slot k raised by neighbour k
+  LL16* peer_inbox[kMaxPeers];   // first element of MY range in neighbour k's halo inbox
+  LL16* my_inbox;                // [n_halo]
 };
 
 // ---- launchers (defined in the .cu files) --------------------------------------------------
@@ -157,9 +153,13 @@ int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci,
 int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w,
                 const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth_flag,
                 double* red_out = nullptr, const PeerAR* peer = nullptr);
-// pack + peer-store + flag + wait of one halo exchange (which: 0 = column `col` of the basis, 1 = solution buffer)
-int launch_halo_push(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int n_send, int which, int col, const int* idx,
-                     const void* v, const int* skip);
+// one halo exchange: gather + peer-store of the boundary entries of v, then wait for / unpack the own halo
+// into halo_out (= v + n_local); seq identifies the exchange (same value on both sides)
+int launch_halo_exchange(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int n_send, int n_halo, const int* idx,
+                         const void* v, void* halo_out, unsigned seq, const int* skip);
+// fused CGS step (adaptive or CGS2): projections + (peer all-reduce) + Givens epilogue + v_j, one cooperative launch
+int launch_orth(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, void* out,
+                const GmresDev& st, int inner_i, int orth_mode, const PeerAR* peer);
 int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth,
                     int j, const double* red_in);
 int launch_pack(bg_context_t ctx, int dtype, int cnt, const int* idx, const void* v, void* buf, const int* skip);

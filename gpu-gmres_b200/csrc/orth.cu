@@ -251,31 +251,32 @@ __device__ __forceinline__ void pipe_produce(const Pipe& pp, unsigned char* ring
 }
 
 // ---------------------------------------------------------------------------- peer memory (multi-GPU)
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
+// Flag-in-data messages over NVLink (internal.h LL16): one 16-byte store carries a double and its
+// sequence number twice; a reader that sees both sequence words equal to the expected one has the value.
+__device__ __forceinline__ void ll_store(LL16* p, double v, unsigned seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(seq),
+               "r"((unsigned)__double2hiint(v)), "r"(seq)
+               : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// wait until *flag has reached seq; a peer that never arrives (crashed rank) must trap, not hang the GPU
-__device__ __forceinline__ void peer_wait(const unsigned* flag, unsigned seq) {
-  const unsigned long long t0 = global_ns();
-  while ((int)(ld_acquire_sys(flag) - seq) < 0) {
-    __nanosleep(20);
-    if (global_ns() - t0 > 30000000000ull) __trap();
+// poll until the element carries `seq`; a peer that never arrives (crashed rank) must trap, not hang the GPU
+__device__ __forceinline__ double ll_wait(const LL16* p, unsigned seq) {
+  unsigned lo, f0, hi, f1;
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+    if (f0 == seq && f1 == seq) break;
+    if ((spin & 1023u) == 1023u) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 30000000000ull) __trap();
+    }
   }
+  return __hiloint2double((int)hi, (int)lo);
 }
 // red[0..cnt) <- sum over the ranks, in rank order (identical bits everywhere).  Called by ALL threads
 // of one CTA per rank.  Slots alternate with the parity of the sequence number: a rank can run at most
@@ -289,52 +290,33 @@ __device__ void peer_allreduce(const PeerAR* __restrict__ P, double* red, int cn
   const size_t slot = (size_t)(seq & 1u) * R;
   for (int t = threadIdx.x; t < R * cnt; t += blockDim.x) {
     const int r = t / cnt, k = t - r * cnt;
-    P->inbox[r][(slot + me) * kArLd + k] = red[k];
+    ll_store(&P->inbox[r][(slot + me) * kArLd + k], red[k], seq);
   }
-  __threadfence_system();
+  double v = 0.0;
+  if ((int)threadIdx.x < cnt)
+    for (int r = 0; r < R; ++r) v += ll_wait(&P->inbox[me][(slot + r) * kArLd + threadIdx.x], seq);
   __syncthreads();
-  if ((int)threadIdx.x < R) {
-    st_release_sys(&P->flag[threadIdx.x][slot + me], seq);
-    peer_wait(&P->flag[me][slot + threadIdx.x], seq);
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < cnt) {
-    double v = 0.0;
-    for (int r = 0; r < R; ++r) v += ld_relaxed_sys(&P->inbox[me][(slot + r) * kArLd + threadIdx.x]);
-    red[threadIdx.x] = v;
-  }
+  if ((int)threadIdx.x < cnt) red[threadIdx.x] = v;
   __syncthreads();
 }
 
-// One halo exchange in one kernel: gather the boundary entries, store them into the neighbours' halo
-// slots of the SAME vector over NVLink, publish a sequence flag per neighbour, then wait for the
-// neighbours' flags -- when the kernel retires, this rank's halo is complete and the SpMV can follow.
+// One halo exchange in one kernel and without any fence: every boundary entry travels as a self-validating
+// 16-byte element into the neighbour's inbox; the same kernel then polls its own inbox and writes the
+// arrived values into the halo slots behind the local vector, so the SpMV that follows reads plain memory.
 template <class VT>
-__global__ void __launch_bounds__(512) halo_push_kernel(const PeerHalo* __restrict__ H, int which, int col,
-                                                         const int* __restrict__ idx, const VT* __restrict__ v,
-                                                         const int* skip) {
+__global__ void __launch_bounds__(256) halo_exchange_kernel(const PeerHalo* __restrict__ H, const int* __restrict__ idx,
+                                                             const VT* __restrict__ v, VT* __restrict__ halo_out, unsigned seq,
+                                                             const int* skip) {
   if (skip && *skip) return;
-  const int nn = H->n_nbr, total = H->send_ptr[nn];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+  const int nn = H->n_nbr, total = H->send_ptr[nn], nh = H->n_halo;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int e = tid; e < total; e += nt) {
     int k = 0;
     while (e >= H->send_ptr[k + 1]) ++k;
-    VT* dst = reinterpret_cast<VT*>(which == 0 ? H->peer_V[k] + (size_t)col * H->peer_ld[k] * sizeof(VT) : H->peer_x[k]) + H->peer_off[k];
-    dst[e - H->send_ptr[k]] = v[idx[e]];
+    ll_store(H->peer_inbox[k] + (e - H->send_ptr[k]), (double)v[idx[e]], seq);
   }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  __shared__ unsigned s_seq;
-  if (threadIdx.x == 0) last = atomicAdd(H->ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last) return;
-  __threadfence_system();
-  if (threadIdx.x == 0) { s_seq = *H->seq + 1u; *H->seq = s_seq; *H->ticket = 0u; }
-  __syncthreads();
-  if ((int)threadIdx.x < nn) {
-    st_release_sys(H->peer_flag[threadIdx.x], s_seq);
-    peer_wait(&H->my_flag[threadIdx.x], s_seq);
-  }
+  const LL16* in = H->my_inbox;
+  for (int i = tid; i < nh; i += nt) halo_out[i] = (VT)ll_wait(in + i, seq);
 }
 
 // ---------------------------------------------------------------------------- dots
@@ -542,6 +524,217 @@ __global__ void __launch_bounds__(kPipeThreads, 1) update_kernel(int n, const VT
   }
 }
 
+// ---------------------------------------------------------------------------- fused orthogonalisation step
+// One cooperative launch per inner iteration replaces dots_kernel + update_kernel (+ the two launches of
+// the conditional second pass): the persistent CTAs stream their tiles of [V(:,0..j) | w] once for the
+// projections, the last CTA to arrive reduces (all-reducing over the GPUs of the box through peer memory
+// in a row-partitioned run), runs the scalar epilogue and publishes a generation number; every CTA then
+// walks ITS OWN tiles again in reverse order for v_j = (w - V h) * scale.  The tiles still sitting in the
+// shared-memory ring when the second phase starts are used in place ("virtual" fills: the producer only
+// completes the barrier), the rest mostly hits the L2 lines the first phase left behind.  When the DGKS
+// test fires (or under CGS2) the same kernel runs the second pass on its own output.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx0(uint64_t* bar) {  // completes a phase that expects no bytes
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(0u) : "memory");
+}
+
+template <class VT>
+__global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* __restrict__ V, int64_t ld, int j,
+                                                                const VT* w, VT* out, GmresDev st, int inner_i,
+                                                                int orth_mode, Pipe pp, const PeerAR* peer) {
+  if (st.flags[F_CONV]) return;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  unsigned char* ring = dyn;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dyn + (size_t)pp.stages * pp.stage_bytes);
+  uint64_t* empty = full + pp.stages;
+  __shared__ double red_w[kConsumerWarps][5];
+  __shared__ double red[kFinMax + 2];
+  __shared__ double cs[kFinMax];
+  __shared__ FinScratch fs;
+  __shared__ bool last;
+  __shared__ int s_ctl[2];
+  __shared__ double s_scale;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned* gen = st.ticket + 1;
+  const unsigned gen0 = ld_acquire_gpu(gen);  // read by every CTA before it takes a ticket
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pp.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int S = pp.stages, G = gridDim.x;
+  const int ntiles = (n + pp.R - 1) / pp.R;
+  const int K = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + G - 1) / G : 0;  // tiles of this CTA
+  const int ncols = j + 1;
+  const int CW = ncols > 20 ? 8 : ncols > 10 ? 4 : ncols > 5 ? 2 : 1, RW = kConsumerWarps / CW;
+  // per-stage parities of the fills (producer) / uses (consumers) so far: stages are not visited round-robin
+  unsigned fbits = 0, fany = 0, ubits = 0;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const VT* extra = pass == 0 ? w : out;
+    // ---------------- phase A: projections of `extra` on V(:,0..j) and its squared norm
+    if (wid == kConsumerWarps) {
+      for (int q = 0; q < K; ++q) {
+        const int t = blockIdx.x + q * G, s = q % S;
+        if ((fany >> s) & 1u) mbar_wait(&empty[s], ((fbits >> s) & 1u) ^ 1u);
+        const int rows = min(pp.R, n - t * pp.R);
+        const uint32_t col_bytes = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;
+        if (lane == 0) mbar_expect_tx(&full[s], col_bytes * (uint32_t)ncols);
+        __syncwarp();
+        unsigned char* tile = ring + (size_t)s * pp.stage_bytes;
+        for (int c = lane; c < ncols; c += 32) {
+          const VT* src = (c < j ? V + (size_t)c * ld : extra) + (size_t)t * pp.R;
+          bulk_g2s(tile + (size_t)c * pp.R * sizeof(VT), src, col_bytes, &full[s]);
+        }
+        fbits ^= 1u << s; fany |= 1u << s;
+      }
+    } else {
+      const int cg = wid % CW, rg = wid / CW;
+      double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int q = 0; q < K; ++q) {
+        const int t = blockIdx.x + q * G, s = q % S;
+        mbar_wait(&full[s], (ubits >> s) & 1u);
+        const VT* tile = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes);
+        const VT* tw = tile + (size_t)j * pp.R;
+        const int rows = min(pp.R, n - t * pp.R);
+#pragma unroll 4
+        for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
+          const double wv = (double)tw[r];
+#pragma unroll
+          for (int a = 0; a < 5; ++a) {
+            const int c = cg + a * CW;
+            if (c < ncols) acc[a] += (double)tile[(size_t)c * pp.R + r] * wv;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        ubits ^= 1u << s;
+      }
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        const double v = warp_sum(acc[a]);
+        if (lane == 0) red_w[wid][a] = v;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x <= j) {
+      const int cg = threadIdx.x % CW, a = threadIdx.x / CW;
+      double v = 0.0;
+      for (int rg = 0; rg < RW; ++rg) v += red_w[cg + CW * rg][a];
+      st.partial[(size_t)blockIdx.x * st.partial_ld + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(st.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    const unsigned gen_next = gen0 + 1u + (unsigned)pass;
+    if (last) {
+      __threadfence();
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = wid + u * (kConsumerWarps + 1);
+        if (k <= j)
+          for (int b = lane; b < (int)gridDim.x; b += 32) v[u] += __ldcg(&st.partial[(size_t)b * st.partial_ld + k]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = wid + u * (kConsumerWarps + 1);
+        const double r = warp_sum(v[u]);
+        if (k <= j && lane == 0) red[k] = r;
+      }
+      fin_prefetch(st, fs, inner_i, threadIdx.x);
+      __syncthreads();
+      if (peer) peer_allreduce(peer, red, j + 1);
+      if (threadIdx.x == 0) {
+        finalize(st, pass == 0 ? FIN_CGS1 : FIN_CGS2, inner_i, 0, orth_mode, red, j, &fs);
+        *st.ticket = 0u;
+        __threadfence();
+        st_release_gpu(gen, gen_next);
+      }
+    }
+    // ---------------- everybody waits for the coefficients of this pass
+    if (threadIdx.x == 0) {
+      for (unsigned spin = 0; ld_acquire_gpu(gen) != gen_next; ++spin)
+        if (spin > (1u << 28)) __trap();
+      s_ctl[0] = __ldcg(&st.flags[F_CONV]);
+      s_ctl[1] = __ldcg(&st.flags[F_REORTH]);
+      s_scale = __ldcg(&st.scal[S_SCALE]);
+    }
+    __syncthreads();
+    if (s_ctl[0]) return;  // converged in this iteration: v_j is not needed (the separate kernels skip it too)
+    const bool again = pass == 0 && s_ctl[1] != 0;
+    if (threadIdx.x < j) cs[threadIdx.x] = -__ldcg(&(pass == 0 ? st.h : st.h2)[threadIdx.x]);
+    __syncthreads();
+    // ---------------- phase B: out = (extra - V c) * scale over the same tiles, last tile first
+    if (wid == kConsumerWarps) {
+      for (int q = 0; q < K; ++q) {
+        const int qq = K - 1 - q, t = blockIdx.x + qq * G, s = qq % S;
+        if ((fany >> s) & 1u) mbar_wait(&empty[s], ((fbits >> s) & 1u) ^ 1u);
+        if (q < S) {
+          // still resident from phase A: complete the barrier without moving a byte
+          if (lane == 0) mbar_arrive_tx0(&full[s]);
+        } else {
+          const int rows = min(pp.R, n - t * pp.R);
+          const uint32_t col_bytes = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;
+          if (lane == 0) mbar_expect_tx(&full[s], col_bytes * (uint32_t)ncols);
+          __syncwarp();
+          unsigned char* tile = ring + (size_t)s * pp.stage_bytes;
+          for (int c = lane; c < ncols; c += 32) {
+            const VT* src = (c < j ? V + (size_t)c * ld : extra) + (size_t)t * pp.R;
+            bulk_g2s(tile + (size_t)c * pp.R * sizeof(VT), src, col_bytes, &full[s]);
+          }
+        }
+        fbits ^= 1u << s; fany |= 1u << s;
+      }
+    } else {
+      const double scale = s_scale;
+      for (int q = 0; q < K; ++q) {
+        const int qq = K - 1 - q, t = blockIdx.x + qq * G, s = qq % S;
+        mbar_wait(&full[s], (ubits >> s) & 1u);
+        const VT* tile = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes);
+        const int rows = min(pp.R, n - t * pp.R);
+        const size_t base = (size_t)t * pp.R;
+        for (int r0 = 0; r0 < rows; r0 += 1024) {
+          double av[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + threadIdx.x + 256 * u;
+            av[u] = r < rows ? (double)tile[(size_t)j * pp.R + r] : 0.0;
+          }
+          for (int k = 0; k < j; ++k) {
+            const double c = cs[k];
+            const VT* col = tile + (size_t)k * pp.R + r0 + threadIdx.x;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (r0 + (int)threadIdx.x + 256 * u < rows) av[u] += c * (double)col[256 * u];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + threadIdx.x + 256 * u;
+            if (r < rows) out[base + r] = (VT)(av[u] * scale);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        ubits ^= 1u << s;
+      }
+    }
+    if (!again) return;
+    // second pass reads `out` through the bulk-copy (async) proxy: order the generic stores before it
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    __syncthreads();
+  }
+}
+
 // out = a * scale (no basis columns: v0 = r/beta, gmres.cu:2342-2343)
 template <class VT>
 __global__ void __launch_bounds__(256) scale_copy_kernel(int n, const VT* a, VT* out, GmresDev st, int use_scale, int force) {
@@ -682,11 +875,12 @@ int launch_dots(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, i
   if (dtype == BG_F32) return dots_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out, peer);
   return dots_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, st, fin, inner_i, mgs_k, orth_mode, need_reorth, red_out, peer);
 }
-int launch_halo_push(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int n_send, int which, int col, const int* idx,
-                     const void* v, const int* skip) {
-  const int g = std::max(1, std::min((n_send + 511) / 512, 32));
-  if (dtype == BG_F32) halo_push_kernel<float><<<g, 512, 0, ctx->stream>>>(d_ph, which, col, idx, (const float*)v, skip);
-  else halo_push_kernel<double><<<g, 512, 0, ctx->stream>>>(d_ph, which, col, idx, (const double*)v, skip);
+int launch_halo_exchange(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int n_send, int n_halo, const int* idx,
+                         const void* v, void* halo_out, unsigned seq, const int* skip) {
+  const int work = std::max(n_send, n_halo);
+  const int g = std::max(1, std::min((work + 255) / 256, ctx->sm_count));
+  if (dtype == BG_F32) halo_exchange_kernel<float><<<g, 256, 0, ctx->stream>>>(d_ph, idx, (const float*)v, (float*)halo_out, seq, skip);
+  else halo_exchange_kernel<double><<<g, 256, 0, ctx->stream>>>(d_ph, idx, (const double*)v, (double*)halo_out, seq, skip);
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
@@ -732,6 +926,37 @@ int launch_update(bg_context_t ctx, int dtype, int n, const void* a, const void*
                   int need_reorth) {
   if (dtype == BG_F32) return update_dispatch<float>(ctx, n, (const float*)a, (const float*)V, ld, j, coef, sgn, (float*)out, st, use_scale, force, need_reorth);
   return update_dispatch<double>(ctx, n, (const double*)a, (const double*)V, ld, j, coef, sgn, (double*)out, st, use_scale, force, need_reorth);
+}
+
+// ring geometry of the fused step: same stage budget, rows chosen so that every CTA owns the same number of tiles
+static Pipe orth_geometry(int ncols, size_t elem, int n, int G) {
+  Pipe p = pipe_geometry(ncols, elem);
+  const int64_t per = ((int64_t)n + G - 1) / G;                  // rows per CTA
+  const int64_t k = std::max<int64_t>(1, (per + p.R - 1) / p.R); // tiles per CTA
+  int R = (int)(((per + k - 1) / k + 31) / 32 * 32);
+  p.R = std::max(32, std::min(R, p.R));
+  p.stage_bytes = (uint32_t)(((size_t)std::max(1, ncols) * p.R * elem + 127) / 128 * 128);
+  return p;
+}
+template <class VT>
+static int orth_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int j, const VT* w, VT* out, const GmresDev& st,
+                         int i, int om, const PeerAR* peer) {
+  if (j < 1 || j > kFinMax) { set_error("orth: j=%d outside 1..%d", j, kFinMax); return BG_ERR_ARG; }
+  const int G = std::max(1, std::min((n + 31) / 32, ctx->sm_count));
+  Pipe pp = orth_geometry(j + 1, sizeof(VT), n, G);
+  const size_t smem = (size_t)pp.stages * pp.stage_bytes + 2 * sizeof(uint64_t) * pp.stages;
+  BG_TRY(pipe_smem_attr(orth_kernel<VT>, ctx));
+  GmresDev stv = st;
+  void* args[] = {(void*)&n, (void*)&V, (void*)&ld, (void*)&j, (void*)&w, (void*)&out, (void*)&stv, (void*)&i, (void*)&om, (void*)&pp, (void*)&peer};
+  // cooperative launch: the CTAs wait for each other inside the kernel, so co-residency must be guaranteed
+  BG_CUDA(cudaLaunchCooperativeKernel((const void*)orth_kernel<VT>, dim3(G), dim3(kPipeThreads), args, smem, ctx->stream));
+  ctx->launches++;
+  return BG_OK;
+}
+int launch_orth(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, void* out, const GmresDev& st,
+                int inner_i, int orth_mode, const PeerAR* peer) {
+  if (dtype == BG_F32) return orth_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, (float*)out, st, inner_i, orth_mode, peer);
+  return orth_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, (double*)out, st, inner_i, orth_mode, peer);
 }
 
 int launch_solve_y(bg_context_t ctx, const GmresDev& st, int k, int force) {

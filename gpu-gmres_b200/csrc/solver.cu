@@ -727,8 +727,8 @@ static_assert(sizeof(Status) <= 128, "status slot");
 // optional per-phase timing (bg_solver_profile): event pairs around kernel groups
 struct Prof {
   std::vector<cudaEvent_t>* pool = nullptr;
-  std::vector<std::pair<int, int>> spans[6];  // event index pairs per phase
-  int64_t calls[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<std::pair<int, int>> spans[7];  // event index pairs per phase
+  int64_t calls[7] = {0, 0, 0, 0, 0, 0, 0};
   size_t used = 0;
   cudaStream_t stream = nullptr;
   int mark() {
@@ -737,7 +737,7 @@ struct Prof {
     return (int)used++;
   }
 };
-enum { PH_SPMV = 0, PH_TRSV = 1, PH_ORTH = 2, PH_OTHER = 3, PH_DOTS = 4, PH_UPDATE = 5 };
+enum { PH_SPMV = 0, PH_TRSV = 1, PH_ORTH = 2, PH_OTHER = 3, PH_DOTS = 4, PH_UPDATE = 5, PH_HALO = 6 };
 
 struct Driver {
   bg_context_t ctx; bg_solver_t S; bg_matrix_t A; bg_precond_t M; const bg_gmres_opts& o;
@@ -746,9 +746,10 @@ struct Driver {
   Prof* prof = nullptr;
   bool permuted = false;  // A, b, x and all work vectors are in the preconditioner's block-major row order
   DistHooks* dh = nullptr;  // row-partitioned run: halo exchange before every SpMV, allreduce inside every dots step
+  bool fused_orth = true;   // BG_FUSED_ORTH=0 selects the separate dots / update kernels
   // y = alpha A x (+ beta b): x must have room for the halo behind its n entries when dh is set
   int spmv(double alpha, void* xv, double beta, const void* bv, void* y, bool axpby) {
-    if (dh) BG_TRY(dh->exchange(xv, skip));
+    if (dh) { Span sh(prof, PH_HALO); BG_TRY(dh->exchange(xv, skip)); }
     return launch_spmv(ctx, A, alpha, xv, beta, bv, y, axpby, skip);
   }
   int dots(const void* Vp, int j, const void* w, int fin, int i, int mk, int nr) {
@@ -797,6 +798,9 @@ struct Driver {
       return launch_update(ctx, S->dtype, n, S->w.p, nullptr, ld, 0, nullptr, 0.0, col(i + 1), st, 1, 0, 0);
     }
     const int j = i + 1;
+    // one cooperative launch: projections, (peer all-reduce,) Givens epilogue, v_j, conditional second pass
+    if (fused_orth && (!dh || dh->peer_ar()))
+      return launch_orth(ctx, S->dtype, n, col(0), ld, j, S->w.p, col(j), st, i, o.orth, dh ? dh->peer_ar() : nullptr);
     { Span sd(prof, PH_DOTS); BG_TRY(dots(col(0), j, S->w.p, FIN_CGS1, i, 0, 0)); }
     { Span su(prof, PH_UPDATE); BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(0), ld, j, st.h, -1.0, col(j), st, 1, 0, 0)); }
     BG_TRY(dots(col(0), j, col(j), FIN_CGS2, i, 0, 1));
@@ -908,6 +912,7 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
   }
   if (dh && !permuted) { set_error("a row-partitioned solve needs a block-Jacobi (BG_TRSV_BLOCK) ILU preconditioner"); return BG_ERR_UNSUPPORTED; }
   Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof, permuted, dh};
+  { const char* e = getenv("BG_FUSED_ORTH"); D.fused_orth = !(e && e[0] == '0'); }
   BG_TRY(launch_state_reset(ctx, st, o.tol, o.reorth_eta));
   // normb = || M_L^-1 b ||   (gmres.cu:2294-2296)
   BG_TRY(D.apply_left(d_b, S->bb.p, nullptr));
@@ -1043,8 +1048,8 @@ int bg::gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_pr
   int rc = gmres_solve_impl(ctx, S, A, M, d_b, d_x, o, &rr, &prof, dh);
   if (rc < 0) return rc;
   if (r) *r = rr;
-  double ms[6] = {0, 0, 0, 0, 0, 0};
-  for (int ph = 0; ph < 6; ++ph)
+  double ms[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int ph = 0; ph < 7; ++ph)
     for (auto& sp : prof.spans[ph]) {
       float t = 0;
       cudaEventElapsedTime(&t, S->prof_events[sp.first], S->prof_events[sp.second]);
@@ -1055,6 +1060,7 @@ int bg::gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_pr
   out->spmv_calls = prof.calls[PH_SPMV]; out->trsv_calls = prof.calls[PH_TRSV]; out->orth_calls = prof.calls[PH_ORTH];
   out->dots_ms = ms[PH_DOTS]; out->update_ms = ms[PH_UPDATE];
   out->dots_calls = prof.calls[PH_DOTS]; out->update_calls = prof.calls[PH_UPDATE];
+  out->halo_ms = ms[PH_HALO]; out->halo_calls = prof.calls[PH_HALO];
   // algorithmic bytes of the work actually performed (iters_done inner iterations)
   bg_matrix_info mi; bg_precond_info pi;
   bg_matrix_get_info(A, &mi); bg_precond_get_info(M, &pi);

@@ -84,7 +84,7 @@ class PhaseStats(C.Structure):
                 ("spmv_bytes", C.c_int64), ("trsv_bytes", C.c_int64), ("orth_bytes", C.c_int64), ("other_bytes", C.c_int64),
                 ("spmv_calls", C.c_int64), ("trsv_calls", C.c_int64), ("orth_calls", C.c_int64),
                 ("dots_ms", C.c_double), ("update_ms", C.c_double), ("dots_bytes", C.c_int64), ("update_bytes", C.c_int64),
-                ("dots_calls", C.c_int64), ("update_calls", C.c_int64)]
+                ("dots_calls", C.c_int64), ("update_calls", C.c_int64), ("halo_ms", C.c_double), ("halo_calls", C.c_int64)]
 
 
 _lib = None
@@ -473,6 +473,12 @@ class Dist:
         r, st = GmresResult(), PhaseStats()
         _chk(lib().bg_dist_profile(self.h, _p(d_b), _p(d_x), C.byref(opts), C.byref(r), C.byref(st)))
         return r, st
+
+    def bench_comm(self, what, count=33, reps=200):
+        """Device microseconds per halo exchange (what=0) or all-reduce of `count` doubles (what=1); collective."""
+        us = C.c_double()
+        _chk(lib().bg_dist_bench_comm(self.h, int(what), int(count), int(reps), C.byref(us)))
+        return us.value
 
     def set_transport(self, transport):
         """TRANSPORT_P2P (peer-memory kernels over NVLink) or TRANSPORT_NCCL; same choice on every rank."""

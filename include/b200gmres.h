@@ -236,6 +236,8 @@ typedef struct {
   /* the two kernels of the fused orthogonalisation step on their own (first pass only) */
   double dots_ms, update_ms;
   int64_t dots_bytes, update_bytes, dots_calls, update_calls;
+  /* row-partitioned solves: the halo exchange on its own (it is also contained in spmv_ms) */
+  double halo_ms; int64_t halo_calls;
 } bg_phase_stats;
 BG_API int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b,
                              void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st);
@@ -275,6 +277,9 @@ BG_API int bg_dist_gmres_solve_host(bg_dist_t D, const void* h_b_local, void* h_
    counted under spmv, waiting for slower ranks shows up in the dots / halo phases) */
 BG_API int bg_dist_profile(bg_dist_t D, const void* d_b_local, void* d_x_local, const bg_gmres_opts* o,
                            bg_gmres_result* r, bg_phase_stats* st);
+/* diagnostic, collective: `reps` back-to-back halo exchanges (what = 0) or all-reduces of `count` doubles
+   (what = 1) with the transport in use; device time per operation in microseconds */
+BG_API int bg_dist_bench_comm(bg_dist_t D, int what, int count, int reps, double* us_per_op);
 typedef struct {
   int nranks, rank; int64_t n_global; int n_local, n_halo, n_neighbors;
   int64_t halo_messages, allreduces;      /* issued so far */
