@@ -99,16 +99,25 @@ struct bg_dist_s : DistHooks {
   std::vector<void*> ipc_open;   // mappings of the other ranks' memory, closed in the destructor
   int send_count = 0;
   uint32_t solve_index = 0, exchange_in_solve = 0;
+  bool fuse_halo = true;  // B200GMRES_FUSE_HALO=0: separate halo_exchange_kernel instead of the SpMV-carried exchange
 
   const PeerAR* peer_ar() override { return transport == BG_TRANSPORT_P2P && nranks > 1 ? d_par.as<PeerAR>() : nullptr; }
 
+  unsigned next_seq() { return (unsigned)(((uint64_t)solve_index << 20) + (uint64_t)(++exchange_in_solve)); }
+  bool halo_args(HaloArgs* h) override {
+    if (transport != BG_TRANSPORT_P2P || nranks == 1 || !fuse_halo) return false;
+    h->ph = d_ph.as<PeerHalo>(); h->send_idx = send_idx.as<int>(); h->n_send = send_count; h->n_local = n_local;
+    h->seq = next_seq();
+    halo_msgs += (int64_t)nbr.size();
+    return true;
+  }
   int exchange(void* vec, const int* skip) override {
     if (nranks == 1 || nbr.empty()) return BG_OK;
     const size_t es = dtype_size(dtype);
     if (transport == BG_TRANSPORT_P2P) {
       // sequence number of this exchange: (solve, launch within the solve) -- identical on both sides
       // because every rank enqueues the same sequence until convergence (later launches are skipped)
-      const unsigned seq = (unsigned)(((uint64_t)solve_index << 20) + (uint64_t)(++exchange_in_solve));
+      const unsigned seq = next_seq();
       halo_msgs += (int64_t)nbr.size();
       return launch_halo_exchange(ctx, dtype, d_ph.as<PeerHalo>(), send_count, n_halo, send_idx.as<int>(), vec,
                                   (char*)vec + (size_t)n_local * es, seq, skip);
@@ -277,6 +286,7 @@ int setup_p2p(bg_dist_t D) {
   BG_CUDA(cudaStreamSynchronize(st));
   D->p2p_ready = true;
   D->transport = BG_TRANSPORT_P2P;
+  { const char* e = getenv("B200GMRES_FUSE_HALO"); D->fuse_halo = !(e && e[0] == '0'); }
   return BG_OK;
 }
 }  // namespace

@@ -60,6 +60,7 @@ struct bg_matrix_s {
   bg::DevBuf rp, ci, val;            // CSR
   bg::DevBuf s_ptr, s_col, s_val;    // sliced ELL
   int sell_rpt = 1, sell_height = 32, sell_slices = 0;
+  int sell_width = 0;  // > 0: every slice has this many entries per row (stencils): kernels skip the slice pointers
   // host CSR (compute dtype) kept so that a symmetrically permuted copy P A P^T can be built when a
   // preconditioner asks for its own row order; one cached copy per ordering serial
   std::vector<int> h_rp, h_ci;
@@ -139,10 +140,21 @@ struct PeerHalo {
   LL16* peer_inbox[kMaxPeers];   // first element of MY range in neighbour k's halo inbox
   LL16* my_inbox;                // [n_halo]
 };
+// arguments of a SpMV that carries its own halo exchange (spmv.cu, HALO variants): the first wave of CTAs
+// stores this rank's boundary entries of x into the neighbours' inboxes, rows with halo columns read their
+// operands straight from the own inbox (polling the sequence number carried by every element)
+struct HaloArgs {
+  const PeerHalo* ph = nullptr;
+  const int* send_idx = nullptr;
+  int n_send = 0, n_local = 0;
+  unsigned seq = 0;
+};
 
 // ---- launchers (defined in the .cu files) --------------------------------------------------
 int launch_spmv(bg_context_t ctx, bg_matrix_t A, double alpha, const void* x, double beta, const void* b,
-                void* y, bool axpby, const int* skip_flag);
+                void* y, bool axpby, const int* skip_flag, const HaloArgs* halo = nullptr);
+// true when launch_spmv can carry the halo exchange itself for this matrix (uniform-width sliced ELL)
+bool spmv_supports_halo(bg_matrix_t A);
 // generic CSR y = A x with independent value/vector types (used for the warm-start U*x)
 int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci, const void* val, int val_dt,
                           const void* x, void* y, int vec_dt, const int* skip_flag);
@@ -224,6 +236,8 @@ struct DistHooks {
   virtual int exchange(void* vec, const int* skip) = 0;  // fill vec[n_local .. n_local+n_halo) from the neighbours
   virtual int allreduce(double* buf, int count) = 0;     // sum over ranks, in place, on the context stream
   virtual const PeerAR* peer_ar() { return nullptr; }    // non-null: dots_kernel all-reduces through peer memory itself
+  // peer transport only: describe the NEXT halo exchange (consumes a sequence number) for a SpMV that carries it
+  virtual bool halo_args(HaloArgs*) { return false; }
   virtual ~DistHooks() {}
 };
 int gmres_solve_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,

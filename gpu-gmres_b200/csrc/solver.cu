@@ -180,6 +180,9 @@ static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::ve
     std::vector<T> sv;
     build_sell(A->n, rp.data(), ci.data(), v.data(), A->sell_height, sp, sc, sv);
     A->sell_slices = (int)sp.size() - 1;
+    A->sell_width = A->sell_slices > 0 ? (int)((sp[1] - sp[0]) / A->sell_height) : 0;
+    for (int q = 0; q < A->sell_slices; ++q)
+      if (sp[q + 1] - sp[q] != (int64_t)A->sell_width * A->sell_height) { A->sell_width = 0; break; }
     A->plan.sell_padded = sp.back();
     A->plan.slice = A->sell_height;
     BG_TRY(upload_vec(A->s_ptr, sp, s));
@@ -749,7 +752,12 @@ struct Driver {
   bool fused_orth = true;   // BG_FUSED_ORTH=0 selects the separate dots / update kernels
   // y = alpha A x (+ beta b): x must have room for the halo behind its n entries when dh is set
   int spmv(double alpha, void* xv, double beta, const void* bv, void* y, bool axpby) {
-    if (dh) { Span sh(prof, PH_HALO); BG_TRY(dh->exchange(xv, skip)); }
+    if (dh) {
+      HaloArgs ha;
+      if (spmv_supports_halo(A) && dh->halo_args(&ha)) return launch_spmv(ctx, A, alpha, xv, beta, bv, y, axpby, skip, &ha);
+      Span sh(prof, PH_HALO);
+      BG_TRY(dh->exchange(xv, skip));
+    }
     return launch_spmv(ctx, A, alpha, xv, beta, bv, y, axpby, skip);
   }
   int dots(const void* Vp, int j, const void* w, int fin, int i, int mk, int nr) {

@@ -12,6 +12,9 @@
 // x is gathered through L1/L2 (it fits the 126 MB L2 for every single-GPU config of BASELINE.json).
 // HBM-bound: algorithmic bytes (s+4)*nnz + 4(n+1) + 2*s*n.
 #include "internal.h"
+#include "peer.cuh"
+
+#include <cstdlib>
 
 namespace bg {
 
@@ -115,6 +118,106 @@ __global__ void __launch_bounds__(128) spmv_sell_f64(int n, int nslices, const i
   }
 }
 
+// sliced ELL with the SAME width W in every slice (stencil matrices: 5- and 7-point grids): no slice pointer
+// to chase, all 2W 128-bit loads of a thread are issued before the first use, then all W*RPT gathers of x --
+// two dependent memory round trips per slice instead of 2+W.  HALO = the kernel carries the halo exchange of
+// a row-partitioned run (internal.h HaloArgs): columns >= n_local are read from the peer-written inbox.
+template <class VT> struct SellVec;
+// loads of the matrix stream as volatile asm: issued in program order, i.e. ALL of a thread's index and
+// value loads leave before the first dependent gather (the compiler otherwise interleaves them to save registers)
+__device__ __forceinline__ int4 ldnc(const int4* p) { int4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+__device__ __forceinline__ int2 ldnc(const int2* p) { int2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ float4 ldnc(const float4* p) { float4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v; }
+__device__ __forceinline__ double2 ldnc(const double2* p) { double2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; }
+template <> struct SellVec<float> {
+  static constexpr int RPT = 4;
+  using VI = int4; using VV = float4;
+  __device__ static void idx(const VI& c, int* o) { o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
+  __device__ static void val(const VV& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct SellVec<double> {
+  static constexpr int RPT = 2;
+  using VI = int2; using VV = double2;
+  __device__ static void idx(const VI& c, int* o) { o[0] = c.x; o[1] = c.y; }
+  __device__ static void val(const VV& v, double* o) { o[0] = v.x; o[1] = v.y; }
+};
+template <class VT, int W, bool AXPBY, bool HALO>
+__global__ void __launch_bounds__(128, 8) spmv_sell_w(int n, int nslices, const int* __restrict__ cols, const VT* __restrict__ vals,
+                                                   const VT* __restrict__ x, VT* __restrict__ y, VT alpha, VT beta,
+                                                   const VT* __restrict__ b, const int* skip, HaloArgs h) {
+  if (skip && *skip) return;
+  using SV = SellVec<VT>;
+  constexpr int RPT = SV::RPT, H = 32 * RPT;
+  if (HALO) {
+    // the first wave of CTAs (always scheduled before anything can wait) stores this rank's boundary
+    // entries into the neighbours' inboxes; nothing in this phase depends on another rank
+    const int pushers = min((int)gridDim.x, 148) * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < pushers) {
+      const PeerHalo* P = h.ph;
+      for (int e = tid; e < h.n_send; e += pushers) {
+        int k = 0;
+        while (e >= P->send_ptr[k + 1]) ++k;
+        ll_store(P->peer_inbox[k] + (e - P->send_ptr[k]), (double)x[h.send_idx[e]], h.seq);
+      }
+    }
+  }
+  const int warps_per_block = blockDim.x / 32, lane = threadIdx.x & 31;
+  for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < nslices; s += gridDim.x * warps_per_block) {
+    const size_t base = (size_t)s * H * W;
+    const typename SV::VI* cp = reinterpret_cast<const typename SV::VI*>(cols + base) + lane;
+    const typename SV::VV* vp = reinterpret_cast<const typename SV::VV*>(vals + base) + lane;
+    typename SV::VI cc[W];
+    typename SV::VV vv[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) cc[k] = ldnc(cp + k * 32);
+#pragma unroll
+    for (int k = 0; k < W; ++k) vv[k] = ldnc(vp + k * 32);
+    VT xv[W][RPT];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      int ci[RPT];
+      SV::idx(cc[k], ci);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        if (HALO && ci[r] >= h.n_local) xv[k][r] = (VT)ll_wait(h.ph->my_inbox + (ci[r] - h.n_local), h.seq);
+        else xv[k][r] = x[ci[r]];
+      }
+    }
+    VT acc[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      VT va[RPT];
+      SV::val(vv[k], va);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) acc[r] += va[r] * xv[k][r];
+    }
+    const int row = s * H + lane * RPT;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+      if (row + r < n) y[row + r] = AXPBY ? alpha * acc[r] + beta * b[row + r] : acc[r];
+  }
+}
+template <class VT, int W>
+static void sell_w_launch(bg_context_t ctx, bg_matrix_t A, int blocks, const VT* x, VT* y, double alpha, double beta, const VT* b,
+                          bool axpby, const int* skip, const HaloArgs* halo) {
+  const int n = A->n, ns = A->sell_slices;
+  const int* c = A->s_col.as<int>();
+  const VT* v = A->s_val.as<VT>();
+  const HaloArgs h = halo ? *halo : HaloArgs();
+  if (halo) {
+    if (axpby) spmv_sell_w<VT, W, true, true><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)alpha, (VT)beta, b, skip, h);
+    else spmv_sell_w<VT, W, false, true><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)1, (VT)0, nullptr, skip, h);
+  } else {
+    if (axpby) spmv_sell_w<VT, W, true, false><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)alpha, (VT)beta, b, skip, h);
+    else spmv_sell_w<VT, W, false, false><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)1, (VT)0, nullptr, skip, h);
+  }
+}
+static bool sell_w_supported(int w) { return w == 3 || w == 5 || w == 7; }
+bool spmv_supports_halo(bg_matrix_t A) { return A->format == BG_SPMV_SELL && sell_w_supported(A->sell_width); }
+
 template <class VT, class MT, int LANES>
 static void csr_launch(bg_context_t ctx, int n, const int* rp, const int* ci, const MT* val, const VT* x, VT* y,
                        double alpha, double beta, const VT* b, bool axpby, const int* skip) {
@@ -140,15 +243,28 @@ static void csr_dispatch(bg_context_t ctx, int lanes, int n, const int* rp, cons
 }
 
 int launch_spmv(bg_context_t ctx, bg_matrix_t A, double alpha, const void* x, double beta, const void* b, void* y,
-                bool axpby, const int* skip) {
+                bool axpby, const int* skip, const HaloArgs* halo) {
   const int n = A->n;
   if (n == 0) return BG_OK;
+  if (halo && !spmv_supports_halo(A)) { set_error("this matrix layout cannot carry the halo exchange inside the SpMV"); return BG_ERR_UNSUPPORTED; }
   if (A->format == BG_SPMV_SELL) {
     const int wpb = 4;
     int64_t blocks = ((int64_t)A->sell_slices + wpb - 1) / wpb;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    if (A->dtype == BG_F32) {
+    static const bool use_w = [] { const char* e = getenv("BG_SPMV_FIXED_WIDTH"); return !(e && e[0] == '0'); }();
+    if (sell_w_supported(A->sell_width) && (use_w || halo)) {
+      const int w = A->sell_width;
+      if (A->dtype == BG_F32) {
+        if (w == 3) sell_w_launch<float, 3>(ctx, A, (int)blocks, (const float*)x, (float*)y, alpha, beta, (const float*)b, axpby, skip, halo);
+        else if (w == 5) sell_w_launch<float, 5>(ctx, A, (int)blocks, (const float*)x, (float*)y, alpha, beta, (const float*)b, axpby, skip, halo);
+        else sell_w_launch<float, 7>(ctx, A, (int)blocks, (const float*)x, (float*)y, alpha, beta, (const float*)b, axpby, skip, halo);
+      } else {
+        if (w == 3) sell_w_launch<double, 3>(ctx, A, (int)blocks, (const double*)x, (double*)y, alpha, beta, (const double*)b, axpby, skip, halo);
+        else if (w == 5) sell_w_launch<double, 5>(ctx, A, (int)blocks, (const double*)x, (double*)y, alpha, beta, (const double*)b, axpby, skip, halo);
+        else sell_w_launch<double, 7>(ctx, A, (int)blocks, (const double*)x, (double*)y, alpha, beta, (const double*)b, axpby, skip, halo);
+      }
+    } else if (A->dtype == BG_F32) {
       if (axpby) spmv_sell_f32<true><<<(int)blocks, 128, 0, ctx->stream>>>(n, A->sell_slices, A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.as<float>(), (const float*)x, (float*)y, (float)alpha, (float)beta, (const float*)b, skip);
       else spmv_sell_f32<false><<<(int)blocks, 128, 0, ctx->stream>>>(n, A->sell_slices, A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.as<float>(), (const float*)x, (float*)y, 1.f, 0.f, nullptr, skip);
     } else {
