@@ -363,13 +363,13 @@ extern "C" int bg_dist_destroy(bg_dist_t D) {
 extern "C" int bg_dist_gmres_solve(bg_dist_t D, const void* d_b, void* d_x, const bg_gmres_opts* o, bg_gmres_result* r) {
   if (!D || !d_b || !d_x || !o) return BG_ERR_ARG;
   D->solve_index++; D->exchange_in_solve = 0;
-  return gmres_solve_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, D);
+  return gmres_solve_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, D->nranks > 1 ? D : nullptr);  // one rank: plain single-GPU solve
 }
 
 extern "C" int bg_dist_profile(bg_dist_t D, const void* d_b, void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st) {
   if (!D || !d_b || !d_x || !o || !st) return BG_ERR_ARG;
   D->solve_index++; D->exchange_in_solve = 0;
-  return gmres_profile_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, st, D);
+  return gmres_profile_dist(D->ctx, D->S, D->A, D->M, d_b, d_x, o, r, st, D->nranks > 1 ? D : nullptr);
 }
 
 extern "C" int bg_dist_bench_comm(bg_dist_t D, int what, int count, int reps, double* us) {

@@ -349,7 +349,7 @@ extern "C" void bg_precond_opts_default(bg_precond_opts* o) {
   o->ilut_tau = 1e-3;
   o->chunk_bytes = 4096;
   o->stages = 2;
-  o->warps_per_cta = 4;
+  o->warps_per_cta = 3;
 }
 
 template <class T> static int upload_level_stream(bg_context_t ctx, const LevelStream<T>& h, LevelStreamDev& d) {
@@ -484,7 +484,7 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
   M->use_tma = o.use_tma != 0;
   M->fb_chunk_bytes = o.chunk_bytes > 0 ? o.chunk_bytes : 4096;
   M->fb.stages = std::min(8, std::max(2, o.stages > 0 ? o.stages : 2));
-  M->fb.warps_per_cta = std::min(16, std::max(1, o.warps_per_cta > 0 ? o.warps_per_cta : 4));
+  M->fb.warps_per_cta = std::min(16, std::max(1, o.warps_per_cta > 0 ? o.warps_per_cta : 3));
   int rc = precond_install_dt<T>(M, F.L, F.U, true, block ? blk.data() : nullptr, nb);
   if (rc < 0) { delete M; return rc; }
   *out = M;

@@ -144,7 +144,7 @@ typedef struct {
   int ilut_lfil; double ilut_tau; /* used by bg_precond_create_ilut                                */
   int chunk_bytes;     /* BG_TRSV_BLOCK: target size of one bulk copy of the factor stream (4096) */
   int stages;          /* BG_TRSV_BLOCK: ring slots per warp (2)                                  */
-  int warps_per_cta;   /* BG_TRSV_BLOCK: block solves per CTA (4)                                 */
+  int warps_per_cta;   /* BG_TRSV_BLOCK: block solves per CTA (3)                                 */
 } bg_precond_opts;
 BG_API void bg_precond_opts_default(bg_precond_opts* o);
 /* MyNONE (preconditioner.h) */
