@@ -330,7 +330,7 @@ def run_single(args, local, nx, precond, steps, headline):
         info, pinfo = A.info(), M.info()
         trsv_kernel = "trsv_block_fused (L and U solve of every diagonal block, one launch)" if args.schedule == "block" else "trsv_level_walk/_wide (L and U solve)"
         kernels = {
-            "spmv_sell_f64": (st.spmv_ms, st.spmv_bytes, st.spmv_calls),
+            "spmv_sell_w<double,5> (sliced ELL, fixed width, all loads in flight)" if info.format == bg.SPMV_SELL else "spmv_csr_vector": (st.spmv_ms, st.spmv_bytes, st.spmv_calls),
             trsv_kernel: (st.trsv_ms, st.trsv_bytes, st.trsv_calls),
             "dots_kernel (V^T w and w.w, TMA-staged tiles)": (st.dots_ms, st.dots_bytes, st.dots_calls),
             "update_kernel (w - V h, normalised, TMA-staged tiles)": (st.update_ms, st.update_bytes, st.update_calls),
@@ -534,7 +534,7 @@ def ncu_traffic(kernel):
     if not os.path.exists(p):
         return None
     for key, val in json.load(open(p)).items():
-        if kernel.startswith(key):
+        if kernel.startswith(key) or key in kernel:
             return val
     return None
 
