@@ -180,6 +180,10 @@ static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::ve
     std::vector<T> sv;
     build_sell(A->n, rp.data(), ci.data(), v.data(), A->sell_height, sp, sc, sv);
     A->sell_slices = (int)sp.size() - 1;
+    // a few short slices (grid boundaries) must not cost the fixed-width kernels: pad every slice to the
+    // longest row when that adds at most 5 % of storage
+    if ((int64_t)A->plan.max_row * A->sell_height * A->sell_slices <= sp.back() + sp.back() / 20 && (int64_t)A->plan.max_row * A->sell_height * A->sell_slices != sp.back())
+      build_sell(A->n, rp.data(), ci.data(), v.data(), A->sell_height, sp, sc, sv, A->plan.max_row);
     A->sell_width = A->sell_slices > 0 ? (int)((sp[1] - sp[0]) / A->sell_height) : 0;
     for (int q = 0; q < A->sell_slices; ++q)
       if (sp[q + 1] - sp[q] != (int64_t)A->sell_width * A->sell_height) { A->sell_width = 0; break; }

@@ -668,11 +668,11 @@ SpmvPlan inspect_rows(int n, const int* rp) {
 
 template <class T>
 void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std::vector<int64_t>& slice_ptr,
-                std::vector<int>& cols, std::vector<T>& vals) {
+                std::vector<int>& cols, std::vector<T>& vals, int min_width) {
   const int ns = (n + slice - 1) / slice;
   slice_ptr.assign(ns + 1, 0);
   for (int s = 0; s < ns; ++s) {
-    int mx = 0;
+    int mx = min_width;
     for (int i = s * slice; i < std::min(n, (s + 1) * slice); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
     slice_ptr[s + 1] = slice_ptr[s] + (int64_t)mx * slice;
   }
@@ -692,7 +692,7 @@ void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std:
       for (; k < wid; ++k) cols[slice_ptr[s] + (int64_t)k * slice + t] = i;
     }
 }
-template void build_sell<float>(int, const int*, const int*, const float*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<float>&);
-template void build_sell<double>(int, const int*, const int*, const double*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<double>&);
+template void build_sell<float>(int, const int*, const int*, const float*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<float>&, int);
+template void build_sell<double>(int, const int*, const int*, const double*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<double>&, int);
 
 }  // namespace bg

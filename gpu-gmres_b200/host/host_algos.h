@@ -144,9 +144,9 @@ struct SpmvPlan {
   int64_t sell_padded = 0;
 };
 SpmvPlan inspect_rows(int n, const int* rp);
-// sliced ELL (slice height 32, slices padded to their own max row length); slice_ptr in entries.
+// sliced ELL (slices padded to max(their own longest row, min_width)); slice_ptr in entries.
 template <class T>
 void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std::vector<int64_t>& slice_ptr,
-                std::vector<int>& cols, std::vector<T>& vals);
+                std::vector<int>& cols, std::vector<T>& vals, int min_width = 0);
 
 }  // namespace bg
