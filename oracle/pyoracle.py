@@ -57,6 +57,18 @@ def ilupp():
     return _ilupp
 
 
+_ref_gmres = None
+
+
+def ref_gmres_lib():
+    """The reference's own gmres.cu / preconditioner.cu / leftILU.cu compiled unchanged (oracle/_ref/libref_gmres.so)."""
+    global _ref_gmres
+    p = os.path.join(_HERE, "_ref", "libref_gmres.so")
+    if _ref_gmres is None and os.path.exists(p):
+        _ref_gmres = C.CDLL(p)
+    return _ref_gmres
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -204,3 +216,91 @@ def ilupp_gmres(fac, b, restart=100, max_iter=6000, rel_tol=8.0, abs_tol=8.0):
 
 def ilupp_free(fac):
     ilupp().ilupp_destroy(fac.pop("_handle"))
+
+
+# --------------------------------------------------------------------------- the reference's compiled host solver
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def ref_host_gmres_ilu0(rowptr, col, val, b, x0, m, max_iter, tol, f):
+    """Reference GMRES() (src/gmres.cu:1904-2066) + MyILU0::HostPrecond, REAL = float, factors f (dict of ilu0())."""
+    L = ref_gmres_lib(); n = len(rowptr) - 1
+    x = np.array(x0, dtype=np.float32, copy=True)
+    it, t = C.c_int(max_iter), C.c_float(tol)
+    lv, uv = _f32(f["lv"]).copy(), _f32(f["uv"]).copy()
+    lp, li, up, ui = (_i32(f[k]).copy() for k in ("lp", "li", "up", "ui"))
+    L.ref_gmres_ilu0.restype = C.c_int
+    flag = L.ref_gmres_ilu0(C.c_int(n), _p(_f32(val)), _p(_i32(rowptr)), _p(_i32(col)), _p(lv), _p(lp), _p(li), _p(uv), _p(up), _p(ui),
+                            _p(x), _p(_f32(b)), C.c_int(m), C.byref(it), C.byref(t))
+    return flag, x, it.value, t.value
+
+
+def ref_host_gmres_none(rowptr, col, val, b, x0, m, max_iter, tol):
+    L = ref_gmres_lib(); n = len(rowptr) - 1
+    x = np.array(x0, dtype=np.float32, copy=True)
+    it, t = C.c_int(max_iter), C.c_float(tol)
+    L.ref_gmres_none.restype = C.c_int
+    flag = L.ref_gmres_none(C.c_int(n), _p(_f32(val)), _p(_i32(rowptr)), _p(_i32(col)), _p(x), _p(_f32(b)), C.c_int(m), C.byref(it), C.byref(t))
+    return flag, x, it.value, t.value
+
+
+def ref_host_ilu0_apply(f, vec):
+    L = ref_gmres_lib(); n = len(f["lp"]) - 1
+    out = np.zeros(n, dtype=np.float32)
+    lv, uv = _f32(f["lv"]).copy(), _f32(f["uv"]).copy()
+    lp, li, up, ui = (_i32(f[k]).copy() for k in ("lp", "li", "up", "ui"))
+    L.ref_ilu0_hostprecond(C.c_int(n), _p(lv), _p(lp), _p(li), _p(uv), _p(up), _p(ui), _p(_f32(vec)), _p(out))
+    return out
+
+
+def _split_args(g):
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64).copy()
+    return [f64(g["lv"]), _i32(g["lp"]).copy(), _i32(g["li"]).copy(), f64(g["uv"]), _i32(g["up"]).copy(), _i32(g["ui"]).copy(),
+            _f32(g["middle"]).copy(), _i32(g["permRow"]).copy(), _i32(g["permCol"]).copy(), _f32(g["lscale"]).copy(), _f32(g["rscale"]).copy()]
+
+
+def ref_host_gmresilu_split(rowptr, col, val, b, x0, m, max_iter, tol, g):
+    """Reference GMRESilu() (src/gmres.cu:2069-2252) + MyILUPPfloat host twins on ILU++ factors g (double), float vectors."""
+    L = ref_gmres_lib(); n = len(rowptr) - 1
+    x = np.array(x0, dtype=np.float32, copy=True)
+    it, t = C.c_int(max_iter), C.c_float(tol)
+    a = _split_args(g)
+    L.ref_gmresilu_split.restype = C.c_int
+    flag = L.ref_gmresilu_split(C.c_int(n), _p(_f32(val)), _p(_i32(rowptr)), _p(_i32(col)), *[_p(v) for v in a], _p(x), _p(_f32(b)),
+                                C.c_int(m), C.byref(it), C.byref(t))
+    return flag, x, it.value, t.value
+
+
+def ref_host_split_apply(which, g, vec):
+    """which: 1 left, 2 right, 3 starting_value, 4 rhs (MyILUPPfloat::HostPrecond_*)."""
+    L = ref_gmres_lib(); n = len(g["lp"]) - 1
+    out = np.zeros(n, dtype=np.float32)
+    a = _split_args(g)
+    L.ref_split_hostprecond(C.c_int(which), C.c_int(n), *[_p(v) for v in a], _p(_f32(vec)), _p(out))
+    return out
+
+
+def ref_get_level(is_l, rowptr, col, val):
+    L = ref_gmres_lib(); n = len(rowptr) - 1
+    level = np.zeros(n, dtype=np.int32)
+    L.ref_getLevel(C.c_int(int(is_l)), _p(_f32(val)), _p(_i32(rowptr)), _p(_i32(col)), _p(level), C.c_int(n))
+    return level
+
+
+def ref_generate_level(rowptr, col, val):
+    L = ref_gmres_lib(); n = len(rowptr) - 1
+    node = np.zeros(n, dtype=np.int32); level = np.zeros(n, dtype=np.int32)
+    L.ref_generateLevel(C.c_int(n), _p(_f32(val)), _p(_i32(rowptr)), _p(_i32(col)), _p(node), _p(level))
+    return node, level
+
+
+def ref_left_ilu(rowptr, col, val):
+    """Reference leftILU() (src/leftILU.cu:27-336).  Needs a CUDA device (it cudaMallocs even when every level runs on the CPU)."""
+    L = ref_gmres_lib(); n = len(rowptr) - 1; nnz = int(rowptr[-1])
+    rp, ci, v = _i32(rowptr).copy(), _i32(col).copy(), _f32(val).copy()
+    lp, up = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32)
+    li, ui = np.zeros(nnz + n, np.int32), np.zeros(nnz + n, np.int32)
+    lv, uv = np.zeros(nnz + n, np.float32), np.zeros(nnz + n, np.float32)
+    L.ref_leftILU(C.c_int(n), _p(v), _p(rp), _p(ci), _p(lv), _p(lp), _p(li), _p(uv), _p(up), _p(ui))
+    return dict(lp=lp, li=li[: lp[-1]], lv=lv[: lp[-1]], up=up, ui=ui[: up[-1]], uv=uv[: up[-1]])

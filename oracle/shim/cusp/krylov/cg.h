@@ -1,0 +1,2 @@
+#pragma once
+#include "../csr_matrix.h"

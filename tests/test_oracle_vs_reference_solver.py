@@ -1,0 +1,114 @@
+"""Pins the oracle's GMRES / GMRESilu / preconditioner / level-set restatements against the REFERENCE'S OWN
+solver code: src/gmres.cu, src/preconditioner.cu, src/leftILU.cu compiled unchanged by nvcc into
+oracle/_ref/libref_gmres.so (oracle/Makefile; stand-in headers under oracle/shim/, aborting stubs for the
+removed legacy cuSPARSE / cuBLAS device entry points).  Only the reference's HOST twins run here, in the
+reference's own precision (REAL = float, gmres.h:55): results must be BIT-IDENTICAL to the oracle's f32 /
+f32f64 instantiations -- flag, iteration count (*max_iter), achieved residual (*tol) and every entry of x.
+
+The test that calls the reference's leftILU() needs a CUDA device (it cudaMallocs before anything else,
+src/leftILU.cu:60-90) and is marked gpu.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+CASES = ["pg2d_24x20", "th3d_8x7x6", "rand_300"]
+
+
+def _need(oracle):
+    if oracle.ref_gmres_lib() is None:
+        pytest.skip("oracle/_ref/libref_gmres.so not built (needs /root/reference at build time)")
+
+
+def _ilu0(oracle, g):
+    f = oracle.ilu0(g["rowptr"], g["col"], g["val"], "f32")
+    pc = oracle.Precond(oracle.PC_ILU0, len(g["rowptr"]) - 1, "f32", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+    return f, pc
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("m,x0,tol", [(32, 0.0, 1e-6), (5, 1.0, 1e-6), (32, 0.0, 1e-3), (7, 0.5, 3e-5)])
+def test_gmres_ilu0_bit_identical_with_reference_host_gmres(oracle, name, m, x0, tol):
+    """GMRES() src/gmres.cu:1904-2066 + MyILU0::HostPrecond src/preconditioner.cu:205-251."""
+    _need(oracle)
+    g = load_golden(name)
+    rp, ci, v, b = g["rowptr"], g["col"], g["val"], g["b"]
+    n = len(rp) - 1
+    f, pc = _ilu0(oracle, g)
+    fo, xo, ito, ro, _ = oracle.gmres(rp, ci, v, b, np.full(n, x0), m, 400, tol, pc)
+    fr, xr, itr, rr = oracle.ref_host_gmres_ilu0(rp, ci, v, b, np.full(n, x0), m, 400, tol, f)
+    assert (fo, ito) == (fr, itr)          # return value and *max_iter
+    assert np.float32(ro) == np.float32(rr)  # *tol out
+    assert np.array_equal(xo, xr)
+
+
+@pytest.mark.parametrize("name", ["pg2d_24x20", "th3d_8x7x6"])
+def test_gmres_unpreconditioned_bit_identical(oracle, name):
+    _need(oracle)
+    g = load_golden(name)
+    rp, ci, v, b = g["rowptr"], g["col"], g["val"], g["b"]
+    n = len(rp) - 1
+    pc = oracle.Precond(oracle.PC_NONE, n, "f32")
+    fo, xo, ito, ro, _ = oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 150, 1e-5, pc)
+    fr, xr, itr, rr = oracle.ref_host_gmres_none(rp, ci, v, b, np.zeros(n), 32, 150, 1e-5)
+    assert (fo, ito) == (fr, itr) and np.float32(ro) == np.float32(rr) and np.array_equal(xo, xr)
+
+
+@pytest.mark.parametrize("name", ["pg2d_24x20", "th3d_8x7x6"])
+def test_gmresilu_split_bit_identical_with_reference(oracle, name):
+    """GMRESilu() src/gmres.cu:2069-2252 + MyILUPPfloat::HostPrecond_{left,right,starting_value}
+    src/preconditioner.cu:1350-1416 on the ILU++ factors of the golden fixture (double factors, float vectors)."""
+    _need(oracle)
+    g = load_golden(name + "_split")
+    rp, ci, v, b = g["rowptr"], g["col"], g["val"], g["b"]
+    n = len(rp) - 1
+    keys = ("lp", "li", "lv", "up", "ui", "uv", "middle", "lscale", "rscale", "permRow", "permCol")
+    pc = oracle.Precond(oracle.PC_SPLIT, n, "f32f64", **{k: g[k] for k in keys})
+    rng = np.random.default_rng(3)
+    vec = rng.standard_normal(n)
+    for which in (1, 2, 3):
+        assert np.array_equal(pc.apply(which, vec), oracle.ref_host_split_apply(which, g, vec))
+    for m, x0, tol in ((32, np.zeros(n), 1e-6), (6, np.ones(n), 1e-5), (32, g["f32f64_warm_x0"], 1e-6)):
+        fo, xo, ito, ro, _ = oracle.gmres(rp, ci, v, b, x0, m, 2000, tol, pc)
+        fr, xr, itr, rr = oracle.ref_host_gmresilu_split(rp, ci, v, b, x0, m, 2000, tol, g)
+        assert (fo, ito) == (fr, itr) and np.float32(ro) == np.float32(rr)
+        assert np.array_equal(xo, xr)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_level_sets_and_ilu0_apply_bit_identical(oracle, bg, name):
+    """getLevel src/gmres.cu:1033-1077 and generateLevel src/leftILU.cu:339-368, the reference's compiled code vs
+    the oracle AND vs the product's host code (bg_host_trsv_levels / bg_host_factor_levels)."""
+    _need(oracle)
+    g = load_golden(name)
+    rp, ci, v = g["rowptr"], g["col"], g["val"]
+    f, pc = _ilu0(oracle, g)
+    for is_l, (p, i, val) in ((True, (f["lp"], f["li"], f["lv"])), (False, (f["up"], f["ui"], f["uv"]))):
+        ref = oracle.ref_get_level(is_l, p, i, val)
+        assert np.array_equal(ref, oracle.get_level(is_l, p, i, val))
+        assert np.array_equal(ref, bg.host_trsv_levels(is_l, p, i, val.astype(np.float32)))
+    node, level = oracle.ref_generate_level(rp, ci, v)
+    assert np.array_equal(level, oracle.generate_level(rp, ci, v)[0])
+    assert np.array_equal(level, bg.host_factor_levels(rp, ci, v.astype(np.float32)))
+    x = np.random.default_rng(5).standard_normal(len(rp) - 1)
+    assert np.array_equal(pc.apply(0, x), oracle.ref_host_ilu0_apply(f, x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_reference_leftILU_matches_product_and_oracle(oracle, bg, name):
+    """leftILU() src/leftILU.cu:27-336 run as the reference runs it (on a CUDA device): L/U pattern bit-exact,
+    values bit-exact with the oracle's f32 factorisation and with bg_host_ilu0."""
+    _need(oracle)
+    g = load_golden(name)
+    rp, ci, v = g["rowptr"], g["col"], g["val"]
+    ref = oracle.ref_left_ilu(rp, ci, v)
+    f = oracle.ilu0(rp, ci, v, "f32")
+    F = bg.host_ilu0(rp, ci, v.astype(np.float32))
+    for k in ("lp", "li", "up", "ui"):
+        assert np.array_equal(ref[k], f[k]) and np.array_equal(ref[k], F[k]), k
+    # leftILU stores 1.0 on L's diagonal slot and the factored values elsewhere
+    for k in ("lv", "uv"):
+        assert np.array_equal(ref[k], f[k].astype(np.float32)), k
+        assert np.array_equal(ref[k], F[k]), k
