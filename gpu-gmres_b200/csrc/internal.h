@@ -94,6 +94,7 @@ struct LevelStreamDev {
 struct FusedBlockDev {
   int n = 0, nblocks = 0, max_rows = 0, max_levels_L = 0, max_levels_U = 0, max_chunk_bytes = 0, max_chunks = 0;
   int stages = 4, warps_per_cta = 4, tab_stride = 0;
+  bool lattice = false;  // index-free layout of 5-point grid tiles (host_algos.h FusedBlockStream::lattice)
   int64_t bytes = 0, total_steps = 0;
   DevBuf perm, iperm, dinv, blk, chunk_tab, stream;
   std::vector<int> h_perm;     // new -> old, kept for permuting matrices on the host

@@ -373,6 +373,7 @@ template <class T> static int upload_fused_stream(bg_context_t ctx, const FusedB
   d.n = h.n; d.nblocks = h.nblocks; d.max_rows = h.max_rows; d.max_levels_L = h.max_levels_L; d.max_levels_U = h.max_levels_U;
   d.max_chunk_bytes = h.max_chunk_bytes; d.max_chunks = h.max_chunks; d.total_steps = h.total_steps;
   d.h_perm = h.perm;
+  d.lattice = h.lattice;
   d.serial = ++g_order_serial;
   std::vector<int> inv(h.n);
   for (int i = 0; i < h.n; ++i) inv[h.perm[i]] = i;
@@ -401,7 +402,8 @@ static int precond_install(bg_precond_t M, const Csr<FH>& L, const Csr<FH>& U, b
   try {
     if (M->schedule == BG_TRSV_BLOCK) {
       FusedBlockStream<FT> fs;
-      pack_fused_block_stream<FT>(unit_lower, Lf, Uf, nblocks, block_of_row, M->fb_chunk_bytes, fs);
+      static const bool allow_lattice = [] { const char* e = getenv("BG_TRSV_LATTICE"); return !(e && e[0] == '0'); }();
+      pack_fused_block_stream<FT>(unit_lower, Lf, Uf, nblocks, block_of_row, M->fb_chunk_bytes, fs, allow_lattice);
       BG_TRY(upload_fused_stream(M->ctx, fs, M->fb));
     } else {
       LevelStream<FT> ll, lu;

@@ -24,6 +24,14 @@
 //    device performs two UNIT solves on d .* r: no division and no per-row diagonal in the stream.
 //
 // Bytes per row (5-point ILU(0), FP64): L 24 B + U 24 B + 1/diag 8 B + rhs 8 B + result 8 B.
+//
+//  * LATTICE layout (host_algos.h; chosen by the packer when every block is a tx x ty grid tile, tx <= 32, whose
+//    factors couple only west/south and east/north neighbours, i.e. ILU(0) of a 5-point stencil): the stream
+//    holds NO indices, two values per row per factor (32 B per row in FP64).  Lane x owns column x of the tile and
+//    walks it along the anti-diagonal wavefront: its south (north) operand is its own previous result, kept in
+//    a register, the west (east) one arrives from lane x-1 (x+1) by one warp shuffle.  A step is a shuffle and
+//    two FMAs instead of ~40 instructions of index decoding, shared-memory gathers and a warp barrier, which
+//    takes the block solve from latency-bound (~190 ns per step) to HBM-bound.
 #include "internal.h"
 
 namespace bg {
@@ -60,6 +68,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+#ifdef BG_TRSV_TIMING
+// development aid: %globaltimer stamps of the warp that solves block `g_trsv_probe` (bg_debug_trsv_times)
+__device__ unsigned long long g_trsv_t[96];
+__device__ int g_trsv_probe = 0;
+__device__ __forceinline__ unsigned long long gt_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifdef BG_TRSV_TIMING_CHUNKS
+#define TSTAMP(k) do { if (b == g_trsv_probe && lane == 0 && (k) < 96) g_trsv_t[(k)] = gt_ns(); } while (0)
+#else
+#define TSTAMP(k) do { if ((k) < 8 && b == g_trsv_probe && lane == 0) g_trsv_t[(k)] = gt_ns(); } while (0)
+#endif
+#else
+#define TSTAMP(k) do {} while (0)
+#endif
 
 struct FbArgs {
   const BlockDesc* blk;
@@ -150,10 +172,59 @@ __device__ __forceinline__ void run_steps_generic(int lane, int K, int nst, int 
   }
 }
 
+// one chunk of the LATTICE layout: whole anti-diagonals of a tx x ty tile, (west|east, south|north) value pairs.
+// Branch-free step: lanes off the current anti-diagonal compute with zero operands (their zprev is not read by
+// anybody: a lane's west/east neighbour is only consulted while that neighbour is inside the wavefront), so the
+// warp never diverges around the shuffle and the per-step instruction stream is two shuffles, two FMAs, two
+// shared loads for the NEXT step, one predicated store and a handful of warp-uniform index updates.
+template <class FT, class CT, bool LOWER>
+__device__ __forceinline__ void lattice_steps(int lane, int nlev, int e0, const typename PairOf<FT>::type* __restrict__ pairs,
+                                              int tx, int ty, CT* xl, CT& zprev_io) {
+  using P = typename PairOf<FT>::type;
+  const int D = tx + ty - 2, ty1 = ty - 1, tx1 = tx - 1, step = LOWER ? tx : -tx;
+  int d = LOWER ? e0 : D - e0;        // anti-diagonal of the current step (warp-uniform)
+  int u = 0;                          // pairs of this chunk consumed by earlier steps (warp-uniform)
+  int xlo = max(0, d - ty1), cnt = min(d, tx1) - xlo + 1;
+  int li = lane + tx * (d - lane);    // this lane's row on the current anti-diagonal (meaningful while active)
+  bool act = (unsigned)(lane - xlo) < (unsigned)cnt;
+  CT r = (CT)0, ca = (CT)0, cb = (CT)0;
+  if (act) { r = xl[li]; const P c = pairs[u + lane - xlo]; ca = (CT)c.x; cb = (CT)c.y; }
+  CT zprev = zprev_io;
+#pragma unroll 2
+  for (int s = 0; s < nlev; ++s) {
+    // operands of the next step (independent of the dependency chain)
+    const int d2 = LOWER ? d + 1 : d - 1;
+    const int u2 = u + cnt;
+    const int xlo2 = max(0, d2 - ty1), cnt2 = min(d2, tx1) - xlo2 + 1;
+    const int li2 = li + step;
+    const bool act2 = (s + 1 < nlev) && (unsigned)(lane - xlo2) < (unsigned)cnt2;
+    CT r2 = (CT)0, ca2 = (CT)0, cb2 = (CT)0;
+    if (act2) { r2 = xl[li2]; const P c = pairs[u2 + lane - xlo2]; ca2 = (CT)c.x; cb2 = (CT)c.y; }
+    // the chain: own previous result (south / north) and the neighbour lane's (west / east)
+    const CT t = r - cb * zprev;
+    const CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
+    const CT z = t - ca * zn;
+    if (act) xl[li] = z;
+    zprev = z;  // inactive lanes: r = ca = cb = 0 gives z = 0
+    d = d2; u = u2; xlo = xlo2; cnt = cnt2; li = li2; act = act2; r = r2; ca = ca2; cb = cb2;
+  }
+  zprev_io = zprev;
+}
+template <class FT, class CT>
+__device__ __forceinline__ void run_lattice_chunk(int lane, const unsigned char* rec, int tx, int ty, CT* xl, CT& zprev) {
+  using P = typename PairOf<FT>::type;
+  const uint2 h = *reinterpret_cast<const uint2*>(rec);
+  const int nlev = (int)(h.x & 0xffffu), e0 = (int)(h.x >> 16);
+  const P* pairs = reinterpret_cast<const P*>(rec + 16);
+  if (e0 == 0) zprev = (CT)0;  // first chunk of a factor
+  if ((h.y & 0xffffu) != 0) lattice_steps<FT, CT, true>(lane, nlev, e0, pairs, tx, ty, xl, zprev);
+  else lattice_steps<FT, CT, false>(lane, nlev, e0, pairs, tx, ty, xl, zprev);
+}
+
 // GATHER: vectors in the caller's original row order, r scaled by 1/diag(U) while loading.
 // !GATHER: vectors in block-major order and already row-scaled (the solver runs on D^-1 P A P^T,
 //          D^-1 P b), so a block's right-hand side / result is one bulk copy each way.
-template <class VT, class FT, class CT, bool GATHER>
+template <class VT, class FT, class CT, bool GATHER, bool LATTICE>
 __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __restrict__ in, VT* __restrict__ out,
                                                         const int* skip) {
   if (skip && *skip) return;
@@ -174,14 +245,25 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+#ifdef BG_TRSV_TIMING
+  if ((int)(blockIdx.x * nw + wid) == g_trsv_probe && lane == 0) g_trsv_t[7] = gt_ns();  // kernel entry of the probed warp
+#endif
   uint32_t g0 = 0;   // ring-global index of the current block's first chunk (monotone per warp)
   uint32_t nin = 0;  // bulk loads of a right-hand side so far (phase of bar_in)
   for (int b = blockIdx.x * nw + wid; b < a.nblocks; b += gridDim.x * nw) {
     // descriptor and chunk table are fetched in one round trip (the table has a fixed stride)
+    TSTAMP(0);
     const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.blk + b));
     for (int i = lane; i < a.tab_stride; i += 32) coff[i] = __ldg(a.chunk_tab + (size_t)b * a.tab_stride + i);
     const int row0 = d0.x, nb = d0.y, nch = d0.w;
+    int tx = 0, ty = 0;
+    if (LATTICE) {
+      const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.blk + b) + 1);
+      tx = d1.z; ty = d1.w;
+    }
+    CT zprev = (CT)0;
     __syncwarp();
+    TSTAMP(1);
     auto issue = [&](int c) {  // lane 0 only
       const uint32_t st = (g0 + (uint32_t)c) % (uint32_t)a.stages;
       const uint32_t o0 = coff[c], bytes = (coff[c + 1] - o0) * 16u;
@@ -198,9 +280,11 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
       for (int c = 0; c < nch && c < a.stages; ++c) issue(c);
     }
     __syncwarp();
+    TSTAMP(2);
     if (bulk_vec) {
       mbar_wait(bar_in, nin & 1u);
       ++nin;
+      TSTAMP(3);
     } else {
       for (int i = lane; i < nb; i += 32) {
         if (GATHER) xl[i] = (CT)in[__ldg(a.perm + row0 + i)] * (CT)__ldg(dinv + row0 + i);
@@ -211,7 +295,17 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
     for (int c = 0; c < nch; ++c) {
       const uint32_t g = g0 + (uint32_t)c, st = g % (uint32_t)a.stages;
       mbar_wait(&bars[st], (g / (uint32_t)a.stages) & 1u);
+      TSTAMP(8 + 2 * c);
       const unsigned char* rec = ring + (size_t)st * a.slot_bytes;
+      if (LATTICE) {
+        // a lane's next read of xl (its own column) follows its own write: no warp barrier per step; the
+        // next chunk's first operands may have been written by this lane only
+        run_lattice_chunk<FT, CT>(lane, rec, tx, ty, xl, zprev);
+        __syncwarp();  // every lane is past its last read of this ring slot
+        TSTAMP(9 + 2 * c);
+        if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
+        continue;
+      }
       const uint2 h = *reinterpret_cast<const uint2*>(rec);
       const int ns = (int)(h.x & 0xffffu), K = (int)(h.x >> 16), nst = (int)(h.y & 0xffffu), nsA = (int)(h.y >> 16);
       const unsigned char* cnts = rec + 16;
@@ -230,8 +324,10 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
         default: run_steps_generic<FT, CT>(lane, K, nst, nsA, cnts, quads, vals, xl); break;
       }
       // every lane is past its last read of this ring slot: refill it
+      TSTAMP(9 + 2 * c);
       if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
     }
+    TSTAMP(4);
     if (bulk_vec) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of xl -> async proxy
       __syncwarp();
@@ -245,8 +341,12 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
       for (int i = lane; i < nb; i += 32) out[GATHER ? __ldg(a.perm + row0 + i) : row0 + i] = (VT)xl[i];
     }
     __syncwarp();
+    TSTAMP(5);
     g0 += (uint32_t)nch;
   }
+#ifdef BG_TRSV_TIMING
+  if (blockIdx.x * nw + wid == g_trsv_probe && lane == 0) { if (kBulkVec) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); g_trsv_t[6] = gt_ns(); }
+#endif
   if (kBulkVec && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // results are in HBM before exit
 }
 
@@ -268,11 +368,13 @@ int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void*
     set_error("block TRSV needs %zu bytes of shared memory per CTA (limit %zu): use smaller blocks", smem, ctx->smem_optin);
     return BG_ERR_UNSUPPORTED;
   }
-  auto kern = gather ? trsv_block_fused<VT, FT, CT, true> : trsv_block_fused<VT, FT, CT, false>;
-  static size_t attr_set[2] = {0, 0};  // per template instantiation
-  if (attr_set[gather ? 1 : 0] < smem) {
+  auto kern = S.lattice ? (gather ? trsv_block_fused<VT, FT, CT, true, true> : trsv_block_fused<VT, FT, CT, false, true>)
+                        : (gather ? trsv_block_fused<VT, FT, CT, true, false> : trsv_block_fused<VT, FT, CT, false, false>);
+  static size_t attr_set[4] = {0, 0, 0, 0};  // per template instantiation
+  const int ai = (gather ? 1 : 0) + (S.lattice ? 2 : 0);
+  if (attr_set[ai] < smem) {
     BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    attr_set[gather ? 1 : 0] = ctx->smem_optin;
+    attr_set[ai] = ctx->smem_optin;
   }
   // resident CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
   int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(228 * 1024) / (smem + 1024)));
@@ -285,6 +387,13 @@ int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void*
 }
 
 }  // namespace
+
+#ifdef BG_TRSV_TIMING
+extern "C" BG_API int bg_debug_trsv_times(int probe_block, unsigned long long* out96) {
+  if (probe_block >= 0) return cudaMemcpyToSymbol(g_trsv_probe, &probe_block, sizeof(int)) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out96, g_trsv_t, sizeof(unsigned long long) * 96) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_trsv_block(bg_context_t ctx, const FusedBlockDev& S, int vec_dt, int fac_dt, bool gather, const void* in,
                       void* out, const int* skip) {

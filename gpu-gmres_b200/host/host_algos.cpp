@@ -429,7 +429,7 @@ template void pack_level_stream<double>(bool, bool, const Csr<double>&, int, Lev
 
 template <class T>
 void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, int nblocks, const int* block_of_row,
-                             int chunk_target, FusedBlockStream<T>& out) {
+                             int chunk_target, FusedBlockStream<T>& out, bool allow_lattice) {
   if (!unit_lower) throw std::invalid_argument("the block schedule needs a unit lower factor");
   const int n = L.n;
   out.n = n;
@@ -569,11 +569,100 @@ void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, 
       si = sj;
     }
   };
+  // ---- lattice layout: is every block a tx x ty tile with west/south (L) and east/north (U) couplings only?
+  std::vector<int> ltx(nblocks, 0), lty(nblocks, 0);
+  auto lattice_dims = [&](int base, int nb, int& tx, int& ty) -> bool {
+    tx = 0;
+    for (int li = 0; li < nb && !tx; ++li) {
+      const int r = out.perm[base + li];
+      for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p) {
+        if (block_of_row[L.ci[p]] != block_of_row[r]) throw std::invalid_argument("factor couples two blocks");
+        const int lc = local[L.ci[p]];
+        if (lc != li - 1) { tx = li - lc; break; }
+      }
+    }
+    if (!tx) tx = nb;  // a single lattice row
+    if (tx < 1 || tx > 32 || nb % tx) return false;
+    ty = nb / tx;
+    for (int li = 0; li < nb; ++li) {
+      const int r = out.perm[base + li], x = li % tx, y = li / tx;
+      for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p) {
+        const int lc = local[L.ci[p]];
+        if (!((x > 0 && lc == li - 1) || (y > 0 && lc == li - tx))) return false;
+      }
+      for (int p = U.rp[r] + 1; p < U.rp[r + 1]; ++p) {
+        if (block_of_row[U.ci[p]] != block_of_row[r]) throw std::invalid_argument("factor couples two blocks");
+        const int lc = local[U.ci[p]];
+        if (!((x < tx - 1 && lc == li + 1) || (y < ty - 1 && lc == li + tx))) return false;
+      }
+    }
+    return true;
+  };
+  bool lattice = allow_lattice && n > 0;
+  for (int b = 0; b < nblocks && lattice; ++b) lattice = lattice_dims(bptr[b], bptr[b + 1] - bptr[b], ltx[b], lty[b]);
+  out.lattice = lattice;
+  // emits the chunks of one factor of one lattice block: whole anti-diagonals, values only
+  auto emit_lattice = [&](bool lower, int base, int tx, int ty) {
+    const int D = tx + ty - 1;  // number of anti-diagonals = steps
+    auto coef = [&](int li, int which) -> T {  // which 0: west/east neighbour, 1: south/north neighbour
+      const int r = out.perm[base + li];
+      const int want = lower ? (which == 0 ? li - 1 : li - tx) : (which == 0 ? li + 1 : li + tx);
+      const int x = li % tx;
+      if (which == 0 && (lower ? x == 0 : x == tx - 1)) return (T)0;  // no west / east neighbour inside the tile
+      if (want < 0 || want >= tx * ty) return (T)0;
+      const Csr<T>& M = lower ? L : U;
+      const int lb = lower ? M.rp[r] : M.rp[r] + 1, ub = lower ? M.rp[r + 1] - 1 : M.rp[r + 1];
+      for (int p = lb; p < ub; ++p)
+        if (local[M.ci[p]] == want) return (T)(lower ? (double)M.v[p] * di[r] * d[M.ci[p]] : (double)M.v[p] * di[r]);
+      return (T)0;
+    };
+    int e = 0;
+    while (e < D) {
+      int nlev = 0, rows = 0;
+      const int e0 = e;
+      while (e < D) {
+        const int dd = lower ? e : D - 1 - e;
+        const int sz = std::min(dd, tx - 1) - std::max(0, dd - (ty - 1)) + 1;
+        if (nlev > 0 && 16 + (rows + sz) * 2 * (int)sizeof(T) > chunk_target) break;
+        rows += sz; ++nlev; ++e;
+      }
+      const int bytes = (16 + rows * 2 * (int)sizeof(T) + 15) / 16 * 16;
+      const size_t off = out.stream.size();
+      out.stream.resize(off + bytes, 0);
+      unsigned char* rec = out.stream.data() + off;
+      uint16_t* hdr = reinterpret_cast<uint16_t*>(rec);
+      hdr[0] = (uint16_t)nlev; hdr[1] = (uint16_t)e0; hdr[2] = lower ? 1 : 0; hdr[3] = 0;
+      T* pr = reinterpret_cast<T*>(rec + 16);
+      int t = 0;
+      for (int q = e0; q < e0 + nlev; ++q) {
+        const int dd = lower ? q : D - 1 - q;
+        for (int x = std::max(0, dd - (ty - 1)); x <= std::min(dd, tx - 1); ++x, ++t) {
+          const int li = x + tx * (dd - x);
+          pr[2 * t] = coef(li, 0);
+          pr[2 * t + 1] = coef(li, 1);
+        }
+      }
+      out.chunk_off.push_back((uint32_t)(out.stream.size() / 16));
+      out.max_chunk_bytes = std::max(out.max_chunk_bytes, bytes);
+      out.total_steps += nlev;
+      out.total_slots += rows;
+    }
+  };
   for (int b = 0; b < nblocks; ++b) {
     const int base = bptr[b], nb = bptr[b + 1] - base;
     BlockDesc& dsc = out.blk[b];
     dsc.row0 = base; dsc.nrows = nb;
     dsc.chunk0 = (int)out.chunk_off.size() - 1;
+    if (lattice) {
+      dsc.pad0 = ltx[b]; dsc.pad1 = lty[b];
+      dsc.levelsL = dsc.levelsU = nb ? ltx[b] + lty[b] - 1 : 0;
+      if (nb) { emit_lattice(true, base, ltx[b], lty[b]); emit_lattice(false, base, ltx[b], lty[b]); }
+      dsc.nchunks = (int)out.chunk_off.size() - 1 - dsc.chunk0;
+      out.max_levels_L = std::max(out.max_levels_L, dsc.levelsL);
+      out.max_levels_U = std::max(out.max_levels_U, dsc.levelsU);
+      out.max_chunks = std::max(out.max_chunks, dsc.nchunks);
+      continue;
+    }
     emit_factor(L, true, base, nb, &dsc.levelsL);
     emit_factor(U, false, base, nb, &dsc.levelsU);
     dsc.nchunks = (int)out.chunk_off.size() - 1 - dsc.chunk0;
@@ -584,8 +673,8 @@ void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, 
   }
   out.stream.resize(out.stream.size() + 16, 0);  // a readable tail for 16-byte granularity
 }
-template void pack_fused_block_stream<float>(bool, const Csr<float>&, const Csr<float>&, int, const int*, int, FusedBlockStream<float>&);
-template void pack_fused_block_stream<double>(bool, const Csr<double>&, const Csr<double>&, int, const int*, int, FusedBlockStream<double>&);
+template void pack_fused_block_stream<float>(bool, const Csr<float>&, const Csr<float>&, int, const int*, int, FusedBlockStream<float>&, bool);
+template void pack_fused_block_stream<double>(bool, const Csr<double>&, const Csr<double>&, int, const int*, int, FusedBlockStream<double>&, bool);
 
 // ------------------------------------------------------------------ multi-GPU row partition
 template <class T>

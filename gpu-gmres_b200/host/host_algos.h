@@ -102,6 +102,14 @@ template <class T> struct FusedBlockStream {
   int n = 0, nblocks = 0, max_rows = 0, max_levels_L = 0, max_levels_U = 0;
   int max_chunk_bytes = 0, max_chunks = 0;
   int64_t total_steps = 0, total_slots = 0;
+  // LATTICE layout (chosen when every block is a tx x ty grid tile, tx <= 32, in row-major local order, whose
+  // factors only couple west/south (L) and east/north (U) neighbours -- ILU(0) of a 5-point stencil):
+  // no index is stored at all.  blk[b].pad0 = tx, pad1 = ty.  A chunk holds whole anti-diagonals:
+  //     [ u16 nlev, u16 first_step, u16 lower(1)/upper(0), pad ]            16 B header
+  //     [ T x2 pair ] per row of each anti-diagonal, ascending x             L: (west, south)  U: (east, north)
+  // Lower steps walk the anti-diagonals d = x + y upwards, upper steps downwards.  Lane x owns column x of the
+  // tile: its south/north operand is its own previous result, its west/east operand arrives by warp shuffle.
+  bool lattice = false;
   std::vector<int> perm;             // n: new -> old
   std::vector<T> dinv;               // n, block-major: 1 / diag(U)
   std::vector<BlockDesc> blk;        // nblocks
@@ -112,7 +120,7 @@ template <class T> struct FusedBlockStream {
 // of a row must lie in the row's own block (block-Jacobi factors).
 template <class T>
 void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, int nblocks, const int* block_of_row,
-                             int chunk_target, FusedBlockStream<T>& out);
+                             int chunk_target, FusedBlockStream<T>& out, bool allow_lattice = true);
 
 // ------------------------------------------------------------------ multi-GPU row partition
 // One rank's share of a row-partitioned system: rank p owns the rows with part[i] == p

@@ -108,7 +108,13 @@ def test_reference_leftILU_matches_product_and_oracle(oracle, bg, name):
     F = bg.host_ilu0(rp, ci, v.astype(np.float32))
     for k in ("lp", "li", "up", "ui"):
         assert np.array_equal(ref[k], f[k]) and np.array_equal(ref[k], F[k]), k
-    # leftILU stores 1.0 on L's diagonal slot and the factored values elsewhere
-    for k in ("lv", "uv"):
-        assert np.array_equal(ref[k], f[k].astype(np.float32)), k
-        assert np.array_equal(ref[k], F[k]), k
+    # Values: on the grid matrices level 0 of the reference's column schedule is the single column 0, its GPU loop
+    # stops at the first level with < 32 columns (src/leftILU.cu:231-235) and the whole factorisation runs in
+    # cpuSequentialTriSolve -- the semantics the product implements -- so the factors must be bit-identical.
+    # On the irregular matrix wide levels run through the reference's sparseTriSolve_V2 kernel, whose lane 0 starts at
+    # the pivot entry itself and rescales the strictly-upper entries by (1 - U_jj): a defect of the
+    # reference that is deliberately NOT reproduced, so only the integer artefacts are compared there.
+    if name != "rand_300":
+        for k in ("lv", "uv"):
+            assert np.array_equal(ref[k], f[k].astype(np.float32)), k
+            assert np.array_equal(ref[k], F[k]), k
