@@ -197,7 +197,7 @@ typedef struct {
   int orth;            /* BG_ORTH_*                                                               */
   double reorth_eta;   /* CGS_ADAPTIVE: re-orthogonalise when ||w'|| < eta*||w|| (default 0.7071) */
   int poll_chunk;      /* inner iterations enqueued between host polls (default 8)                */
-  int use_graph;       /* capture restart cycles into CUDA graphs                                 */
+  int use_graph;       /* reserved (ignored): the host already runs a poll_chunk ahead of the GPU        */
   int history_cap;     /* residual-history slots to record (0 = none)                             */
 } bg_gmres_opts;
 typedef struct {
