@@ -30,7 +30,13 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (nx, ny, tile, method) in ((96, 80, 16, "strips"), (300, 280, 32, "strips"), (96, 80, 16, "metis")):
+    # (nx, ny, tile, partition, vector dtype): strips = contiguous rows (<= 2 neighbours per rank), metis = k-way
+    # parts of the off-diagonal graph (several neighbours per rank once world > 2), f32 = the reference's REAL
+    cases = ((96, 80, 16, "strips", "f64"), (300, 280, 32, "strips", "f64"), (96, 80, 16, "metis", "f64"),
+             (257, 199, 32, "metis", "f64"), (96, 80, 16, "strips", "f32"))
+    for (nx, ny, tile, method, dtn) in cases:
+        dtc, npdt, tdt = (bg.F32, np.float32, torch.float32) if dtn == "f32" else (bg.F64, np.float64, torch.float64)
+        tol = 1e-5 if dtn == "f32" else 1e-8
         rp, ci, v, b = synth.pg2d(nx, ny, seed=7)
         n = len(rp) - 1
         if method == "strips":
@@ -45,12 +51,12 @@ def main():
         ids = [bg.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx = bg.Context(local)
-        D = bg.Dist(ctx, plan, ids[0], dtype=bg.F64, m=32, opts=o)
+        D = bg.Dist(ctx, plan, ids[0], dtype=dtc, m=32, opts=o)
         a = plan.arrays()
-        db = torch.from_numpy(np.ascontiguousarray(b[a["l2g"]])).to(dev)
-        dx = torch.zeros(plan.info.n_local, dtype=torch.float64, device=dev)
+        db = torch.from_numpy(np.ascontiguousarray(b[a["l2g"]]).astype(npdt)).to(dev)
+        dx = torch.zeros(plan.info.n_local, dtype=tdt, device=dev)
         torch.cuda.synchronize()
-        opts = bg.gmres_opts(m=32, tol=1e-8, max_iter=3000, reorth_eta=0.1)
+        opts = bg.gmres_opts(m=32, tol=tol, max_iter=3000, reorth_eta=0.1)
         # both transports: our peer-memory kernels (default) and the NCCL baseline; second solve of each is the warm time
         per_transport = {}
         avail = bool(D.info().p2p_available)
@@ -68,9 +74,9 @@ def main():
         x = np.zeros(n)
         for q in range(world):
             sz = int((part == q).sum())
-            t = dx.clone() if q == rank else torch.zeros(sz, dtype=torch.float64, device=dev)
+            t = dx.clone() if q == rank else torch.zeros(sz, dtype=tdt, device=dev)
             dist.broadcast(t, src=q)
-            x[part == q] = t.cpu().numpy()
+            x[part == q] = t.cpu().numpy().astype(np.float64)
         info = D.info()
         if rank == 0:
             A = sp.csr_matrix((v, ci, rp), shape=(n, n))
@@ -82,16 +88,17 @@ def main():
             o1 = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=tile * tile,
                                  block_method=bg.PART_GRID2D if method == "strips" else bg.PART_METIS,
                                  dims=[nx, ny, 1, tile, tile, 1])
-            A1 = bg.Matrix(c1, rp, ci, v, dtype=bg.F64)
-            M1 = bg.Precond.ilu0(c1, rp, ci, v, dtype=bg.F64, opts=o1)
-            S1 = bg.Solver(c1, n, 32, dtype=bg.F64)
-            d1b = torch.from_numpy(b).to(dev)
-            d1x = torch.zeros(n, dtype=torch.float64, device=dev)
+            A1 = bg.Matrix(c1, rp, ci, v, dtype=dtc)
+            M1 = bg.Precond.ilu0(c1, rp, ci, v, dtype=dtc, opts=o1)
+            S1 = bg.Solver(c1, n, 32, dtype=dtc)
+            d1b = torch.from_numpy(b.astype(npdt)).to(dev)
+            d1x = torch.zeros(n, dtype=tdt, device=dev)
             torch.cuda.synchronize()
             r1 = S1.solve(A1, M1, d1b.data_ptr(), d1x.data_ptr(), opts)
-            good = r.flag == 0 and err < 1e-6 and res < 1e-7 and len({t["iters"] for t in per_transport.values()}) == 1
+            lim = (5e-3, 1e-4) if dtn == "f32" else (1e-6, 1e-7)
+            good = r.flag == 0 and err < lim[0] and res < lim[1] and len({t["iters"] for t in per_transport.values()}) == 1
             ok = ok and good
-            print(json.dumps(dict(case=f"pg2d {nx}x{ny} {method}", ranks=world, flag=r.flag, iters=r.iters, iters_1gpu=r1.iters, resid=r.resid,
+            print(json.dumps(dict(case=f"pg2d {nx}x{ny} {method} {dtn}", ranks=world, flag=r.flag, iters=r.iters, iters_1gpu=r1.iters, resid=r.resid,
                                   true_rel_residual=res, x_err_vs_direct=err, halo_bytes=int(info.halo_bytes_per_exchange),
                                   neighbors=int(info.n_neighbors), transport=("p2p" if info.transport == bg.TRANSPORT_P2P else "nccl"), transports=per_transport,
                                   solve_ms=round(r.solve_ms, 3),
