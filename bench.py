@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--precond", default="ilu0", choices=["ilu0", "ilut"])
     ap.add_argument("--schedule", default="block", choices=["block", "level"])
     ap.add_argument("--blocks", default="grid", choices=["grid", "metis"])
-    ap.add_argument("--tile", type=int, default=32)
+    ap.add_argument("--tile", type=int, default=32, help="block-Jacobi tile width in grid nodes (<= 32: one lane per tile column)")
+    ap.add_argument("--tile-y", type=int, default=0, help="tile height (0 = same as --tile)")
     ap.add_argument("--ilut-tau", type=float, default=1e-2)
     ap.add_argument("--ilut-lfil", type=int, default=5)
     ap.add_argument("--factor-dtype", default="f64", choices=["f32", "f64"])
@@ -64,6 +65,8 @@ def parse():
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1: peer-memory kernels over NVLink (default) or the NCCL baseline")
     ap.add_argument("--cpu-nx", type=int, default=652, help="grid edge of the bounded CPU sample (0 = same as --nx); 652^2 = n/4")
     a = ap.parse_args()
+    if a.tile_y <= 0:
+        a.tile_y = a.tile
     if a.nx <= 0:
         a.nx = 3162 if a.workload == "pg10m" else 1304
     return a
@@ -260,9 +263,9 @@ def run_single(args, local, nx, precond, steps, headline):
     fdt = bg.F32 if args.factor_dtype == "f32" else bg.F64
     t_setup = time.perf_counter()
     if args.schedule == "block":
-        o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile, factor_dtype=fdt,
+        o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile_y, factor_dtype=fdt,
                             block_method=bg.PART_GRID2D if args.blocks == "grid" else bg.PART_METIS,
-                            dims=[nx, nx, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
+                            dims=[nx, nx, 1, args.tile, args.tile_y, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     else:
         o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(precond == "ilut"))
@@ -410,8 +413,8 @@ def run_dist(args, rank, world, local):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     fdt = bg.F32 if args.factor_dtype == "f32" else bg.F64
     ny_local = ys[rank + 1] - ys[rank]
-    o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile, factor_dtype=fdt, block_method=bg.PART_GRID2D,
-                        dims=[nx, ny_local, 1, args.tile, args.tile, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
+    o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile_y, factor_dtype=fdt, block_method=bg.PART_GRID2D,
+                        dims=[nx, ny_local, 1, args.tile, args.tile_y, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     D = bg.Dist(ctx, plan, ids[0], dtype=bg.F64, m=32, opts=o, ilut=(args.precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
     if args.transport == "nccl" or not D.info().p2p_available:
@@ -505,7 +508,7 @@ def run_dist(args, rank, world, local):
             "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{workload_name(nx)} DC solve, GMRES(32), rel. residual {args.tol:g}",
                        "n": n, "nnz": nnz, "precond": args.precond, "trsv_schedule": "block",
-                       "partition": f"{world} horizontal strips (contiguous rows), per-rank block-Jacobi ILU, tiles {args.tile}x{args.tile}",
+                       "partition": f"{world} horizontal strips (contiguous rows), per-rank block-Jacobi ILU, tiles {args.tile}x{args.tile_y}",
                        "orth": args.orth, "reorth_eta": args.eta,
                        "l2_policy": "per-rank Krylov basis 33 x n/N x 8 B = %.0f MB" % (33 * n * 8 / 1e6 / world)},
             "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),

@@ -187,6 +187,43 @@ def host_ilut(rowptr, col, val, tau, lfil, block_of_row=None):
     return _factors_out(h)
 
 
+FILE_TRIPLETS, FILE_CSR_F32, FILE_CSR_F64 = 0, 1, 2
+
+
+class HostCsrInfo(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("n_cols", C.c_int), ("nnz", C.c_int64), ("dtype", C.c_int), ("empty_rows", C.c_int)]
+
+
+def host_read_matrix(path, file_format):
+    """Matrix file in one of the reference's formats -> (rowptr, col, val, n_cols, empty_rows)."""
+    h = C.c_void_p()
+    _chk(lib().bg_host_read_matrix(str(path).encode(), int(file_format), C.byref(h)))
+    info = HostCsrInfo()
+    _chk(lib().bg_host_csr_get_info(h, C.byref(info)))
+    rp = np.zeros(info.n_rows + 1, np.int32); ci = np.zeros(info.nnz, np.int32); v = np.zeros(info.nnz, _NP[info.dtype])
+    _chk(lib().bg_host_csr_get(h, _p(rp), _p(ci), _p(v)))
+    lib().bg_host_csr_destroy(h)
+    return rp, ci, v, info.n_cols, info.empty_rows
+
+
+def host_write_csr(path, file_format, rowptr, col, val, n_cols=None):
+    n = len(rowptr) - 1
+    val = np.ascontiguousarray(val)
+    _chk(lib().bg_host_write_csr(str(path).encode(), int(file_format), n, n if n_cols is None else int(n_cols), _p(_i32(rowptr)), _p(_i32(col)),
+                                 _p(val), dtype_code(val.dtype)))
+
+
+def host_read_vector(path, n, dtype=F64):
+    out = np.zeros(n, _NP[dtype])
+    _chk(lib().bg_host_read_vector(str(path).encode(), int(n), int(dtype), _p(out)))
+    return out
+
+
+def host_write_vector(path, x):
+    x = np.ascontiguousarray(x)
+    _chk(lib().bg_host_write_vector(str(path).encode(), len(x), dtype_code(x.dtype), _p(x)))
+
+
 def host_partition(Ap, Ai, npart, n_nodes):
     m = len(Ap) - 1
     ps, npt, pinv, q = np.zeros(npart + 1, np.int64), np.zeros(m, np.int64), np.zeros(m, np.int64), np.zeros(m, np.int64)

@@ -133,6 +133,25 @@ BG_API int bg_host_partition3_post(int64_t m, const int64_t* Ap, const int64_t* 
 BG_API int bg_host_block_partition(int method, int n, const int* rowptr, const int* col, int nblocks,
                                    const int* dims, int* block_of_row);
 
+/* ---- matrix / vector files in the reference's own formats (no GPU needed) ----
+   BG_FILE_TRIPLETS  text: '%' comments, "numRows numCols nnz", then "row col val" lines, 1-based, any order;
+                     read like readSparseMatrix + genCSRFormat (src_thermal/SpMV_gen.cpp:93-201): sorted by (row, col),
+                     float values
+   BG_FILE_CSR_F32 / BG_FILE_CSR_F64  binary: int m, n, nnz; int rowPtr[m+1]; int colIdx[nnz]; float|double val[nnz]
+                     = writeCSR / writeCSRmySpMatrix[Double] (src/formatConvert.cpp:425-485) */
+enum { BG_FILE_TRIPLETS = 0, BG_FILE_CSR_F32 = 1, BG_FILE_CSR_F64 = 2 };
+typedef struct bg_host_csr_s* bg_host_csr_t;
+typedef struct { int n_rows, n_cols; int64_t nnz; int dtype; int empty_rows; } bg_host_csr_info;
+BG_API int bg_host_read_matrix(const char* path, int file_format, bg_host_csr_t* M);
+BG_API int bg_host_csr_get_info(bg_host_csr_t M, bg_host_csr_info* info);
+BG_API int bg_host_csr_get(bg_host_csr_t M, int* rowptr, int* col, void* val); /* any pointer may be NULL */
+BG_API int bg_host_csr_destroy(bg_host_csr_t M);
+BG_API int bg_host_write_csr(const char* path, int file_format, int n_rows, int n_cols, const int* rowptr, const int* col,
+                             const void* val, int val_dtype);
+/* one value per line: readInputVector (src_thermal/SpMV_gen.cpp:36-53) / writeOutputVector ("%20.18e") */
+BG_API int bg_host_read_vector(const char* path, int n, int dtype, void* out);
+BG_API int bg_host_write_vector(const char* path, int n, int dtype, const void* x);
+
 /* ---- preconditioners ---- */
 typedef struct {
   int trsv_schedule;   /* BG_TRSV_LEVEL (default) or BG_TRSV_BLOCK                               */

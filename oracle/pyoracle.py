@@ -304,3 +304,41 @@ def ref_left_ilu(rowptr, col, val):
     lv, uv = np.zeros(nnz + n, np.float32), np.zeros(nnz + n, np.float32)
     L.ref_leftILU(C.c_int(n), _p(v), _p(rp), _p(ci), _p(lv), _p(lp), _p(li), _p(uv), _p(up), _p(ui))
     return dict(lp=lp, li=li[: lp[-1]], lv=lv[: lp[-1]], up=up, ui=ui[: up[-1]], uv=uv[: up[-1]])
+
+
+# --------------------------------------------------------------------------- the reference's file readers
+_ref_io = None
+
+
+def ref_io_lib():
+    global _ref_io
+    p = os.path.join(_HERE, "_ref", "libref_io.so")
+    if _ref_io is None and os.path.exists(p):
+        _ref_io = C.CDLL(p)
+    return _ref_io
+
+
+def ref_read_sparse_matrix(path):
+    """readSparseMatrix(format 0) + genCSRFormat (src_thermal/SpMV_gen.cpp:93-201) -> (rowptr, col, val float32)."""
+    L = ref_io_lib()
+    nr, nc, nnz = C.c_int(), C.c_int(), C.c_int()
+    L.ref_readSparseMatrix(str(path).encode(), C.byref(nr), C.byref(nc), C.byref(nnz), None, None, None)
+    val = np.zeros(nnz.value, np.float32); rp = np.zeros(nr.value + 1, np.int32); ci = np.zeros(nnz.value, np.int32)
+    L.ref_readSparseMatrix(str(path).encode(), C.byref(nr), C.byref(nc), C.byref(nnz), _p(val), _p(rp), _p(ci))
+    return rp, ci, val, nc.value
+
+
+def ref_read_input_vector(path, n):
+    y = np.zeros(n, np.float32)
+    ref_io_lib().ref_readInputVector(_p(y), str(path).encode(), C.c_int(n))
+    return y
+
+
+def ref_write_output_vector(path, x):
+    x = _f32(x).copy()
+    ref_io_lib().ref_writeOutputVector(_p(x), str(path).encode(), C.c_int(len(x)))
+
+
+def ref_write_csr(path, rowptr, col, val, n_cols):
+    rp, ci, v = _i32(rowptr).copy(), _i32(col).copy(), _f32(val).copy()
+    ref().ref_writeCSR(C.c_int(len(rp) - 1), C.c_int(n_cols), C.c_int(len(ci)), _p(rp), _p(ci), _p(v), str(path).encode())

@@ -8,7 +8,11 @@ void coo2csr_in(int n, int nz, float* a, int* i_idx, int* j_idx);
 void coo2csrDouble_in(int n, int nz, double* a, int* i_idx, int* j_idx);
 void partition(cs_dl* A, int npart, int nNodes, UF_long* part_size, UF_long* node_part,
                UF_long* pinv, UF_long* q);
+void writeCSR(int m, int n, int nnz, int* rowPtr, int* colIdx, float* val, const char* filename);
 extern "C" {
+void ref_writeCSR(int m, int n, int nnz, int* rowPtr, int* colIdx, float* val, const char* filename) {
+  writeCSR(m, n, nnz, rowPtr, colIdx, val, filename);  // src/formatConvert.cpp:425-445
+}
 void ref_computeSpMV(float* x, const float* val, const int* rp, const int* ci, const float* y, int n) {
   computeSpMV(x, val, rp, ci, y, n);
 }
