@@ -157,7 +157,7 @@ extern "C" int bg_host_write_vector(const char* path, int n, int dtype, const vo
   if (!path || n < 0 || (n && !x)) return BG_ERR_ARG;
   FileCloser fc{std::fopen(path, "w")};
   if (!fc.f) { bg::set_error("cannot open file: %s", path); return BG_ERR_ARG; }
-  for (int i = 0; i < n; ++i) std::fprintf(fc.f, "%20.18e\n", dtype == BG_F64 ? ((const double*)x)[i] : (double)((const float*)x)[i]);  // writeOutputVector
-  std::fprintf(fc.f, "\n");
+  // writeOutputVector(float*, const char*, int), src_thermal/SpMV_gen.cpp:55-69
+  for (int i = 0; i < n; ++i) std::fprintf(fc.f, "%20.18e\n", dtype == BG_F64 ? ((const double*)x)[i] : (double)((const float*)x)[i]);
   return BG_OK;
 }

@@ -82,7 +82,7 @@ def test_vector_files_match_reference(bg, oracle, tmp_path):
     bg.host_write_vector(p, x)
     assert np.array_equal(bg.host_read_vector(p, 37, bg.F64), x)  # "%20.18e" round-trips a double
     with pytest.raises(Exception):
-        bg.host_read_vector(p, 39, bg.F64)  # 37 values + the blank line writeOutputVector appends
+        bg.host_read_vector(p, 38, bg.F64)
     if oracle.ref_io_lib() is None:
         pytest.skip("oracle/_ref/libref_io.so not built")
     xf = x.astype(np.float32)
