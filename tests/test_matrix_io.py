@@ -93,3 +93,30 @@ def test_vector_files_match_reference(bg, oracle, tmp_path):
     assert pr.read_text() == pb.read_text()
     assert np.array_equal(bg.host_read_vector(pr, 37, bg.F32), xf)
     assert np.array_equal(oracle.ref_read_input_vector(pb, 37), xf)
+
+
+@pytest.mark.gpu
+def test_file_driver_end_to_end(bg, tmp_path):
+    """tools/gmres_file.py = the thermal driver's flow (src_thermal/main1.cu) on files in the reference's formats."""
+    import os
+    import subprocess
+    import sys
+
+    import scipy.sparse as sp
+    from b200gmres import synth
+
+    rp, ci, v, b = synth.th3d(9, 8, 7, seed=21)
+    n = len(rp) - 1
+    pa, pb, px = tmp_path / "A.mtx", tmp_path / "b.txt", tmp_path / "x.txt"
+    _triplet_file(pa, rp, ci, v, seed=2)
+    bg.host_write_vector(pb, b.astype(np.float32))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--dtype", "f64", "--tol", "1e-8", "--schedule", "block"]):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "gmres_file.py"), str(pa), str(pb), str(px)] + extra,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "GPU GMRES flag = 0" in out.stdout
+        x = bg.host_read_vector(px, n, bg.F64)
+        A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+        rel = np.linalg.norm(b - A @ x) / np.linalg.norm(b)
+        assert rel < (1e-6 if extra else 2e-4)
