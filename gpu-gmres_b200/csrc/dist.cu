@@ -31,6 +31,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -265,11 +266,14 @@ int setup_p2p(bg_dist_t D) {
   PeerAR par;
   std::memset(&par, 0, sizeof(par));
   par.nranks = R; par.rank = me;
+  double tmo = 120.0;
+  if (const char* e = getenv("B200GMRES_PEER_TIMEOUT_S")) { const double t = atof(e); if (t >= 1.0) tmo = t; }
+  par.timeout_ns = (unsigned long long)(tmo * 1e9);
   par.seq = (unsigned*)(D->window.as<char>() + wl.counters);
   for (int r = 0; r < R; ++r) par.inbox[r] = (LL16*)(win[r] + WindowLayout(R, all[r].n_halo).ar_inbox);
   PeerHalo ph;
   std::memset(&ph, 0, sizeof(ph));
-  ph.n_nbr = nn; ph.n_halo = D->n_halo;
+  ph.n_nbr = nn; ph.n_halo = D->n_halo; ph.timeout_ns = par.timeout_ns;
   ph.my_inbox = (LL16*)(D->window.as<char>() + wl.halo_inbox);
   for (int k = 0; k <= nn; ++k) ph.send_ptr[k] = D->send_ptr[k];
   for (int k = 0; k < nn; ++k) {

@@ -130,6 +130,7 @@ struct __align__(16) LL16 { unsigned lo, f0, hi, f1; };
 // identical without any further exchange.
 struct PeerAR {
   int nranks, rank;
+  unsigned long long timeout_ns; // a poll that lasts longer traps (dead peer)
   unsigned* seq;                 // local counter of executed all-reduces
   LL16* inbox[kMaxPeers];        // inbox[r]: rank r's [2][nranks][kArLd] elements (peer-mapped for r != rank)
 };
@@ -137,6 +138,7 @@ struct PeerAR {
 // neighbours' halo inboxes and copies its own arrived inbox into the halo slots behind the local vector.
 struct PeerHalo {
   int n_nbr, n_halo;
+  unsigned long long timeout_ns;
   int send_ptr[kMaxPeers + 1];   // entries [send_ptr[k], send_ptr[k+1]) of send_idx go to neighbour k
   LL16* peer_inbox[kMaxPeers];   // first element of MY range in neighbour k's halo inbox
   LL16* my_inbox;                // [n_halo]

@@ -268,7 +268,7 @@ __device__ void peer_allreduce(const PeerAR* __restrict__ P, double* red, int cn
   }
   double v = 0.0;
   if ((int)threadIdx.x < cnt)
-    for (int r = 0; r < R; ++r) v += ll_wait(&P->inbox[me][(slot + r) * kArLd + threadIdx.x], seq);
+    for (int r = 0; r < R; ++r) v += ll_wait(&P->inbox[me][(slot + r) * kArLd + threadIdx.x], seq, P->timeout_ns);
   __syncthreads();
   if ((int)threadIdx.x < cnt) red[threadIdx.x] = v;
   __syncthreads();
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(const PeerHalo* __re
     ll_store(H->peer_inbox[k] + (e - H->send_ptr[k]), (double)v[idx[e]], seq);
   }
   const LL16* in = H->my_inbox;
-  for (int i = tid; i < nh; i += nt) halo_out[i] = (VT)ll_wait(in + i, seq);
+  for (int i = tid; i < nh; i += nt) halo_out[i] = (VT)ll_wait(in + i, seq, H->timeout_ns);
 }
 
 // ---------------------------------------------------------------------------- dots

@@ -16,8 +16,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// poll until the element carries `seq`; a peer that never arrives (crashed rank) must trap, not hang the GPU
-__device__ __forceinline__ double ll_wait(const LL16* p, unsigned seq) {
+// poll until the element carries `seq`; a peer that never arrives (crashed rank) must trap, not hang the GPU.
+// timeout_ns comes from the owning descriptor (B200GMRES_PEER_TIMEOUT_S, default 120 s: ranks may enter a solve
+// with host-side skew, e.g. unequal setup work before the first collective call).
+__device__ __forceinline__ double ll_wait(const LL16* p, unsigned seq, unsigned long long timeout_ns) {
   unsigned lo, f0, hi, f1;
   unsigned long long t0 = 0;
   for (unsigned spin = 0;; ++spin) {
@@ -26,7 +28,7 @@ __device__ __forceinline__ double ll_wait(const LL16* p, unsigned seq) {
     if ((spin & 1023u) == 1023u) {
       const unsigned long long t = global_ns();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 30000000000ull) __trap();
+      else if (t - t0 > timeout_ns) __trap();
     }
   }
   return __hiloint2double((int)hi, (int)lo);

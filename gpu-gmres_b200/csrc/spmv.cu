@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128, 8) spmv_sell_w(int n, int nslices, const 
       SV::idx(cc[k], ci);
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
-        if (HALO && ci[r] >= h.n_local) xv[k][r] = (VT)ll_wait(h.ph->my_inbox + (ci[r] - h.n_local), h.seq);
+        if (HALO && ci[r] >= h.n_local) xv[k][r] = (VT)ll_wait(h.ph->my_inbox + (ci[r] - h.n_local), h.seq, h.ph->timeout_ns);
         else xv[k][r] = x[ci[r]];
       }
     }
