@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--tile", type=int, default=32, help="block-Jacobi tile width in grid nodes (<= 32: one lane per tile column)")
     ap.add_argument("--tile-y", type=int, default=0, help="tile height (0 = same as --tile)")
     ap.add_argument("--ilut-tau", type=float, default=1e-2)
-    ap.add_argument("--ilut-lfil", type=int, default=5)
+    ap.add_argument("--ilut-lfil", type=int, default=3)
     ap.add_argument("--factor-dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--orth", default="cgs", choices=["mgs", "cgs", "cgs2"])
     ap.add_argument("--eta", type=float, default=0.1, help="CGS re-orthogonalisation threshold (DGKS): second pass when ||w'|| < eta ||w||")
