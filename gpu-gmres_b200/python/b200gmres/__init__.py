@@ -435,6 +435,44 @@ class Solver:
 
 
 # ------------------------------------------------------------------ row-partitioned (multi-GPU) solve
+class TransientStats(C.Structure):
+    _fields_ = [("steps", C.c_int), ("iters_max", C.c_int), ("not_converged", C.c_int), ("iters_total", C.c_int64),
+                ("launches", C.c_int64), ("last_resid", C.c_double), ("device_ms", C.c_double)]
+
+
+class Transient:
+    """Backward-Euler loop on the device: rhs = B u(t) + (C/h) x, warm-started GMRES, port sampling (bg_transient_*)."""
+
+    def __init__(self, ctx, S, A, M, c_over_h, B, pwl, probes=()):
+        """c_over_h, B: (rowptr, col, val) CSR triples (n x n and n x nsrc); pwl: list of (times, values) per source."""
+        n = len(c_over_h[0]) - 1
+        cv = np.ascontiguousarray(c_over_h[2], dtype=np.float64)
+        bv = np.ascontiguousarray(B[2], dtype=np.float64)
+        ptr = np.zeros(len(pwl) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(t) for t, _ in pwl])
+        tt = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t, _ in pwl]) if pwl else np.zeros(0))
+        vv = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for _, v in pwl]) if pwl else np.zeros(0))
+        pi = _i32(np.asarray(probes, dtype=np.int32))
+        self.h, self.nprobe = C.c_void_p(), len(pi)
+        _chk(lib().bg_transient_create(ctx.h, S.h, A.h, M.h, n, _p(_i32(c_over_h[0])), _p(_i32(c_over_h[1])), _p(cv), len(pwl),
+                                       _p(_i32(B[0])), _p(_i32(B[1])), _p(bv), F64, _p(ptr), _p(tt), _p(vv), len(pi),
+                                       _p(pi) if len(pi) else None, C.byref(self.h)))
+
+    def run(self, d_x, t0, h, nsteps, opts):
+        st = TransientStats()
+        probe = np.zeros((nsteps, self.nprobe)) if self.nprobe else None
+        rc = lib().bg_transient_run(self.h, _p(d_x), C.c_double(t0), C.c_double(h), int(nsteps), C.byref(opts), C.byref(st),
+                                    _p(probe) if probe is not None else None)
+        if rc < 0:
+            _chk(rc)
+        return rc, st, probe
+
+    def close(self):
+        if self.h:
+            lib().bg_transient_destroy(self.h)
+            self.h = C.c_void_p()
+
+
 class DistPlanInfo(C.Structure):
     _fields_ = [("nranks", C.c_int), ("rank", C.c_int), ("n_global", C.c_int64), ("n_local", C.c_int), ("n_halo", C.c_int),
                 ("nnz_local", C.c_int64), ("n_neighbors", C.c_int), ("send_count", C.c_int64)]

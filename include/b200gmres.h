@@ -261,6 +261,25 @@ typedef struct {
 BG_API int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b,
                              void* d_x, const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* st);
 
+/* ---- backward-Euler transient loop resident on the device ----
+   Replaces the host loop of src/mna_solve_gpu_gmres.cpp:564-647: per step u = interp1(PWL sources, t_i),
+   rhs = B u + (C/h) x_{i-1} (two SpMVs on the device instead of cs_dl_gaxpy on the CPU), GMRES warm-started from
+   x_{i-1} with the preconditioner built once, and port sampling.  A must be G + C/h.  No vector crosses PCIe in
+   the loop.  Source k is piecewise linear through (pwl_t, pwl_v)[pwl_ptr[k] .. pwl_ptr[k+1]) and constant outside. */
+typedef struct bg_transient_s* bg_transient_t;
+typedef struct {
+  int steps, iters_max, not_converged; int64_t iters_total, launches; double last_resid, device_ms;
+} bg_transient_stats;
+BG_API int bg_transient_create(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, int n, const int* c_rowptr,
+                               const int* c_col, const void* c_val /* C/h, n x n */, int nsrc, const int* b_rowptr,
+                               const int* b_col, const void* b_val /* B, n x nsrc */, int val_dtype, const int* pwl_ptr,
+                               const double* pwl_t, const double* pwl_v, int nprobe, const int* probe_idx,
+                               bg_transient_t* T);
+/* d_x: x(t0) on entry, x(t0 + nsteps h) on return; h_probe (may be NULL): [nsteps][nprobe] sampled node values */
+BG_API int bg_transient_run(bg_transient_t T, void* d_x, double t0, double h, int nsteps, const bg_gmres_opts* o,
+                            bg_transient_stats* st, double* h_probe);
+BG_API int bg_transient_destroy(bg_transient_t T);
+
 /* ---- row-partitioned solve across the GPUs of one box (the reference is single-GPU) ----
    One process per GPU.  Every rank builds its own plan from the GLOBAL CSR pattern and the row ->
    rank map `part` (bg_host_block_partition with nblocks = nranks, or any map of the caller, e.g. from

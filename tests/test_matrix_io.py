@@ -119,4 +119,4 @@ def test_file_driver_end_to_end(bg, tmp_path):
         x = bg.host_read_vector(px, n, bg.F64)
         A = sp.csr_matrix((v, ci, rp), shape=(n, n))
         rel = np.linalg.norm(b - A @ x) / np.linalg.norm(b)
-        assert rel < (1e-6 if extra else 2e-4)
+        assert rel < (1e-5 if extra else 2e-4)  # the rhs file carries float32 digits; the stopping test is on the preconditioned residual

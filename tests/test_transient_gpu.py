@@ -1,0 +1,74 @@
+"""Device-resident backward-Euler loop (bg_transient_*) against a host time-stepping with direct solves:
+the reference's loop (src/mna_solve_gpu_gmres.cpp:564-647) computes rhs = B u(t_i) + (C/h) x_{i-1} on the CPU, solves
+with the factor built once, warm-starts from x_{i-1} and samples the ports."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.mark.parametrize("dtc", [1, 0])
+def test_transient_matches_host_time_stepping(bg, ctx, dtc):
+    from b200gmres import synth
+
+    nx, ny = 40, 30
+    rp, ci, v, b0 = synth.pg2d(nx, ny, seed=31, c_over_h=0.2)
+    _, _, v0, _ = synth.pg2d(nx, ny, seed=31, c_over_h=0.0)
+    n = len(rp) - 1
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    G = sp.csr_matrix((v0, ci, rp), shape=(n, n))
+    Ch = sp.csr_matrix(A - G)
+    Ch.eliminate_zeros(); Ch.sort_indices()
+    # sources: 3 PWL current sources driving random node subsets + 1 constant supply carrying the DC right-hand side
+    rng = np.random.default_rng(5)
+    nsrc = 4
+    cols, rows, vals = [], [], []
+    for k in range(3):
+        nodes = rng.choice(n, size=25, replace=False)
+        rows += list(nodes); cols += [k] * len(nodes); vals += list(-rng.uniform(0.5e-3, 2e-3, size=len(nodes)))
+    nzb = np.flatnonzero(b0)
+    rows += list(nzb); cols += [3] * len(nzb); vals += list(b0[nzb])
+    B = sp.csr_matrix((vals, (rows, cols)), shape=(n, nsrc)); B.sort_indices()
+    pwl = [(np.array([0.0, 2.0, 5.0, 9.0]), np.array([0.0, 1.0, 0.2, 1.5])),
+           (np.array([1.0, 3.0, 4.0]), np.array([1.0, 0.0, 2.0])),
+           (np.array([0.0, 20.0]), np.array([0.5, 2.5])),
+           (np.array([0.0]), np.array([1.0]))]
+    probes = [0, n // 3, n - 1]
+    h, nsteps = 0.5, 24
+    npdt, tdt = (np.float64, torch.float64) if dtc == 1 else (np.float32, torch.float32)
+    tol = 1e-10 if dtc == 1 else 1e-6
+
+    def u_of(t):
+        return np.array([np.interp(t, tt, vv) for tt, vv in pwl])
+
+    lu = spla.splu(A.tocsc())
+    x_ref = lu.solve(B @ u_of(0.0))  # operating point at t0
+    x0 = x_ref.copy()
+    probe_ref = np.zeros((nsteps, len(probes)))
+    for i in range(1, nsteps + 1):
+        x_ref = lu.solve(B @ u_of(h * i) + Ch @ x_ref)
+        probe_ref[i - 1] = x_ref[probes]
+
+    Am = bg.Matrix(ctx, rp, ci, v, dtype=dtc)
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=dtc)
+    S = bg.Solver(ctx, n, 32, dtype=dtc)
+    T = bg.Transient(ctx, S, Am, M, (Ch.indptr, Ch.indices, Ch.data), (B.indptr, B.indices, B.data), pwl, probes)
+    dx = torch.from_numpy(x0.astype(npdt)).cuda()
+    torch.cuda.synchronize()
+    rc, st, probe = T.run(dx.data_ptr(), 0.0, h, nsteps, bg.gmres_opts(m=32, tol=tol, max_iter=500, orth=bg.ORTH_MGS))
+    ctx.sync()
+    x = dx.cpu().numpy().astype(np.float64)
+    assert rc == 0 and st.steps == nsteps and st.not_converged == 0
+    lim = 1e-7 if dtc == 1 else 2e-3
+    assert np.linalg.norm(x - x_ref) <= lim * np.linalg.norm(x_ref)
+    assert np.abs(probe - probe_ref).max() <= lim * np.abs(probe_ref).max()
+    # warm start pays: far fewer iterations per step than a cold DC solve needs
+    dc = torch.zeros(n, dtype=tdt, device="cuda")
+    db = torch.from_numpy((B @ u_of(0.0)).astype(npdt)).cuda()
+    torch.cuda.synchronize()
+    r_dc = S.solve(Am, M, db.data_ptr(), dc.data_ptr(), bg.gmres_opts(m=32, tol=tol, max_iter=500, orth=bg.ORTH_MGS))
+    assert st.iters_total / nsteps < r_dc.iters
+    T.close(); S.close(); M.close(); Am.close()
