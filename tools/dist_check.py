@@ -32,9 +32,12 @@ def main():
     ok = True
     # (nx, ny, tile, partition, vector dtype): strips = contiguous rows (<= 2 neighbours per rank), metis = k-way
     # parts of the off-diagonal graph (several neighbours per rank once world > 2), f32 = the reference's REAL
-    cases = ((96, 80, 16, "strips", "f64"), (300, 280, 32, "strips", "f64"), (96, 80, 16, "metis", "f64"),
-             (257, 199, 32, "metis", "f64"), (96, 80, 16, "strips", "f32"))
-    for (nx, ny, tile, method, dtn) in cases:
+    cases = ((96, 80, 16, "strips", "f64", "cgs"), (300, 280, 32, "strips", "f64", "cgs"), (96, 80, 16, "metis", "f64", "cgs"),
+             (257, 199, 32, "metis", "f64", "cgs"), (96, 80, 16, "strips", "f32", "cgs"),
+             # strict MGS: i+1 all-reduces per iteration through dots_kernel; CGS2: two all-reduces inside one orth_kernel
+             (96, 80, 16, "strips", "f64", "mgs"), (96, 80, 16, "metis", "f64", "cgs2"))
+    for (nx, ny, tile, method, dtn, orthn) in cases:
+        orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[orthn]
         dtc, npdt, tdt = (bg.F32, np.float32, torch.float32) if dtn == "f32" else (bg.F64, np.float64, torch.float64)
         tol = 1e-5 if dtn == "f32" else 1e-8
         rp, ci, v, b = synth.pg2d(nx, ny, seed=7)
@@ -56,7 +59,7 @@ def main():
         db = torch.from_numpy(np.ascontiguousarray(b[a["l2g"]]).astype(npdt)).to(dev)
         dx = torch.zeros(plan.info.n_local, dtype=tdt, device=dev)
         torch.cuda.synchronize()
-        opts = bg.gmres_opts(m=32, tol=tol, max_iter=3000, reorth_eta=0.1)
+        opts = bg.gmres_opts(m=32, tol=tol, max_iter=3000, reorth_eta=0.1, orth=orth)
         # both transports: our peer-memory kernels (default) and the NCCL baseline; second solve of each is the warm time
         per_transport = {}
         avail = bool(D.info().p2p_available)
@@ -98,7 +101,7 @@ def main():
             lim = (5e-3, 1e-4) if dtn == "f32" else (1e-6, 1e-7)
             good = r.flag == 0 and err < lim[0] and res < lim[1] and len({t["iters"] for t in per_transport.values()}) == 1
             ok = ok and good
-            print(json.dumps(dict(case=f"pg2d {nx}x{ny} {method} {dtn}", ranks=world, flag=r.flag, iters=r.iters, iters_1gpu=r1.iters, resid=r.resid,
+            print(json.dumps(dict(case=f"pg2d {nx}x{ny} {method} {dtn} {orthn}", ranks=world, flag=r.flag, iters=r.iters, iters_1gpu=r1.iters, resid=r.resid,
                                   true_rel_residual=res, x_err_vs_direct=err, halo_bytes=int(info.halo_bytes_per_exchange),
                                   neighbors=int(info.n_neighbors), transport=("p2p" if info.transport == bg.TRANSPORT_P2P else "nccl"), transports=per_transport,
                                   solve_ms=round(r.solve_ms, 3),
