@@ -28,6 +28,26 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 inline size_t dtype_size(int dt) { return dt == BG_F64 ? 8 : 4; }
 
+// Programmatic dependent launch: the kernel may start (launch latency, CTA prologue, loads of constant data)
+// while its predecessor on the stream drains; it must execute pdl_wait() before touching anything the
+// predecessor wrote.  BG_PDL=0 falls back to plain stream launches.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // simple owning device buffer
 struct DevBuf {
   void* p = nullptr;

@@ -20,6 +20,11 @@
 
 namespace bg {
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("BG_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -145,6 +145,10 @@ template <class VT, int W, bool AXPBY, bool HALO>
 __global__ void __launch_bounds__(128, 8) spmv_sell_w(int n, int nslices, const int* __restrict__ cols, const VT* __restrict__ vals,
                                                    const VT* __restrict__ x, VT* __restrict__ y, VT alpha, VT beta,
                                                    const VT* __restrict__ b, const int* skip, HaloArgs h) {
+  // launched with programmatic stream serialisation: everything above this line overlapped the tail of the
+  // previous kernel; x, b and the skip flag are its outputs
+  pdl_wait();
+  pdl_launch_dependents();  // the triangular solve that follows may start its prologue (factor stream prefetch) now
   if (skip && *skip) return;
   using SV = SellVec<VT>;
   constexpr int RPT = SV::RPT, H = 32 * RPT;
@@ -208,11 +212,11 @@ static void sell_w_launch(bg_context_t ctx, bg_matrix_t A, int blocks, const VT*
   const VT* v = A->s_val.as<VT>();
   const HaloArgs h = halo ? *halo : HaloArgs();
   if (halo) {
-    if (axpby) spmv_sell_w<VT, W, true, true><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)alpha, (VT)beta, b, skip, h);
-    else spmv_sell_w<VT, W, false, true><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)1, (VT)0, nullptr, skip, h);
+    if (axpby) launch_pdl(spmv_sell_w<VT, W, true, true>, dim3(blocks), dim3(128), 0, ctx->stream, n, ns, c, v, x, y, (VT)alpha, (VT)beta, b, skip, h);
+    else launch_pdl(spmv_sell_w<VT, W, false, true>, dim3(blocks), dim3(128), 0, ctx->stream, n, ns, c, v, x, y, (VT)1, (VT)0, nullptr, skip, h);
   } else {
-    if (axpby) spmv_sell_w<VT, W, true, false><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)alpha, (VT)beta, b, skip, h);
-    else spmv_sell_w<VT, W, false, false><<<blocks, 128, 0, ctx->stream>>>(n, ns, c, v, x, y, (VT)1, (VT)0, nullptr, skip, h);
+    if (axpby) launch_pdl(spmv_sell_w<VT, W, true, false>, dim3(blocks), dim3(128), 0, ctx->stream, n, ns, c, v, x, y, (VT)alpha, (VT)beta, b, skip, h);
+    else launch_pdl(spmv_sell_w<VT, W, false, false>, dim3(blocks), dim3(128), 0, ctx->stream, n, ns, c, v, x, y, (VT)1, (VT)0, nullptr, skip, h);
   }
 }
 static bool sell_w_supported(int w) { return w == 3 || w == 5 || w == 7; }

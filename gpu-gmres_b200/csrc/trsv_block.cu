@@ -227,7 +227,6 @@ __device__ __forceinline__ void run_lattice_chunk(int lane, const unsigned char*
 template <class VT, class FT, class CT, bool GATHER, bool LATTICE>
 __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __restrict__ in, VT* __restrict__ out,
                                                         const int* skip) {
-  if (skip && *skip) return;
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   unsigned char* mine = smem + (size_t)wid * a.warp_smem;
@@ -248,6 +247,10 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
 #ifdef BG_TRSV_TIMING
   if ((int)(blockIdx.x * nw + wid) == g_trsv_probe && lane == 0) g_trsv_t[7] = gt_ns();  // kernel entry of the probed warp
 #endif
+  // Launched with programmatic stream serialisation: until pdl_wait() below, only constant data (block
+  // descriptors, chunk tables, the factor stream) is touched, so the first chunks of every warp are already on
+  // their way while the SpMV that produces `in` is still running.
+  bool waited = false;
   uint32_t g0 = 0;   // ring-global index of the current block's first chunk (monotone per warp)
   uint32_t nin = 0;  // bulk loads of a right-hand side so far (phase of bar_in)
   for (int b = blockIdx.x * nw + wid; b < a.nblocks; b += gridDim.x * nw) {
@@ -272,12 +275,22 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
     };
     const bool bulk_vec = kBulkVec && (((uint32_t)row0 * sizeof(VT)) & 15u) == 0 && (((uint32_t)nb * sizeof(VT)) & 15u) == 0 && nb > 0;
     if (lane == 0) {
+      for (int c = 0; c < nch && c < a.stages; ++c) issue(c);  // factor stream: constant data, may precede pdl_wait
+    }
+    if (!waited) {
+      pdl_wait();
+      waited = true;
+      if (skip && *skip) {  // a skipped launch must still drain the bulk copies it started
+        if (lane == 0) for (int c = 0; c < nch && c < a.stages; ++c) mbar_wait(&bars[(g0 + (uint32_t)c) % (uint32_t)a.stages], ((g0 + (uint32_t)c) / (uint32_t)a.stages) & 1u);
+        return;
+      }
+    }
+    if (lane == 0) {
       if (kBulkVec) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous result has left xl
       if (bulk_vec) {
         mbar_expect_tx(bar_in, (uint32_t)nb * sizeof(VT));
         bulk_g2s(xl, in + row0, (uint32_t)nb * sizeof(VT), bar_in);
       }
-      for (int c = 0; c < nch && c < a.stages; ++c) issue(c);
     }
     __syncwarp();
     TSTAMP(2);
@@ -347,6 +360,7 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
 #ifdef BG_TRSV_TIMING
   if (blockIdx.x * nw + wid == g_trsv_probe && lane == 0) { if (kBulkVec) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); g_trsv_t[6] = gt_ns(); }
 #endif
+  if (!waited) pdl_wait();  // a warp without any block still orders itself behind the previous kernel
   if (kBulkVec && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // results are in HBM before exit
 }
 
@@ -380,7 +394,7 @@ int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void*
   int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(228 * 1024) / (smem + 1024)));
   ctas_per_sm = std::min(ctas_per_sm, 2048 / (warps * 32));
   const int blocks = std::max(1, std::min((S.nblocks + warps - 1) / warps, ctx->sm_count * ctas_per_sm));
-  kern<<<blocks, warps * 32, smem, ctx->stream>>>(a, (const VT*)in, (VT*)out, skip);
+  BG_CUDA(launch_pdl(kern, dim3(blocks), dim3(warps * 32), smem, ctx->stream, a, (const VT*)in, (VT*)out, skip));
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
