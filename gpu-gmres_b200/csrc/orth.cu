@@ -821,10 +821,11 @@ static Pipe pipe_geometry(int ncols, size_t elem) {
   return p;
 }
 template <class K> static int pipe_smem_attr(K kernel, bg_context_t ctx) {
-  static bool done = false;  // per kernel instantiation
-  if (!done) {
+  static bool done[64] = {};  // per kernel instantiation and per device (the attribute is per device)
+  const int d = ctx->device & 63;
+  if (!done[d]) {
     BG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 8192));
-    done = true;
+    done[d] = true;
   }
   return BG_OK;
 }

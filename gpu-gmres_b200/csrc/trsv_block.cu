@@ -384,11 +384,11 @@ int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void*
   }
   auto kern = S.lattice ? (gather ? trsv_block_fused<VT, FT, CT, true, true> : trsv_block_fused<VT, FT, CT, false, true>)
                         : (gather ? trsv_block_fused<VT, FT, CT, true, false> : trsv_block_fused<VT, FT, CT, false, false>);
-  static size_t attr_set[4] = {0, 0, 0, 0};  // per template instantiation
-  const int ai = (gather ? 1 : 0) + (S.lattice ? 2 : 0);
-  if (attr_set[ai] < smem) {
+  static size_t attr_set[64][4] = {};  // per template instantiation and per device (the attribute is per device)
+  const int ai = (gather ? 1 : 0) + (S.lattice ? 2 : 0), dv = ctx->device & 63;
+  if (attr_set[dv][ai] < smem) {
     BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    attr_set[ai] = ctx->smem_optin;
+    attr_set[dv][ai] = ctx->smem_optin;
   }
   // resident CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
   int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(228 * 1024) / (smem + 1024)));
