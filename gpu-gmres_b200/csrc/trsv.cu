@@ -70,15 +70,115 @@ __device__ __forceinline__ void ls_row(const LsArgs<FT>& a, int l, int t, int R,
   store_out<VT, CT>(xf, out, r, acc);
 }
 
-// one CTA walks levels [l0,l1): every level fits a few sweeps of the block
+// one CTA walks levels [l0,l1): every level fits a few sweeps of the block.
+// The walk is a chain of dependent L2 round trips, so everything that does not depend on the previous level is
+// taken off the chain: the level table is staged in shared memory once, the row ids and column indices of level
+// l+1 are fetched into registers while level l waits for its operands, and after the barrier the x gathers (the
+// only loads that depend on level l) are issued together with the values, diagonal and right-hand side -- one
+// round trip per level instead of three.  Rows with more than KP off-diagonals take the plain path.
+constexpr int kWalkKP = 3, kWalkRP = 2;
 template <class VT, class FT, class CT, bool UNIT>
 __global__ void __launch_bounds__(1024) trsv_level_walk(LsArgs<FT> a, int l0, int l1, XformDev<VT> xf,
-                                                        const VT* __restrict__ in, CT* xs, VT* out, const int* skip) {
+                                                        const VT* __restrict__ in, CT* xs, VT* out, const int* skip, int staged) {
   if (skip && *skip) return;
-  for (int l = l0; l < l1; ++l) {
-    const int R = a.lev_ptr[l + 1] - a.lev_ptr[l], K = a.lev_K[l];
-    const int64_t off = a.lev_off[l];
-    for (int t = threadIdx.x; t < R; t += blockDim.x) ls_row<VT, FT, CT, UNIT>(a, l, t, R, K, off, xf, in, xs, out);
+  extern __shared__ __align__(16) unsigned char lw_smem[];
+  constexpr int KP = kWalkKP, RP = kWalkRP;
+  const int nl = l1 - l0, tid = threadIdx.x, bd = blockDim.x;
+  if (!staged) {  // level table too large for shared memory: the plain walk
+    for (int l = l0; l < l1; ++l) {
+      const int R = a.lev_ptr[l + 1] - a.lev_ptr[l], K = a.lev_K[l];
+      const int64_t off = a.lev_off[l];
+      for (int t = tid; t < R; t += bd) ls_row<VT, FT, CT, UNIT>(a, l, t, R, K, off, xf, in, xs, out);
+      __syncthreads();  // orders this CTA's global writes of xs before the next level's reads
+    }
+    return;
+  }
+  int64_t* s_off = reinterpret_cast<int64_t*>(lw_smem);
+  int* s_ptr = reinterpret_cast<int*>(s_off + nl);
+  int* s_K = s_ptr + (nl + 1);
+  for (int i = tid; i <= nl; i += bd) s_ptr[i] = a.lev_ptr[l0 + i];
+  for (int i = tid; i < nl; i += bd) { s_K[i] = a.lev_K[l0 + i]; s_off[i] = a.lev_off[l0 + i]; }
+  __syncthreads();
+  int nr[RP], nc[RP][KP];  // row ids and columns of the NEXT level (independent of the dependency chain)
+  auto is_fast = [&](int li) { return li < nl && s_K[li] <= KP && s_ptr[li + 1] - s_ptr[li] <= RP * bd; };
+  auto prefetch = [&](int li) {
+    const int p0 = s_ptr[li], R = s_ptr[li + 1] - p0, K = s_K[li];
+    const int64_t off = s_off[li];
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+      const int t = tid + q * bd;
+      nr[q] = -1;
+      if (t < R) {
+        nr[q] = a.rows[p0 + t];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) nc[q][k] = k < K ? a.cols[off + (int64_t)k * R + t] : -1;
+      }
+    }
+  };
+  // the factor slabs stream from HBM exactly once per solve: pull the slab of a level into L2 a few levels
+  // before it is needed (fire-and-forget, one prefetch per 128-byte line), so that the loads on the chain are L2 hits
+  auto l2_prefetch = [&](int li) {
+    if (li >= nl) return;
+    const int p0 = s_ptr[li], R = s_ptr[li + 1] - p0, K = s_K[li];
+    const int64_t off = s_off[li];
+    for (int t = tid * 16; t < R; t += bd * 16) {
+      for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vals + off + (int64_t)k * R + t));
+      if (!UNIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.diag + p0 + t));
+    }
+    for (int t = tid * 32; t < R; t += bd * 32) {
+      for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cols + off + (int64_t)k * R + t));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rows + p0 + t));
+    }
+  };
+  constexpr int kAhead = 4;
+  for (int q = 0; q < kAhead; ++q) l2_prefetch(q);
+  bool fast = is_fast(0);
+  if (fast) prefetch(0);
+  for (int li = 0; li < nl; ++li) {
+    const int p0 = s_ptr[li], R = s_ptr[li + 1] - p0, K = s_K[li];
+    const int64_t off = s_off[li];
+    l2_prefetch(li + kAhead);
+    if (fast) {
+      int r[RP], c[RP][KP];
+      CT acc[RP], dg[RP], xv[RP][KP], vv[RP][KP];
+#pragma unroll
+      for (int q = 0; q < RP; ++q) {
+        r[q] = nr[q];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) c[q][k] = nc[q][k];
+      }
+      // the x gathers (the chain) and every other operand of this level leave together
+#pragma unroll
+      for (int q = 0; q < RP; ++q) {
+        if (r[q] < 0) continue;
+        const int t = tid + q * bd;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          xv[q][k] = (CT)0; vv[q][k] = (CT)0;
+          if (c[q][k] >= 0) { xv[q][k] = xs[c[q][k]]; vv[q][k] = (CT)a.vals[off + (int64_t)k * R + t]; }
+        }
+        acc[q] = load_rhs<VT, CT>(xf, in, r[q]);
+        dg[q] = UNIT ? (CT)1 : (CT)a.diag[p0 + t];
+      }
+      const bool fast_next = is_fast(li + 1);
+      if (fast_next) prefetch(li + 1);  // in flight while the gathers above return
+#pragma unroll
+      for (int q = 0; q < RP; ++q) {
+        if (r[q] < 0) continue;
+        CT v = acc[q];
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          if (c[q][k] >= 0) v -= vv[q][k] * xv[q][k];  // same order and operations as ls_row
+        if (!UNIT) v /= dg[q];
+        xs[r[q]] = v;
+        store_out<VT, CT>(xf, out, r[q], v);
+      }
+      fast = fast_next;
+    } else {
+      for (int t = tid; t < R; t += bd) ls_row<VT, FT, CT, UNIT>(a, l0 + li, t, R, K, off, xf, in, xs, out);
+      fast = is_fast(li + 1);
+      if (fast) prefetch(li + 1);
+    }
     __syncthreads();  // orders this CTA's global writes of xs before the next level's reads
   }
 }
@@ -109,7 +209,16 @@ static int level_run(bg_context_t ctx, const LevelStreamDev& S, const void* in, 
       for (int l = l0; l < l1; ++l) maxR = std::max(maxR, S.h_lev_ptr[l + 1] - S.h_lev_ptr[l]);
       int threads = 32;
       while (threads < maxR && threads < 1024) threads <<= 1;
-      trsv_level_walk<VT, FT, CT, UNIT><<<1, threads, 0, ctx->stream>>>(a, l0, l1, xf, (const VT*)in, (CT*)xs, (VT*)out, skip);
+      // level table (16 bytes per level) staged in shared memory when it fits the opt-in limit
+      const size_t tab = (size_t)(l1 - l0) * 16 + 16;
+      const int staged = tab <= ctx->smem_optin - 4096 ? 1 : 0;
+      auto kern = trsv_level_walk<VT, FT, CT, UNIT>;
+      static bool attr_done[64] = {};
+      if (staged && tab > 48 * 1024 && !attr_done[ctx->device & 63]) {
+        BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 4096));
+        attr_done[ctx->device & 63] = true;
+      }
+      kern<<<1, threads, staged ? tab : 0, ctx->stream>>>(a, l0, l1, xf, (const VT*)in, (CT*)xs, (VT*)out, skip, staged);
     } else {
       const int R = S.h_lev_ptr[l1] - S.h_lev_ptr[l0];
       int blocks = (R + 255) / 256;
