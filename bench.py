@@ -218,6 +218,10 @@ def main():
         run_reference(args, rank)
         return
 
+    if world > 1:
+        # rank 0 must print ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        os.environ["NCCL_DEBUG"] = os.environ.get("BG_NCCL_DEBUG", "WARN")
+
     import torch
     import torch.distributed as dist
 
