@@ -102,12 +102,20 @@ struct TrsvXform {      // prologue / epilogue of the split preconditioner
   const void* scale_epi = nullptr;  // rscale
 };
 
-struct LevelStreamDev {
-  int n = 0, n_levels = 0, max_level_rows = 0;
-  DevBuf lev_ptr, lev_K, lev_off, rows, cols, vals, diag;
-  std::vector<int> seg_begin, seg_end, seg_single, h_lev_ptr;
-  std::vector<int> level;
+// device copy of host_algos.h SyncFreeStream (BG_TRSV_LEVEL, any factor; trsv.cu trsv_syncfree)
+struct SyncFreeDev {
+  int n = 0, n_levels = 0, n_slices = 0, max_K = 0, max_level_rows = 0;
+  DevBuf slice_slot, slice_off, rows, cols, vals, diag;
   int64_t bytes = 0;
+  unsigned seq = 0;        // sequence number of the flag-in-data packets, one per launch
+};
+// device copy of host_algos.h LatticeGlobal (BG_TRSV_LEVEL, 5-point ILU(0) in natural order; trsv_lattice_global)
+struct LatticeGlobalDev {
+  bool on = false;
+  int nx = 0, ny = 0, strips = 0, steps = 0;
+  DevBuf lower, upper, bnd;  // bnd: [2][strips][ny] boundary packets (L half, U half)
+  int64_t bytes = 0;
+  unsigned seq = 0;
 };
 
 // device copy of host_algos.h FusedBlockStream (block-Jacobi L+U solve, trsv_block.cu)
@@ -205,8 +213,13 @@ int launch_update(bg_context_t ctx, int dtype, int n, const void* a, const void*
 int launch_solve_y(bg_context_t ctx, const GmresDev& st, int k, int force);
 int launch_state_reset(bg_context_t ctx, const GmresDev& st, double tol, double eta);
 
-int launch_trsv_level(bg_context_t ctx, const LevelStreamDev& S, int vec_dt, int fac_dt, bool unit,
+// one triangular solve in the reference's level order; xs = n flag-in-data packets (16 bytes each) of scratch
+int launch_trsv_level(bg_context_t ctx, SyncFreeDev& S, int vec_dt, int fac_dt, bool unit,
                       const void* in, void* xs, void* out, const TrsvXform& xf, const int* skip_flag);
+// z = U^-1 L^-1 r with the global factors of a 5-point grid (two launches); tmp = n values of the compute type
+int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt, int fac_dt, const void* in, void* tmp,
+                               void* out, const int* skip_flag);
+int lattice_global_capacity(bg_context_t ctx, int vec_dt, int fac_dt);
 // z = U^-1 L^-1 r per diagonal block.  gather = vectors are in the ORIGINAL row order (the kernel
 // goes through perm); otherwise they are in the block-major order of the stream.
 int launch_trsv_block(bg_context_t ctx, const FusedBlockDev& S, int vec_dt, int fac_dt, bool gather,
@@ -228,13 +241,17 @@ int launch_copy(bg_context_t ctx, int dtype, int n, const void* in, void* out, c
 struct bg_precond_s {
   bg_context_t ctx = nullptr;
   int kind = BG_PRECOND_NONE, n = 0, dtype = BG_F64, factor_dtype = BG_F64, schedule = BG_TRSV_LEVEL;
-  bool unit_lower = true, use_tma = true;
+  bool unit_lower = true, use_tma = true, allow_lattice = true;
+  int lg_levels = 0;
   int fb_chunk_bytes = 2048;
   int64_t nnzL = 0, nnzU = 0;
   bg::DevBuf dinv;                                 // DIAG
-  bg::LevelStreamDev lsL, lsU;                     // BG_TRSV_LEVEL
+  bg::SyncFreeDev lsL, lsU;                        // BG_TRSV_LEVEL (any factor)
+  bg::LatticeGlobalDev lg;                         // BG_TRSV_LEVEL (5-point ILU(0), natural order)
+  std::vector<int> levelL, levelU;                 // getLevel of the factors (parity API)
   bg::FusedBlockDev fb;                            // BG_TRSV_BLOCK
-  bg::DevBuf xsL, xsU, tmp;                        // scratch vectors (compute type)
+  bg::DevBuf xsL, xsU;                             // sync-free solves: n flag-in-data packets each
+  bg::DevBuf tmp, tmp2;                            // scratch vectors (compute type)
   bg::DevBuf middle, lscale, rscale, permRow, permCol, invPermCol;  // SPLIT
   bg::DevBuf u_rp, u_ci, u_val;                    // raw CSR U for the warm-start product
   int ct_dtype() const { return (dtype == BG_F64 || factor_dtype == BG_F64) ? BG_F64 : BG_F32; }

@@ -359,16 +359,28 @@ extern "C" void bg_precond_opts_default(bg_precond_opts* o) {
   o->chunk_bytes = 4096;
   o->stages = 2;
   o->warps_per_cta = 3;
+  o->lattice = 1;
 }
 
-template <class T> static int upload_level_stream(bg_context_t ctx, const LevelStream<T>& h, LevelStreamDev& d) {
+template <class T> static int upload_syncfree_stream(bg_context_t ctx, const SyncFreeStream<T>& h, SyncFreeDev& d) {
   cudaStream_t s = ctx->stream;
-  d.n = h.n; d.n_levels = h.n_levels; d.max_level_rows = h.max_level_rows;
-  d.seg_begin = h.seg_begin; d.seg_end = h.seg_end; d.seg_single = h.seg_single; d.h_lev_ptr = h.lev_ptr; d.level = h.level;
-  BG_TRY(upload_vec(d.lev_ptr, h.lev_ptr, s)); BG_TRY(upload_vec(d.lev_K, h.lev_K, s));
-  BG_TRY(upload_vec(d.lev_off, h.lev_off, s)); BG_TRY(upload_vec(d.rows, h.rows, s));
-  BG_TRY(upload_vec(d.cols, h.cols, s)); BG_TRY(upload_vec(d.vals, h.vals, s)); BG_TRY(upload_vec(d.diag, h.diag, s));
-  d.bytes = (int64_t)h.cols.size() * (4 + sizeof(T)) + (int64_t)h.rows.size() * (4 + sizeof(T));
+  d.n = h.n; d.n_levels = h.n_levels; d.n_slices = h.n_slices; d.max_K = h.max_K; d.max_level_rows = h.max_level_rows;
+  BG_TRY(upload_vec(d.slice_slot, h.slice_slot, s)); BG_TRY(upload_vec(d.slice_off, h.slice_off, s));
+  BG_TRY(upload_vec(d.rows, h.rows, s)); BG_TRY(upload_vec(d.cols, h.cols, s));
+  BG_TRY(upload_vec(d.vals, h.vals, s)); BG_TRY(upload_vec(d.diag, h.diag, s));
+  d.bytes = (int64_t)h.cols.size() * (4 + sizeof(T)) + (int64_t)h.rows.size() * (4 + sizeof(T)) + (int64_t)h.slice_slot.size() * 12;
+  BG_CUDA(cudaStreamSynchronize(s));
+  return BG_OK;
+}
+template <class T> static int upload_lattice_global(bg_context_t ctx, const LatticeGlobal<T>& h, LatticeGlobalDev& d) {
+  cudaStream_t s = ctx->stream;
+  d.nx = h.nx; d.ny = h.ny; d.strips = h.strips; d.steps = h.steps;
+  BG_TRY(upload_vec(d.lower, h.lower, s)); BG_TRY(upload_vec(d.upper, h.upper, s));
+  const size_t bnd = (size_t)2 * h.strips * h.ny * 16;
+  BG_TRY(d.bnd.alloc(bnd));
+  BG_CUDA(cudaMemsetAsync(d.bnd.p, 0, bnd, s));
+  d.bytes = (int64_t)(h.lower.size() + h.upper.size()) * sizeof(T);
+  d.on = true;
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }
@@ -407,20 +419,37 @@ static int precond_install(bg_precond_t M, const Csr<FH>& L, const Csr<FH>& U, b
   try {
     if (M->schedule == BG_TRSV_BLOCK) {
       FusedBlockStream<FT> fs;
-      static const bool allow_lattice = [] { const char* e = getenv("BG_TRSV_LATTICE"); return !(e && e[0] == '0'); }();
-      pack_fused_block_stream<FT>(unit_lower, Lf, Uf, nblocks, block_of_row, M->fb_chunk_bytes, fs, allow_lattice);
+      pack_fused_block_stream<FT>(unit_lower, Lf, Uf, nblocks, block_of_row, M->fb_chunk_bytes, fs, M->allow_lattice);
       BG_TRY(upload_fused_stream(M->ctx, fs, M->fb));
     } else {
-      LevelStream<FT> ll, lu;
-      pack_level_stream<FT>(true, unit_lower, Lf, 2048, ll);
-      pack_level_stream<FT>(false, false, Uf, 2048, lu);
-      BG_TRY(upload_level_stream(M->ctx, ll, M->lsL));
-      BG_TRY(upload_level_stream(M->ctx, lu, M->lsU));
+      // the parity artefact: getLevel of both factors (src/gmres.cu:1033-1077)
+      M->levelL.resize(M->n); M->levelU.resize(M->n);
+      trsv_levels<FT>(true, M->n, Lf.rp.data(), Lf.ci.data(), Lf.v.data(), M->levelL.data());
+      trsv_levels<FT>(false, M->n, Uf.rp.data(), Uf.ci.data(), Uf.v.data(), M->levelU.data());
+      int nx = 0;
+      if (M->allow_lattice && unit_lower && M->kind == BG_PRECOND_LU && detect_lattice2d<FT>(Lf, Uf, &nx) &&
+          (nx + 31) / 32 <= lattice_global_capacity(M->ctx, M->dtype, M->factor_dtype)) {
+        LatticeGlobal<FT> lg;
+        pack_lattice_global<FT>(Lf, Uf, nx, lg);
+        BG_TRY(upload_lattice_global(M->ctx, lg, M->lg));
+        M->lg_levels = nx + M->n / nx - 1;
+      } else {
+        SyncFreeStream<FT> ll, lu;
+        pack_syncfree_stream<FT>(true, unit_lower, Lf, ll);
+        pack_syncfree_stream<FT>(false, false, Uf, lu);
+        BG_TRY(upload_syncfree_stream(M->ctx, ll, M->lsL));
+        BG_TRY(upload_syncfree_stream(M->ctx, lu, M->lsU));
+      }
     }
   } catch (const std::exception& e) { set_error("schedule construction failed: %s", e.what()); return BG_ERR_ARG; }
-  BG_TRY(M->xsL.alloc((size_t)M->n * 8));
-  BG_TRY(M->xsU.alloc((size_t)M->n * 8));
+  if (M->schedule == BG_TRSV_LEVEL && !M->lg.on) {  // flag-in-data packets of the sync-free solves (sequence 0 = never written)
+    BG_TRY(M->xsL.alloc((size_t)M->n * 16));
+    BG_TRY(M->xsU.alloc((size_t)M->n * 16));
+    BG_CUDA(cudaMemset(M->xsL.p, 0, (size_t)M->n * 16));
+    BG_CUDA(cudaMemset(M->xsU.p, 0, (size_t)M->n * 16));
+  }
   BG_TRY(M->tmp.alloc((size_t)M->n * 8));
+  if (M->kind == BG_PRECOND_SPLIT) BG_TRY(M->tmp2.alloc((size_t)M->n * 8));
   return BG_OK;
 }
 template <class FH>
@@ -431,6 +460,7 @@ static int precond_install_dt(bg_precond_t M, const Csr<FH>& L, const Csr<FH>& U
 
 static bg_precond_t precond_new(bg_context_t ctx, int kind, int n, int dtype) {
   bg_precond_t M = new bg_precond_s;
+  { const char* e = getenv("BG_TRSV_LATTICE"); M->allow_lattice = !(e && e[0] == '0'); }
   M->ctx = ctx; M->kind = kind; M->n = n; M->dtype = dtype; M->factor_dtype = dtype;
   return M;
 }
@@ -493,6 +523,7 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
   M->schedule = o.trsv_schedule;
   M->factor_dtype = o.factor_dtype < 0 ? dtype : o.factor_dtype;
   M->use_tma = o.use_tma != 0;
+  M->allow_lattice = M->allow_lattice && o.lattice != 0;
   M->fb_chunk_bytes = o.chunk_bytes > 0 ? o.chunk_bytes : 4096;
   M->fb.stages = std::min(8, std::max(2, o.stages > 0 ? o.stages : 2));
   M->fb.warps_per_cta = std::min(16, std::max(1, o.warps_per_cta > 0 ? o.warps_per_cta : 3));
@@ -556,6 +587,7 @@ extern "C" int bg_precond_create_lu(bg_context_t ctx, int n, const int* lp, cons
   bg_precond_t M = precond_new(ctx, BG_PRECOND_LU, n, dtype);
   M->schedule = BG_TRSV_LEVEL;
   M->factor_dtype = d.factor_dtype < 0 ? fdt : d.factor_dtype;
+  M->allow_lattice = M->allow_lattice && d.lattice != 0;
   int rc = precond_install_dt<double>(M, L, U, true, nullptr, 1);
   if (rc < 0) { delete M; return rc; }
   *out = M;
@@ -615,10 +647,10 @@ int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, v
       if (which == BG_PC_RIGHT || which == BG_PC_START) return launch_copy(ctx, M->dtype, n, in, out, skip);
       if (M->schedule == BG_TRSV_BLOCK)  // `permuted`: vectors already in the block-major order of the stream
         return launch_trsv_block(ctx, M->fb, M->dtype, M->factor_dtype, !permuted, in, out, skip);
+      if (M->lg.on) return launch_trsv_lattice_global(ctx, M->lg, M->dtype, M->factor_dtype, in, M->tmp.p, out, skip);
       TrsvXform xf;
-      const bool same = M->ct_dtype() == M->dtype;
-      BG_TRY(launch_trsv_level(ctx, M->lsL, M->dtype, M->factor_dtype, M->unit_lower, in, M->xsL.p, same ? nullptr : M->tmp.p, xf, skip));
-      return launch_trsv_level(ctx, M->lsU, M->dtype, M->factor_dtype, false, same ? M->xsL.p : M->tmp.p, M->xsU.p, out, xf, skip);
+      BG_TRY(launch_trsv_level(ctx, M->lsL, M->dtype, M->factor_dtype, M->unit_lower, in, M->xsL.p, M->tmp.p, xf, skip));
+      return launch_trsv_level(ctx, M->lsU, M->dtype, M->factor_dtype, false, M->tmp.p, M->xsU.p, out, xf, skip);
     }
     case BG_PRECOND_SPLIT: {
       TrsvXform xf;
@@ -633,8 +665,8 @@ int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, v
       if (which == BG_PC_START) {
         // y = diag(middle)^-1 U scatter_{permCol}(rscale .* x)   (preconditioner.cu:1561-1589)
         BG_TRY(launch_scatter_scale(ctx, M->dtype, n, in, M->rscale.p, M->permCol.as<int>(), M->tmp.p));
-        BG_TRY(launch_csr_spmv_mixed(ctx, n, M->u_rp.as<int>(), M->u_ci.as<int>(), M->u_val.p, M->factor_dtype, M->tmp.p, M->xsU.p, BG_F64, nullptr));
-        return launch_divide_cast(ctx, M->dtype, n, M->xsU.p, M->middle.p, out);
+        BG_TRY(launch_csr_spmv_mixed(ctx, n, M->u_rp.as<int>(), M->u_ci.as<int>(), M->u_val.p, M->factor_dtype, M->tmp.p, M->tmp2.p, BG_F64, nullptr));
+        return launch_divide_cast(ctx, M->dtype, n, M->tmp2.p, M->middle.p, out);
       }
       set_error("a split preconditioner has no single-sided application (use LEFT/RIGHT)");
       return BG_ERR_ARG;
@@ -658,9 +690,12 @@ extern "C" int bg_precond_get_info(bg_precond_t M, bg_precond_info* o) {
     if (M->schedule == BG_TRSV_BLOCK) {
       o->levelsL = M->fb.max_levels_L; o->levelsU = M->fb.max_levels_U; o->nblocks = M->fb.nblocks; o->max_block_rows = M->fb.max_rows;
       o->stream_bytes = M->fb.bytes;
+      o->lattice = M->fb.lattice ? 1 : 0;
     } else {
-      o->levelsL = M->lsL.n_levels; o->levelsU = M->lsU.n_levels; o->nblocks = 1; o->max_block_rows = M->n;
-      o->stream_bytes = M->lsL.bytes + M->lsU.bytes;
+      o->levelsL = M->lg.on ? M->lg_levels : M->lsL.n_levels; o->levelsU = M->lg.on ? M->lg_levels : M->lsU.n_levels;
+      o->nblocks = 1; o->max_block_rows = M->n;
+      o->stream_bytes = M->lg.on ? M->lg.bytes : M->lsL.bytes + M->lsU.bytes;
+      o->lattice = M->lg.on ? 1 : 0;
     }
     // B_trsv = (s_f+4)(nnzL+nnzU) + 8(n+1) + 4 s n  (+ 3 s n + 8 n for the split vectors)
     o->trsv_bytes = (sf + 4) * (M->nnzL + M->nnzU) + 8 * (n + 1) + 4 * s * n + (M->kind == BG_PRECOND_SPLIT ? 3 * s * n + 8 * n : 0);
@@ -672,7 +707,7 @@ extern "C" int bg_precond_get_info(bg_precond_t M, bg_precond_info* o) {
 extern "C" int bg_precond_get_levels(bg_precond_t M, int is_lower, int* level) {
   if (!M || !level) return BG_ERR_ARG;
   if (M->schedule != BG_TRSV_LEVEL || (M->kind != BG_PRECOND_LU && M->kind != BG_PRECOND_SPLIT)) return BG_ERR_UNSUPPORTED;
-  const std::vector<int>& l = is_lower ? M->lsL.level : M->lsU.level;
+  const std::vector<int>& l = is_lower ? M->levelL : M->levelU;
   std::copy(l.begin(), l.end(), level);
   return BG_OK;
 }

@@ -4,13 +4,20 @@
 // 1612,1637) and the nine element-wise scale/permute/convert kernels wrapped around them
 // (src/preconditioner.cu:1424-1558), which are folded into the solve's prologue / epilogue here.
 //
-// Two schedules (DESIGN.md "SpTRSV"):
-//  * LEVEL  -- the reference's global dependency levels (getLevel, src/gmres.cu:1033-1077), rows
-//    stored level by level as ELL slabs.  Runs of thin levels are walked by ONE CTA with
-//    __syncthreads between levels (no launch or grid barrier per level); fat levels get a launch
-//    of their own.  Exact same operator as the reference; latency-bound by the dependency chain.
+// Schedules (DESIGN.md "SpTRSV"):
+//  * LEVEL  -- the reference's operator: the GLOBAL factors, dependencies = the level sets of getLevel
+//    (src/gmres.cu:1033-1077).  Two all-SM kernels, no launch and no grid barrier per level:
+//      - trsv_syncfree (any factor): rows sorted by level and cut into 32-row slices that never span two
+//        levels; persistent warps take slices in order and wait for exactly the rows they read through
+//        flag-in-data packets in L2 (value + sequence number in one 16-byte store), so a level costs one
+//        L2 hand-off instead of a launch / grid barrier, and independent chains overlap.
+//      - trsv_lattice_global (ILU(0) factors of a 5-point grid in natural order, detected on the host): one
+//        warp per 32-column strip walks the anti-diagonal wavefront with its operands in registers (south /
+//        north = own previous result, west / east = neighbour lane by shuffle); only the strip boundary
+//        column crosses L2.  No indices are stored; a level costs a shuffle and two FMAs.
 //  * BLOCK  -- block-Jacobi ILU, see trsv_block.cu.
 #include "internal.h"
+#include "peer.cuh"
 
 namespace bg {
 
@@ -48,193 +55,241 @@ __device__ __forceinline__ void store_out(const XformDev<VT>& xf, VT* __restrict
   }
 }
 
-// ------------------------------------------------------------------ LEVEL schedule
-template <class FT> struct LsArgs {
-  const int *lev_ptr, *lev_K, *rows, *cols;
-  const int64_t* lev_off;
+// ------------------------------------------------------------------ sync-free LEVEL schedule (any factor)
+__device__ __forceinline__ LL16 ll_load(const LL16* p) {
+  LL16 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.lo), "=r"(v.f0), "=r"(v.hi), "=r"(v.f1) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool ll_ok(const LL16& v, unsigned seq) { return v.f0 == seq && v.f1 == seq; }
+__device__ __forceinline__ double ll_val(const LL16& v) { return __hiloint2double((int)v.hi, (int)v.lo); }
+
+template <class FT> struct SfArgs {
+  const int *slice_slot, *rows, *cols;
+  const int64_t* slice_off;
   const FT *vals, *diag;
+  int n_slices;
+  unsigned seq;
+  unsigned long long timeout_ns;
 };
 
+// One warp per slice (<= 32 rows of ONE level), slices taken in ascending order by a fixed set of resident warps:
+// a warp only ever waits for rows of earlier slices, which are finished or held by a running warp, so the walk
+// cannot deadlock as long as the whole grid is resident (launcher).  Everything that does not depend on other rows
+// (row ids, columns, values, right-hand side, diagonal) is loaded before the first poll; the K packet loads of a
+// row leave together and only the ones that were not ready yet are polled again.  Same operations in the same
+// order as the reference's host solve (acc = rhs; acc -= v_k x_k in stored order; acc /= diag).
+constexpr int kSfKP = 4;
 template <class VT, class FT, class CT, bool UNIT>
-__device__ __forceinline__ void ls_row(const LsArgs<FT>& a, int l, int t, int R, int K, int64_t off,
-                                       const XformDev<VT>& xf, const VT* __restrict__ in, CT* xs, VT* out) {
-  const int s = a.lev_ptr[l] + t;
-  const int r = a.rows[s];
-  CT acc = load_rhs<VT, CT>(xf, in, r);
-  for (int k = 0; k < K; ++k) {
-    const int c = a.cols[off + (int64_t)k * R + t];
-    if (c >= 0) acc -= (CT)a.vals[off + (int64_t)k * R + t] * xs[c];
-  }
-  if (!UNIT) acc /= (CT)a.diag[s];
-  xs[r] = acc;
-  store_out<VT, CT>(xf, out, r, acc);
-}
-
-// one CTA walks levels [l0,l1): every level fits a few sweeps of the block.
-// The walk is a chain of dependent L2 round trips, so everything that does not depend on the previous level is
-// taken off the chain: the level table is staged in shared memory once, the row ids and column indices of level
-// l+1 are fetched into registers while level l waits for its operands, and after the barrier the x gathers (the
-// only loads that depend on level l) are issued together with the values, diagonal and right-hand side -- one
-// round trip per level instead of three.  Rows with more than KP off-diagonals take the plain path.
-constexpr int kWalkKP = 3, kWalkRP = 2;
-template <class VT, class FT, class CT, bool UNIT>
-__global__ void __launch_bounds__(1024) trsv_level_walk(LsArgs<FT> a, int l0, int l1, XformDev<VT> xf,
-                                                        const VT* __restrict__ in, CT* xs, VT* out, const int* skip, int staged) {
+__global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> xf, const VT* __restrict__ in, LL16* xs,
+                                                     VT* out, const int* skip) {
+  pdl_wait();
   if (skip && *skip) return;
-  extern __shared__ __align__(16) unsigned char lw_smem[];
-  constexpr int KP = kWalkKP, RP = kWalkRP;
-  const int nl = l1 - l0, tid = threadIdx.x, bd = blockDim.x;
-  if (!staged) {  // level table too large for shared memory: the plain walk
-    for (int l = l0; l < l1; ++l) {
-      const int R = a.lev_ptr[l + 1] - a.lev_ptr[l], K = a.lev_K[l];
-      const int64_t off = a.lev_off[l];
-      for (int t = tid; t < R; t += bd) ls_row<VT, FT, CT, UNIT>(a, l, t, R, K, off, xf, in, xs, out);
-      __syncthreads();  // orders this CTA's global writes of xs before the next level's reads
-    }
-    return;
-  }
-  int64_t* s_off = reinterpret_cast<int64_t*>(lw_smem);
-  int* s_ptr = reinterpret_cast<int*>(s_off + nl);
-  int* s_K = s_ptr + (nl + 1);
-  for (int i = tid; i <= nl; i += bd) s_ptr[i] = a.lev_ptr[l0 + i];
-  for (int i = tid; i < nl; i += bd) { s_K[i] = a.lev_K[l0 + i]; s_off[i] = a.lev_off[l0 + i]; }
-  __syncthreads();
-  int nr[RP], nc[RP][KP];  // row ids and columns of the NEXT level (independent of the dependency chain)
-  auto is_fast = [&](int li) { return li < nl && s_K[li] <= KP && s_ptr[li + 1] - s_ptr[li] <= RP * bd; };
-  auto prefetch = [&](int li) {
-    const int p0 = s_ptr[li], R = s_ptr[li + 1] - p0, K = s_K[li];
-    const int64_t off = s_off[li];
+  constexpr int KP = kSfKP;
+  const int lane = threadIdx.x & 31;
+  const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), G = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int q = g; q < a.n_slices; q += G) {
+    const int s0 = a.slice_slot[q], R = a.slice_slot[q + 1] - s0;
+    const int64_t off = a.slice_off[q];
+    const int K = (int)((a.slice_off[q + 1] - off) / R);
+    if (lane >= R) continue;
+    const int r = a.rows[s0 + lane];
+    CT acc = load_rhs<VT, CT>(xf, in, r);
+    const CT dg = UNIT ? (CT)1 : (CT)a.diag[s0 + lane];
+    for (int k0 = 0; k0 < K; k0 += KP) {
+      int c[KP];
+      CT v[KP];
+      LL16 pk[KP];
 #pragma unroll
-    for (int q = 0; q < RP; ++q) {
-      const int t = tid + q * bd;
-      nr[q] = -1;
-      if (t < R) {
-        nr[q] = a.rows[p0 + t];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) nc[q][k] = k < K ? a.cols[off + (int64_t)k * R + t] : -1;
+      for (int j = 0; j < KP; ++j) {
+        c[j] = k0 + j < K ? a.cols[off + (int64_t)(k0 + j) * R + lane] : -1;
+        v[j] = c[j] >= 0 ? (CT)a.vals[off + (int64_t)(k0 + j) * R + lane] : (CT)0;
       }
-    }
-  };
-  // the factor slabs stream from HBM exactly once per solve: pull the slab of a level into L2 a few levels
-  // before it is needed (fire-and-forget, one prefetch per 128-byte line), so that the loads on the chain are L2 hits
-  auto l2_prefetch = [&](int li) {
-    if (li >= nl) return;
-    const int p0 = s_ptr[li], R = s_ptr[li + 1] - p0, K = s_K[li];
-    const int64_t off = s_off[li];
-    for (int t = tid * 16; t < R; t += bd * 16) {
-      for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vals + off + (int64_t)k * R + t));
-      if (!UNIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.diag + p0 + t));
-    }
-    for (int t = tid * 32; t < R; t += bd * 32) {
-      for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cols + off + (int64_t)k * R + t));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rows + p0 + t));
-    }
-  };
-  constexpr int kAhead = 4;
-  for (int q = 0; q < kAhead; ++q) l2_prefetch(q);
-  bool fast = is_fast(0);
-  if (fast) prefetch(0);
-  for (int li = 0; li < nl; ++li) {
-    const int p0 = s_ptr[li], R = s_ptr[li + 1] - p0, K = s_K[li];
-    const int64_t off = s_off[li];
-    l2_prefetch(li + kAhead);
-    if (fast) {
-      int r[RP], c[RP][KP];
-      CT acc[RP], dg[RP], xv[RP][KP], vv[RP][KP];
 #pragma unroll
-      for (int q = 0; q < RP; ++q) {
-        r[q] = nr[q];
+      for (int j = 0; j < KP; ++j)
+        if (c[j] >= 0) pk[j] = ll_load(xs + c[j]);
 #pragma unroll
-        for (int k = 0; k < KP; ++k) c[q][k] = nc[q][k];
-      }
-      // the x gathers (the chain) and every other operand of this level leave together
-#pragma unroll
-      for (int q = 0; q < RP; ++q) {
-        if (r[q] < 0) continue;
-        const int t = tid + q * bd;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          xv[q][k] = (CT)0; vv[q][k] = (CT)0;
-          if (c[q][k] >= 0) { xv[q][k] = xs[c[q][k]]; vv[q][k] = (CT)a.vals[off + (int64_t)k * R + t]; }
+      for (int j = 0; j < KP; ++j)
+        if (c[j] >= 0) {
+          const double x = ll_ok(pk[j], a.seq) ? ll_val(pk[j]) : ll_wait(xs + c[j], a.seq, a.timeout_ns);
+          acc -= v[j] * (CT)x;
         }
-        acc[q] = load_rhs<VT, CT>(xf, in, r[q]);
-        dg[q] = UNIT ? (CT)1 : (CT)a.diag[p0 + t];
-      }
-      const bool fast_next = is_fast(li + 1);
-      if (fast_next) prefetch(li + 1);  // in flight while the gathers above return
-#pragma unroll
-      for (int q = 0; q < RP; ++q) {
-        if (r[q] < 0) continue;
-        CT v = acc[q];
-#pragma unroll
-        for (int k = 0; k < KP; ++k)
-          if (c[q][k] >= 0) v -= vv[q][k] * xv[q][k];  // same order and operations as ls_row
-        if (!UNIT) v /= dg[q];
-        xs[r[q]] = v;
-        store_out<VT, CT>(xf, out, r[q], v);
-      }
-      fast = fast_next;
-    } else {
-      for (int t = tid; t < R; t += bd) ls_row<VT, FT, CT, UNIT>(a, l0 + li, t, R, K, off, xf, in, xs, out);
-      fast = is_fast(li + 1);
-      if (fast) prefetch(li + 1);
     }
-    __syncthreads();  // orders this CTA's global writes of xs before the next level's reads
+    if (!UNIT) acc /= dg;
+    ll_store(xs + r, (double)acc, a.seq);
+    store_out<VT, CT>(xf, out, r, acc);
   }
-}
-// one fat level spread over the whole GPU
-template <class VT, class FT, class CT, bool UNIT>
-__global__ void __launch_bounds__(256) trsv_level_wide(LsArgs<FT> a, int l, XformDev<VT> xf, const VT* __restrict__ in,
-                                                       CT* xs, VT* out, const int* skip) {
-  if (skip && *skip) return;
-  const int R = a.lev_ptr[l + 1] - a.lev_ptr[l], K = a.lev_K[l];
-  const int64_t off = a.lev_off[l];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < R; t += gridDim.x * blockDim.x)
-    ls_row<VT, FT, CT, UNIT>(a, l, t, R, K, off, xf, in, xs, out);
 }
 
-template <class VT, class FT, bool UNIT>
-static int level_run(bg_context_t ctx, const LevelStreamDev& S, const void* in, void* xs, void* out,
-                     const TrsvXform& x, const int* skip) {
-  using CT = decltype(VT() * FT());
-  LsArgs<FT> a{S.lev_ptr.as<int>(), S.lev_K.as<int>(), S.rows.as<int>(), S.cols.as<int>(), S.lev_off.as<int64_t>(),
-               S.vals.as<FT>(), S.diag.as<FT>()};
-  XformDev<VT> xf{x.pro, x.epi, x.pro == 1 ? x.perm : nullptr, x.epi == 1 ? x.perm : nullptr,
-                  (const VT*)x.scale_pro, (const VT*)x.scale_epi};
-  // left-split and right-split never occur in the same solve, so one perm pointer suffices
-  for (size_t g = 0; g < S.seg_begin.size(); ++g) {
-    const int l0 = S.seg_begin[g], l1 = S.seg_end[g];
-    if (S.seg_single[g]) {
-      int maxR = 0;
-      for (int l = l0; l < l1; ++l) maxR = std::max(maxR, S.h_lev_ptr[l + 1] - S.h_lev_ptr[l]);
-      int threads = 32;
-      while (threads < maxR && threads < 1024) threads <<= 1;
-      // level table (16 bytes per level) staged in shared memory when it fits the opt-in limit
-      const size_t tab = (size_t)(l1 - l0) * 16 + 16;
-      const int staged = tab <= ctx->smem_optin - 4096 ? 1 : 0;
-      auto kern = trsv_level_walk<VT, FT, CT, UNIT>;
-      static bool attr_done[64] = {};
-      if (staged && tab > 48 * 1024 && !attr_done[ctx->device & 63]) {
-        BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 4096));
-        attr_done[ctx->device & 63] = true;
+// ------------------------------------------------------------------ global lattice wavefront (5-point ILU(0))
+__device__ __forceinline__ uint32_t lg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int BYTES> __device__ __forceinline__ void cp_async(void* dst, const void* src) {
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lg_smem_u32(dst)), "l"(src) : "memory");
+  else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lg_smem_u32(dst)), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lg_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class FT> struct LgArgs {
+  const FT* coef;  // host_algos.h LatticeGlobal::lower / upper
+  LL16* bnd;       // [strips][ny] boundary column of every strip (flag-in-data packets)
+  int nx, ny, strips, steps;
+  unsigned seq;
+  unsigned long long timeout_ns;
+};
+constexpr int kLgBS = kLatticeBlockSteps, kLgStages = 8;
+template <class TIN, class FT, bool LOWER> constexpr size_t lg_smem_bytes() {
+  return (size_t)kLgStages * kLgBS * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN));
+}
+
+// One warp (= one CTA, one SM) per strip of 32 grid columns.  LOWER: strips left to right, lane x handles row
+// y = d - x at step d;  UPPER: strips right to left, lane x handles y = ny-1 - (d - (31-x)).  The coefficient
+// stream and the right-hand side of a block of kLgBS steps are staged kLgStages-1 blocks ahead with cp.async
+// (every lane copies and later reads only its own slots: no barrier anywhere); the boundary values a strip needs
+// from its upstream neighbour are fetched one block ahead by lanes 0..kLgBS-1 as flag-in-data packets and handed to
+// the edge lane by shuffle, so in steady state no load sits on the dependency chain.
+template <class TIN, class TOUT, class FT, class CT, bool LOWER>
+__global__ void __launch_bounds__(32) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
+                                                          const int* skip) {
+  extern __shared__ __align__(16) unsigned char lg_smem[];
+  constexpr int NV = LOWER ? 2 : 3, BS = kLgBS, NS = kLgStages;
+  FT* s_coef = reinterpret_cast<FT*>(lg_smem);
+  TIN* s_rhs = reinterpret_cast<TIN*>(lg_smem + (size_t)NS * BS * 32 * NV * sizeof(FT));
+  pdl_wait();
+  if (skip && *skip) return;
+  const int lane = threadIdx.x;
+  const int s = LOWER ? (int)blockIdx.x : a.strips - 1 - (int)blockIdx.x;  // CTAs in dependency order
+  const int X = 32 * s + lane, nx = a.nx, ny = a.ny;
+  const bool colok = X < nx;
+  const int lag = LOWER ? lane : 31 - lane;
+  const int nblk = a.steps / BS;
+  const FT* cstream = a.coef + (size_t)s * a.steps * 32 * NV;
+  const bool has_up = LOWER ? s > 0 : s < a.strips - 1, has_down = LOWER ? s < a.strips - 1 : s > 0;
+  const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
+  LL16* bnd_out = a.bnd + (size_t)s * ny;
+  const int edge_in = LOWER ? 0 : 31, edge_out = LOWER ? 31 : 0;
+  auto row_of = [&](int d) { const int t = d - lag; return LOWER ? t : ny - 1 - t; };
+  auto issue = [&](int blk) {
+    if (blk < nblk) {
+      const int st = blk % NS;
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int d = blk * BS + j;
+        FT* cdst = s_coef + (size_t)(st * BS + j) * 32 * NV;
+        const FT* csrc = cstream + (size_t)d * 32 * NV;
+        cp_async<2 * sizeof(FT)>(cdst + 2 * lane, csrc + 2 * lane);
+        if (!LOWER) cp_async<sizeof(FT)>(cdst + 64 + lane, csrc + 64 + lane);
+        const int y = row_of(d);
+        if (colok && (unsigned)y < (unsigned)ny) cp_async<sizeof(TIN)>(s_rhs + (st * BS + j) * 32 + lane, in + (size_t)y * nx + X);
       }
-      kern<<<1, threads, staged ? tab : 0, ctx->stream>>>(a, l0, l1, xf, (const VT*)in, (CT*)xs, (VT*)out, skip, staged);
-    } else {
-      const int R = S.h_lev_ptr[l1] - S.h_lev_ptr[l0];
-      int blocks = (R + 255) / 256;
-      blocks = std::min(blocks, ctx->sm_count * 8);
-      trsv_level_wide<VT, FT, CT, UNIT><<<blocks, 256, 0, ctx->stream>>>(a, l0, xf, (const VT*)in, (CT*)xs, (VT*)out, skip);
     }
-    ctx->launches++;
+    cp_async_commit();  // always (possibly empty) so that the wait below counts uniformly
+  };
+  LL16 pk = {0u, 0u, 0u, 0u};
+  int pk_y = -1;  // row of the packet this lane prefetched for the coming block (-1: none)
+  auto bnd_fetch = [&](int blk) {
+    const int d = blk * BS + lane, y = LOWER ? d : ny - 1 - d;
+    pk_y = (has_up && lane < BS && blk < nblk && (unsigned)y < (unsigned)ny) ? y : -1;
+    if (pk_y >= 0) pk = ll_load(bnd_in + pk_y);
+  };
+  for (int b = 0; b < NS - 1; ++b) issue(b);
+  bnd_fetch(0);
+  CT zprev = (CT)0;
+  for (int blk = 0; blk < nblk; ++blk) {
+    issue(blk + NS - 1);
+    cp_async_wait<NS - 1>();  // block blk has landed (this lane's own copies)
+    double bval = 0.0;
+    if (pk_y >= 0) bval = ll_ok(pk, a.seq) ? ll_val(pk) : ll_wait(bnd_in + pk_y, a.seq, a.timeout_ns);
+    bnd_fetch(blk + 1);  // in flight during the steps below
+    const int st = blk % NS;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      const int d = blk * BS + j, y = row_of(d);
+      const bool act = colok && (unsigned)y < (unsigned)ny;
+      const FT* c = s_coef + (size_t)(st * BS + j) * 32 * NV;
+      const CT ca = (CT)c[2 * lane], cb = (CT)c[2 * lane + 1];
+      CT r = act ? (CT)s_rhs[(st * BS + j) * 32 + lane] : (CT)0;
+      if (!LOWER) r *= (CT)c[64 + lane];
+      CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
+      const double be = __shfl_sync(0xffffffffu, bval, j);
+      if (lane == edge_in) zn = (CT)be;
+      const CT t = r - cb * zprev;  // south / north: own previous result
+      const CT z = t - ca * zn;     // west / east: neighbour lane (or the upstream strip)
+      if (act) {
+        out[(size_t)y * nx + X] = (TOUT)z;
+        if (lane == edge_out && has_down) ll_store(bnd_out + y, (double)z, a.seq);
+      }
+      zprev = act ? z : (CT)0;
+    }
   }
+}
+
+template <class VT, class FT>
+static int lattice_run(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {
+  using CT = decltype(VT() * FT());
+  const unsigned long long tmo = 5ull * 1000000000ull;
+  auto kl = trsv_lattice_global<VT, CT, FT, CT, true>;
+  auto ku = trsv_lattice_global<CT, VT, FT, CT, false>;
+  const size_t sl = lg_smem_bytes<VT, FT, true>(), su = lg_smem_bytes<CT, FT, false>();
+  static bool attr_done[64] = {};
+  if (!attr_done[ctx->device & 63]) {
+    BG_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
+    BG_CUDA(cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)su));
+    attr_done[ctx->device & 63] = true;
+  }
+  LgArgs<FT> al{S.lower.as<FT>(), S.bnd.as<LL16>(), S.nx, S.ny, S.strips, S.steps, ++S.seq, tmo};
+  BG_CUDA(launch_pdl(kl, dim3(S.strips), dim3(32), sl, ctx->stream, al, (const VT*)in, (CT*)tmp, skip));
+  LgArgs<FT> au{S.upper.as<FT>(), S.bnd.as<LL16>() + (size_t)S.strips * S.ny, S.nx, S.ny, S.strips, S.steps, S.seq, tmo};
+  BG_CUDA(launch_pdl(ku, dim3(S.strips), dim3(32), su, ctx->stream, au, (const CT*)tmp, (VT*)out, skip));
+  ctx->launches += 2;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
 }
 
-int launch_trsv_level(bg_context_t ctx, const LevelStreamDev& S, int vec_dt, int fac_dt, bool unit, const void* in,
+int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt, int fac_dt, const void* in, void* tmp,
+                               void* out, const int* skip) {
+  if (vec_dt == BG_F32 && fac_dt == BG_F32) return lattice_run<float, float>(ctx, S, in, tmp, out, skip);
+  if (vec_dt == BG_F32 && fac_dt == BG_F64) return lattice_run<float, double>(ctx, S, in, tmp, out, skip);
+  if (vec_dt == BG_F64 && fac_dt == BG_F32) return lattice_run<double, float>(ctx, S, in, tmp, out, skip);
+  return lattice_run<double, double>(ctx, S, in, tmp, out, skip);
+}
+// strips that can be resident at once (one warp per CTA, shared memory bound): beyond that the general kernel runs
+int lattice_global_capacity(bg_context_t ctx, int vec_dt, int fac_dt) {
+  const size_t ct = (vec_dt == BG_F64 || fac_dt == BG_F64) ? 8 : 4, ft = dtype_size(fac_dt);
+  const size_t su = (size_t)kLgStages * kLgBS * 32 * (3 * ft + ct) + 1024;
+  const int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / su);
+  return ctx->sm_count * std::max(per_sm, 1);
+}
+
+template <class VT, class FT, bool UNIT>
+static int syncfree_run(bg_context_t ctx, SyncFreeDev& S, const void* in, void* xs, void* out, const TrsvXform& x,
+                        const int* skip) {
+  using CT = decltype(VT() * FT());
+  SfArgs<FT> a{S.slice_slot.as<int>(), S.rows.as<int>(), S.cols.as<int>(), S.slice_off.as<int64_t>(), S.vals.as<FT>(),
+               S.diag.as<FT>(), S.n_slices, ++S.seq, 5ull * 1000000000ull};
+  // left-split and right-split never occur in the same solve, so one perm pointer suffices
+  XformDev<VT> xf{x.pro, x.epi, x.pro == 1 ? x.perm : nullptr, x.epi == 1 ? x.perm : nullptr,
+                  (const VT*)x.scale_pro, (const VT*)x.scale_epi};
+  // resident warps: deep enough to have the operands of the coming levels loaded before the dependency front
+  // arrives, shallow enough that the warps polling ahead of the front do not flood L2
+  static const int depth = [] { const char* e = getenv("BG_SF_DEPTH"); const int d = e ? atoi(e) : 8; return d > 0 ? d : 8; }();
+  const double per_level = (double)S.n_slices / std::max(1, S.n_levels);
+  int warps = (int)std::min<double>((double)ctx->sm_count * 32, std::max<double>(ctx->sm_count, per_level * depth));
+  warps = std::min(warps, std::max(1, S.n_slices));
+  const int threads = warps <= 4 * ctx->sm_count ? 32 : 128;
+  const int blocks = (warps * 32 + threads - 1) / threads;  // <= 16 CTAs per SM: always resident
+  BG_CUDA(launch_pdl(trsv_syncfree<VT, FT, CT, UNIT>, dim3(blocks), dim3(threads), 0, ctx->stream, a, xf, (const VT*)in,
+                     (LL16*)xs, (VT*)out, skip));
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+
+int launch_trsv_level(bg_context_t ctx, SyncFreeDev& S, int vec_dt, int fac_dt, bool unit, const void* in,
                       void* xs, void* out, const TrsvXform& xf, const int* skip) {
   if (S.n == 0) return BG_OK;
-#define BG_L(VT, FT) (unit ? level_run<VT, FT, true>(ctx, S, in, xs, out, xf, skip) : level_run<VT, FT, false>(ctx, S, in, xs, out, xf, skip))
+#define BG_L(VT, FT) (unit ? syncfree_run<VT, FT, true>(ctx, S, in, xs, out, xf, skip) : syncfree_run<VT, FT, false>(ctx, S, in, xs, out, xf, skip))
   if (vec_dt == BG_F32 && fac_dt == BG_F32) return BG_L(float, float);
   if (vec_dt == BG_F32 && fac_dt == BG_F64) return BG_L(float, double);
   if (vec_dt == BG_F64 && fac_dt == BG_F32) return BG_L(double, float);

@@ -367,65 +367,148 @@ int block_partition(int method, int n, const int* rp, const int* ci, int nblocks
 }
 
 // ------------------------------------------------------------------ packers
+void trsv_levels_structural(bool lower, int n, const int* rp, const int* ci, int* level) {
+  std::fill(level, level + n, 0);
+  if (lower) {
+    for (int i = 0; i < n; ++i) {
+      int best = 0;
+      for (int p = rp[i]; p < rp[i + 1]; ++p)
+        if (ci[p] < i) best = std::max(best, level[ci[p]] + 1);
+      level[i] = best;
+    }
+  } else {
+    for (int i = n - 1; i >= 0; --i) {
+      int best = 0;
+      for (int p = rp[i]; p < rp[i + 1]; ++p)
+        if (ci[p] > i) best = std::max(best, level[ci[p]] + 1);
+      level[i] = best;
+    }
+  }
+}
+
 template <class T>
-void pack_level_stream(bool lower, bool unit, const Csr<T>& M, int thin_rows, LevelStream<T>& out) {
+void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream<T>& out) {
   const int n = M.n;
   out.n = n;
   out.level.resize(n);
+  out.sched_level.resize(n);
   trsv_levels(lower, n, M.rp.data(), M.ci.data(), M.v.data(), out.level.data());
-  out.n_levels = bucket_levels(n, out.level.data(), out.lev_ptr, out.rows);
-  const int nl = out.n_levels;
-  out.lev_K.assign(nl, 0);
-  out.lev_off.assign(nl + 1, 0);
-  out.max_level_rows = 0;
-  for (int l = 0; l < nl; ++l) {
-    int K = 0;
-    for (int s = out.lev_ptr[l]; s < out.lev_ptr[l + 1]; ++s) {
-      const int r = out.rows[s];
-      K = std::max(K, M.rp[r + 1] - M.rp[r] - 1);
+  trsv_levels_structural(lower, n, M.rp.data(), M.ci.data(), out.sched_level.data());
+  std::vector<int> lev_ptr;
+  out.n_levels = bucket_levels(n, out.sched_level.data(), lev_ptr, out.rows);
+  out.slice_slot.assign(1, 0);
+  out.slice_off.assign(1, 0);
+  out.max_K = out.max_level_rows = 0;
+  for (int l = 0; l < out.n_levels; ++l) {
+    out.max_level_rows = std::max(out.max_level_rows, lev_ptr[l + 1] - lev_ptr[l]);
+    for (int s0 = lev_ptr[l]; s0 < lev_ptr[l + 1]; s0 += 32) {
+      const int R = std::min(32, lev_ptr[l + 1] - s0);
+      int K = 0;
+      for (int t = 0; t < R; ++t) {
+        const int r = out.rows[s0 + t];
+        K = std::max(K, M.rp[r + 1] - M.rp[r] - 1);
+      }
+      out.max_K = std::max(out.max_K, K);
+      out.slice_slot.push_back(s0 + R);
+      out.slice_off.push_back(out.slice_off.back() + (int64_t)K * R);
     }
-    out.lev_K[l] = K;
-    const int R = out.lev_ptr[l + 1] - out.lev_ptr[l];
-    out.max_level_rows = std::max(out.max_level_rows, R);
-    out.lev_off[l + 1] = out.lev_off[l] + (int64_t)K * R;
   }
-  out.cols.assign(out.lev_off[nl], -1);
-  out.vals.assign(out.lev_off[nl], (T)0);
+  out.n_slices = (int)out.slice_slot.size() - 1;
+  out.cols.assign(out.slice_off.back(), -1);
+  out.vals.assign(out.slice_off.back(), (T)0);
   out.diag.assign(n, (T)1);
-  for (int l = 0; l < nl; ++l) {
-    const int R = out.lev_ptr[l + 1] - out.lev_ptr[l];
+  for (int q = 0; q < out.n_slices; ++q) {
+    const int s0 = out.slice_slot[q], R = out.slice_slot[q + 1] - s0;
+    const int64_t off = out.slice_off[q];
     for (int t = 0; t < R; ++t) {
-      const int s = out.lev_ptr[l] + t, r = out.rows[s];
+      const int r = out.rows[s0 + t];
       const int lb = M.rp[r], ub = M.rp[r + 1];
+      if (ub <= lb) throw std::invalid_argument("triangular factor row without a diagonal");
       const int dpos = lower ? ub - 1 : lb;
-      if (!unit) out.diag[s] = M.v[dpos];
+      if (!unit) out.diag[s0 + t] = M.v[dpos];
       int k = 0;
       for (int p = lb; p < ub; ++p) {
         if (p == dpos) continue;
-        out.cols[out.lev_off[l] + (int64_t)k * R + t] = M.ci[p];
-        out.vals[out.lev_off[l] + (int64_t)k * R + t] = M.v[p];
+        if (lower ? M.ci[p] >= r : M.ci[p] <= r) throw std::invalid_argument("entry on the wrong side of the diagonal");
+        out.cols[off + (int64_t)k * R + t] = M.ci[p];
+        out.vals[off + (int64_t)k * R + t] = M.v[p];
         ++k;
       }
     }
   }
-  // launch plan
-  out.seg_begin.clear(); out.seg_end.clear(); out.seg_single.clear();
-  int l = 0;
-  while (l < nl) {
-    const int R = out.lev_ptr[l + 1] - out.lev_ptr[l];
-    if (R > thin_rows) {
-      out.seg_begin.push_back(l); out.seg_end.push_back(l + 1); out.seg_single.push_back(0);
-      ++l;
-    } else {
-      int e = l;
-      while (e < nl && out.lev_ptr[e + 1] - out.lev_ptr[e] <= thin_rows) ++e;
-      out.seg_begin.push_back(l); out.seg_end.push_back(e); out.seg_single.push_back(1);
-      l = e;
+}
+template void pack_syncfree_stream<float>(bool, bool, const Csr<float>&, SyncFreeStream<float>&);
+template void pack_syncfree_stream<double>(bool, bool, const Csr<double>&, SyncFreeStream<double>&);
+
+template <class T> bool detect_lattice2d(const Csr<T>& L, const Csr<T>& U, int* nx_out) {
+  const int n = L.n;
+  if (n < 4 || U.n != n) return false;
+  int nx = 0;
+  for (int r = 0; r < n && !nx; ++r)
+    for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p)
+      if (L.ci[p] != r - 1) { nx = r - L.ci[p]; break; }
+  if (nx < 2 || n % nx) return false;
+  for (int r = 0; r < n; ++r) {
+    const int x = r % nx;
+    if (L.rp[r + 1] <= L.rp[r] || L.ci[L.rp[r + 1] - 1] != r) return false;
+    if (U.rp[r + 1] <= U.rp[r] || U.ci[U.rp[r]] != r || U.v[U.rp[r]] == (T)0) return false;
+    for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p) {
+      const int c = L.ci[p];
+      if (!((x > 0 && c == r - 1) || c == r - nx)) return false;
+    }
+    for (int p = U.rp[r] + 1; p < U.rp[r + 1]; ++p) {
+      const int c = U.ci[p];
+      if (!((x < nx - 1 && c == r + 1) || c == r + nx)) return false;
     }
   }
+  *nx_out = nx;
+  return true;
 }
-template void pack_level_stream<float>(bool, bool, const Csr<float>&, int, LevelStream<float>&);
-template void pack_level_stream<double>(bool, bool, const Csr<double>&, int, LevelStream<double>&);
+template bool detect_lattice2d<float>(const Csr<float>&, const Csr<float>&, int*);
+template bool detect_lattice2d<double>(const Csr<double>&, const Csr<double>&, int*);
+
+template <class T> void pack_lattice_global(const Csr<T>& L, const Csr<T>& U, int nx, LatticeGlobal<T>& out) {
+  const int n = L.n, ny = n / nx;
+  constexpr int BS = kLatticeBlockSteps;
+  out.nx = nx; out.ny = ny;
+  out.strips = (nx + 31) / 32;
+  out.steps = (ny + 31 + BS - 1) / BS * BS;
+  out.lower.assign((size_t)out.strips * out.steps * 64, (T)0);
+  out.upper.assign((size_t)out.strips * out.steps * 96, (T)0);
+  auto find = [](const Csr<T>& M, int r, int c, int lb, int ub) -> double {
+    for (int p = lb; p < ub; ++p)
+      if (M.ci[p] == c) return (double)M.v[p];
+    return 0.0;
+  };
+  for (int s = 0; s < out.strips; ++s)
+    for (int d = 0; d < ny + 31; ++d)
+      for (int x = 0; x < 32; ++x) {
+        const int X = 32 * s + x;
+        if (X >= nx) continue;
+        {  // lower: lane x lags x steps
+          const int y = d - x;
+          if (y >= 0 && y < ny) {
+            const int r = y * nx + X;
+            T* q = &out.lower[((size_t)s * out.steps + d) * 64 + 2 * x];
+            q[0] = (T)(X > 0 ? find(L, r, r - 1, L.rp[r], L.rp[r + 1] - 1) : 0.0);
+            q[1] = (T)(y > 0 ? find(L, r, r - nx, L.rp[r], L.rp[r + 1] - 1) : 0.0);
+          }
+        }
+        {  // upper: lane x lags 31 - x steps, rows walked downwards
+          const int y = ny - 1 - (d - (31 - x));
+          if (y >= 0 && y < ny) {
+            const int r = y * nx + X;
+            const double di = 1.0 / (double)U.v[U.rp[r]];
+            T* q = &out.upper[((size_t)s * out.steps + d) * 96];
+            q[2 * x] = (T)(X < nx - 1 ? find(U, r, r + 1, U.rp[r] + 1, U.rp[r + 1]) * di : 0.0);
+            q[2 * x + 1] = (T)(y < ny - 1 ? find(U, r, r + nx, U.rp[r] + 1, U.rp[r + 1]) * di : 0.0);
+            q[64 + x] = (T)di;
+          }
+        }
+      }
+}
+template void pack_lattice_global<float>(const Csr<float>&, const Csr<float>&, int, LatticeGlobal<float>&);
+template void pack_lattice_global<double>(const Csr<double>&, const Csr<double>&, int, LatticeGlobal<double>&);
 
 template <class T>
 void pack_fused_block_stream(bool unit_lower, const Csr<T>& L, const Csr<T>& U, int nblocks, const int* block_of_row,

@@ -56,24 +56,52 @@ int block_partition(int method, int n, const int* rp, const int* ci, int nblocks
                     int* block_of_row);
 
 // ------------------------------------------------------------------ device stream packers
-// Level stream (BG_TRSV_LEVEL): rows sorted by (level, row id); per level an ELL slab.
-//   slot s in [lev_ptr[l], lev_ptr[l+1]) holds row rows[s];
-//   off-diagonal entry k of that slot:  cols/vals[lev_off[l] + k*R_l + (s - lev_ptr[l])], col -1 = padding
-//   diag[s] (1 for unit-lower)
-template <class T> struct LevelStream {
-  int n = 0, n_levels = 0, max_level_rows = 0;
-  std::vector<int> level;            // per row (for parity checks)
-  std::vector<int> lev_ptr, lev_K, rows;
-  std::vector<int64_t> lev_off;
-  std::vector<int> cols;
+// Structural triangular-solve levels: like trsv_levels but over EVERY stored off-diagonal entry, whatever its
+// value (getLevel stops at / skips |v| < 1e-9, so a factor holding an explicit tiny entry would be scheduled
+// below a row it still reads).  This is the dependency spec the device schedules execute; trsv_levels stays
+// the parity artefact.  The two agree whenever the factor stores no |v| < 1e-9 entry (always true for
+// bg_host_ilu0 / splitLU_csr output).
+void trsv_levels_structural(bool lower, int n, const int* rp, const int* ci, int* level);
+
+// Sync-free stream (BG_TRSV_LEVEL, general factors; trsv.cu trsv_syncfree): rows sorted by (structural level,
+// row id) -- slot s holds row rows[s] -- and cut into SLICES of <= 32 consecutive slots that never span two
+// levels, so a slice (= one warp) only ever waits for rows of earlier slices.  Slice q covers slots
+// [slice_slot[q], slice_slot[q+1]) = R rows; off-diagonal entry k of its t-th row sits at
+// cols/vals[slice_off[q] + k*R + t] (column -1 = padding); K_q = (slice_off[q+1] - slice_off[q]) / R.
+// diag[s] per slot (1 for unit-lower).
+template <class T> struct SyncFreeStream {
+  int n = 0, n_levels = 0, n_slices = 0, max_K = 0, max_level_rows = 0;
+  std::vector<int> level;        // per row: getLevel (parity API)
+  std::vector<int> sched_level;  // per row: structural level the slices follow
+  std::vector<int> slice_slot;   // n_slices + 1
+  std::vector<int64_t> slice_off;  // n_slices + 1
+  std::vector<int> rows, cols;
   std::vector<T> vals, diag;
-  // launch plan: consecutive levels [seg_begin[i], seg_end[i]) ; seg_single[i]=1 -> one CTA walks
-  // them with __syncthreads, 0 -> exactly one fat level launched over many CTAs
-  std::vector<int> seg_begin, seg_end, seg_single;
 };
 // lower: diagonal is the LAST entry of each row (unit => value ignored); upper: FIRST entry.
 template <class T>
-void pack_level_stream(bool lower, bool unit, const Csr<T>& M, int thin_rows, LevelStream<T>& out);
+void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream<T>& out);
+
+// Global lattice stream (BG_TRSV_LEVEL, ILU(0) factors of a 5-point stencil in natural order; trsv.cu
+// trsv_lattice_global): the factors of an nx x ny grid (row = y*nx + x) that couple only west/south (L, unit
+// lower) and east/north (U) neighbours are solved EXACTLY (global operator, not block-Jacobi) by one warp per
+// 32-column STRIP walking the anti-diagonal wavefront: lane x of strip s owns column 32 s + x, its south (north)
+// operand is its own previous result, its west (east) operand comes from the neighbour lane by warp shuffle,
+// and the first lane's comes from the neighbouring strip through a small boundary buffer in L2.
+// No index is stored.  Per strip and step d (= anti-diagonal inside the strip; steps padded to a multiple of
+// kLatticeBlockSteps) the stream holds, for the 32 lanes,
+//     L:  32 x (west, south)                      lane x handles y = d - x
+//     U:  32 x (east, north) then 32 x dinv       lane x handles y = ny-1 - (d - (31-x)); values pre-scaled
+//                                                 by dinv = 1/diag(U) so the device solves a unit system
+// lanes outside the grid hold zeros.  Strip s, step d starts at value index (s*steps + d) * 32 * NV (NV = 2 / 3).
+constexpr int kLatticeBlockSteps = 8;
+template <class T> struct LatticeGlobal {
+  int nx = 0, ny = 0, strips = 0, steps = 0;
+  std::vector<T> lower, upper;
+};
+// true (and nx set) when L (unit lower, diagonal last) and U (diagonal first) have the lattice pattern above
+template <class T> bool detect_lattice2d(const Csr<T>& L, const Csr<T>& U, int* nx);
+template <class T> void pack_lattice_global(const Csr<T>& L, const Csr<T>& U, int nx, LatticeGlobal<T>& out);
 
 // Fused block stream (BG_TRSV_BLOCK): every diagonal block's forward AND backward solve is done
 // by one warp out of shared memory in one kernel.  Rows are renumbered block-major

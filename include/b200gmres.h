@@ -50,7 +50,8 @@ enum { BG_PRECOND_NONE = 0, BG_PRECOND_DIAG = 1, BG_PRECOND_LU = 2, BG_PRECOND_S
    classical GS with DGKS-style re-orthogonalisation */
 enum { BG_ORTH_MGS = 0, BG_ORTH_CGS_ADAPTIVE = 1, BG_ORTH_CGS2 = 2 };
 /* triangular-solve schedule */
-enum { BG_TRSV_LEVEL = 0,  /* global level sets, bit-exact with getLevel (gmres.cu:1033-1077)      */
+enum { BG_TRSV_LEVEL = 0,  /* the reference's operator: global factors, dependencies = the level sets of
+                              getLevel (gmres.cu:1033-1077); sync-free all-SM kernels (trsv.cu)       */
        BG_TRSV_BLOCK = 1 };/* block-Jacobi: each block's L and U solve by one warp out of shared
                               memory, rows renumbered block-major (the solver permutes A, b, x)   */
 /* row-block partitioners for BG_TRSV_BLOCK and for the multi-GPU row partition */
@@ -164,6 +165,8 @@ typedef struct {
   int chunk_bytes;     /* BG_TRSV_BLOCK: target size of one bulk copy of the factor stream (4096) */
   int stages;          /* BG_TRSV_BLOCK: ring slots per warp (2)                                  */
   int warps_per_cta;   /* BG_TRSV_BLOCK: block solves per CTA (3)                                 */
+  int lattice;         /* 1 (default): index-free wavefront layouts when the factors are those of a
+                          5-point grid (detected from the pattern); 0: always the general streams  */
 } bg_precond_opts;
 BG_API void bg_precond_opts_default(bg_precond_opts* o);
 /* MyNONE (preconditioner.h) */
@@ -202,6 +205,7 @@ typedef struct {
   int nblocks, max_block_rows;
   int64_t trsv_bytes;          /* algorithmic bytes of one full application, SURVEY 8d           */
   int64_t stream_bytes;        /* bytes of the packed factor streams actually read per apply     */
+  int lattice;                 /* 1: an index-free lattice layout is in use                       */
 } bg_precond_info;
 BG_API int bg_precond_get_info(bg_precond_t M, bg_precond_info* info);
 /* level sets the device schedule was built from (BG_TRSV_LEVEL only), for parity tests */

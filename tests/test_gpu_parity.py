@@ -112,13 +112,17 @@ def oracle_ilu0_pc(oracle, bg, rp, ci, v, mode, blk=None):
 
 @pytest.mark.parametrize("name", ["pg2d_61x47", "th3d_13x11x9", "rand_2000"])
 @pytest.mark.parametrize("dtc", [0, 1])
-def test_ilu0_level_schedule_matches_oracle(bg, ctx, oracle, name, dtc):
+@pytest.mark.parametrize("lattice", [1, 0])
+def test_ilu0_level_schedule_matches_oracle(bg, ctx, oracle, name, dtc, lattice):
+    """Reference operator (global factors): the wavefront-strip kernel where the factors are a 5-point grid
+    (lattice=1 on pg2d), the sync-free slice kernel everywhere else."""
     rp, ci, v, b = CASES[name]
     mode = "f32" if dtc == 0 else "f64"
     dt = np_dt(dtc)
     n = len(rp) - 1
     f, pc = oracle_ilu0_pc(oracle, bg, rp, ci, v, mode)
-    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=dtc)
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=dtc, opts=bg.precond_opts(lattice=lattice))
+    assert M.info().lattice == (1 if lattice and name.startswith("pg2d") else 0)
     # level sets the device schedule was built from == getLevel (bit-exact integer artefact)
     assert np.array_equal(M.levels(True), oracle.get_level(1, f["lp"], f["li"], f["lv"], mode))
     assert np.array_equal(M.levels(False), oracle.get_level(0, f["up"], f["ui"], f["uv"], mode))
@@ -128,8 +132,39 @@ def test_ilu0_level_schedule_matches_oracle(bg, ctx, oracle, name, dtc):
     M.apply(bg.PC_FULL, din.data_ptr(), dout.data_ptr())
     got = host(ctx, dout)
     want = pc.apply(0, b)
-    # same operations in the same order per row: FP64 agrees to the last bits, FP32 to a few ulp (FMA)
+    # same operations in the same order per row: FP64 agrees to the last bits, FP32 to a few ulp (FMA); the
+    # strip kernel solves the row-scaled unit system D^-1 U, which moves the last bit or two
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < (5e-6 if dtc == 0 else 1e-14)
+    # a second application must not see the first one's packets (sequence numbers)
+    dout.zero_()
+    M.apply(bg.PC_FULL, din.data_ptr(), dout.data_ptr())
+    assert np.array_equal(host(ctx, dout), got)
+    M.close()
+
+
+def test_level_schedule_with_explicit_tiny_entries(bg, ctx):
+    """caller-supplied factors holding explicit |v| < 1e-9 entries.  getLevel stops at / skips them
+    (the parity artefact keeps doing so), the device schedule follows the structural dependencies, so every
+    stored entry is applied in order."""
+    rng = np.random.default_rng(5)
+    n = 900
+    L = sp.tril(sp.random(n, n, density=0.004, random_state=rng, format="csr"), -1).tolil()
+    U = sp.triu(sp.random(n, n, density=0.004, random_state=rng, format="csr"), 1).tolil()
+    for i in range(1, n):
+        L[i, i - 1] = 1e-12 if i % 3 == 0 else 0.4   # the FIRST entry of many rows is tiny
+    for i in range(n - 1):
+        U[i, i + 1] = 1e-12 if i % 4 == 0 else -0.3
+    L = (L.tocsr() + sp.eye(n)).tocsr(); U = (U.tocsr() + 2.5 * sp.eye(n)).tocsr()
+    L.sort_indices(); U.sort_indices()
+    b = rng.uniform(-1, 1, n)
+    M = bg.Precond.lu(ctx, L.indptr, L.indices, L.data, U.indptr, U.indices, U.data, dtype=1)
+    din, dout = dev(b, np.float64), dev(np.zeros(n), np.float64)
+    M.apply(bg.PC_FULL, din.data_ptr(), dout.data_ptr())
+    got = host(ctx, dout)
+    Lu = sp.tril(L, -1) + sp.eye(n)  # unit lower: the stored diagonal is ignored (DIAG_TYPE_UNIT)
+    want = sp.linalg.spsolve_triangular(U.tocsr(), sp.linalg.spsolve_triangular(Lu.tocsr(), b, lower=True), lower=False)
+    assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want)
+    assert np.array_equal(M.levels(True), bg.host_trsv_levels(1, L.indptr, L.indices, L.data))  # parity API unchanged
     M.close()
 
 

@@ -143,6 +143,22 @@ def test_ilut_reduces_to_ilu_and_improves(bg, oracle):
     assert it_ilut < g["f64_meta"][1]
 
 
+def test_level_stream_packers(tmp_path):
+    """The two BG_TRSV_LEVEL streams (sync-free slices for any factor, index-free strips for 5-point ILU(0)),
+    interpreted on the host the way trsv_syncfree / trsv_lattice_global consume them: no row is read before it
+    is published (no device deadlock), slices never span levels, explicit |v| < 1e-9 entries are scheduled
+    structurally, and the result equals a plain CSR forward/backward solve."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "stream_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "stream_check.cpp"),
+                           os.path.join(root, "gpu-gmres_b200", "host", "host_algos.cpp"),
+                           "/usr/local/cuda/lib64/libmetis_static.a", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_fused_block_stream_packer(tmp_path):
     """The packed factor stream of the block-Jacobi solve, interpreted on the host step by step the
     way trsv_block_fused consumes it, reproduces a plain CSR forward/backward solve."""
