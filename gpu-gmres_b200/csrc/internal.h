@@ -112,8 +112,8 @@ struct SyncFreeDev {
 // device copy of host_algos.h LatticeGlobal (BG_TRSV_LEVEL, 5-point ILU(0) in natural order; trsv_lattice_global)
 struct LatticeGlobalDev {
   bool on = false;
-  int nx = 0, ny = 0, strips = 0, steps = 0;
-  DevBuf lower, upper, bnd;  // bnd: [2][strips][ny] boundary packets (L half, U half)
+  int nx = 0, ny = 0, strips = 0;
+  DevBuf lower, upper, udinv, bnd;  // bnd: [2][strips][ny] boundary packets (L half, U half)
   int64_t bytes = 0;
   unsigned seq = 0;
 };

@@ -374,12 +374,12 @@ template <class T> static int upload_syncfree_stream(bg_context_t ctx, const Syn
 }
 template <class T> static int upload_lattice_global(bg_context_t ctx, const LatticeGlobal<T>& h, LatticeGlobalDev& d) {
   cudaStream_t s = ctx->stream;
-  d.nx = h.nx; d.ny = h.ny; d.strips = h.strips; d.steps = h.steps;
-  BG_TRY(upload_vec(d.lower, h.lower, s)); BG_TRY(upload_vec(d.upper, h.upper, s));
+  d.nx = h.nx; d.ny = h.ny; d.strips = h.strips;
+  BG_TRY(upload_vec(d.lower, h.lower, s)); BG_TRY(upload_vec(d.upper, h.upper, s)); BG_TRY(upload_vec(d.udinv, h.udinv, s));
   const size_t bnd = (size_t)2 * h.strips * h.ny * 16;
   BG_TRY(d.bnd.alloc(bnd));
   BG_CUDA(cudaMemsetAsync(d.bnd.p, 0, bnd, s));
-  d.bytes = (int64_t)(h.lower.size() + h.upper.size()) * sizeof(T);
+  d.bytes = (int64_t)(h.lower.size() + h.upper.size() + h.udinv.size()) * sizeof(T);
   d.on = true;
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;

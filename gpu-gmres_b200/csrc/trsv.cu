@@ -16,6 +16,8 @@
 //        north = own previous result, west / east = neighbour lane by shuffle); only the strip boundary
 //        column crosses L2.  No indices are stored; a level costs a shuffle and two FMAs.
 //  * BLOCK  -- block-Jacobi ILU, see trsv_block.cu.
+#include <type_traits>
+
 #include "internal.h"
 #include "peer.cuh"
 
@@ -132,30 +134,38 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <class FT> struct LgArgs {
-  const FT* coef;  // host_algos.h LatticeGlobal::lower / upper
+  const FT* pair;  // host_algos.h LatticeGlobal::lower / upper
+  const FT* dinv;  // LatticeGlobal::udinv (upper only)
   LL16* bnd;       // [strips][ny] boundary column of every strip (flag-in-data packets)
-  int nx, ny, strips, steps;
+  int nx, ny, strips;
   unsigned seq;
   unsigned long long timeout_ns;
 };
-constexpr int kLgBS = kLatticeBlockSteps, kLgStages = 8;
-template <class TIN, class FT, bool LOWER> constexpr size_t lg_smem_bytes() {
-  return (size_t)kLgStages * kLgBS * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN));
+constexpr int kLgBS = 8;     // steps per block (prefetch / boundary / flush granularity)
+constexpr int kLgOutRows = 64;
+template <class TIN, class TOUT, class FT, bool LOWER> constexpr size_t lg_smem_bytes(int NR) {
+  return (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN)) + (size_t)kLgOutRows * 32 * sizeof(TOUT);
 }
 
-// One warp (= one CTA, one SM) per strip of 32 grid columns.  LOWER: strips left to right, lane x handles row
-// y = d - x at step d;  UPPER: strips right to left, lane x handles y = ny-1 - (d - (31-x)).  The coefficient
-// stream and the right-hand side of a block of kLgBS steps are staged kLgStages-1 blocks ahead with cp.async
-// (every lane copies and later reads only its own slots: no barrier anywhere); the boundary values a strip needs
-// from its upstream neighbour are fetched one block ahead by lanes 0..kLgBS-1 as flag-in-data packets and handed to
-// the edge lane by shuffle, so in steady state no load sits on the dependency chain.
-template <class TIN, class TOUT, class FT, class CT, bool LOWER>
+// One warp (= one CTA, one SM) per strip of 32 grid columns; "time row" t = y (LOWER, strips left to right) or
+// ny-1-y (UPPER, strips right to left); lane x reaches time row t at step t + lag, lag = x (LOWER) / 31-x (UPPER).
+// Every HBM access is a coalesced 32-node row segment: coefficient pairs, 1/diag and the right-hand side of the
+// time rows of block b+PF are staged with cp.async into a ring of NR rows (each lane copies and later reads only
+// its own column, so no barrier is needed anywhere), and results wait in a small ring until all 32 lanes have
+// passed a row, then leave as one 256-byte store.  The boundary values a strip needs from its upstream neighbour
+// are fetched one block ahead by lanes 0..kLgBS-1 as flag-in-data packets and handed to the edge lane by shuffle,
+// so in steady state no load sits on the dependency chain: a step is two shuffles and two FMAs.
+template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR, int PF>
 __global__ void __launch_bounds__(32) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
                                                           const int* skip) {
+  static_assert((NR & (NR - 1)) == 0 && NR > 8 * PF + 38, "ring too small for the prefetch distance plus the lane skew");
   extern __shared__ __align__(16) unsigned char lg_smem[];
-  constexpr int NV = LOWER ? 2 : 3, BS = kLgBS, NS = kLgStages;
-  FT* s_coef = reinterpret_cast<FT*>(lg_smem);
-  TIN* s_rhs = reinterpret_cast<TIN*>(lg_smem + (size_t)NS * BS * 32 * NV * sizeof(FT));
+  constexpr int BS = kLgBS, NRO = kLgOutRows;
+  using P = typename std::conditional<sizeof(FT) == 8, double2, float2>::type;
+  P* s_pair = reinterpret_cast<P*>(lg_smem);
+  FT* s_dinv = reinterpret_cast<FT*>(lg_smem + (size_t)NR * 32 * sizeof(P));
+  TIN* s_rhs = reinterpret_cast<TIN*>(lg_smem + (size_t)NR * 32 * (LOWER ? 2 : 3) * sizeof(FT));
+  TOUT* s_out = reinterpret_cast<TOUT*>(lg_smem + (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN)));
   pdl_wait();
   if (skip && *skip) return;
   const int lane = threadIdx.x;
@@ -163,25 +173,23 @@ __global__ void __launch_bounds__(32) trsv_lattice_global(LgArgs<FT> a, const TI
   const int X = 32 * s + lane, nx = a.nx, ny = a.ny;
   const bool colok = X < nx;
   const int lag = LOWER ? lane : 31 - lane;
-  const int nblk = a.steps / BS;
-  const FT* cstream = a.coef + (size_t)s * a.steps * 32 * NV;
+  const int nblk = (ny + 31 + BS - 1) / BS;
+  const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
+  const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
   const bool has_up = LOWER ? s > 0 : s < a.strips - 1, has_down = LOWER ? s < a.strips - 1 : s > 0;
   const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
   LL16* bnd_out = a.bnd + (size_t)s * ny;
   const int edge_in = LOWER ? 0 : 31, edge_out = LOWER ? 31 : 0;
-  auto row_of = [&](int d) { const int t = d - lag; return LOWER ? t : ny - 1 - t; };
-  auto issue = [&](int blk) {
-    if (blk < nblk) {
-      const int st = blk % NS;
+  auto yrow = [&](int t) { return LOWER ? t : ny - 1 - t; };
+  auto issue = [&](int blk) {  // time rows [8 blk, 8 blk + 8)
 #pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        const int d = blk * BS + j;
-        FT* cdst = s_coef + (size_t)(st * BS + j) * 32 * NV;
-        const FT* csrc = cstream + (size_t)d * 32 * NV;
-        cp_async<2 * sizeof(FT)>(cdst + 2 * lane, csrc + 2 * lane);
-        if (!LOWER) cp_async<sizeof(FT)>(cdst + 64 + lane, csrc + 64 + lane);
-        const int y = row_of(d);
-        if (colok && (unsigned)y < (unsigned)ny) cp_async<sizeof(TIN)>(s_rhs + (st * BS + j) * 32 + lane, in + (size_t)y * nx + X);
+    for (int j = 0; j < BS; ++j) {
+      const int t = blk * BS + j;
+      if (t < ny) {
+        const int y = yrow(t), slot = (t & (NR - 1)) * 32 + lane;
+        cp_async<sizeof(P)>(s_pair + slot, gpair + (size_t)y * 32);
+        if (!LOWER) cp_async<sizeof(FT)>(s_dinv + slot, gdinv + (size_t)y * 32);
+        if (colok) cp_async<sizeof(TIN)>(s_rhs + slot, in + (size_t)y * nx + X);
       }
     }
     cp_async_commit();  // always (possibly empty) so that the wait below counts uniformly
@@ -189,62 +197,77 @@ __global__ void __launch_bounds__(32) trsv_lattice_global(LgArgs<FT> a, const TI
   LL16 pk = {0u, 0u, 0u, 0u};
   int pk_y = -1;  // row of the packet this lane prefetched for the coming block (-1: none)
   auto bnd_fetch = [&](int blk) {
-    const int d = blk * BS + lane, y = LOWER ? d : ny - 1 - d;
-    pk_y = (has_up && lane < BS && blk < nblk && (unsigned)y < (unsigned)ny) ? y : -1;
+    const int t = blk * BS + lane;  // the edge lane has no lag: it reaches time row t at step t
+    pk_y = (has_up && lane < BS && t < ny) ? yrow(t) : -1;
     if (pk_y >= 0) pk = ll_load(bnd_in + pk_y);
   };
-  for (int b = 0; b < NS - 1; ++b) issue(b);
+  for (int b = 0; b < PF; ++b) issue(b);
   bnd_fetch(0);
   CT zprev = (CT)0;
+  int t = -lag;  // this lane's time row at the current step
   for (int blk = 0; blk < nblk; ++blk) {
-    issue(blk + NS - 1);
-    cp_async_wait<NS - 1>();  // block blk has landed (this lane's own copies)
+    issue(blk + PF);
+    cp_async_wait<PF>();  // the rows of block blk (and everything older) have landed: this lane's own copies
     double bval = 0.0;
     if (pk_y >= 0) bval = ll_ok(pk, a.seq) ? ll_val(pk) : ll_wait(bnd_in + pk_y, a.seq, a.timeout_ns);
     bnd_fetch(blk + 1);  // in flight during the steps below
-    const int st = blk % NS;
 #pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      const int d = blk * BS + j, y = row_of(d);
-      const bool act = colok && (unsigned)y < (unsigned)ny;
-      const FT* c = s_coef + (size_t)(st * BS + j) * 32 * NV;
-      const CT ca = (CT)c[2 * lane], cb = (CT)c[2 * lane + 1];
-      CT r = act ? (CT)s_rhs[(st * BS + j) * 32 + lane] : (CT)0;
-      if (!LOWER) r *= (CT)c[64 + lane];
+    for (int j = 0; j < BS; ++j, ++t) {
+      const bool act = colok && (unsigned)t < (unsigned)ny;
+      const int slot = (t & (NR - 1)) * 32 + lane;
+      CT ca = (CT)0, cb = (CT)0, r = (CT)0;
+      if (act) {
+        const P c = s_pair[slot];
+        ca = (CT)c.x; cb = (CT)c.y;
+        r = (CT)s_rhs[slot];
+        if (!LOWER) r *= (CT)s_dinv[slot];
+      }
       CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
       const double be = __shfl_sync(0xffffffffu, bval, j);
       if (lane == edge_in) zn = (CT)be;
-      const CT t = r - cb * zprev;  // south / north: own previous result
-      const CT z = t - ca * zn;     // west / east: neighbour lane (or the upstream strip)
+      const CT tt = r - cb * zprev;  // south / north: own previous result
+      const CT z = tt - ca * zn;     // west / east: neighbour lane (or the upstream strip)
       if (act) {
-        out[(size_t)y * nx + X] = (TOUT)z;
-        if (lane == edge_out && has_down) ll_store(bnd_out + y, (double)z, a.seq);
+        s_out[(t & (NRO - 1)) * 32 + lane] = (TOUT)z;
+        if (lane == edge_out && has_down) ll_store(bnd_out + yrow(t), (double)z, a.seq);
       }
       zprev = act ? z : (CT)0;
+    }
+    // rows every lane has passed: one coalesced store per row (each lane re-reads its own column)
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      const int tf = blk * BS - 31 + j;
+      if (colok && (unsigned)tf < (unsigned)ny) out[(size_t)yrow(tf) * nx + X] = s_out[(tf & (NRO - 1)) * 32 + lane];
     }
   }
 }
 
-template <class VT, class FT>
-static int lattice_run(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {
+template <class VT, class FT, int NR, int PF>
+static int lattice_launch(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {
   using CT = decltype(VT() * FT());
   const unsigned long long tmo = 5ull * 1000000000ull;
-  auto kl = trsv_lattice_global<VT, CT, FT, CT, true>;
-  auto ku = trsv_lattice_global<CT, VT, FT, CT, false>;
-  const size_t sl = lg_smem_bytes<VT, FT, true>(), su = lg_smem_bytes<CT, FT, false>();
+  auto kl = trsv_lattice_global<VT, CT, FT, CT, true, NR, PF>;
+  auto ku = trsv_lattice_global<CT, VT, FT, CT, false, NR, PF>;
+  const size_t sl = lg_smem_bytes<VT, CT, FT, true>(NR), su = lg_smem_bytes<CT, VT, FT, false>(NR);
   static bool attr_done[64] = {};
   if (!attr_done[ctx->device & 63]) {
     BG_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     BG_CUDA(cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)su));
     attr_done[ctx->device & 63] = true;
   }
-  LgArgs<FT> al{S.lower.as<FT>(), S.bnd.as<LL16>(), S.nx, S.ny, S.strips, S.steps, ++S.seq, tmo};
+  LgArgs<FT> al{S.lower.as<FT>(), nullptr, S.bnd.as<LL16>(), S.nx, S.ny, S.strips, ++S.seq, tmo};
   BG_CUDA(launch_pdl(kl, dim3(S.strips), dim3(32), sl, ctx->stream, al, (const VT*)in, (CT*)tmp, skip));
-  LgArgs<FT> au{S.upper.as<FT>(), S.bnd.as<LL16>() + (size_t)S.strips * S.ny, S.nx, S.ny, S.strips, S.steps, S.seq, tmo};
+  LgArgs<FT> au{S.upper.as<FT>(), S.udinv.as<FT>(), S.bnd.as<LL16>() + (size_t)S.strips * S.ny, S.nx, S.ny, S.strips, S.seq, tmo};
   BG_CUDA(launch_pdl(ku, dim3(S.strips), dim3(32), su, ctx->stream, au, (const CT*)tmp, (VT*)out, skip));
   ctx->launches += 2;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
+}
+// deep ring (one strip per SM) while the strips fit the SMs, a shallower one beyond (several strips per SM)
+template <class VT, class FT>
+static int lattice_run(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {
+  if (S.strips <= ctx->sm_count) return lattice_launch<VT, FT, 128, 7>(ctx, S, in, tmp, out, skip);
+  return lattice_launch<VT, FT, 64, 3>(ctx, S, in, tmp, out, skip);
 }
 
 int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt, int fac_dt, const void* in, void* tmp,
@@ -257,7 +280,7 @@ int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt
 // strips that can be resident at once (one warp per CTA, shared memory bound): beyond that the general kernel runs
 int lattice_global_capacity(bg_context_t ctx, int vec_dt, int fac_dt) {
   const size_t ct = (vec_dt == BG_F64 || fac_dt == BG_F64) ? 8 : 4, ft = dtype_size(fac_dt);
-  const size_t su = (size_t)kLgStages * kLgBS * 32 * (3 * ft + ct) + 1024;
+  const size_t su = (size_t)64 * 32 * (3 * ft + ct) + (size_t)kLgOutRows * 32 * ct + 1024;  // the shallow ring
   const int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / su);
   return ctx->sm_count * std::max(per_sm, 1);
 }

@@ -469,43 +469,21 @@ template bool detect_lattice2d<double>(const Csr<double>&, const Csr<double>&, i
 
 template <class T> void pack_lattice_global(const Csr<T>& L, const Csr<T>& U, int nx, LatticeGlobal<T>& out) {
   const int n = L.n, ny = n / nx;
-  constexpr int BS = kLatticeBlockSteps;
   out.nx = nx; out.ny = ny;
   out.strips = (nx + 31) / 32;
-  out.steps = (ny + 31 + BS - 1) / BS * BS;
-  out.lower.assign((size_t)out.strips * out.steps * 64, (T)0);
-  out.upper.assign((size_t)out.strips * out.steps * 96, (T)0);
-  auto find = [](const Csr<T>& M, int r, int c, int lb, int ub) -> double {
-    for (int p = lb; p < ub; ++p)
-      if (M.ci[p] == c) return (double)M.v[p];
-    return 0.0;
-  };
-  for (int s = 0; s < out.strips; ++s)
-    for (int d = 0; d < ny + 31; ++d)
-      for (int x = 0; x < 32; ++x) {
-        const int X = 32 * s + x;
-        if (X >= nx) continue;
-        {  // lower: lane x lags x steps
-          const int y = d - x;
-          if (y >= 0 && y < ny) {
-            const int r = y * nx + X;
-            T* q = &out.lower[((size_t)s * out.steps + d) * 64 + 2 * x];
-            q[0] = (T)(X > 0 ? find(L, r, r - 1, L.rp[r], L.rp[r + 1] - 1) : 0.0);
-            q[1] = (T)(y > 0 ? find(L, r, r - nx, L.rp[r], L.rp[r + 1] - 1) : 0.0);
-          }
-        }
-        {  // upper: lane x lags 31 - x steps, rows walked downwards
-          const int y = ny - 1 - (d - (31 - x));
-          if (y >= 0 && y < ny) {
-            const int r = y * nx + X;
-            const double di = 1.0 / (double)U.v[U.rp[r]];
-            T* q = &out.upper[((size_t)s * out.steps + d) * 96];
-            q[2 * x] = (T)(X < nx - 1 ? find(U, r, r + 1, U.rp[r] + 1, U.rp[r + 1]) * di : 0.0);
-            q[2 * x + 1] = (T)(y < ny - 1 ? find(U, r, r + nx, U.rp[r] + 1, U.rp[r + 1]) * di : 0.0);
-            q[64 + x] = (T)di;
-          }
-        }
-      }
+  const size_t slots = (size_t)out.strips * ny * 32;
+  out.lower.assign(slots * 2, (T)0);
+  out.upper.assign(slots * 2, (T)0);
+  out.udinv.assign(slots, (T)0);
+  for (int r = 0; r < n; ++r) {
+    const int X = r % nx, y = r / nx;
+    const size_t q = ((size_t)(X / 32) * ny + y) * 32 + X % 32;
+    for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p) out.lower[2 * q + (L.ci[p] == r - 1 && X > 0 ? 0 : 1)] = L.v[p];
+    const double di = 1.0 / (double)U.v[U.rp[r]];
+    out.udinv[q] = (T)di;
+    for (int p = U.rp[r] + 1; p < U.rp[r + 1]; ++p)
+      out.upper[2 * q + (U.ci[p] == r + 1 && X < nx - 1 ? 0 : 1)] = (T)((double)U.v[p] * di);
+  }
 }
 template void pack_lattice_global<float>(const Csr<float>&, const Csr<float>&, int, LatticeGlobal<float>&);
 template void pack_lattice_global<double>(const Csr<double>&, const Csr<double>&, int, LatticeGlobal<double>&);

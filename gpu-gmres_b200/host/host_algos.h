@@ -88,16 +88,15 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
 // 32-column STRIP walking the anti-diagonal wavefront: lane x of strip s owns column 32 s + x, its south (north)
 // operand is its own previous result, its west (east) operand comes from the neighbour lane by warp shuffle,
 // and the first lane's comes from the neighbouring strip through a small boundary buffer in L2.
-// No index is stored.  Per strip and step d (= anti-diagonal inside the strip; steps padded to a multiple of
-// kLatticeBlockSteps) the stream holds, for the 32 lanes,
-//     L:  32 x (west, south)                      lane x handles y = d - x
-//     U:  32 x (east, north) then 32 x dinv       lane x handles y = ny-1 - (d - (31-x)); values pre-scaled
-//                                                 by dinv = 1/diag(U) so the device solves a unit system
-// lanes outside the grid hold zeros.  Strip s, step d starts at value index (s*steps + d) * 32 * NV (NV = 2 / 3).
-constexpr int kLatticeBlockSteps = 8;
+// No index is stored.  Per strip s the stream holds the coefficients of its 32 columns row by row,
+//     lower[((s*ny + y)*32 + x)*2 + {0,1}] = (west, south) coefficient of node (32 s + x, y)
+//     upper[((s*ny + y)*32 + x)*2 + {0,1}] = (east, north) coefficient, pre-scaled by dinv = 1/diag(U)
+//     udinv[(s*ny + y)*32 + x]             = dinv                      (the device solves a unit upper system)
+// so a warp stages whole 32-node row segments with coalesced copies and each lane consumes its own column along
+// the wavefront (lane x reaches row y x steps after lane 0).  Columns outside the grid hold zeros.
 template <class T> struct LatticeGlobal {
-  int nx = 0, ny = 0, strips = 0, steps = 0;
-  std::vector<T> lower, upper;
+  int nx = 0, ny = 0, strips = 0;
+  std::vector<T> lower, upper, udinv;
 };
 // true (and nx set) when L (unit lower, diagonal last) and U (diagonal first) have the lattice pattern above
 template <class T> bool detect_lattice2d(const Csr<T>& L, const Csr<T>& U, int* nx);

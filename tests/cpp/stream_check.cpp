@@ -132,43 +132,46 @@ template <class T> static void grid_factors(int nx, int ny, unsigned seed, doubl
     }
 }
 
-// trsv_lattice_global, one factor: strips in dependency order, 32 lanes, steps of kLatticeBlockSteps
+// trsv_lattice_global, one factor: strips in dependency order, 32 lanes, blocks of 8 steps; lane x reaches time
+// row t (= y for L, ny-1-y for U) at step t + lag
 template <class T>
 static void lattice_emulate(const LatticeGlobal<T>& S, bool lower, const std::vector<double>& in, std::vector<double>& out) {
-  const int nx = S.nx, ny = S.ny, NV = lower ? 2 : 3;
-  const std::vector<T>& coef = lower ? S.lower : S.upper;
+  const int nx = S.nx, ny = S.ny, BS = 8;
+  const std::vector<T>& pair = lower ? S.lower : S.upper;
   std::vector<double> bnd((size_t)S.strips * ny, 0.0);
   std::vector<char> bnd_ok((size_t)S.strips * ny, 0);
+  const int nblk = (ny + 31 + BS - 1) / BS;
   for (int b = 0; b < S.strips; ++b) {
     const int s = lower ? b : S.strips - 1 - b;
     const bool has_up = lower ? s > 0 : s < S.strips - 1, has_down = lower ? s < S.strips - 1 : s > 0;
     const int up = lower ? s - 1 : s + 1, edge_in = lower ? 0 : 31, edge_out = lower ? 31 : 0;
     double zprev[32] = {0};
-    for (int d = 0; d < S.steps; ++d) {
+    for (int d = 0; d < nblk * BS; ++d) {
       double z[32];
       for (int lane = 0; lane < 32; ++lane) {
         const int X = 32 * s + lane, lag = lower ? lane : 31 - lane, t = d - lag, y = lower ? t : ny - 1 - t;
-        const bool act = X < nx && y >= 0 && y < ny;
-        const T* c = &coef[((size_t)s * S.steps + d) * 32 * NV];
-        const double ca = (double)c[2 * lane], cb = (double)c[2 * lane + 1];
-        double r = act ? in[(size_t)y * nx + X] : 0.0;
-        if (!lower) r *= (double)c[64 + lane];
+        const bool act = X < nx && t >= 0 && t < ny;
+        double ca = 0, cb = 0, r = 0;
+        if (act) {
+          const size_t q = ((size_t)s * ny + y) * 32 + lane;
+          ca = (double)pair[2 * q]; cb = (double)pair[2 * q + 1];
+          r = in[(size_t)y * nx + X];
+          if (!lower) r *= (double)S.udinv[q];
+        }
         double zn = lower ? (lane > 0 ? zprev[lane - 1] : 0.0) : (lane < 31 ? zprev[lane + 1] : 0.0);
         if (lane == edge_in) {
           const int ye = lower ? d : ny - 1 - d;  // the edge lane has no lag
           zn = 0.0;
-          if (has_up && ye >= 0 && ye < ny) {
+          if (has_up && d < ny) {
             if (!bnd_ok[(size_t)up * ny + ye]) { std::printf("lattice: strip %d step %d reads an unpublished boundary row %d\n", s, d, ye); std::exit(1); }
             zn = bnd[(size_t)up * ny + ye];
           }
         }
         const double tt = r - cb * zprev[lane];
-        z[lane] = tt - ca * zn;
+        z[lane] = act ? tt - ca * zn : 0.0;
         if (act) {
           out[(size_t)y * nx + X] = z[lane];
           if (lane == edge_out && has_down) { bnd[(size_t)s * ny + y] = z[lane]; bnd_ok[(size_t)s * ny + y] = 1; }
-        } else {
-          z[lane] = 0.0;
         }
       }
       for (int lane = 0; lane < 32; ++lane) zprev[lane] = z[lane];

@@ -13,6 +13,7 @@ from b200gmres import synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--nx", type=int, default=1304)
+ap.add_argument("--ny", type=int, default=0, help="grid height (default: square)")
 ap.add_argument("--reps", type=int, default=50)
 ap.add_argument("--th3d", type=int, default=0, help="edge of a 3-D thermal grid instead of the 2-D power grid")
 ap.add_argument("--modes", default="lattice,syncfree,block")
@@ -21,8 +22,9 @@ if a.th3d:
     rp, ci, v, b = synth.th3d(a.th3d, a.th3d, a.th3d, seed=synth.SEED_BASE + 3)
     dims, meth, rows = [a.th3d] * 3 + [8, 8, 8], bg.PART_GRID3D, 512
 else:
-    rp, ci, v, b = synth.pg2d(a.nx, a.nx, seed=synth.SEED_BASE + 2)
-    dims, meth, rows = [a.nx, a.nx, 1, 32, 32, 1], bg.PART_GRID2D, 1024
+    ny = a.ny or a.nx
+    rp, ci, v, b = synth.pg2d(a.nx, ny, seed=synth.SEED_BASE + 2)
+    dims, meth, rows = [a.nx, ny, 1, 32, 32, 1], bg.PART_GRID2D, 1024
 n = len(rp) - 1
 ctx = bg.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream)
@@ -55,7 +57,7 @@ for mode in a.modes.split(","):
         else:
             err = float(np.linalg.norm(x - ref) / np.linalg.norm(ref))
     moved = info.stream_bytes + 4 * 8 * n
-    print(json.dumps({"mode": mode, "n": n, "lattice": info.lattice, "levelsL": info.levelsL, "us_per_apply": us, "setup_s": setup,
+    print(json.dumps({"mode": mode, "n": n, "nx": a.nx, "ny": a.ny or a.nx, "sf_depth": os.environ.get("BG_SF_DEPTH"), "lattice": info.lattice, "levelsL": info.levelsL, "us_per_apply": us, "setup_s": setup,
                       "stream_bytes": info.stream_bytes, "moved_GBps": moved / us / 1e3, "algorithmic_GBps": info.trsv_bytes / us / 1e3,
                       "vs_first_level_mode": err}), flush=True)
     M.close()
