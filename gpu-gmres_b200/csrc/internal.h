@@ -245,7 +245,9 @@ struct bg_precond_s {
   int lg_levels = 0;
   int fb_chunk_bytes = 2048;
   int64_t nnzL = 0, nnzU = 0;
-  bg::DevBuf dinv;                                 // DIAG
+  bg::DevBuf dinv;                                 // DIAG, AINV (middle diagonal)
+  bg_matrix_t m1 = nullptr, m2 = nullptr;          // AINV: explicit inverse factors (owned)
+  ~bg_precond_s() { delete m1; delete m2; }
   bg::SyncFreeDev lsL, lsU;                        // BG_TRSV_LEVEL (any factor)
   bg::LatticeGlobalDev lg;                         // BG_TRSV_LEVEL (5-point ILU(0), natural order)
   std::vector<int> levelL, levelU;                 // getLevel of the factors (parity API)

@@ -305,6 +305,17 @@ extern "C" int bg_host_ilut(int n, const int* rp, const int* ci, const void* v, 
   if (lfil < 0 || tau < 0) return BG_ERR_ARG;
   return host_factor(true, n, rp, ci, v, dt, tau, lfil, blk, F);
 }
+extern "C" int bg_host_ainv(int n, const int* rp, const int* ci, const void* v, int dt, double droptol, bg_factors_t* out) {
+  if (!out || n < 0 || droptol < 0 || (n && (!rp || !ci || !v))) return BG_ERR_ARG;
+  bg_factors_t F = new bg_factors_s;
+  F->n = n; F->dtype = dt;
+  try {
+    if (dt == BG_F64) ainv_biconjugation<double>(n, rp, ci, (const double*)v, droptol, F->f64);
+    else ainv_biconjugation<float>(n, rp, ci, (const float*)v, droptol, F->f32);
+  } catch (const std::exception& e) { set_error("AINV construction failed: %s", e.what()); delete F; return BG_ERR_ARG; }
+  *out = F;
+  return BG_OK;
+}
 extern "C" int bg_factors_get_info(bg_factors_t F, bg_factors_info* o) {
   if (!F || !o) return BG_ERR_ARG;
   o->n = F->n; o->dtype = F->dtype;
@@ -496,6 +507,24 @@ extern "C" int bg_precond_create_diag(bg_context_t ctx, int n, const int* rp, co
   return BG_OK;
 }
 
+extern "C" int bg_precond_create_ainv(bg_context_t ctx, int n, const int* p1, const int* c1, const void* v1, const void* diag,
+                                      const int* p2, const int* c2, const void* v2, int vdt, int dtype, bg_precond_t* out) {
+  if (!ctx || !out || n < 0 || (n && (!p1 || !c1 || !v1)) || (p2 && (!c2 || !v2))) return BG_ERR_ARG;
+  BG_CUDA(cudaSetDevice(ctx->device));
+  bg_precond_t M = precond_new(ctx, BG_PRECOND_AINV, n, dtype);
+  int rc = bg_matrix_create_csr(ctx, n, n ? p1[n] : 0, p1, c1, v1, vdt, BG_HOST, dtype, BG_SPMV_AUTO, &M->m1);
+  if (rc >= 0 && p2) rc = bg_matrix_create_csr(ctx, n, n ? p2[n] : 0, p2, c2, v2, vdt, BG_HOST, dtype, BG_SPMV_AUTO, &M->m2);
+  if (rc >= 0 && diag)
+    rc = dtype == BG_F32 ? upload_vec(M->dinv, to_vec<float>(diag, vdt, n), ctx->stream) : upload_vec(M->dinv, to_vec<double>(diag, vdt, n), ctx->stream);
+  if (rc >= 0) rc = M->tmp.alloc((size_t)n * 8);
+  if (rc >= 0) rc = M->tmp2.alloc((size_t)n * 8);
+  cudaStreamSynchronize(ctx->stream);
+  if (rc < 0) { delete M; return rc; }
+  M->nnzL = M->m1->nnz; M->nnzU = M->m2 ? M->m2->nnz : 0;
+  *out = M;
+  return BG_OK;
+}
+
 static int make_blocks(const bg_precond_opts& o, int n, const int* rp, const int* ci, std::vector<int>& blk, int* nblocks) {
   blk.assign(n, 0);
   const int rows = std::max(32, o.block_rows);
@@ -643,6 +672,15 @@ int precond_apply(bg_context_t ctx, bg_precond_t M, int which, const void* in, v
     case BG_PRECOND_DIAG:
       if (which == BG_PC_RIGHT || which == BG_PC_START) return launch_copy(ctx, M->dtype, n, in, out, skip);
       return launch_diag_scale(ctx, M->dtype, n, in, M->dinv.p, out, skip);
+    case BG_PRECOND_AINV: {
+      if (which == BG_PC_RIGHT || which == BG_PC_START) return launch_copy(ctx, M->dtype, n, in, out, skip);
+      const bool two = M->m2 != nullptr, scaled = M->dinv.p != nullptr;
+      void* t1 = two || scaled ? M->tmp.p : out;
+      BG_TRY(launch_spmv(ctx, M->m1, 1.0, in, 0.0, nullptr, t1, false, skip));
+      if (scaled) BG_TRY(launch_diag_scale(ctx, M->dtype, n, t1, M->dinv.p, two ? M->tmp2.p : out, skip));
+      if (two) BG_TRY(launch_spmv(ctx, M->m2, 1.0, scaled ? M->tmp2.p : t1, 0.0, nullptr, out, false, skip));
+      return BG_OK;
+    }
     case BG_PRECOND_LU: {
       if (which == BG_PC_RIGHT || which == BG_PC_START) return launch_copy(ctx, M->dtype, n, in, out, skip);
       if (M->schedule == BG_TRSV_BLOCK)  // `permuted`: vectors already in the block-major order of the stream
@@ -701,6 +739,8 @@ extern "C" int bg_precond_get_info(bg_precond_t M, bg_precond_info* o) {
     o->trsv_bytes = (sf + 4) * (M->nnzL + M->nnzU) + 8 * (n + 1) + 4 * s * n + (M->kind == BG_PRECOND_SPLIT ? 3 * s * n + 8 * n : 0);
   } else if (M->kind == BG_PRECOND_DIAG) {
     o->trsv_bytes = 3 * s * n;
+  } else if (M->kind == BG_PRECOND_AINV) {
+    o->trsv_bytes = (s + 4) * (M->nnzL + M->nnzU) + (M->m2 ? 2 : 1) * (4 * (n + 1) + 2 * s * n) + (M->dinv.p ? 3 * s * n : 0);
   }
   return BG_OK;
 }
@@ -716,7 +756,7 @@ extern "C" int bg_precond_destroy(bg_precond_t M) { delete M; return BG_OK; }
 // =========================================================================== solver
 extern "C" void bg_gmres_opts_default(bg_gmres_opts* o) {
   std::memset(o, 0, sizeof(*o));
-  o->m = 32; o->max_iter = 10000; o->tol = 1e-8; o->orth = BG_ORTH_CGS_ADAPTIVE;
+  o->m = 32; o->max_iter = 10000; o->tol = 1e-8; o->orth = BG_ORTH_MGS;  // the reference's order; CGS modes are opt-in
   o->reorth_eta = 0.70710678118654752; o->poll_chunk = 8; o->use_graph = 0; o->history_cap = 0;
 }
 

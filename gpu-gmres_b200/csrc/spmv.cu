@@ -304,4 +304,70 @@ int launch_csr_spmv_mixed(bg_context_t ctx, int n, const int* rp, const int* ci,
   return BG_OK;
 }
 
+
+// ------------------------------------------------------------------ small helpers behind the C ABI
+// fingerprint of a device buffer (two position-weighted 64-bit sums of its 32-bit words): lets the reference-API
+// shim notice that a caller refilled or re-allocated a matrix it handed over as raw device pointers
+__global__ void __launch_bounds__(256) checksum_kernel(const unsigned* __restrict__ w, size_t nwords, unsigned long long* out) {
+  unsigned long long s1 = 0, s2 = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long v = w[i];
+    s1 += v;
+    s2 += v * (2ull * i + 1ull);
+  }
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, s1); atomicAdd(out + 1, s2); }
+}
+// x += V[:, 0..k) y   (Update_GPU, src/gmres.cu:164-189, after the host back-substitution)
+template <class VT> __global__ void __launch_bounds__(256) basis_update_kernel(int n, int64_t ld, int k, const VT* __restrict__ V,
+                                                                               const double* __restrict__ y, VT* x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int c = 0; c < k; ++c) acc += (double)V[i + (size_t)c * ld] * y[c];
+    x[i] = (VT)((double)x[i] + acc);
+  }
+}
+
 }  // namespace bg
+
+extern "C" int bg_device_checksum(bg_context_t ctx, const void* d_ptr, size_t bytes, uint64_t* out2) {
+  if (!ctx || !out2 || (bytes && !d_ptr) || (bytes & 3)) return BG_ERR_ARG;
+  BG_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long* d = nullptr;
+  BG_CUDA(cudaMalloc(&d, 16));
+  BG_CUDA(cudaMemsetAsync(d, 0, 16, ctx->stream));
+  const size_t nw = bytes / 4;
+  if (nw) {
+    const int blocks = (int)std::min<size_t>((size_t)ctx->sm_count * 8, (nw + 255) / 256);
+    bg::checksum_kernel<<<blocks, 256, 0, ctx->stream>>>((const unsigned*)d_ptr, nw, d);
+    ctx->launches++;
+  }
+  unsigned long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return bg::cuda_fail(e, "bg_device_checksum", __FILE__, __LINE__);
+  out2[0] = h[0]; out2[1] = h[1];
+  return BG_OK;
+}
+
+extern "C" int bg_basis_update(bg_context_t ctx, int dtype, int n, int64_t ld, int k, const void* d_V, const double* h_y,
+                               void* d_x) {
+  if (!ctx || n < 0 || k < 0 || k > 4096 || ld < n || (k && (!d_V || !h_y)) || !d_x) return BG_ERR_ARG;
+  if (n == 0 || k == 0) return BG_OK;
+  BG_CUDA(cudaSetDevice(ctx->device));
+  double* dy = nullptr;
+  BG_CUDA(cudaMalloc(&dy, sizeof(double) * k));
+  cudaError_t e = cudaMemcpyAsync(dy, h_y, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream);
+  const int blocks = std::min(ctx->sm_count * 8, (n + 255) / 256);
+  if (e == cudaSuccess) {
+    if (dtype == BG_F32) bg::basis_update_kernel<float><<<blocks, 256, 0, ctx->stream>>>(n, ld, k, (const float*)d_V, dy, (float*)d_x);
+    else bg::basis_update_kernel<double><<<blocks, 256, 0, ctx->stream>>>(n, ld, k, (const double*)d_V, dy, (double*)d_x);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dy);
+  if (e != cudaSuccess) return bg::cuda_fail(e, "bg_basis_update", __FILE__, __LINE__);
+  return BG_OK;
+}

@@ -82,6 +82,15 @@ template <class FT> struct SfArgs {
 // row leave together and only the ones that were not ready yet are polled again.  Same operations in the same
 // order as the reference's host solve (acc = rhs; acc -= v_k x_k in stored order; acc /= diag).
 constexpr int kSfKP = 4;
+#ifdef BG_SF_TIMING
+// development aid (make dbg): %globaltimer stamps of lane 0 of the warps that solve slices [g_sf_q0, g_sf_q0 + 2048):
+// [0] slice taken  [1] operands loaded  [2] all dependencies arrived  [3] result published  (+ SM id)
+__device__ unsigned long long g_sf_t[2048 * 5];
+__device__ int g_sf_q0 = 0;
+#define SF_STAMP(k) do { if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + 2048) g_sf_t[(q - g_sf_q0) * 5 + (k)] = global_ns(); } while (0)
+#else
+#define SF_STAMP(k) do {} while (0)
+#endif
 template <class VT, class FT, class CT, bool UNIT>
 __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> xf, const VT* __restrict__ in, LL16* xs,
                                                      VT* out, const int* skip) {
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
   const int lane = threadIdx.x & 31;
   const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), G = (int)((gridDim.x * blockDim.x) >> 5);
   for (int q = g; q < a.n_slices; q += G) {
+    SF_STAMP(0);
     const int s0 = a.slice_slot[q], R = a.slice_slot[q + 1] - s0;
     const int64_t off = a.slice_off[q];
     const int K = (int)((a.slice_off[q + 1] - off) / R);
@@ -98,6 +108,11 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
     const int r = a.rows[s0 + lane];
     CT acc = load_rhs<VT, CT>(xf, in, r);
     const CT dg = UNIT ? (CT)1 : (CT)a.diag[s0 + lane];
+#ifdef BG_SF_TIMING
+    if (acc == (CT)1.2345e300) return;  // forces the operand loads to complete before the stamp
+    SF_STAMP(1);
+    if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + 2048) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_sf_t[(q - g_sf_q0) * 5 + 4] = sm; }
+#endif
     for (int k0 = 0; k0 < K; k0 += KP) {
       int c[KP];
       CT v[KP];
@@ -117,11 +132,21 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
           acc -= v[j] * (CT)x;
         }
     }
+    SF_STAMP(2);
     if (!UNIT) acc /= dg;
     ll_store(xs + r, (double)acc, a.seq);
     store_out<VT, CT>(xf, out, r, acc);
+    SF_STAMP(3);
   }
 }
+#ifdef BG_SF_TIMING
+}  // namespace bg
+extern "C" BG_API int bg_debug_sf_times(int q0, unsigned long long* out) {
+  if (q0 >= 0) return cudaMemcpyToSymbol(bg::g_sf_q0, &q0, sizeof(int)) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, bg::g_sf_t, sizeof(unsigned long long) * 2048 * 5) == cudaSuccess ? 0 : -1;
+}
+namespace bg {
+#endif
 
 // ------------------------------------------------------------------ global lattice wavefront (5-point ILU(0))
 __device__ __forceinline__ uint32_t lg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -204,34 +229,49 @@ __global__ void __launch_bounds__(32) trsv_lattice_global(LgArgs<FT> a, const TI
   for (int b = 0; b < PF; ++b) issue(b);
   bnd_fetch(0);
   CT zprev = (CT)0;
-  int t = -lag;  // this lane's time row at the current step
   for (int blk = 0; blk < nblk; ++blk) {
     issue(blk + PF);
     cp_async_wait<PF>();  // the rows of block blk (and everything older) have landed: this lane's own copies
     double bval = 0.0;
     if (pk_y >= 0) bval = ll_ok(pk, a.seq) ? ll_val(pk) : ll_wait(bnd_in + pk_y, a.seq, a.timeout_ns);
     bnd_fetch(blk + 1);  // in flight during the steps below
+    __syncwarp();
+    // operands of the 8 steps into registers (inactive steps: zeros, which make z = 0), so that the chain below
+    // is branch-free register code: per step two shuffles, a select and two FMAs
+    const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
+    CT ca[BS], cb[BS], r[BS], be[BS], zs[BS];
 #pragma unroll
-    for (int j = 0; j < BS; ++j, ++t) {
+    for (int j = 0; j < BS; ++j) {
+      const int t = t0 + j;
       const bool act = colok && (unsigned)t < (unsigned)ny;
-      const int slot = (t & (NR - 1)) * 32 + lane;
-      CT ca = (CT)0, cb = (CT)0, r = (CT)0;
-      if (act) {
-        const P c = s_pair[slot];
-        ca = (CT)c.x; cb = (CT)c.y;
-        r = (CT)s_rhs[slot];
-        if (!LOWER) r *= (CT)s_dinv[slot];
-      }
+      const int slot = (t & (NR - 1)) * 32 + lane;  // always a valid ring address
+      const P c = s_pair[slot];
+      CT rr = (CT)s_rhs[slot];
+      if (!LOWER) rr *= (CT)s_dinv[slot];
+      ca[j] = act ? (CT)c.x : (CT)0;
+      cb[j] = act ? (CT)c.y : (CT)0;
+      r[j] = act ? rr : (CT)0;
+      be[j] = (CT)__shfl_sync(0xffffffffu, bval, j);
+    }
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
       CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
-      const double be = __shfl_sync(0xffffffffu, bval, j);
-      if (lane == edge_in) zn = (CT)be;
-      const CT tt = r - cb * zprev;  // south / north: own previous result
-      const CT z = tt - ca * zn;     // west / east: neighbour lane (or the upstream strip)
-      if (act) {
-        s_out[(t & (NRO - 1)) * 32 + lane] = (TOUT)z;
-        if (lane == edge_out && has_down) ll_store(bnd_out + yrow(t), (double)z, a.seq);
+      zn = lane == edge_in ? be[j] : zn;
+      const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
+      zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
+      zs[j] = zprev;
+    }
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      const int t = t0 + j;
+      if (colok && (unsigned)t < (unsigned)ny) s_out[(t & (NRO - 1)) * 32 + lane] = (TOUT)zs[j];
+    }
+    if (lane == edge_out && has_down) {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int t = t0 + j;
+        if ((unsigned)t < (unsigned)ny) ll_store(bnd_out + yrow(t), (double)zs[j], a.seq);
       }
-      zprev = act ? z : (CT)0;
     }
     // rows every lane has passed: one coalesced store per row (each lane re-reads its own column)
 #pragma unroll

@@ -260,6 +260,106 @@ void ilut(int n, const int* rp, const int* ci, const T* v, double tau, int lfil,
 template void ilut<float>(int, const int*, const int*, const float*, double, int, const int*, Factors<float>&);
 template void ilut<double>(int, const int*, const int*, const double*, double, int, const int*, Factors<double>&);
 
+// ------------------------------------------------------------------ AINV
+namespace {
+template <class T> struct SpVec { std::vector<int> idx; std::vector<T> val; };  // ascending indices
+// y = x - alpha * z on sparse vectors, dropping created entries below tol (never the entry `keep`)
+template <class T> void sp_axpy_drop(SpVec<T>& x, double alpha, const SpVec<T>& z, double tol, int keep, SpVec<T>& tmp) {
+  tmp.idx.clear(); tmp.val.clear();
+  size_t a = 0, b = 0;
+  while (a < x.idx.size() || b < z.idx.size()) {
+    int k; double val;
+    if (b >= z.idx.size() || (a < x.idx.size() && x.idx[a] < z.idx[b])) { k = x.idx[a]; val = (double)x.val[a]; ++a; }
+    else if (a >= x.idx.size() || z.idx[b] < x.idx[a]) { k = z.idx[b]; val = -alpha * (double)z.val[b]; ++b; if (std::fabs(val) < tol && k != keep) continue; }
+    else { k = x.idx[a]; val = (double)x.val[a] - alpha * (double)z.val[b]; ++a; ++b; if (std::fabs(val) < tol && k != keep) continue; }
+    tmp.idx.push_back(k); tmp.val.push_back((T)val);
+  }
+  x.idx.swap(tmp.idx); x.val.swap(tmp.val);
+}
+// one biconjugation sweep: columns z_i with  z_i = e_i - sum_{j<i} (a_j^T z_i / p_j) z_j,  a_j^T = row j of M;
+// candidates j are found through the columns of M (MT = M^T in CSR) touched by the pattern of z_i
+template <class T>
+void biconj(int n, const Csr<T>& M, const Csr<T>& MT, double tol, std::vector<SpVec<T>>& Z, std::vector<double>& p) {
+  Z.assign(n, SpVec<T>());
+  p.assign(n, 0.0);
+  std::set<int> cand;
+  SpVec<T> tmp;
+  std::vector<T> dense(n, (T)0);
+  for (int i = 0; i < n; ++i) {
+    SpVec<T>& z = Z[i];
+    z.idx.assign(1, i); z.val.assign(1, (T)1);
+    cand.clear();
+    for (int q = MT.rp[i]; q < MT.rp[i + 1]; ++q) if (MT.ci[q] < i) cand.insert(MT.ci[q]);
+    while (!cand.empty()) {
+      const int j = *cand.begin();
+      cand.erase(cand.begin());
+      for (size_t t = 0; t < z.idx.size(); ++t) dense[z.idx[t]] = z.val[t];
+      double dot = 0;
+      for (int q = M.rp[j]; q < M.rp[j + 1]; ++q) dot += (double)M.v[q] * (double)dense[M.ci[q]];
+      for (size_t t = 0; t < z.idx.size(); ++t) dense[z.idx[t]] = (T)0;
+      if (dot == 0.0 || p[j] == 0.0) continue;
+      const size_t before = z.idx.size();
+      std::vector<int> old(z.idx);
+      sp_axpy_drop(z, dot / p[j], Z[j], tol, i, tmp);
+      if (z.idx.size() != before || z.idx != old)  // new pattern entries k (< j) open later rows j' in (j, i)
+        for (int k : z.idx)
+          if (!std::binary_search(old.begin(), old.end(), k))
+            for (int q = MT.rp[k]; q < MT.rp[k + 1]; ++q) if (MT.ci[q] > j && MT.ci[q] < i) cand.insert(MT.ci[q]);
+    }
+    double dot = 0;
+    for (size_t t = 0; t < z.idx.size(); ++t) dense[z.idx[t]] = z.val[t];
+    for (int q = M.rp[i]; q < M.rp[i + 1]; ++q) dot += (double)M.v[q] * (double)dense[M.ci[q]];
+    for (size_t t = 0; t < z.idx.size(); ++t) dense[z.idx[t]] = (T)0;
+    p[i] = dot;
+  }
+}
+template <class T> Csr<T> transpose_csr(const Csr<T>& M) {
+  Csr<T> Tm;
+  Tm.n = M.n;
+  Tm.rp.assign(M.n + 1, 0);
+  for (int c : M.ci) Tm.rp[c + 1]++;
+  for (int i = 0; i < M.n; ++i) Tm.rp[i + 1] += Tm.rp[i];
+  Tm.ci.resize(M.ci.size()); Tm.v.resize(M.v.size());
+  std::vector<int> cur(Tm.rp.begin(), Tm.rp.end() - 1);
+  for (int i = 0; i < M.n; ++i)
+    for (int q = M.rp[i]; q < M.rp[i + 1]; ++q) { const int d = cur[M.ci[q]]++; Tm.ci[d] = i; Tm.v[d] = M.v[q]; }
+  return Tm;
+}
+}  // namespace
+
+template <class T>
+void ainv_biconjugation(int n, const int* rp, const int* ci, const T* v, double droptol, Factors<T>& F) {
+  Csr<T> A;
+  sorted_copy(n, rp, ci, v, (const int*)nullptr, A);
+  const Csr<T> AT = transpose_csr(A);
+  std::vector<SpVec<T>> Z, W;
+  std::vector<double> p, q;
+  biconj(n, A, AT, droptol, Z, p);   // z_i: A-conjugation against the rows of A
+  biconj(n, AT, A, droptol, W, q);   // w_i: the same against the rows of A^T (= columns of A)
+  F.zero_pivots = 0;
+  // F.L = D^-1 W^T: row i = w_i / p_i
+  F.L.n = F.U.n = n;
+  F.L.rp.assign(1, 0); F.L.ci.clear(); F.L.v.clear();
+  for (int i = 0; i < n; ++i) {
+    double piv = p[i];
+    if (std::fabs(piv) < (double)kEps) { F.zero_pivots++; piv = piv < 0 ? -(double)kEps : (double)kEps; }
+    for (size_t t = 0; t < W[i].idx.size(); ++t) { F.L.ci.push_back(W[i].idx[t]); F.L.v.push_back((T)((double)W[i].val[t] / piv)); }
+    F.L.rp.push_back((int)F.L.ci.size());
+  }
+  // F.U = Z: the z_i are its columns
+  Csr<T> ZT;
+  ZT.n = n;
+  ZT.rp.assign(1, 0);
+  for (int i = 0; i < n; ++i) {
+    for (size_t t = 0; t < Z[i].idx.size(); ++t) { ZT.ci.push_back(Z[i].idx[t]); ZT.v.push_back(Z[i].val[t]); }
+    ZT.rp.push_back((int)ZT.ci.size());
+  }
+  F.U = transpose_csr(ZT);
+  F.unit_lower = false;
+}
+template void ainv_biconjugation<float>(int, const int*, const int*, const float*, double, Factors<float>&);
+template void ainv_biconjugation<double>(int, const int*, const int*, const double*, double, Factors<double>&);
+
 // ------------------------------------------------------------------ partitioning
 namespace {
 void finish_partition(int64_t m, int npart, const int64_t* node_part, int64_t* part_size, int64_t* pinv,

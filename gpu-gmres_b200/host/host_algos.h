@@ -44,6 +44,13 @@ template <class T>
 void ilut(int n, const int* rp, const int* ci, const T* v, double tau, int lfil, const int* block,
           Factors<T>& F);
 
+// Sparse approximate inverse by left-looking biconjugation with dropping (Benzi-Tuma AINV; the role of CUSP's
+// nonsym_bridson_ainv(A, droptol) in MyAINV::Initilize, src/preconditioner.cu:140-201):  A^-1 ~ Z D^-1 W^T.
+// Output in the factor container: F.L = D^-1 W^T (CSR, applied first), F.U = Z (CSR, applied second).
+// Entries of z_i / w_i below droptol in magnitude are dropped as they are created (the unit diagonal is kept).
+template <class T>
+void ainv_biconjugation(int n, const int* rp, const int* ci, const T* v, double droptol, Factors<T>& F);
+
 // partition / partition3 post-processing, src/partition.cpp:22-99, src/partition3.cpp:68-117
 void partition_ref(int64_t m, const int64_t* Ap, const int64_t* Ai, int npart, int64_t nNodes,
                    int64_t* part_size, int64_t* node_part, int64_t* pinv, int64_t* q);

@@ -1,11 +1,20 @@
-// preconditioner.h (B200 shim) -- the reference's Preconditioner hierarchy (src/preconditioner.h:34-357)
-// with the same class names, public data members the drivers poke, and virtual interface; device
-// work is forwarded to bg_precond_* (include/b200gmres.h).  The legacy cuSPARSE/cusp members are gone.
-// HostPrecond* (the CPU twins) are intentionally not provided: this build has no CPU path.
+// preconditioner.h (B200 shim) -- the reference's Preconditioner hierarchy (src/preconditioner.h:34-357,
+// src_thermal/preconditioner.h) with the same class names, public data members the drivers poke, and virtual
+// interface; device work is forwarded to bg_precond_* (include/b200gmres.h).  The legacy cuSPARSE/cusp members are
+// gone.  This build has no CPU compute path: HostPrecond* take HOST vectors like the reference's CPU twins, copy them
+// to the device, apply the same operator there and copy the result back.
 #ifndef PRECONDITIONER_H_
 #define PRECONDITIONER_H_
+#include <assert.h>
+#include <sys/time.h>
 #include "SpMV.h"
+#include "config.h"
+#include "SpMV_kernel.h"
 #include "defs.h"
+#include "leftILU.h"
+#ifndef MAX_STR_LEN  // src_thermal keeps this enum here (src_thermal/preconditioner.h:30), src/ in defs.h (src/defs.h:15)
+enum PreconditionerType { NONE, DIAG, ILU0, AINV };
+#endif
 
 class Preconditioner {
  public:
@@ -49,6 +58,16 @@ class MyILU0 : public Preconditioner {
 // the reference's MyILUK / MyILUPP(MySpMatrix) run ITSOL ilukC and then ignore it, using leftILU
 // factors: they behave like MyILU0.
 class MyILUK : public MyILU0 {};
+// approximate inverse applied as  o = W_t (D (Z i))  (MyAINV::HostPrecond / DevPrecond, src/preconditioner.cu:110-137).
+// The reference builds the factors with CUSP's nonsym_bridson_ainv(A, 0.1), which is outside the replaced layer:
+// Initilize(A) builds them with the shim's own Benzi-Tuma biconjugation (same drop tolerance) on the host, and
+// Initilize(factors) takes factors produced elsewhere (e.g. by a CUSP build).
+class MyAINV : public Preconditioner {
+ public:
+  void Initilize(const MySpMatrix& mySpM);
+  void Initilize(int n, const int* z_rowIndices, const int* z_indices, const float* z_val, const float* diag_val,
+                 const int* w_t_rowIndices, const int* w_t_indices, const float* w_t_val);
+};
 // split preconditioner from ILU++ factors, FP64 factors / FP32 vectors
 // (MyILUPPfloat::Initilize, src/preconditioner.cu:1205-1334)
 class MyILUPPfloat : public Preconditioner {
@@ -57,5 +76,13 @@ class MyILUPPfloat : public Preconditioner {
   void Initilize(const MySpMatrixDouble& PrLeft, const MySpMatrixDouble& PrRight, const MySpMatrix& PrMiddle,
                  const MySpMatrix& PrPermRow, const MySpMatrix& PrPermCol, const MySpMatrix& PrLscale,
                  const MySpMatrix& PrRscale, int restart);
+};
+// the same with FP64 scaling vectors (MyILUPP::Initilize, src/preconditioner.cu:872-1016); used by gmresInterfacePG
+class MyILUPP : public Preconditioner {
+ public:
+  void Initilize(const MySpMatrix& mySpM);
+  void Initilize(const MySpMatrixDouble& PrLeft, const MySpMatrixDouble& PrRight, const MySpMatrix& PrMiddle,
+                 const MySpMatrix& PrPermRow, const MySpMatrix& PrPermCol, const MySpMatrixDouble& PrLscale,
+                 const MySpMatrixDouble& PrRscale);
 };
 #endif

@@ -6,7 +6,9 @@
 // meaning and return conventions (0 = converged, 1 = not converged; *max_iter / *tol are in-out,
 // SURVEY Q2/Q3; hard failures print and abort like the reference's exit(-1)).
 // Pure host C++: device memory is reached through bg_device_malloc / bg_memcpy_* so this file
-// needs no CUDA runtime.  There is no CPU compute path here: the Host* twins abort.
+// needs no CUDA runtime.  There is no CPU compute path here: the reference's host twins (GMRES, GMRESilu,
+// GMRES_tran, HostPrecond*, GMRES_host_PG) keep their host-array signatures but upload, run the same
+// algorithm on the device and copy the result back.
 //
 // The vectors are float (the reference's REAL, gmres.h:55); environment switches select the
 // device schedule without touching driver source:
@@ -17,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <utility>
 #include <vector>
@@ -47,25 +50,42 @@ bg_context_t ctx() {
   return g_ctx;
 }
 
-// device CSR handed over as raw pointers (SpMatrixGPU / MySpMatrix / GMRESilu_GPU arguments):
-// one bg_matrix_t per distinct value array, built on first use
+// device CSR handed over as raw pointers (SpMatrixGPU / MySpMatrix / GMRESilu_GPU arguments): the caller owns the
+// arrays and may refill them in place, or free them and get the same addresses back for a different matrix, without
+// telling anybody.  So a cached bg_matrix_t is only reused when the device arrays still carry the
+// fingerprint (bg_device_checksum over values, column indices and row pointers: one pass at SpMV cost) taken when it
+// was built; otherwise it is rebuilt.
 struct MatKey {
   const void* val; int n; long long nnz;
   bool operator<(const MatKey& o) const { return val != o.val ? val < o.val : n != o.n ? n < o.n : nnz < o.nnz; }
 };
-std::map<MatKey, bg_matrix_t> g_mats;
+struct MatEntry { bg_matrix_t A; uint64_t fp[6]; };
+std::map<MatKey, MatEntry> g_mats;
+void fingerprint(const float* d_val, const int* d_rowIndices, const int* d_indices, int n, long long nnz, uint64_t fp[6]) {
+  CHK(bg_device_checksum(ctx(), d_val, sizeof(float) * (size_t)nnz, fp));
+  CHK(bg_device_checksum(ctx(), d_indices, sizeof(int) * (size_t)nnz, fp + 2));
+  CHK(bg_device_checksum(ctx(), d_rowIndices, sizeof(int) * (size_t)(n + 1), fp + 4));
+}
 bg_matrix_t matrix_for(const float* d_val, const int* d_rowIndices, const int* d_indices, int n, long long nnz) {
   MatKey k{d_val, n, nnz};
+  uint64_t fp[6];
+  fingerprint(d_val, d_rowIndices, d_indices, n, nnz, fp);
   auto it = g_mats.find(k);
-  if (it != g_mats.end()) return it->second;
-  bg_matrix_t A = nullptr;
-  CHK(bg_matrix_create_csr(ctx(), n, nnz, d_rowIndices, d_indices, d_val, BG_F32, BG_DEVICE, BG_F32, BG_SPMV_AUTO, &A));
-  g_mats[k] = A;
-  return A;
+  if (it != g_mats.end()) {
+    if (std::memcmp(fp, it->second.fp, sizeof(fp)) == 0) return it->second.A;
+    bg_matrix_destroy(it->second.A);  // same address, different contents
+    g_mats.erase(it);
+  }
+  MatEntry e;
+  e.A = nullptr;
+  std::memcpy(e.fp, fp, sizeof(fp));
+  CHK(bg_matrix_create_csr(ctx(), n, nnz, d_rowIndices, d_indices, d_val, BG_F32, BG_DEVICE, BG_F32, BG_SPMV_AUTO, &e.A));
+  g_mats[k] = e;
+  return e.A;
 }
 void forget_matrix(const void* d_val) {
   for (auto it = g_mats.begin(); it != g_mats.end();)
-    if (it->first.val == d_val) { bg_matrix_destroy(it->second); it = g_mats.erase(it); } else ++it;
+    if (it->first.val == d_val) { bg_matrix_destroy(it->second.A); it = g_mats.erase(it); } else ++it;
 }
 
 std::map<std::pair<int, int>, bg_solver_t> g_solvers;  // (n, m) -> workspace, FP32
@@ -79,17 +99,28 @@ bg_solver_t solver_for(int n, int m) {
   return S;
 }
 
-int orth_mode() {
+// the reference's order is strict MGS (gmres.cu:2356-2359) and so is the shim's default; B200GMRES_ORTH=cgs selects
+// the fused one-reduction CGS step (restart <= 32 only: longer restarts, e.g. the ILU++ path's 100, stay on MGS)
+int orth_mode(int m) {
   const char* e = std::getenv("B200GMRES_ORTH");
-  return e && std::strcmp(e, "mgs") == 0 ? BG_ORTH_MGS : BG_ORTH_CGS_ADAPTIVE;
+  return e && std::strcmp(e, "cgs") == 0 && m <= 32 ? BG_ORTH_CGS_ADAPTIVE : BG_ORTH_MGS;
 }
+
+// host vector -> device scratch -> host (the host twins' copies)
+struct DevVec {
+  float* p = nullptr;
+  explicit DevVec(size_t n) { CHK(bg_device_malloc(ctx(), sizeof(float) * (n ? n : 1), (void**)&p)); }
+  ~DevVec() { bg_device_free(ctx(), p); }
+  DevVec(const DevVec&) = delete;
+  DevVec& operator=(const DevVec&) = delete;
+};
 
 // common tail of every GMRES*_GPU entry point: in-out max_iter / tol, 0/1 result
 int run_gmres(bg_solver_t S, bg_matrix_t A, Preconditioner& M, const float* d_b, float* d_x, int m, int* max_iter,
               float* tol) {
   bg_gmres_opts o;
   bg_gmres_opts_default(&o);
-  o.m = m; o.max_iter = *max_iter; o.tol = (double)*tol; o.orth = orth_mode();
+  o.m = m; o.max_iter = *max_iter; o.tol = (double)*tol; o.orth = orth_mode(o.m);
   bg_gmres_result r;
   const int rc = bg_gmres_solve(ctx(), S, A, (bg_precond_t)M.bg_handle, d_b, d_x, &o, &r);
   if (rc < 0) die("bg_gmres_solve");
@@ -143,7 +174,8 @@ void mySpMatrixDoubleFree(MySpMatrixDouble* m) {  // src/SpMV_alloc.cu:197-211
   m->val = nullptr; m->indices = m->rowIndices = nullptr;
 }
 
-void genCSRFormat(SpMatrix* m, float* val, int* rowIndices, int* indices) {  // src_thermal/SpMV_gen.cpp:189-201
+// weak: the reference keeps SpMV_gen.cpp in its build and its own definition then wins
+__attribute__((weak)) void genCSRFormat(SpMatrix* m, float* val, int* rowIndices, int* indices) {  // src_thermal/SpMV_gen.cpp:189-201
   for (int i = 0; i < m->numNZEntries; ++i) { val[i] = m->nzentries[i].val; indices[i] = m->nzentries[i].colNum; }
   for (int i = 0; i < m->numRows; ++i) rowIndices[i] = m->rowPtrs[i];
   rowIndices[m->numRows] = m->numNZEntries;
@@ -182,15 +214,19 @@ Preconditioner::Preconditioner()
 Preconditioner::~Preconditioner() {
   if (bg_handle) bg_precond_destroy((bg_precond_t)bg_handle);
 }
-static void no_host_path(const char* what) {
-  std::fprintf(stderr, "b200gmres shim: %s is the reference's CPU twin; this build has no CPU compute path\n", what);
-  std::exit(-1);
+// the reference's CPU twins take host vectors; here the operator only exists on the device
+static void host_apply(Preconditioner* p, int which, const float* in, float* out) {
+  const size_t n = (size_t)p->numRows;
+  DevVec di(n), dout(n);
+  CHK(bg_memcpy_h2d(ctx(), di.p, in, sizeof(float) * n));
+  CHK(bg_precond_apply(ctx(), (bg_precond_t)p->bg_handle, which, di.p, dout.p));
+  CHK(bg_memcpy_d2h(ctx(), out, dout.p, sizeof(float) * n));
 }
-void Preconditioner::HostPrecond(const ValueType*, ValueType*) { no_host_path("HostPrecond"); }
-void Preconditioner::HostPrecond_rhs(const ValueType*, ValueType*) { no_host_path("HostPrecond_rhs"); }
-void Preconditioner::HostPrecond_right(const ValueType*, ValueType*) { no_host_path("HostPrecond_right"); }
-void Preconditioner::HostPrecond_left(const ValueType*, ValueType*) { no_host_path("HostPrecond_left"); }
-void Preconditioner::HostPrecond_starting_value(const ValueType*, ValueType*) { no_host_path("HostPrecond_starting_value"); }
+void Preconditioner::HostPrecond(const ValueType* i, ValueType* o) { host_apply(this, BG_PC_FULL, i, o); }
+void Preconditioner::HostPrecond_rhs(const ValueType* i, ValueType* o) { host_apply(this, BG_PC_RHS, i, o); }
+void Preconditioner::HostPrecond_right(const ValueType* i, ValueType* o) { host_apply(this, BG_PC_RIGHT, i, o); }
+void Preconditioner::HostPrecond_left(const ValueType* i, ValueType* o) { host_apply(this, BG_PC_LEFT, i, o); }
+void Preconditioner::HostPrecond_starting_value(const ValueType* i, ValueType* o) { host_apply(this, BG_PC_START, i, o); }
 static void dev_apply(Preconditioner* p, int which, const float* in, float* out) {
   CHK(bg_precond_apply(ctx(), (bg_precond_t)p->bg_handle, which, in, out));
   CHK(bg_context_synchronize(ctx()));  // the reference's DevPrecond ends with cudaDeviceSynchronize (preconditioner.cu:283)
@@ -242,6 +278,37 @@ void MyILUPPfloat::Initilize(const MySpMatrixDouble& L, const MySpMatrixDouble& 
                               rs.val, BG_F32, Pr.indices, Pc.indices, BG_F32, nullptr, (bg_precond_t*)&bg_handle));
 }
 
+void MyILUPP::Initilize(const MySpMatrix&) {
+  std::fprintf(stderr, "b200gmres shim: MyILUPP needs the ILU++ factors (use the 7-argument Initilize)\n");
+  std::exit(-1);
+}
+void MyILUPP::Initilize(const MySpMatrixDouble& L, const MySpMatrixDouble& U, const MySpMatrix& D, const MySpMatrix& Pr,
+                        const MySpMatrix& Pc, const MySpMatrixDouble& ls, const MySpMatrixDouble& rs) {
+  // src/preconditioner.cu:872-1016: as MyILUPPfloat with FP64 scaling vectors (rounded to the FP32 vector type here)
+  numRows = L.numRows;
+  std::vector<double> mid(D.val, D.val + numRows);
+  CHK(bg_precond_create_split(ctx(), numRows, L.rowIndices, L.indices, L.val, U.rowIndices, U.indices, U.val, BG_F64, mid.data(),
+                              ls.val, rs.val, BG_F64, Pr.indices, Pc.indices, BG_F32, nullptr, (bg_precond_t*)&bg_handle));
+}
+void MyAINV::Initilize(int n, const int* zp, const int* zi, const float* zv, const float* diag, const int* wp, const int* wi,
+                       const float* wv) {  // o = w_t (D (z i)), src/preconditioner.cu:110-127
+  numRows = n;
+  CHK(bg_precond_create_ainv(ctx(), n, zp, zi, zv, diag, wp, wi, wv, BG_F32, BG_F32, (bg_precond_t*)&bg_handle));
+}
+void MyAINV::Initilize(const MySpMatrix& A) {  // src/preconditioner.cu:140-201 with the library's own biconjugation, drop 0.1
+  numRows = A.numRows;
+  bg_factors_t F = nullptr;
+  CHK(bg_host_ainv(numRows, A.rowIndices, A.indices, A.val, BG_F32, 0.1, &F));
+  bg_factors_info fi;
+  CHK(bg_factors_get_info(F, &fi));
+  std::vector<int> p1(numRows + 1), c1(fi.nnzL), p2(numRows + 1), c2(fi.nnzU);
+  std::vector<float> v1(fi.nnzL), v2(fi.nnzU);
+  CHK(bg_factors_get(F, p1.data(), c1.data(), v1.data(), p2.data(), c2.data(), v2.data()));
+  bg_factors_destroy(F);
+  CHK(bg_precond_create_ainv(ctx(), numRows, p1.data(), c1.data(), v1.data(), nullptr, p2.data(), c2.data(), v2.data(), BG_F32, BG_F32,
+                             (bg_precond_t*)&bg_handle));
+}
+
 // ------------------------------------------------------------------------------------------ leftILU.h
 static int* dup_i(const std::vector<int>& v) {
   int* p = (int*)std::malloc(sizeof(int) * (v.size() ? v.size() : 1));
@@ -272,7 +339,76 @@ void generateLevel(const int numRows, const float* h_val, const int* h_rowIndice
   CHK(bg_host_bucket_levels(numRows, level.data(), &nl, lp.data(), node.data()));
 }
 
+static float* dup_f(const std::vector<float>& v) {
+  float* p = (float*)std::malloc(sizeof(float) * (v.size() ? v.size() : 1));
+  std::memcpy(p, v.data(), sizeof(float) * v.size());
+  return p;
+}
+void csr2csc(const int n, const float* val, const int* rp, const int* ci, float*& csc_val, int*& csc_colIndices,
+             int*& csc_indices) {  // src/leftILU.cu:371-417: stable transpose (rows ascending inside a column)
+  std::vector<int> cp(n + 1, 0);
+  for (int q = 0; q < rp[n]; ++q) cp[ci[q] + 1]++;
+  for (int c = 0; c < n; ++c) cp[c + 1] += cp[c];
+  std::vector<int> cur(cp.begin(), cp.end() - 1), ri(rp[n]);
+  std::vector<float> cv(rp[n]);
+  for (int r = 0; r < n; ++r)
+    for (int q = rp[r]; q < rp[r + 1]; ++q) { const int d = cur[ci[q]]++; ri[d] = r; cv[d] = val[q]; }
+  csc_val = dup_f(cv); csc_colIndices = dup_i(cp); csc_indices = dup_i(ri);
+}
+// one split for both orientations: `lower_first_unit` = the CSC flavour puts the unit diagonal first in L
+// (src/leftILU.cu:420-478), the CSR flavour appends it last (:481-541); |v| < 1e-9 entries are dropped (Q5)
+static void split_lu(const int n, const float* val, const int* ptr, const int* idx, bool csc, float*& L_val, int*& L_ptr, int*& L_idx,
+                     float*& U_val, int*& U_ptr, int*& U_idx) {
+  std::vector<int> lp(1, 0), up(1, 0), li, ui;
+  std::vector<float> lv, uv;
+  for (int k = 0; k < n; ++k) {
+    if (csc) { lv.push_back(1.0f); li.push_back(k); }
+    for (int q = ptr[k]; q < ptr[k + 1]; ++q) {
+      const int o = idx[q];
+      const float v = val[q];
+      if (std::fabs(v) < 1e-9f) continue;
+      const bool to_u = csc ? o <= k : o >= k;
+      if (to_u) { uv.push_back(v); ui.push_back(o); } else { lv.push_back(v); li.push_back(o); }
+    }
+    if (!csc) { lv.push_back(1.0f); li.push_back(k); }
+    lp.push_back((int)li.size()); up.push_back((int)ui.size());
+  }
+  L_val = dup_f(lv); L_ptr = dup_i(lp); L_idx = dup_i(li);
+  U_val = dup_f(uv); U_ptr = dup_i(up); U_idx = dup_i(ui);
+}
+void splitLU_csc(const int n, const float* v, const int* cp, const int* ri, float*& L_val, int*& L_colIndices, int*& L_indices,
+                 float*& U_val, int*& U_colIndices, int*& U_indices) {
+  split_lu(n, v, cp, ri, true, L_val, L_colIndices, L_indices, U_val, U_colIndices, U_indices);
+}
+void splitLU_csr(const int n, const float* v, const int* rp, const int* ci, float*& L_val, int*& L_rowIndices, int*& L_indices,
+                 float*& U_val, int*& U_rowIndices, int*& U_indices) {
+  split_lu(n, v, rp, ci, false, L_val, L_rowIndices, L_indices, U_val, U_rowIndices, U_indices);
+}
+
 // ------------------------------------------------------------------------------------------ gmres.h
+float difftime(timeval& st, timeval& et) {  // src/gmres.cu:8-12, milliseconds
+  return (float)((et.tv_sec - st.tv_sec) * 1000.0 + (et.tv_usec - st.tv_usec) / 1000.0);
+}
+void ApplyPlaneRotation(float* dx, float* dy, float cs, float sn) {  // src/gmres.cu:192-197
+  const float temp = cs * (*dx) + sn * (*dy);
+  *dy = -sn * (*dx) + cs * (*dy);
+  *dx = temp;
+}
+void GeneratePlaneRotation(float dx, float dy, float* cs, float* sn) {  // src/gmres.cu:200-216 (double intermediates)
+  if (dy == 0.0f) { *cs = 1.0f; *sn = 0.0f; }
+  else if (std::fabs(dy) > std::fabs(dx)) { const float t = dx / dy; *sn = (float)(1.0 / std::sqrt(1.0 + (double)t * t)); *cs = t * (*sn); }
+  else { const float t = dy / dx; *cs = (float)(1.0 / std::sqrt(1.0 + (double)t * t)); *sn = t * (*cs); }
+}
+void Update_GPU(float* d_x, const int k, const float* H, const int m, const float* s, const float* d_v, const int n) {
+  // src/gmres.cu:164-189: back-substitution of the (k+1) x (k+1) triangle on the host, x += V y on the device
+  std::vector<double> y(s, s + k + 1);
+  for (int i = k; i >= 0; --i) {
+    y[i] /= (double)H[i + i * (m + 1)];
+    for (int j = i - 1; j >= 0; --j) y[j] -= (double)H[j + i * (m + 1)] * y[i];
+  }
+  CHK(bg_basis_update(ctx(), BG_F32, n, n, k + 1, d_v, y.data(), d_x));
+}
+
 GMRES_GPU_Data::GMRES_GPU_Data()
     : numRows(0), s(nullptr), cs(nullptr), sn(nullptr), H(nullptr), d_r(nullptr), d_rr(nullptr), d_bb(nullptr), d_temp(nullptr),
       d_v(nullptr), d_w(nullptr), d_ww(nullptr), bg_handle(nullptr) {}
@@ -317,6 +453,80 @@ int GMRESilu_GPU(float* d_val, int* d_rowIndices, int* d_indices, int nnz, float
   return run_gmres(solver_for(n, m), matrix_for(d_val, d_rowIndices, d_indices, n, nnz), M, d_b, d_x, m, max_iter, tol);
 }
 
+int GMRES_GPU_leftILU0(SpMatrixGPU* Sparse, SpMatrix* spm, dim3* grid, dim3* block, float* d_x, const float* d_b, const int n,
+                       const int m, int* max_iter, float* tol, const float* l_val, const int* l_rowIndices, const int* l_indices,
+                       const float* u_val, const int* u_rowIndices, const int* u_indices) {  // src/gmres.cu:1440-1700
+  MyILU0 M;  // borrows the caller's host factors for the upload only
+  M.numRows = n;
+  CHK(bg_precond_create_lu(ctx(), n, l_rowIndices, l_indices, l_val, u_rowIndices, u_indices, u_val, BG_F32, BG_F32, nullptr,
+                           (bg_precond_t*)&M.bg_handle));
+  return GMRES_GPU(Sparse, spm, grid, block, d_x, d_b, n, m, max_iter, tol, M);
+}
+int GMRES_GPU_leftDiag(SpMatrixGPU* Sparse, SpMatrix* spm, dim3* grid, dim3* block, float* d_x, const float* d_b, const int n,
+                       const int m, int* max_iter, float* tol, const float* m_val, const int* m_rowIndices,
+                       const int* m_indices) {  // src/gmres.cu:1186-1231: M given explicitly, applied by one SpMV
+  MyAINV M;
+  M.Initilize(n, m_rowIndices, m_indices, m_val, nullptr, nullptr, nullptr, nullptr);
+  return GMRES_GPU(Sparse, spm, grid, block, d_x, d_b, n, m, max_iter, tol, M);
+}
+
+// ---- host twins: host arrays in, host arrays out, the algorithm itself on the device
+static int host_gmres(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, int n, int m,
+                      int* max_iter, float* tol, Preconditioner& M) {
+  bg_matrix_t A = nullptr;
+  CHK(bg_matrix_create_csr(ctx(), n, rowIndices[n], rowIndices, indices, val, BG_F32, BG_HOST, BG_F32, BG_SPMV_AUTO, &A));
+  bg_gmres_opts o;
+  bg_gmres_opts_default(&o);
+  o.m = m; o.max_iter = *max_iter; o.tol = (double)*tol; o.orth = orth_mode(m);
+  bg_gmres_result r;
+  const int rc = bg_gmres_solve_host(ctx(), solver_for(n, m), A, (bg_precond_t)M.bg_handle, b, x, &o, &r);
+  bg_matrix_destroy(A);
+  if (rc < 0) die("bg_gmres_solve_host");
+  *max_iter = r.iters;
+  *tol = (float)r.resid;
+  return rc;
+}
+int GMRES(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, const int n, const int m,
+          int* max_iter, float* tol, Preconditioner& M) {  // src/gmres.cu:1904-2066
+  return host_gmres(val, rowIndices, indices, x, b, n, m, max_iter, tol, M);
+}
+int GMRES(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, const int n, const int m,
+          int* max_iter, float* tol) {
+  return host_gmres(val, rowIndices, indices, x, b, n, m, max_iter, tol, *none_precond(n));
+}
+int GMRESilu(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, const int n, const int m,
+             int* max_iter, float* tol, Preconditioner& M) {  // src/gmres.cu:2069-2252 (split algebra follows the preconditioner kind)
+  return host_gmres(val, rowIndices, indices, x, b, n, m, max_iter, tol, M);
+}
+int GMRES_tran(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, const int n, const int m,
+               const int max_iter, const float tol, Preconditioner& M) {  // src/gmres.cu:2449-2564
+  int it = max_iter;
+  float t = tol;
+  return host_gmres(val, rowIndices, indices, x, b, n, m, &it, &t, M);
+}
+int GMRES_leftILU0(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, const int n,
+                   const int m, int* max_iter, float* tol, const float* l_val, const int* l_rowIndices, const int* l_indices,
+                   const float* u_val, const int* u_rowIndices, const int* u_indices) {
+  MyILU0 M;
+  M.numRows = n;
+  CHK(bg_precond_create_lu(ctx(), n, l_rowIndices, l_indices, l_val, u_rowIndices, u_indices, u_val, BG_F32, BG_F32, nullptr,
+                           (bg_precond_t*)&M.bg_handle));
+  return host_gmres(val, rowIndices, indices, x, b, n, m, max_iter, tol, M);
+}
+int GMRES_leftDiag(const float* val, const int* rowIndices, const int* indices, float* x, const float* b, const int n,
+                   const int m, int* max_iter, float* tol, const float* m_val, const int* m_rowIndices, const int* m_indices) {
+  MyAINV M;
+  M.Initilize(n, m_rowIndices, m_indices, m_val, nullptr, nullptr, nullptr, nullptr);
+  return host_gmres(val, rowIndices, indices, x, b, n, m, max_iter, tol, M);
+}
+
+void b200gmresShimRelease() {
+  for (auto& e : g_mats) bg_matrix_destroy(e.second.A);
+  g_mats.clear();
+  for (auto& e : g_solvers) bg_solver_destroy(e.second);
+  g_solvers.clear();
+}
+
 // ------------------------------------------------------------------------------------------ gmres_interface_pg.h
 gmresInterfacePGfloat::gmresInterfacePGfloat()
     : matrixSize(0), nnz(0), h_val(nullptr), h_rowPtr(nullptr), h_colIdx(nullptr), d_val(nullptr), d_rowPtr(nullptr), d_colIdx(nullptr),
@@ -340,7 +550,7 @@ int gmresInterfacePGfloat::GMRES_dev_PG() {  // src/gmres_interface_pg.cu:110-13
   tol = 1e-7f;  // gmres_tol_global, gmres_interface_pg.cu:7
   bg_gmres_opts o;
   bg_gmres_opts_default(&o);
-  o.m = restart; o.max_iter = max_it; o.tol = (double)tol; o.orth = orth_mode();
+  o.m = restart; o.max_iter = max_it; o.tol = (double)tol; o.orth = orth_mode(o.m);
   bg_gmres_result r;
   // H2D of xgmres_h (warm start) and rhs_h, solve, D2H of the solution: one call
   const int rc = bg_gmres_solve_host(ctx(), (bg_solver_t)bg_solver, (bg_matrix_t)bg_matrix, (bg_precond_t)((Preconditioner*)Precond)->bg_handle,
@@ -351,9 +561,45 @@ int gmresInterfacePGfloat::GMRES_dev_PG() {  // src/gmres_interface_pg.cu:110-13
   if (rc != 0) std::printf("Failed to converge.\n");
   return rc;
 }
-int gmresInterfacePGfloat::GMRES_host_PG() {
-  no_host_path("gmresInterfacePGfloat::GMRES_host_PG");
-  return 1;
+int gmresInterfacePGfloat::GMRES_host_PG() { return GMRES_dev_PG(); }  // src/gmres_interface_pg.cu:86-108: same vectors, device solve
+
+gmresInterfacePG::gmresInterfacePG()
+    : matrixSize(0), h_val(nullptr), h_rowPtr(nullptr), h_colIdx(nullptr), x_h(nullptr), x_d(nullptr), xgmres_h(nullptr), rhs_h(nullptr),
+      Precond(nullptr), max_it(0), tol(0.f), bg_matrix(nullptr), bg_solver(nullptr) {}
+void gmresInterfacePG::setPrecondPG(MySpMatrix* A, MySpMatrixDouble* L, MySpMatrixDouble* U, MySpMatrix* D, MySpMatrix* Pr, MySpMatrix* Pc,
+                                    MySpMatrixDouble* ls, MySpMatrixDouble* rs) {  // src/gmres_interface_pg.cu:9-28
+  matrixSize = A->numRows;
+  h_val = A->val; h_rowPtr = A->rowIndices; h_colIdx = A->indices;
+  CHK(bg_matrix_create_csr(ctx(), matrixSize, h_rowPtr[matrixSize], h_rowPtr, h_colIdx, h_val, BG_F32, BG_HOST, BG_F32, BG_SPMV_AUTO,
+                           (bg_matrix_t*)&bg_matrix));
+  xgmres_h = (float*)std::malloc(sizeof(float) * (size_t)matrixSize);
+  rhs_h = (float*)std::malloc(sizeof(float) * (size_t)matrixSize);
+  MyILUPP* p = new MyILUPP();
+  p->Initilize(*L, *U, *D, *Pr, *Pc, *ls, *rs);
+  Precond = (Preconditioner*)p;
+  CHK(bg_solver_create(ctx(), matrixSize, restart, BG_F32, (bg_solver_t*)&bg_solver));
+}
+int gmresInterfacePG::GMRES_host_PG() {  // src/gmres_interface_pg.cu:62-84
+  max_it = 10000;
+  tol = 1e-7f;
+  bg_gmres_opts o;
+  bg_gmres_opts_default(&o);
+  o.m = restart; o.max_iter = max_it; o.tol = (double)tol; o.orth = orth_mode(o.m);
+  bg_gmres_result r;
+  const int rc = bg_gmres_solve_host(ctx(), (bg_solver_t)bg_solver, (bg_matrix_t)bg_matrix, (bg_precond_t)((Preconditioner*)Precond)->bg_handle,
+                                     rhs_h, xgmres_h, &o, &r);
+  if (rc < 0) die("bg_gmres_solve_host");
+  max_it = r.iters;
+  tol = (float)r.resid;
+  if (rc != 0) std::printf("Failed to converge.\n");
+  return rc;
+}
+gmresInterfacePG::~gmresInterfacePG() {
+  std::free(xgmres_h);
+  std::free(rhs_h);
+  if (bg_solver) bg_solver_destroy((bg_solver_t)bg_solver);
+  if (bg_matrix) bg_matrix_destroy((bg_matrix_t)bg_matrix);
+  delete (Preconditioner*)Precond;
 }
 gmresInterfacePGfloat::~gmresInterfacePGfloat() {
   std::free(xgmres_h);

@@ -45,7 +45,7 @@ enum { BG_SPMV_AUTO = 0, BG_SPMV_CSR_VECTOR = 1, BG_SPMV_SELL = 2, BG_SPMV_CSR_W
 /* which half of the preconditioner to apply (≙ DevPrecond / DevPrecond_left / _right / _rhs /
    _starting_value, preconditioner.h:53-80) */
 enum { BG_PC_FULL = 0, BG_PC_LEFT = 1, BG_PC_RIGHT = 2, BG_PC_START = 3, BG_PC_RHS = 4 };
-enum { BG_PRECOND_NONE = 0, BG_PRECOND_DIAG = 1, BG_PRECOND_LU = 2, BG_PRECOND_SPLIT = 3 };
+enum { BG_PRECOND_NONE = 0, BG_PRECOND_DIAG = 1, BG_PRECOND_LU = 2, BG_PRECOND_SPLIT = 3, BG_PRECOND_AINV = 4 };
 /* Arnoldi orthogonalisation: strict MGS (the reference, gmres.cu:2356-2359) or one-reduction
    classical GS with DGKS-style re-orthogonalisation */
 enum { BG_ORTH_MGS = 0, BG_ORTH_CGS_ADAPTIVE = 1, BG_ORTH_CGS2 = 2 };
@@ -115,6 +115,13 @@ BG_API int bg_host_ilu0(int n, const int* rowptr, const int* col, const void* va
    (src/mna_solve_gpu_gmres.cpp:316-344) and hands them to bg_precond_create_split. */
 BG_API int bg_host_ilut(int n, const int* rowptr, const int* col, const void* val, int val_dtype,
                         double tau, int lfil, const int* block_of_row, bg_factors_t* F);
+/* sparse approximate inverse A^-1 ~ Z D^-1 W^T by left-looking biconjugation with drop tolerance (Benzi-Tuma AINV):
+   the role CUSP's nonsym_bridson_ainv(A, 0.1) plays in MyAINV::Initilize (src/preconditioner.cu:140-201; CUSP itself
+   is outside the replaced layer, so the factors are this library's own -- parity with CUSP's pattern is not claimed).
+   In the returned container "L" = D^-1 W^T and "U" = Z (general CSR, not triangular): feed them to
+   bg_precond_create_ainv as (m1, no diagonal, m2). */
+BG_API int bg_host_ainv(int n, const int* rowptr, const int* col, const void* val, int val_dtype, double droptol,
+                        bg_factors_t* F);
 typedef struct { int n; int dtype; int64_t nnzL, nnzU; int zero_pivots; } bg_factors_info;
 BG_API int bg_factors_get_info(bg_factors_t F, bg_factors_info* info);
 /* copy out; any pointer may be NULL */
@@ -174,6 +181,13 @@ BG_API int bg_precond_create_none(bg_context_t ctx, int n, int dtype, bg_precond
 /* MyDIAG::Initilize (src/preconditioner.cu:500-540): entry nearest the diagonal, inverted */
 BG_API int bg_precond_create_diag(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
                                   const void* h_val, int val_dtype, int dtype, bg_precond_t* M);
+/* explicit approximate inverse, applied as sparse products: out = M2 * (d .* (M1 * in)).  M2 and d may be NULL.
+   MyAINV::DevPrecond / HostPrecond (src/preconditioner.cu:110-137: z-factor product, diagonal, w_t-factor product)
+   and the explicit-inverse argument of GMRES_GPU_leftDiag (src/gmres.cu:1186-1231, one product).  The factors come
+   from the caller (the reference builds them with CUSP's bridson_ainv, which stays outside this library). */
+BG_API int bg_precond_create_ainv(bg_context_t ctx, int n, const int* m1_rowptr, const int* m1_col, const void* m1_val,
+                                  const void* diag, const int* m2_rowptr, const int* m2_col, const void* m2_val,
+                                  int val_dtype, int dtype, bg_precond_t* M);
 /* MyILU0::Initilize (src/preconditioner.cu:288-362): leftILU on the host, upload, level analysis */
 BG_API int bg_precond_create_ilu0(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
                                   const void* h_val, int val_dtype, int dtype, const bg_precond_opts* o,
@@ -344,6 +358,13 @@ BG_API int bg_device_malloc(bg_context_t ctx, size_t bytes, void** d_ptr);
 BG_API int bg_device_free(bg_context_t ctx, void* d_ptr);
 BG_API int bg_memcpy_h2d(bg_context_t ctx, void* d_dst, const void* h_src, size_t bytes);
 BG_API int bg_memcpy_d2h(bg_context_t ctx, void* h_dst, const void* d_src, size_t bytes);
+/* fingerprint of a device buffer (bytes must be a multiple of 4): two position-weighted sums of its 32-bit words.
+   The reference-API shim uses it to notice that a caller refilled / re-allocated a matrix it passes as raw device
+   pointers (GMRESilu_GPU, SpMatrixGPU) instead of trusting the address */
+BG_API int bg_device_checksum(bg_context_t ctx, const void* d_ptr, size_t bytes, uint64_t* out2);
+/* x += V[:, 0..k) y with y on the host: the device half of Update_GPU (src/gmres.cu:164-189) */
+BG_API int bg_basis_update(bg_context_t ctx, int dtype, int n, int64_t ld, int k, const void* d_V, const double* h_y,
+                           void* d_x);
 BG_API int bg_host_alloc_pinned(size_t bytes, void** h_ptr);
 BG_API int bg_host_free_pinned(void* h_ptr);
 
