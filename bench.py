@@ -2,22 +2,31 @@
 """bench.py -- time-to-solution of the GMRES(m)+ILU hot path on B200 (BASELINE.json metric).
 
     python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA library through the C ABI)
-    python bench.py --impl reference --gpus 1 --steps 5 ...  # the reference's CPU path (ILU++ GMRES)
+    python bench.py --impl reference --gpus 1 ...            # the reference's CPU path (ILU++ GMRES), same n
 
-One "step" is one complete DC solve (relative residual 1e-8, GMRES(32)) of the synthetic
-ibmpg6-sized 2-D power grid (BASELINE.json configs[1]; n = 1304^2 = 1 700 416 unknowns) with the
-factorisation done once outside the timed region, exactly like the reference drivers reuse their
-preconditioner across solves (src/mna_solve_gpu_gmres.cpp:518-531, 608-621).
+One "step" is one complete DC solve (relative residual 1e-8, GMRES(32)) of the synthetic 10 M-node 2-D power
+grid BASELINE.json's north_star quotes the target on (pg2d 3162^2), with the factorisation done once outside the
+timed region, exactly like the reference drivers reuse their preconditioner across solves
+(src/mna_solve_gpu_gmres.cpp:518-531, 608-621).  `--workload ibmpg6` makes BASELINE configs[1] (1304^2) the headline.
 
 Printed JSON (one line, rank 0): the contract keys plus
-  roofline      dominant kernel group (from CUDA-event pairs around every launch group of a
-                profiled solve, bg_solver_profile) against MEASURED_PEAKS.json
-  cpu_baseline  the reference's own CPU implementation (oracle/_ref/libilupp.so = vendored ILU++
-                GMRES, kind "reference") or the oracle port, timed on this box's host cores
-  e2e           the same solve through the host-buffer entry point (bg_gmres_solve_host ≙
-                gmresInterfacePGfloat::GMRES_dev_PG): H2D of x and rhs, solve, D2H of x in the
-                timed region.
-Only the cpu_baseline / --impl reference legs touch oracle/.
+  roofline            dominant kernel (CUDA-event pairs around every launch group of a profiled solve,
+                      bg_solver_profile) against MEASURED_PEAKS.json: `achieved`/`frac` on ALGORITHMIC bytes,
+                      `moved_*` on the bytes the kernel actually moves (packed streams, bg_precond_info.stream_bytes)
+  kernels             the same two fractions for every kernel group; iteration_roofline for the whole iteration
+  reference_operator  N=1: the same solve with the reference's own operator (global ILU(0), level schedule) when the
+                      headline runs block-Jacobi tiles, and vice versa (`block_jacobi`)
+  reference_exact     N=1: level schedule + strict MGS (every choice the reference's) on the configs[1] grid, with
+                      x_vs_oracle = ||x - x_oracle|| / ||x_oracle|| against the CPU oracle's solve of the same system
+  configs1            BASELINE configs[1] as SURVEY 8 a20 defines it: ILU++ threshold factors (the reference's own
+                      producer) through bg_precond_create_split = GMRESilu_GPU, ibmpg6-sized grid
+  configs0            BASELINE configs[0]: ibmpg1-sized grid on the reference's compiled CPU GMRES()+MyILU0 (FP32,
+                      oracle/_ref/libref_gmres.so) next to the same solve on the GPU
+  cpu_baseline        the like-for-like CPU arm: the oracle's FP64 port of GMRES(32)+ILU(0) (src/gmres.cu:1904-2066),
+                      one full solve of the configs[1]-sized grid, reported AT THAT SIZE (no extrapolation)
+  e2e                 the same solve through the host-buffer entry point (bg_gmres_solve_host ≙
+                      gmresInterfacePGfloat::GMRES_dev_PG): H2D of x and rhs, solve, D2H of x in the timed region.
+Only the cpu_baseline / reference_exact check / configs0 / --impl reference legs touch oracle/.
 """
 from __future__ import annotations
 
@@ -49,9 +58,13 @@ def parse():
                     help="pg10m: the 10M-node power grid BASELINE.json's north_star quotes the target on (3162^2); "
                          "ibmpg6: BASELINE configs[1] (1304^2 = 1.7M nodes)")
     ap.add_argument("--nx", type=int, default=0, help="grid edge, overrides --workload; n = nx*nx")
-    ap.add_argument("--no-configs1", action="store_true", help="N=1: skip the secondary BASELINE configs[1] solve (ibmpg6-sized, ILUT)")
+    ap.add_argument("--quick", action="store_true", help="N=1: headline only (no secondary configs, no CPU legs)")
+    ap.add_argument("--no-configs1", action="store_true", help="N=1: skip the ILU++-factor solve of BASELINE configs[1]")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N=1: also check the block-Jacobi solve of the configs[1] grid against the oracle given the same blocks")
     ap.add_argument("--precond", default="ilu0", choices=["ilu0", "ilut"])
-    ap.add_argument("--schedule", default="block", choices=["block", "level"])
+    ap.add_argument("--schedule", default="block", choices=["block", "level"],
+                    help="block: block-Jacobi ILU tiles (performance mode); level: the reference's global operator")
     ap.add_argument("--blocks", default="grid", choices=["grid", "metis"])
     ap.add_argument("--tile", type=int, default=32, help="block-Jacobi tile width in grid nodes (<= 32: one lane per tile column)")
     ap.add_argument("--tile-y", type=int, default=0, help="tile height (0 = same as --tile)")
@@ -61,9 +74,7 @@ def parse():
     ap.add_argument("--orth", default="cgs", choices=["mgs", "cgs", "cgs2"])
     ap.add_argument("--eta", type=float, default=0.1, help="CGS re-orthogonalisation threshold (DGKS): second pass when ||w'|| < eta ||w||")
     ap.add_argument("--tol", type=float, default=1e-8)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1: peer-memory kernels over NVLink (default) or the NCCL baseline")
-    ap.add_argument("--cpu-nx", type=int, default=652, help="grid edge of the bounded CPU sample (0 = same as --nx); 652^2 = n/4")
     a = ap.parse_args()
     if a.tile_y <= 0:
         a.tile_y = a.tile
@@ -77,7 +88,14 @@ def workload_name(nx):
         return "pg2d 3162x3162 = synthetic 10M-node power grid (the workload BASELINE.json's north_star states the target on)"
     if nx == 1304:
         return "pg2d 1304x1304 (ibmpg6-sized, BASELINE configs[1])"
+    if nx == 174:
+        return "pg2d 174x174 (ibmpg1-sized, BASELINE configs[0])"
     return f"pg2d {nx}x{nx}"
+
+
+def config_of(nx, n, nnz, tol):
+    """Identical for both arms (the driver compares them): what is solved, not how."""
+    return {"workload": f"{workload_name(nx)} DC solve, GMRES, rel. residual {tol:g}", "n": int(n), "nnz": int(nnz), "tol": tol}
 
 
 def peaks():
@@ -130,78 +148,90 @@ class ClockSampler:
                 "samples": len(sm), "scope": scope}
 
 
+_WL = {}
+
+
 def workload(nx):
     from b200gmres import synth
 
-    rp, ci, v, b = synth.pg2d(nx, nx, seed=synth.SEED_BASE + 2)
-    return rp, ci, v, b
+    if nx not in _WL:
+        _WL.clear()  # one large grid at a time
+        _WL[nx] = synth.pg2d(nx, nx, seed=synth.SEED_BASE + 2)
+    return _WL[nx]
 
 
-# --------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(nx_full, nx_cpu, steps, warmup, tol):
-    """The reference's CPU implementation of the path, timed on the host cores of this box.
+# --------------------------------------------------------------------------- CPU legs (the only users of oracle/)
+def cpu_like_for_like(nx, tol):
+    """The like-for-like CPU arm: the oracle's FP64 port of the reference's host GMRES(32) + MyILU0::HostPrecond
+    (src/gmres.cu:1904-2066, src/preconditioner.cu:205-251), one full DC solve, single thread like the reference.
+    Reported at the size actually run.  Returns (dict, x_oracle)."""
+    from oracle import pyoracle as O
 
-    kind "reference": iluplusplus::gmres with the ILUCDP preconditioner, the `-gmres -ilu` driver
-    path (src/mna_solve_gpu_gmres.cpp:1896-2276), from the vendored ILU++ compiled unchanged into
-    oracle/_ref/libilupp.so.  Single-threaded, as in the reference.  Falls back to the oracle port
-    of GMRES + ILU(0) (kind "port") when that library is absent."""
+    O.build()
+    rp, ci, v, b = workload(nx)
+    n = len(rp) - 1
+    t0 = time.perf_counter()
+    f = O.ilu0(rp, ci, v, "f64")
+    setup_s = time.perf_counter() - t0
+    pc = O.Precond(O.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+    t0 = time.perf_counter()
+    flag, x, iters, res, _ = O.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, tol, pc)
+    ms = 1e3 * (time.perf_counter() - t0)
+    return ({"value": ms, "unit": UNIT, "cores": 1, "kind": "port", "n": int(n), "extrapolated": False,
+             "sample": f"one full DC solve of the {nx}x{nx} grid (n={n}): oracle FP64 port of GMRES(32)+ILU(0) "
+                       f"(gmres.cu:1904-2066 + MyILU0::HostPrecond), {iters} iterations, resid {res:.2e}; the value is for THIS n, not scaled",
+             "setup_s": setup_s, "iters": int(iters), "resid": float(res), "host_cores_online": os.cpu_count()}, x, (int(flag), int(iters), float(res)))
+
+
+def cpu_ilupp(nx, tol):
+    """The reference's `-gmres -ilu` CPU path (src/mna_solve_gpu_gmres.cpp:1896-2276): ILU++ ILUCDP (threshold 1.2)
+    + iluplusplus::gmres, double, single-threaded, from the vendored ILU++ compiled unchanged into
+    oracle/_ref/libilupp.so.  One timed solve; factorisation outside the timed region (reported as setup_s)."""
     import scipy.sparse as sp
 
     from oracle import pyoracle as O
 
-    nx = nx_cpu or nx_full
+    if O.ilupp() is None:
+        return None
     rp, ci, v, b = workload(nx)
     n = len(rp) - 1
-    scale = (nx_full * nx_full) / float(n)
-    times, iters, kind, setup_s = [], None, "port", 0.0
-    if O.ilupp() is not None:
-        kind = "reference"
-        A = sp.csr_matrix((v, ci, rp), shape=(n, n)).tocsc()
-        A.sort_indices()
-        t0 = time.perf_counter()
-        fac = O.ilupp_factor(n, A.indptr, A.indices, A.data, threshold=1.2, mem_factor=1.0)
-        setup_s = time.perf_counter() - t0
-        # restart = 100 is the reference driver's own setting for this path (mna_solve_gpu_gmres.cpp:2063);
-        # with restart 32 the locally patched ILU++ gmres never recomputes r at a restart (SURVEY Q14)
-        # and stagnates.  ILU++ ANDs a relative and an absolute test (both -log10 exponents): the
-        # absolute one is switched off so the stopping rule is the metric's relative residual.
-        ex = -np.log10(tol)
-        for s in range(warmup + steps):
-            t0 = time.perf_counter()
-            x, iters, rt, at = O.ilupp_gmres(fac, b, restart=100, max_iter=1000, rel_tol=ex, abs_tol=-30.0)
-            dt = time.perf_counter() - t0
-            if s >= warmup:
-                times.append(dt)
-        O.ilupp_free(fac)
-        what = f"ILU++ ILUCDP(threshold 1.2) + iluplusplus::gmres(restart 100) double, {iters} iterations, reached 1e-{rt:.2f}"
-    else:
-        O.build()
-        t0 = time.perf_counter()
-        f = O.ilu0(rp, ci, v, "f64")
-        setup_s = time.perf_counter() - t0
-        pc = O.Precond(O.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
-        for s in range(warmup + steps):
-            t0 = time.perf_counter()
-            flag, x, iters, res, _ = O.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, tol, pc)
-            dt = time.perf_counter() - t0
-            if s >= warmup:
-                times.append(dt)
-        what = f"oracle port of GMRES(32)+ILU(0) (gmres.cu:1904-2066) double, {iters} iterations"
-    ms = 1e3 * float(np.mean(times)) * scale
-    sample = f"{what}; full DC solve on the {nx}x{nx} grid (n={n})" + (
-        f", time scaled by n_full/n = {scale:.2f} (iteration count is size-independent for this recipe)" if scale != 1.0 else "")
-    return {"value": ms, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "setup_s": setup_s, "iters": int(iters),
-            "host_cores_online": os.cpu_count()}
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n)).tocsc()
+    A.sort_indices()
+    t0 = time.perf_counter()
+    fac = O.ilupp_factor(n, A.indptr, A.indices, A.data, threshold=1.2, mem_factor=1.0)
+    setup_s = time.perf_counter() - t0
+    # restart = 100 is the reference driver's own setting for this path (mna_solve_gpu_gmres.cpp:2063); with restart 32
+    # the locally patched ILU++ gmres never recomputes r at a restart (SURVEY Q14) and stagnates.  ILU++ ANDs a
+    # relative and an absolute test (both -log10 exponents): the absolute one is switched off so the stopping rule
+    # is the metric's relative residual.
+    t0 = time.perf_counter()
+    x, iters, rt, at = O.ilupp_gmres(fac, b, restart=100, max_iter=1000, rel_tol=-np.log10(tol), abs_tol=-30.0)
+    ms = 1e3 * (time.perf_counter() - t0)
+    O.ilupp_free(fac)
+    true_rel = float(np.linalg.norm(b - _spmv_host(rp, ci, v, x)) / np.linalg.norm(b))
+    return {"value": ms, "unit": UNIT, "cores": 1, "kind": "reference", "n": int(n), "extrapolated": False,
+            "sample": f"one full DC solve of the {nx}x{nx} grid (n={n}), not scaled: ILU++ ILUCDP(threshold 1.2) + "
+                      f"iluplusplus::gmres(restart 100) double, {iters} iterations, reached 1e-{rt:.2f}",
+            "setup_s": setup_s, "iters": int(iters), "true_rel_residual": true_rel, "host_cores_online": os.cpu_count()}
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, on the SAME
+    grid as our arm.  A solve of this size takes about a minute on one core (the reference is single-threaded), so ONE
+    solve is timed whatever --steps / --warmup say; the line reports steps = 1, warmup = 0."""
     if rank != 0:
         return
-    cb = cpu_reference(args.nx, args.cpu_nx, args.steps, args.warmup, args.tol)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
+    rp, ci, v, b = workload(args.nx)
+    n = len(rp) - 1
+    cb = cpu_ilupp(args.nx, args.tol)
+    if cb is None:  # ILU++ not built: the oracle port of GMRES(32)+ILU(0)
+        cb = cpu_like_for_like(args.nx, args.tol)[0]
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload_name(args.nx)} DC solve, GMRES(32), rel. residual {args.tol:g}", "n": args.nx * args.nx},
+            "config": config_of(args.nx, n, len(ci), args.tol),
+            "impl_config": {"algorithm": cb["sample"], "requested_steps": args.steps, "requested_warmup": args.warmup,
+                            "note": "one timed sample: a single-threaded CPU solve of this grid takes of the order of a minute"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -219,45 +249,84 @@ def main():
         return
 
     if world > 1:
-        # rank 0 must print ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("BG_NCCL_DEBUG", "WARN")
+        # rank 0 prints ONE JSON line on stdout: NCCL's log goes to stderr, at INFO so that the communicator's rank
+        # count and the transports it picked are visible to whoever runs this
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("BG_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import torch
     import torch.distributed as dist
 
-    import b200gmres as bg
-
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    if world > 1:
         run_dist(args, rank, world, local)
         return
-    line = run_single(args, local, args.nx, args.precond, args.steps, headline=True)
-    if not args.no_configs1 and args.nx != 1304:
-        # BASELINE configs[1] next to the headline: ibmpg6-sized grid, GMRES(32)+ILUT on 1 B200
-        sec = run_single(args, local, 1304, "ilut", min(args.steps, 10), headline=False)
-        line["configs1"] = {k: sec[k] for k in ("value", "unit", "iters", "ms_per_iteration", "true_rel_residual", "iteration_roofline", "kernels", "e2e", "setup_s")}
-        line["configs1"]["config"] = sec["config"]
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(args.nx, args.cpu_nx, 1, 0, args.tol)
+
+    line = run_single(args, local, args.nx, "ilu0" if args.precond == "ilu0" else "ilut", args.schedule, args.orth, args.steps, headline=True)
+    if not args.quick:
+        other = "level" if args.schedule == "block" else "block"
+        sec = run_single(args, local, args.nx, "ilu0", other, args.orth, min(args.steps, 5), headline=False)
+        line["reference_operator" if other == "level" else "block_jacobi"] = _summary(sec, extra=("iteration_roofline",))
+        # configs[1]-sized grid: the fully reference-exact configuration, checked against the oracle's solve
+        x_oracle = None
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"], x_oracle, ometa = cpu_like_for_like(1304, args.tol)
+        ex = run_single(args, local, 1304, "ilu0", "level", "mgs", min(args.steps, 5), headline=False, keep_x=True)
+        rex = _summary(ex)
+        if x_oracle is not None:
+            rex["x_vs_oracle"] = float(np.linalg.norm(ex["_x"] - x_oracle) / np.linalg.norm(x_oracle))
+            rex["oracle"] = {"flag": ometa[0], "iters": ometa[1], "resid": ometa[2]}
+            rex["iters_equal_oracle"] = bool(ex["iters"] == ometa[1])
+        line["reference_exact"] = rex
+        if args.nx != 1304:
+            bj = run_single(args, local, 1304, "ilu0", "block", args.orth, min(args.steps, 10), headline=False, keep_x=True)
+            s1 = _summary(bj)
+            if args.verify:
+                s1["x_vs_oracle_same_blocks"] = verify_block(1304, args, bj["_x"])
+            line["ibmpg6_block_jacobi"] = s1
+        if not args.no_configs1:
+            line["configs1"] = run_split_ilupp(args, local, 1304, min(args.steps, 10))
+        line["configs0"] = run_configs0(args, local)
     print(json.dumps(line))
 
 
-def run_single(args, local, nx, precond, steps, headline):
+def _summary(sec, extra=()):
+    keys = ("value", "unit", "iters", "ms_per_iteration", "true_rel_residual", "kernels", "e2e", "setup_s", "config", "impl_config") + tuple(extra)
+    return {k: sec[k] for k in keys if k in sec}
+
+
+def verify_block(nx, args, x):
+    """oracle GMRES with the block-Jacobi ILU(0) of the SAME tiles"""
+    import b200gmres as bg
+    from oracle import pyoracle as O
+
+    rp, ci, v, b = workload(nx)
+    n = len(rp) - 1
+    nb, blk = bg.host_block_partition(bg.PART_GRID2D, rp, ci, 0, [nx, nx, 1, args.tile, args.tile_y, 1])
+    f = bg.host_ilu0(rp, ci, v, blk)
+    pc = O.Precond(O.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+    flag, xo, it, res, _ = O.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, args.tol, pc)
+    return {"x_vs_oracle": float(np.linalg.norm(x - xo) / np.linalg.norm(xo)), "oracle_iters": int(it)}
+
+
+def _time_solves(torch, ctx, stream, fn, k):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    e0.record(stream)
+    for _ in range(k):
+        r = fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), r, ctx.launches - l0
+
+
+def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, keep_x=False):
     import torch
 
     import b200gmres as bg
-
-    rank, world = 0, 1
-
-    def barrier():
-        pass
 
     rp, ci, v, b = workload(nx)
     n = len(rp) - 1
@@ -266,7 +335,7 @@ def run_single(args, local, nx, precond, steps, headline):
     A = bg.Matrix(ctx, rp, ci, v, dtype=bg.F64)
     fdt = bg.F32 if args.factor_dtype == "f32" else bg.F64
     t_setup = time.perf_counter()
-    if args.schedule == "block":
+    if schedule == "block":
         o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile_y, factor_dtype=fdt,
                             block_method=bg.PART_GRID2D if args.blocks == "grid" else bg.PART_METIS,
                             dims=[nx, nx, 1, args.tile, args.tile_y, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
@@ -275,7 +344,7 @@ def run_single(args, local, nx, precond, steps, headline):
     M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
     S = bg.Solver(ctx, n, 32, dtype=bg.F64)
-    orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[args.orth]
+    orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[orth_name]
     opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
 
     db = torch.from_numpy(b).cuda()
@@ -293,37 +362,19 @@ def run_single(args, local, nx, precond, steps, headline):
         hx.zero_()
         return S.solve(A, M, hb.numpy(), hx.numpy(), opts, host=True)
 
-    def timed(fn, k):
-        barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launches
-        e0.record(stream)
-        for _ in range(k):
-            r = fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, r, ctx.launches - l0
-
     sampler = ClockSampler(local)
     if headline:
         sampler.start()
         time.sleep(1.0)  # nvidia-smi needs a moment before its first sample
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) if headline else 2):
         step_device()
     tc0 = sampler.mark()
-    ms, r, launches = timed(step_device, steps)
+    ms, r, launches = _time_solves(torch, ctx, stream, step_device, steps)
     tc1 = sampler.mark()
     clocks = sampler.stop(tc0, tc1) if headline else None
-    for _ in range(2):
+    for _ in range(2 if headline else 1):
         step_host()
-    ms_e2e, r_e2e, _ = timed(step_host, steps)
+    ms_e2e, r_e2e, _ = _time_solves(torch, ctx, stream, step_host, steps)
 
     # profiled solve: CUDA-event pairs around every launch group, on the launching stream
     with torch.cuda.stream(stream):
@@ -332,72 +383,217 @@ def run_single(args, local, nx, precond, steps, headline):
     x = dx.cpu().numpy()
     true_rel = float(np.linalg.norm(b - _spmv_host(rp, ci, v, x)) / np.linalg.norm(b))
 
-    if rank == 0:
-        peak, which = peaks()
-        info, pinfo = A.info(), M.info()
-        trsv_kernel = "trsv_block_fused (L and U solve of every diagonal block, one launch)" if args.schedule == "block" else "trsv_level_walk/_wide (L and U solve)"
-        kernels = {
-            "spmv_sell_w<double,5> (sliced ELL, fixed width, all loads in flight)" if info.format == bg.SPMV_SELL else "spmv_csr_vector": (st.spmv_ms, st.spmv_bytes, st.spmv_calls),
-            trsv_kernel: (st.trsv_ms, st.trsv_bytes, st.trsv_calls),
-            "dots_kernel (V^T w and w.w, TMA-staged tiles)": (st.dots_ms, st.dots_bytes, st.dots_calls),
-            "update_kernel (w - V h, normalised, TMA-staged tiles)": (st.update_ms, st.update_bytes, st.update_calls),
-        }
-        if args.orth != "mgs" and st.dots_calls == 0:
-            # fused step: one cooperative launch per inner iteration (projections + Givens epilogue + v_j)
-            kernels = {k: v for k, v in kernels.items() if v[2] > 0}
-            kernels["orth_kernel (fused: V^T w, w.w, Givens, v_j = (w - V h)/||.||; TMA-staged tiles reused from shared memory / L2)"] = (
-                st.orth_ms, st.dots_bytes + st.update_bytes, st.orth_calls)
-        if args.orth == "mgs":
-            kernels = {k: v for k, v in kernels.items() if v[2] > 0}
-            kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls)
-        tot_ms = st.spmv_ms + st.trsv_ms + st.orth_ms + st.other_ms
-        dom = max(kernels, key=lambda k: kernels[k][0])
-        dms, dbytes, dcalls = kernels[dom]
-        ach = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
-        traffic = ncu_traffic(dom)
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "frac_of_nominal_7700": ach / 7700.0,
-                    "traffic": traffic.get("bytes") if traffic else None, "traffic_launch": traffic,
-                    "peak_source": which, "bytes_per_launch": dbytes / max(dcalls, 1), "us_per_launch": 1e3 * dms / max(dcalls, 1),
-                    "launches_timed": int(dcalls), "share_of_step": dms / tot_ms if tot_ms else None,
-                    "how": "CUDA-event pairs on the library stream around every launch of the profiled solve (bg_solver_profile)"}
-        all_bytes = st.spmv_bytes + st.trsv_bytes + st.orth_bytes + st.other_bytes
-        per_kernel = {k: {"ms": p[0], "launches": int(p[2]), "GBps": (p[1] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0),
-                          "frac": (p[1] / (p[0] * 1e-3) / 1e9 / peak if p[0] > 0 else 0.0), "share": p[0] / tot_ms if tot_ms else None}
-                      for k, p in kernels.items()}
-        step_ms = ms / steps
-        line = {
-            "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload_name(nx)} DC solve, GMRES(32), rel. residual {args.tol:g}",
-                       "n": n, "nnz": int(info.nnz), "precond": precond, "trsv_schedule": args.schedule,
-                       "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "factor_dtype": args.factor_dtype,
-                       "orth": args.orth, "reorth_eta": args.eta, "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
-                       "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
-            "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
-            "ms_per_iteration": step_ms / max(r.iters_done, 1),
-            "iteration_roofline": {"bytes_per_iteration": all_bytes / max(rprof.iters_done, 1), "achieved_GBps": all_bytes / (step_ms * 1e-3) / 1e9,
-                                   "frac": all_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                                   "frac_of_nominal_7700": all_bytes / (step_ms * 1e-3) / 1e9 / 7700.0,
-                                   "bytes": "SURVEY.md 8(d): B_spmv + B_trsv + B_orth(j) per inner iteration, restart terms per cycle",
-                                   "note": "peak = measured COPY bandwidth (read+write); read-dominated kernels can exceed it, and the "
-                                           "triangular solve moves fewer bytes than the algorithmic count (16-bit local column ids), so frac may pass 1"},
-            "kernels": per_kernel, "setup_s": t_setup,
-            "roofline": roofline,
-            "e2e": {"value": ms_e2e / steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
+    peak, which = peaks()
+    info, pinfo = A.info(), M.info()
+    s8 = 8
+    # bytes one preconditioner application really moves: the packed factor streams + the vectors it reads and writes
+    # (block tiles: r in, z out; level strips: r in, tmp out, tmp in, z out; sync-free slices add the 16-byte packets)
+    if schedule == "block":
+        trsv_moved_per = pinfo.stream_bytes + 2 * s8 * n
+        trsv_kernel = "trsv_block_fused (L and U solve of every diagonal block, one launch)"
+    elif pinfo.lattice:
+        trsv_moved_per = pinfo.stream_bytes + 4 * s8 * n
+        trsv_kernel = "trsv_lattice_global (global 5-point ILU(0): wavefront strips, L launch + U launch)"
+    else:
+        trsv_moved_per = pinfo.stream_bytes + 4 * s8 * n + 2 * 16 * n
+        trsv_kernel = "trsv_syncfree (global factors: level slices, flag-in-data packets, L launch + U launch)"
+    napply = st.trsv_calls
+    # SpMV moves its sliced-ELL copy (values + 32-bit columns, padded) + x gathers (L2-served) + y
+    spmv_moved_per = (info.sell_padded_nnz * (s8 + 4) if info.format == bg.SPMV_SELL else info.nnz * (s8 + 4) + 4 * (n + 1)) + 2 * s8 * n
+    kernels = {
+        ("spmv_sell_w<double,5> (sliced ELL, fixed width, all loads in flight)" if info.format == bg.SPMV_SELL else "spmv_csr_vector"):
+            (st.spmv_ms, st.spmv_bytes, st.spmv_calls, spmv_moved_per * st.spmv_calls),
+        trsv_kernel: (st.trsv_ms, st.trsv_bytes, st.trsv_calls, trsv_moved_per * napply),
+    }
+    if orth_name == "mgs":
+        # strict MGS: i+1 (dot, axpy) launch pairs per inner iteration; each pair reads v_k and w twice and writes w
+        it = max(rprof.iters_done, 1)
+        moved = sum((5 * (t % 32 + 1) + 3) * s8 * n for t in range(it))
+        kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls, moved)
+    elif st.dots_calls == 0:
+        # fused step: one cooperative launch per inner iteration (projections + Givens epilogue + v_j)
+        kernels["orth_kernel (fused: V^T w, w.w, Givens, v_j = (w - V h)/||.||; TMA-staged tiles reused from shared memory / L2)"] = (
+            st.orth_ms, st.dots_bytes + st.update_bytes, st.orth_calls, st.dots_bytes + st.update_bytes)
+    else:
+        kernels["dots_kernel (V^T w and w.w, TMA-staged tiles)"] = (st.dots_ms, st.dots_bytes, st.dots_calls, st.dots_bytes)
+        kernels["update_kernel (w - V h, normalised, TMA-staged tiles)"] = (st.update_ms, st.update_bytes, st.update_calls, st.update_bytes)
+    tot_ms = st.spmv_ms + st.trsv_ms + st.orth_ms + st.other_ms
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dms, dbytes, dcalls, dmoved = kernels[dom]
+    ach = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+    traffic = ncu_traffic(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "frac_of_nominal_7700": ach / 7700.0,
+                "moved_GBps": dmoved / (dms * 1e-3) / 1e9 if dms > 0 else 0.0, "frac_moved": (dmoved / (dms * 1e-3) / 1e9 / peak) if dms > 0 else 0.0,
+                "traffic": traffic.get("bytes") if traffic else None, "traffic_launch": traffic,
+                "peak_source": which, "bytes_per_launch": dbytes / max(dcalls, 1), "us_per_launch": 1e3 * dms / max(dcalls, 1),
+                "launches_timed": int(dcalls), "share_of_step": dms / tot_ms if tot_ms else None,
+                "how": "CUDA-event pairs on the library stream around every launch of the profiled solve (bg_solver_profile); "
+                       "achieved/frac = SURVEY 8(d) algorithmic bytes, moved_* = bytes the kernel actually moves"}
+    per_kernel = {}
+    for k, p in kernels.items():
+        g_alg = p[1] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0
+        g_mov = p[3] / (p[0] * 1e-3) / 1e9 if p[0] > 0 else 0.0
+        per_kernel[k] = {"ms": p[0], "launches": int(p[2]), "us_per_launch": 1e3 * p[0] / max(p[2], 1),
+                         "GBps_algorithmic": g_alg, "frac_algorithmic": g_alg / peak, "GBps_moved": g_mov, "frac_moved": g_mov / peak,
+                         "share": p[0] / tot_ms if tot_ms else None}
+    step_ms = ms / steps
+    alg_bytes = st.spmv_bytes + st.trsv_bytes + st.orth_bytes + st.other_bytes
+    moved_bytes = sum(p[3] for p in kernels.values()) + st.other_bytes
+    itp = max(rprof.iters_done, 1)
+    line = {
+        "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3) if headline else 2,
+        "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(nx, n, info.nnz, args.tol),
+        "impl_config": {"restart": 32, "precond": precond, "trsv_schedule": schedule, "lattice_layout": bool(pinfo.lattice),
+                        "operator": ("block-Jacobi ILU tiles (changes the preconditioner: iteration drift reported through iters)" if schedule == "block"
+                                     else "the reference's global factors, getLevel dependencies"),
+                        "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "levels": [pinfo.levelsL, pinfo.levelsU],
+                        "factor_dtype": args.factor_dtype, "orth": orth_name, "reorth_eta": args.eta,
+                        "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
+                        "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
+        "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
+        "ms_per_iteration": step_ms / max(r.iters_done, 1),
+        "iteration_roofline": {"bytes_per_iteration_moved": moved_bytes / itp, "moved_GBps": moved_bytes / (step_ms * 1e-3) / 1e9,
+                               "frac": moved_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                               "bytes_per_iteration_survey": alg_bytes / itp,
+                               "frac_survey_count": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                               "frac_of_nominal_7700": moved_bytes / (step_ms * 1e-3) / 1e9 / 7700.0,
+                               "note": "frac = bytes actually moved per solve (packed streams, vectors) / time / measured COPY bandwidth; "
+                                       "frac_survey_count charges SURVEY 8(d)'s general-CSR count (12 B per factor entry + indices), "
+                                       "which the index-free layouts do not move"},
+        "kernels": per_kernel, "setup_s": t_setup,
+        "roofline": roofline,
+        "e2e": {"value": ms_e2e / steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if keep_x:
+        line["_x"] = x
     S.close(); M.close(); A.close(); ctx.close()
     del db, dx, hb, hx
     torch.cuda.empty_cache()
     return line
 
 
+def run_split_ilupp(args, local, nx, steps):
+    """BASELINE configs[1] as SURVEY 8 a20 defines it: factors from the reference's own ILU++ (threshold 1.2,
+    src/mna_solve_gpu_gmres.cpp:316-344) handed over like setPrecondPG does, GMRESilu_GPU algebra (split
+    preconditioning), GMRES(32).  ILU++ runs on the CPU (it is the reference's factor producer), outside the timed region."""
+    import scipy.sparse as sp
+    import torch
+
+    import b200gmres as bg
+    from oracle import pyoracle as O
+
+    if O.ilupp() is None:
+        return {"unavailable": "oracle/_ref/libilupp.so is not built"}
+    rp, ci, v, b = workload(nx)
+    n = len(rp) - 1
+    Ac = sp.csr_matrix((v, ci, rp), shape=(n, n)).tocsc()
+    Ac.sort_indices()
+    t0 = time.perf_counter()
+    fac = O.ilupp_factor(n, Ac.indptr, Ac.indices, Ac.data, threshold=1.2, mem_factor=1.0)
+    t_ilupp = time.perf_counter() - t0
+    keys = ("lp", "li", "lv", "up", "ui", "uv", "middle", "lscale", "rscale", "permRow", "permCol")
+    ctx = bg.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    A = bg.Matrix(ctx, rp, ci, v, dtype=bg.F64)
+    t0 = time.perf_counter()
+    M = bg.Precond.split(ctx, *[fac[k] for k in keys], dtype=bg.F64)
+    t_dev = time.perf_counter() - t0
+    nnzL, nnzU = len(fac["lv"]), len(fac["uv"])
+    O.ilupp_free(fac)
+    S = bg.Solver(ctx, n, 32, dtype=bg.F64)
+    out = {}
+    for orth_name, orth in (("mgs", bg.ORTH_MGS), ("cgs", bg.ORTH_CGS_ADAPTIVE)):
+        opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
+        db = torch.from_numpy(b).cuda()
+        dx = torch.zeros(n, dtype=torch.float64, device="cuda")
+
+        def step():
+            with torch.cuda.stream(stream):
+                dx.zero_()
+            return S.solve(A, M, db.data_ptr(), dx.data_ptr(), opts)
+
+        step()
+        ms, r, _ = _time_solves(torch, ctx, stream, step, steps)
+        with torch.cuda.stream(stream):
+            dx.zero_()
+        rprof, st = S.profile(A, M, db.data_ptr(), dx.data_ptr(), opts)
+        x = dx.cpu().numpy()
+        pinfo = M.info()
+        out[orth_name] = {"value": ms / steps, "unit": UNIT, "iters": int(r.iters), "resid": float(r.resid),
+                          "true_rel_residual": float(np.linalg.norm(b - _spmv_host(rp, ci, v, x)) / np.linalg.norm(b)),
+                          "ms_per_iteration": ms / steps / max(r.iters_done, 1),
+                          "phases_ms": {"spmv": st.spmv_ms, "trsv_L_and_U": st.trsv_ms, "orth": st.orth_ms, "restart_terms": st.other_ms},
+                          "trsv_us_per_solve": 1e3 * st.trsv_ms / max(st.trsv_calls, 1), "trsv_solves": int(st.trsv_calls)}
+    pinfo = M.info()
+    out["config"] = config_of(nx, n, len(ci), args.tol)
+    out["impl_config"] = {"restart": 32, "precond": "ILU++ multilevel ILUCDP, threshold 1.2 (the reference's producer), split: M_L = L, M_R = D U",
+                          "algebra": "GMRESilu_GPU (src/gmres.cu:2254-2446)", "nnzL": nnzL, "nnzU": nnzU, "levels": [pinfo.levelsL, pinfo.levelsU],
+                          "kernel": "trsv_syncfree"}
+    out["setup_s"] = {"ilupp_cpu": t_ilupp, "upload_and_schedule": t_dev}
+    S.close(); M.close(); A.close(); ctx.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_configs0(args, local):
+    """BASELINE configs[0]: ibmpg1-sized grid (174^2 = 30 276 nodes), GMRES(32)+ILU(0) on the reference's CPU path --
+    the reference's own compiled host GMRES() + MyILU0::HostPrecond (src/gmres.cu:1904-2066, FP32, tolerance 1e-6 =
+    its driver default, src/defs.h:12) from oracle/_ref/libref_gmres.so -- next to the same FP32 solve on the GPU."""
+    import torch
+
+    import b200gmres as bg
+    from b200gmres import synth
+    from oracle import pyoracle as O
+
+    rp, ci, v, b = synth.pg2d(174, 174, seed=synth.SEED_BASE + 1)
+    n = len(rp) - 1
+    out = {"config": config_of(174, n, len(ci), 1e-6)}
+    O.build()
+    f32 = O.ilu0(rp, ci, v, "f32")
+    times = []
+    kind = "reference"
+    for _ in range(5):
+        t0 = time.perf_counter()
+        if O.ref_gmres_lib() is not None:
+            flag, x, it, res = O.ref_host_gmres_ilu0(rp, ci, v, b, np.zeros(n), 32, 10000, 1e-6, f32)[:4]
+        else:
+            kind = "port"
+            pc = O.Precond(O.PC_ILU0, n, "f32", **{k: f32[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+            flag, x, it, res, _ = O.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, 1e-6, pc)
+        times.append(time.perf_counter() - t0)
+    out["cpu"] = {"value": 1e3 * float(np.median(times)), "unit": UNIT, "kind": kind, "cores": 1, "iters": int(it), "resid": float(res),
+                  "sample": "5 full solves, median; the reference's compiled GMRES() + MyILU0::HostPrecond, FP32, tol 1e-6"}
+    ctx = bg.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    A = bg.Matrix(ctx, rp, ci, v, dtype=bg.F32)
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F32)
+    S = bg.Solver(ctx, n, 32, dtype=bg.F32)
+    opts = bg.gmres_opts(m=32, tol=1e-6, max_iter=10000, orth=bg.ORTH_MGS)
+    hb = torch.from_numpy(b.astype(np.float32)).pin_memory()
+    hx = torch.zeros(n, dtype=torch.float32).pin_memory()
+
+    def step_host():
+        hx.zero_()
+        return S.solve(A, M, hb.numpy(), hx.numpy(), opts, host=True)
+
+    step_host()
+    ms, r, _ = _time_solves(torch, ctx, stream, step_host, 10)
+    xg = hx.numpy().astype(np.float64)
+    out["gpu"] = {"value": ms / 10, "unit": UNIT, "iters": int(r.iters), "resid": float(r.resid), "dtype": "f32",
+                  "what": "bg_gmres_solve_host (H2D, solve, D2H), level schedule (reference operator), strict MGS",
+                  "x_vs_cpu_reference": float(np.linalg.norm(xg - x) / np.linalg.norm(x))}
+    S.close(); M.close(); A.close(); ctx.close()
+    return out
+
+
 def run_dist(args, rank, world, local):
     """N > 1: the same DC solve, row-partitioned into `world` horizontal strips of the grid (contiguous
-    row blocks, src/partition.cpp's initial assignment), one process per GPU: NCCL halo exchange per
-    SpMV, one NCCL allreduce per orthogonalisation step, per-rank block-Jacobi ILU (dist.cu)."""
+    row blocks, src/partition.cpp's initial assignment), one process per GPU: halo exchange per SpMV, one
+    all-reduce per orthogonalisation step, per-rank block-Jacobi ILU (dist.cu)."""
     import torch
     import torch.distributed as dist
 
@@ -501,25 +697,28 @@ def run_dist(args, rank, world, local):
         step_ms = ms / args.steps
         s8 = 8
         nnz = len(ci)
-        # SURVEY 8(d) bytes per inner iteration summed over all ranks (the halo adds nothing to HBM traffic worth counting)
         it = max(r.iters_done, 1)
+        # per inner iteration, all ranks: SURVEY 8(d) count and the bytes the kernels actually move (index-free tile
+        # streams: rank 0's stream x world)
         orth_b = sum((2 * (t % 32 + 1) + 5) * s8 * n for t in range(it))
         spmv_b = ((s8 + 4) * nnz + 4 * (n + 1) + 2 * s8 * n) * it
-        trsv_b = ((s8 + 4) * (info.precond.nnzL + info.precond.nnzU) * world + 8 * (n + 1) + 4 * s8 * n) * it  # nnz of rank 0 x world
-        all_b = orth_b + spmv_b + trsv_b
+        trsv_b = ((s8 + 4) * (info.precond.nnzL + info.precond.nnzU) * world + 8 * (n + 1) + 4 * s8 * n) * it
+        trsv_m = (info.precond.stream_bytes * world + 2 * s8 * n) * it
+        all_b, all_m = orth_b + spmv_b + trsv_b, orth_b + spmv_b + trsv_m
         line = {
             "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload_name(nx)} DC solve, GMRES(32), rel. residual {args.tol:g}",
-                       "n": n, "nnz": nnz, "precond": args.precond, "trsv_schedule": "block",
-                       "partition": f"{world} horizontal strips (contiguous rows), per-rank block-Jacobi ILU, tiles {args.tile}x{args.tile_y}",
-                       "orth": args.orth, "reorth_eta": args.eta,
-                       "l2_policy": "per-rank Krylov basis 33 x n/N x 8 B = %.0f MB" % (33 * n * 8 / 1e6 / world)},
+            "config": config_of(nx, n, nnz, args.tol),
+            "impl_config": {"restart": 32, "precond": args.precond, "trsv_schedule": "block",
+                            "partition": f"{world} horizontal strips (contiguous rows), per-rank block-Jacobi ILU, tiles {args.tile}x{args.tile_y}",
+                            "orth": args.orth, "reorth_eta": args.eta,
+                            "l2_policy": "per-rank Krylov basis 33 x n/N x 8 B = %.0f MB" % (33 * n * 8 / 1e6 / world)},
             "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
             "ms_per_iteration": step_ms / it,
-            "iteration_roofline": {"bytes_per_iteration": all_b / it, "achieved_GBps": all_b / (step_ms * 1e-3) / 1e9,
-                                   "frac": all_b / (step_ms * 1e-3) / 1e9 / (peak * world), "peak": peak * world,
-                                   "bytes": "SURVEY.md 8(d) per inner iteration, all ranks; peak = N x measured HBM copy bandwidth"},
+            "iteration_roofline": {"bytes_per_iteration_moved": all_m / it, "moved_GBps": all_m / (step_ms * 1e-3) / 1e9,
+                                   "frac": all_m / (step_ms * 1e-3) / 1e9 / (peak * world), "peak": peak * world,
+                                   "bytes_per_iteration_survey": all_b / it, "frac_survey_count": all_b / (step_ms * 1e-3) / 1e9 / (peak * world),
+                                   "note": "all ranks; peak = N x measured HBM copy bandwidth; frac on bytes actually moved"},
             "comm": {"halo_bytes_per_exchange_rank0": int(info.halo_bytes_per_exchange), "neighbors_rank0": int(info.n_neighbors),
                      "allreduce_doubles_max": 34,
                      "backend": ("peer-memory kernels over NVLink (CUDA IPC windows): all-reduce fused into dots_kernel, halo = one gather+peer-store kernel"

@@ -32,6 +32,13 @@ ctx.sync()
 t = (C.c_ulonglong * (2048 * 5))()
 L.bg_debug_sf_times(C.c_int(-1), t)
 t = np.array(t[:], dtype=np.int64).reshape(2048, 5)
+lm = len(cnt) // 2
+b0 = t[t[:, 0] > 0][:, 0].min()
+for l in range(lm, lm + 3):
+    a0, a1 = int(first_slice[l]) - q0, int(first_slice[l + 1]) - q0
+    rows = t[a0:a1]
+    print(f"  level {l}: {a1-a0} slices; taken(min..max) {rows[:,0].min()-b0}..{rows[:,0].max()-b0}  deps arrived {sorted((rows[:,2]-b0).tolist())[:6]} .. max {rows[:,2].max()-b0}  published min {rows[:,3].min()-b0} max {rows[:,3].max()-b0}")
+    print("     per slice (deps_arrived, published, sm):", [(int(r[2]-b0), int(r[3]-b0), int(r[4])) for r in rows[:12]])
 ok = t[:, 3] > 0
 t = t[ok]
 base = t[:, 0].min()
@@ -42,5 +49,6 @@ for nm, d in (("taken->operands loaded", d01), ("operands->deps arrived", d12), 
 # pace of the front: publication time of consecutive slices
 pub = np.sort(t[:, 3]) - base
 print("  publication times of the first 48 stamped slices (ns from first take):", (pub[:48]).tolist())
+# three consecutive levels in detail: when each slice saw its dependencies arrive (t2) and published (t3)
 span = pub[-1] - pub[0]
 print(f"  {len(pub)} slices published over {span} ns -> {span/len(pub):.0f} ns per slice")
