@@ -78,9 +78,12 @@ template <class FT> struct SfArgs {
 // One warp per slice (<= 32 rows of ONE level), slices taken in ascending order by a fixed set of resident warps:
 // a warp only ever waits for rows of earlier slices, which are finished or held by a running warp, so the walk
 // cannot deadlock as long as the whole grid is resident (launcher).  Everything that does not depend on other rows
-// (row ids, columns, values, right-hand side, diagonal) is loaded before the first poll; the K packet loads of a
-// row leave together and only the ones that were not ready yet are polled again.  Same operations in the same
-// order as the reference's host solve (acc = rhs; acc -= v_k x_k in stored order; acc /= diag).
+// (row ids, columns, values, right-hand side, diagonal) is loaded before the first poll; the packet loads of a
+// row leave together and the warp re-polls, AS A WHOLE, only the ones that were not ready yet, until a warp vote
+// says every lane has its operands.  The vote keeps the warp converged: 32 lanes spinning in private loops are
+// executed one divergent path after the other, which measured 10 us per dependency hop instead of one L2 round trip
+// (~0.4 us; tools/probe/relay_probe.cu, profiles/r02_syncfree_probe.txt).  Same operations in the same order as the
+// reference's host solve (acc = rhs; acc -= v_k x_k in stored order; acc /= diag).
 constexpr int kSfKP = 4;
 #ifdef BG_SF_TIMING
 // development aid (make dbg): %globaltimer stamps of lane 0 of the warps that solve slices [g_sf_q0, g_sf_q0 + 2048):
@@ -104,10 +107,11 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
     const int s0 = a.slice_slot[q], R = a.slice_slot[q + 1] - s0;
     const int64_t off = a.slice_off[q];
     const int K = (int)((a.slice_off[q + 1] - off) / R);
-    if (lane >= R) continue;
-    const int r = a.rows[s0 + lane];
+    const bool mine = lane < R;  // lanes beyond the slice stay in the loops with nothing to wait for
+    const int t = mine ? lane : 0;
+    const int r = a.rows[s0 + t];
     CT acc = load_rhs<VT, CT>(xf, in, r);
-    const CT dg = UNIT ? (CT)1 : (CT)a.diag[s0 + lane];
+    const CT dg = UNIT ? (CT)1 : (CT)a.diag[s0 + t];
 #ifdef BG_SF_TIMING
     if (acc == (CT)1.2345e300) return;  // forces the operand loads to complete before the stamp
     SF_STAMP(1);
@@ -117,25 +121,42 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
       int c[KP];
       CT v[KP];
       LL16 pk[KP];
+      bool need[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        c[j] = k0 + j < K ? a.cols[off + (int64_t)(k0 + j) * R + lane] : -1;
-        v[j] = c[j] >= 0 ? (CT)a.vals[off + (int64_t)(k0 + j) * R + lane] : (CT)0;
+        c[j] = (mine && k0 + j < K) ? a.cols[off + (int64_t)(k0 + j) * R + t] : -1;
+        v[j] = c[j] >= 0 ? (CT)a.vals[off + (int64_t)(k0 + j) * R + t] : (CT)0;
+        need[j] = c[j] >= 0;
+        pk[j] = LL16{0u, 0u, 0u, 0u};
+      }
+      unsigned long long t_start = 0;
+      for (unsigned spin = 0;; ++spin) {  // warp-uniform: leaves when every lane has all its operands
+        bool all = true;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          if (need[j]) {  // predicated reload of the packets still missing
+            pk[j] = ll_load(xs + c[j]);
+            need[j] = !ll_ok(pk[j], a.seq);
+          }
+          all = all && !need[j];
+        }
+        if (__all_sync(0xffffffffu, all)) break;
+        if ((spin & 4095u) == 4095u) {
+          const unsigned long long now = global_ns();
+          if (t_start == 0) t_start = now;
+          else if (now - t_start > a.timeout_ns) __trap();
+        }
       }
 #pragma unroll
       for (int j = 0; j < KP; ++j)
-        if (c[j] >= 0) pk[j] = ll_load(xs + c[j]);
-#pragma unroll
-      for (int j = 0; j < KP; ++j)
-        if (c[j] >= 0) {
-          const double x = ll_ok(pk[j], a.seq) ? ll_val(pk[j]) : ll_wait(xs + c[j], a.seq, a.timeout_ns);
-          acc -= v[j] * (CT)x;
-        }
+        if (c[j] >= 0) acc -= v[j] * (CT)ll_val(pk[j]);
     }
     SF_STAMP(2);
     if (!UNIT) acc /= dg;
-    ll_store(xs + r, (double)acc, a.seq);
-    store_out<VT, CT>(xf, out, r, acc);
+    if (mine) {
+      ll_store(xs + r, (double)acc, a.seq);
+      store_out<VT, CT>(xf, out, r, acc);
+    }
     SF_STAMP(3);
   }
 }
@@ -166,128 +187,203 @@ template <class FT> struct LgArgs {
   unsigned seq;
   unsigned long long timeout_ns;
 };
-constexpr int kLgBS = 8;     // steps per block (prefetch / boundary / flush granularity)
-constexpr int kLgOutRows = 64;
+constexpr int kLgBS = 8;  // steps per block: granularity of staging, boundary hand-off and result flush
 template <class TIN, class TOUT, class FT, bool LOWER> constexpr size_t lg_smem_bytes(int NR) {
-  return (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN)) + (size_t)kLgOutRows * 32 * sizeof(TOUT);
+  return (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN) + sizeof(TOUT)) + (size_t)NR * 8 + 3 * (size_t)(NR / kLgBS) * 8 + 64;
 }
-
-// One warp (= one CTA, one SM) per strip of 32 grid columns; "time row" t = y (LOWER, strips left to right) or
-// ny-1-y (UPPER, strips right to left); lane x reaches time row t at step t + lag, lag = x (LOWER) / 31-x (UPPER).
-// Every HBM access is a coalesced 32-node row segment: coefficient pairs, 1/diag and the right-hand side of the
-// time rows of block b+PF are staged with cp.async into a ring of NR rows (each lane copies and later reads only
-// its own column, so no barrier is needed anywhere), and results wait in a small ring until all 32 lanes have
-// passed a row, then leave as one 256-byte store.  The boundary values a strip needs from its upstream neighbour
-// are fetched one block ahead by lanes 0..kLgBS-1 as flag-in-data packets and handed to the edge lane by shuffle,
-// so in steady state no load sits on the dependency chain: a step is two shuffles and two FMAs.
-template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR, int PF>
-__global__ void __launch_bounds__(32) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
-                                                          const int* skip) {
-  static_assert((NR & (NR - 1)) == 0 && NR > 8 * PF + 38, "ring too small for the prefetch distance plus the lane skew");
-  extern __shared__ __align__(16) unsigned char lg_smem[];
-  constexpr int BS = kLgBS, NRO = kLgOutRows;
-  using P = typename std::conditional<sizeof(FT) == 8, double2, float2>::type;
-  P* s_pair = reinterpret_cast<P*>(lg_smem);
-  FT* s_dinv = reinterpret_cast<FT*>(lg_smem + (size_t)NR * 32 * sizeof(P));
-  TIN* s_rhs = reinterpret_cast<TIN*>(lg_smem + (size_t)NR * 32 * (LOWER ? 2 : 3) * sizeof(FT));
-  TOUT* s_out = reinterpret_cast<TOUT*>(lg_smem + (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN)));
-  pdl_wait();
-  if (skip && *skip) return;
-  const int lane = threadIdx.x;
-  const int s = LOWER ? (int)blockIdx.x : a.strips - 1 - (int)blockIdx.x;  // CTAs in dependency order
-  const int X = 32 * s + lane, nx = a.nx, ny = a.ny;
-  const bool colok = X < nx;
-  const int lag = LOWER ? lane : 31 - lane;
-  const int nblk = (ny + 31 + BS - 1) / BS;
-  const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
-  const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
-  const bool has_up = LOWER ? s > 0 : s < a.strips - 1, has_down = LOWER ? s < a.strips - 1 : s > 0;
-  const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
-  LL16* bnd_out = a.bnd + (size_t)s * ny;
-  const int edge_in = LOWER ? 0 : 31, edge_out = LOWER ? 31 : 0;
-  auto yrow = [&](int t) { return LOWER ? t : ny - 1 - t; };
-  auto issue = [&](int blk) {  // time rows [8 blk, 8 blk + 8)
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      const int t = blk * BS + j;
-      if (t < ny) {
-        const int y = yrow(t), slot = (t & (NR - 1)) * 32 + lane;
-        cp_async<sizeof(P)>(s_pair + slot, gpair + (size_t)y * 32);
-        if (!LOWER) cp_async<sizeof(FT)>(s_dinv + slot, gdinv + (size_t)y * 32);
-        if (colok) cp_async<sizeof(TIN)>(s_rhs + slot, in + (size_t)y * nx + X);
-      }
+__device__ __forceinline__ void lg_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lg_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lg_smem_u32(bar)) : "memory");
+}
+// arrives (without raising the pending count) once all cp.async copies this thread issued so far have landed
+__device__ __forceinline__ void lg_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(lg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lg_mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long timeout_ns) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(lg_smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spin & 255u) == 255u) {  // a scheduling bug or a dead upstream strip must trap, never hang the GPU
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) __trap();
     }
-    cp_async_commit();  // always (possibly empty) so that the wait below counts uniformly
-  };
-  LL16 pk = {0u, 0u, 0u, 0u};
-  int pk_y = -1;  // row of the packet this lane prefetched for the coming block (-1: none)
-  auto bnd_fetch = [&](int blk) {
-    const int t = blk * BS + lane;  // the edge lane has no lag: it reaches time row t at step t
-    pk_y = (has_up && lane < BS && t < ny) ? yrow(t) : -1;
-    if (pk_y >= 0) pk = ll_load(bnd_in + pk_y);
-  };
-  for (int b = 0; b < PF; ++b) issue(b);
-  bnd_fetch(0);
-  CT zprev = (CT)0;
-  for (int blk = 0; blk < nblk; ++blk) {
-    issue(blk + PF);
-    cp_async_wait<PF>();  // the rows of block blk (and everything older) have landed: this lane's own copies
-    double bval = 0.0;
-    if (pk_y >= 0) bval = ll_ok(pk, a.seq) ? ll_val(pk) : ll_wait(bnd_in + pk_y, a.seq, a.timeout_ns);
-    bnd_fetch(blk + 1);  // in flight during the steps below
-    __syncwarp();
-    // operands of the 8 steps into registers (inactive steps: zeros, which make z = 0), so that the chain below
-    // is branch-free register code: per step two shuffles, a select and two FMAs
-    const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
-    CT ca[BS], cb[BS], r[BS], be[BS], zs[BS];
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      const int t = t0 + j;
-      const bool act = colok && (unsigned)t < (unsigned)ny;
-      const int slot = (t & (NR - 1)) * 32 + lane;  // always a valid ring address
-      const P c = s_pair[slot];
-      CT rr = (CT)s_rhs[slot];
-      if (!LOWER) rr *= (CT)s_dinv[slot];
-      ca[j] = act ? (CT)c.x : (CT)0;
-      cb[j] = act ? (CT)c.y : (CT)0;
-      r[j] = act ? rr : (CT)0;
-      be[j] = (CT)__shfl_sync(0xffffffffu, bval, j);
-    }
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
-      zn = lane == edge_in ? be[j] : zn;
-      const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
-      zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
-      zs[j] = zprev;
-    }
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      const int t = t0 + j;
-      if (colok && (unsigned)t < (unsigned)ny) s_out[(t & (NRO - 1)) * 32 + lane] = (TOUT)zs[j];
-    }
-    if (lane == edge_out && has_down) {
-#pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        const int t = t0 + j;
-        if ((unsigned)t < (unsigned)ny) ll_store(bnd_out + yrow(t), (double)zs[j], a.seq);
-      }
-    }
-    // rows every lane has passed: one coalesced store per row (each lane re-reads its own column)
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      const int tf = blk * BS - 31 + j;
-      if (colok && (unsigned)tf < (unsigned)ny) out[(size_t)yrow(tf) * nx + X] = s_out[(tf & (NRO - 1)) * 32 + lane];
+  }
+}
+__device__ __forceinline__ void lg_wait_progress(volatile int* p, int need, unsigned long long timeout_ns) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0; *p < need; ++spin) {
+    __nanosleep(64);
+    if ((spin & 1023u) == 1023u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) __trap();
     }
   }
 }
 
-template <class VT, class FT, int NR, int PF>
+// One CTA (= one SM) per strip of 32 grid columns, four specialised warps.  "Time row" t = y (LOWER, strips left
+// to right) or ny-1-y (UPPER, strips right to left); lane x of the CHAIN warp reaches time row t at step t + lag,
+// lag = x (LOWER) / 31-x (UPPER).  A lone warp issues about one dependent instruction every four cycles, so
+// everything that is not the recurrence itself is moved off the chain warp:
+//   warp 1 LOADER    stages the coefficient pairs, 1/diag and the right-hand side of 8 time rows per block with
+//                    coalesced cp.async copies into a ring of NR rows, several blocks ahead of the chain, and lets
+//                    the copies arrive on the block's `full` mbarrier
+//   warp 2 BOUNDARY  polls the upstream strip's boundary column (flag-in-data packets in L2, warp-uniform vote
+//                    loop), drops the values into shared memory, arrives on `bfull`
+//   warp 0 CHAIN     per step: operands from shared memory (its own column), west/east value by shuffle (edge
+//                    lane: the boundary value), two FMAs, result to a ring in shared memory; one arrive per block
+//   warp 3 STORER    once all 32 lanes have passed a row: one coalesced 256-byte store of the row, and the edge
+//                    column of the block goes to the downstream strip as 8 packets
+// Rings are protected by two progress counters in shared memory (chain blocks done, storer blocks done).
+template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR>
+__global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
+                                                           const int* skip) {
+  constexpr int BS = kLgBS, NS = NR / BS;
+  constexpr int AHEAD = (NR - 31) / BS - 1;  // blocks a producer may run ahead of the consumer that frees its ring rows
+  static_assert((NR & (NR - 1)) == 0 && AHEAD >= 2, "ring too small for the lane skew");
+  extern __shared__ __align__(16) unsigned char lg_smem[];
+  using P = typename std::conditional<sizeof(FT) == 8, double2, float2>::type;
+  unsigned char* sp = lg_smem;
+  P* s_pair = reinterpret_cast<P*>(sp); sp += (size_t)NR * 32 * sizeof(P);
+  FT* s_dinv = reinterpret_cast<FT*>(sp); sp += LOWER ? 0 : (size_t)NR * 32 * sizeof(FT);
+  TIN* s_rhs = reinterpret_cast<TIN*>(sp); sp += (size_t)NR * 32 * sizeof(TIN);
+  TOUT* s_out = reinterpret_cast<TOUT*>(sp); sp += (size_t)NR * 32 * sizeof(TOUT);
+  double* s_bnd = reinterpret_cast<double*>(sp); sp += (size_t)NR * 8;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sp); sp += (size_t)NS * 8;
+  uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(sp); sp += (size_t)NS * 8;
+  uint64_t* bar_done = reinterpret_cast<uint64_t*>(sp); sp += (size_t)NS * 8;
+  volatile int* prog = reinterpret_cast<volatile int*>(sp);  // [0] chain blocks done, [1] storer blocks done
+  pdl_wait();
+  if (skip && *skip) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { lg_mbar_init(&bar_full[i], 32); lg_mbar_init(&bar_bfull[i], 1); lg_mbar_init(&bar_done[i], 1); }
+    prog[0] = 0; prog[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int s = LOWER ? (int)blockIdx.x : a.strips - 1 - (int)blockIdx.x;  // CTAs in dependency order
+  const int X = 32 * s + lane, nx = a.nx, ny = a.ny;
+  const bool colok = X < nx;
+  const int nblk = (ny + 31 + BS - 1) / BS;
+  const bool has_up = LOWER ? s > 0 : s < a.strips - 1, has_down = LOWER ? s < a.strips - 1 : s > 0;
+  const int edge_in = LOWER ? 0 : 31, edge_out = LOWER ? 31 : 0;
+  const unsigned long long tmo = a.timeout_ns;
+  auto yrow = [&](int t) { return LOWER ? t : ny - 1 - t; };
+
+  if (wid == 1) {  // ---------------------------------------------------------------- LOADER
+    const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
+    const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
+    for (int lb = 0; lb < nblk; ++lb) {
+      if (lb > AHEAD) lg_wait_progress(&prog[0], lb - AHEAD, tmo);  // the ring rows about to be overwritten are dead
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int t = lb * BS + j;
+        if (t < ny) {
+          const int y = yrow(t), slot = (t & (NR - 1)) * 32 + lane;
+          cp_async<sizeof(P)>(s_pair + slot, gpair + (size_t)y * 32);
+          if (!LOWER) cp_async<sizeof(FT)>(s_dinv + slot, gdinv + (size_t)y * 32);
+          if (colok) cp_async<sizeof(TIN)>(s_rhs + slot, in + (size_t)y * nx + X);
+        }
+      }
+      lg_cp_async_arrive(&bar_full[lb % NS]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (wid == 2) {  // --------------------------------------------------------- BOUNDARY IN
+    if (has_up) {
+      const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
+      for (int b = 0; b * BS < ny; ++b) {
+        if (b > AHEAD) lg_wait_progress(&prog[0], b - AHEAD, tmo);
+        const int t = b * BS + lane;  // the edge lane has no lag: it reaches time row t at step t
+        bool need = lane < BS && t < ny;
+        LL16 pk = {0u, 0u, 0u, 0u};
+        unsigned long long t0 = 0;
+        for (unsigned spin = 0;; ++spin) {  // warp-uniform poll
+          if (need) { pk = ll_load(bnd_in + yrow(t)); need = !ll_ok(pk, a.seq); }
+          if (__all_sync(0xffffffffu, !need)) break;
+          if ((spin & 4095u) == 4095u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > tmo) __trap();
+          }
+        }
+        if (lane < BS && t < ny) s_bnd[t & (NR - 1)] = ll_val(pk);
+        __syncwarp();
+        if (lane == 0) lg_mbar_arrive(&bar_bfull[b % NS]);
+      }
+    }
+  } else if (wid == 0) {  // --------------------------------------------------------- CHAIN
+    const int lag = LOWER ? lane : 31 - lane;
+    CT zprev = (CT)0;
+    for (int blk = 0; blk < nblk; ++blk) {
+      if (blk > AHEAD) lg_wait_progress(&prog[1], blk - AHEAD, tmo);  // the result ring rows about to be reused have left
+      const uint32_t par = (uint32_t)(blk / NS) & 1u;
+      lg_mbar_wait(&bar_full[blk % NS], par, tmo);
+      const bool bnd = has_up && blk * BS < ny;
+      if (bnd) lg_mbar_wait(&bar_bfull[blk % NS], par, tmo);
+      const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
+      // every lane inside [0, ny) for all 8 steps and a full strip: no selects on the operands
+      const bool interior = blk * BS - 31 >= 0 && blk * BS + BS - 1 < ny && 32 * s + 31 < nx;
+      CT ca[BS], cb[BS], r[BS], be[BS];
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int t = t0 + j;
+        const int slot = (t & (NR - 1)) * 32 + lane;  // always a valid ring address
+        const P c = s_pair[slot];
+        CT rr = (CT)s_rhs[slot];
+        if (!LOWER) rr *= (CT)s_dinv[slot];
+        const bool act = interior || (colok && (unsigned)t < (unsigned)ny);
+        ca[j] = act ? (CT)c.x : (CT)0;
+        cb[j] = act ? (CT)c.y : (CT)0;
+        r[j] = act ? rr : (CT)0;
+        be[j] = bnd && blk * BS + j < ny ? (CT)s_bnd[(blk * BS + j) & (NR - 1)] : (CT)0;  // same address for all lanes: broadcast
+      }
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
+        zn = lane == edge_in ? be[j] : zn;
+        const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
+        zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
+        s_out[((t0 + j) & (NR - 1)) * 32 + lane] = (TOUT)zprev;  // rows outside [0, ny) are never flushed
+      }
+      __syncwarp();
+      if (lane == 0) {
+        lg_mbar_arrive(&bar_done[blk % NS]);
+        prog[0] = blk + 1;
+      }
+    }
+  } else {  // ----------------------------------------------------------------------- STORER
+    LL16* bnd_out = a.bnd + (size_t)s * ny;
+    for (int b = 0; b < nblk; ++b) {
+      lg_mbar_wait(&bar_done[b % NS], (uint32_t)(b / NS) & 1u, tmo);
+      // the rows the last lane finished in this block: every lane has passed them
+      if (has_down && lane < BS) {
+        const int tf = b * BS - 31 + lane;
+        if ((unsigned)tf < (unsigned)ny) ll_store(bnd_out + yrow(tf), (double)s_out[(tf & (NR - 1)) * 32 + edge_out], a.seq);
+      }
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int tf = b * BS - 31 + j;
+        if (colok && (unsigned)tf < (unsigned)ny) out[(size_t)yrow(tf) * nx + X] = s_out[(tf & (NR - 1)) * 32 + lane];
+      }
+      __syncwarp();
+      if (lane == 0) prog[1] = b + 1;
+    }
+  }
+}
+
+template <class VT, class FT, int NR>
 static int lattice_launch(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {
   using CT = decltype(VT() * FT());
   const unsigned long long tmo = 5ull * 1000000000ull;
-  auto kl = trsv_lattice_global<VT, CT, FT, CT, true, NR, PF>;
-  auto ku = trsv_lattice_global<CT, VT, FT, CT, false, NR, PF>;
+  auto kl = trsv_lattice_global<VT, CT, FT, CT, true, NR>;
+  auto ku = trsv_lattice_global<CT, VT, FT, CT, false, NR>;
   const size_t sl = lg_smem_bytes<VT, CT, FT, true>(NR), su = lg_smem_bytes<CT, VT, FT, false>(NR);
   static bool attr_done[64] = {};
   if (!attr_done[ctx->device & 63]) {
@@ -296,9 +392,9 @@ static int lattice_launch(bg_context_t ctx, LatticeGlobalDev& S, const void* in,
     attr_done[ctx->device & 63] = true;
   }
   LgArgs<FT> al{S.lower.as<FT>(), nullptr, S.bnd.as<LL16>(), S.nx, S.ny, S.strips, ++S.seq, tmo};
-  BG_CUDA(launch_pdl(kl, dim3(S.strips), dim3(32), sl, ctx->stream, al, (const VT*)in, (CT*)tmp, skip));
+  BG_CUDA(launch_pdl(kl, dim3(S.strips), dim3(128), sl, ctx->stream, al, (const VT*)in, (CT*)tmp, skip));
   LgArgs<FT> au{S.upper.as<FT>(), S.udinv.as<FT>(), S.bnd.as<LL16>() + (size_t)S.strips * S.ny, S.nx, S.ny, S.strips, S.seq, tmo};
-  BG_CUDA(launch_pdl(ku, dim3(S.strips), dim3(32), su, ctx->stream, au, (const CT*)tmp, (VT*)out, skip));
+  BG_CUDA(launch_pdl(ku, dim3(S.strips), dim3(128), su, ctx->stream, au, (const CT*)tmp, (VT*)out, skip));
   ctx->launches += 2;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
@@ -306,8 +402,8 @@ static int lattice_launch(bg_context_t ctx, LatticeGlobalDev& S, const void* in,
 // deep ring (one strip per SM) while the strips fit the SMs, a shallower one beyond (several strips per SM)
 template <class VT, class FT>
 static int lattice_run(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {
-  if (S.strips <= ctx->sm_count) return lattice_launch<VT, FT, 128, 7>(ctx, S, in, tmp, out, skip);
-  return lattice_launch<VT, FT, 64, 3>(ctx, S, in, tmp, out, skip);
+  if (S.strips <= ctx->sm_count) return lattice_launch<VT, FT, 128>(ctx, S, in, tmp, out, skip);
+  return lattice_launch<VT, FT, 64>(ctx, S, in, tmp, out, skip);
 }
 
 int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt, int fac_dt, const void* in, void* tmp,
@@ -317,11 +413,11 @@ int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt
   if (vec_dt == BG_F64 && fac_dt == BG_F32) return lattice_run<double, float>(ctx, S, in, tmp, out, skip);
   return lattice_run<double, double>(ctx, S, in, tmp, out, skip);
 }
-// strips that can be resident at once (one warp per CTA, shared memory bound): beyond that the general kernel runs
+// strips that can be resident at once (one CTA per strip, shared memory bound): beyond that the general kernel runs
 int lattice_global_capacity(bg_context_t ctx, int vec_dt, int fac_dt) {
   const size_t ct = (vec_dt == BG_F64 || fac_dt == BG_F64) ? 8 : 4, ft = dtype_size(fac_dt);
-  const size_t su = (size_t)64 * 32 * (3 * ft + ct) + (size_t)kLgOutRows * 32 * ct + 1024;  // the shallow ring
-  const int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / su);
+  const size_t su = (size_t)64 * 32 * (3 * ft + 2 * ct) + 64 * 8 + 3 * 8 * 8 + 64 + 1024;  // the shallow ring
+  const int per_sm = (int)std::min<size_t>(16, (size_t)(227 * 1024) / su);
   return ctx->sm_count * std::max(per_sm, 1);
 }
 

@@ -91,8 +91,9 @@ def test_reference_thermal_drivers_compile_and_link_unchanged(tmp_path):
         shutil.copy(os.path.join(th, main), tmp_path / main)
         os.chmod(tmp_path / main, 0o644)
         _nvcc(inc + ["-c", str(tmp_path / main), "-o", str(tmp_path / (main + ".o"))])
-        _nvcc(["-o", os.path.join(BUILD, exe), str(tmp_path / (main + ".o"))] + objs +
-              ["-L" + PKG, "-lb200gmres_shim", "-lb200gmres", "-lcublas", "-Xlinker", "-rpath," + PKG])
+        # --cudart shared: the driver launches the shim's SpMV kernel symbol itself, so both must use ONE CUDA runtime
+        _nvcc(["--cudart", "shared", "-o", os.path.join(BUILD, exe), str(tmp_path / (main + ".o"))] + objs +
+              ["-L" + PKG, "-lb200gmres_shim", "-lb200gmres", "-lcublas", "-Xlinker", "-rpath," + PKG, "-Xlinker", "-rpath,/usr/local/cuda/lib64"])
         assert os.path.exists(os.path.join(BUILD, exe))
 
 
