@@ -104,7 +104,14 @@ struct bg_dist_s : DistHooks {
 
   const PeerAR* peer_ar() override { return transport == BG_TRANSPORT_P2P && nranks > 1 ? d_par.as<PeerAR>() : nullptr; }
 
-  unsigned next_seq() { return (unsigned)(((uint64_t)solve_index << 20) + (uint64_t)(++exchange_in_solve)); }
+  // (solve, exchange within the solve): identical on every rank although ranks may enqueue different numbers of
+  // (skipped) launches past the stopping iteration of a solve.  32 bits: the solve part wraps after 4096 solves, which
+  // is harmless -- an inbox element always carries the number of the LAST exchange (never one from 4096 solves ago),
+  // and 0, the value of untouched memory, is never produced (the exchange count starts at 1 and stays below 2^20).
+  unsigned next_seq() {
+    exchange_in_solve = exchange_in_solve >= 0xFFFFEu ? 1u : exchange_in_solve + 1u;
+    return ((solve_index & 0xFFFu) << 20) | exchange_in_solve;
+  }
   bool halo_args(HaloArgs* h) override {
     if (transport != BG_TRANSPORT_P2P || nranks == 1 || !fuse_halo) return false;
     h->ph = d_ph.as<PeerHalo>(); h->send_idx = send_idx.as<int>(); h->n_send = send_count; h->n_local = n_local;
@@ -204,7 +211,7 @@ struct WindowLayout {
     ar_inbox = 0;
     counters = ar_inbox + sizeof(LL16) * 2 * R * kArLd;
     halo_inbox = counters + 64;
-    bytes = halo_inbox + sizeof(LL16) * (size_t)std::max(n_halo, 1);
+    bytes = halo_inbox + sizeof(LL16) * 2 * (size_t)std::max(n_halo, 1);  // two buffers (sequence parity)
   }
 };
 
@@ -284,6 +291,7 @@ int setup_p2p(bg_dist_t D) {
     if (slot < 0) { set_error("neighbour lists of ranks %d and %d disagree", me, q); return BG_ERR_COMM; }
     if (pr.recv_ptr[slot + 1] - pr.recv_ptr[slot] != D->send_ptr[k + 1] - D->send_ptr[k]) { set_error("halo sizes of ranks %d and %d disagree", me, q); return BG_ERR_COMM; }
     ph.peer_inbox[k] = (LL16*)(win[q] + WindowLayout(R, pr.n_halo).halo_inbox) + pr.recv_ptr[slot];
+    ph.peer_half[k] = std::max(pr.n_halo, 1);
   }
   BG_TRY(D->d_par.upload(&par, sizeof(par), st));
   BG_TRY(D->d_ph.upload(&ph, sizeof(ph), st));

@@ -168,8 +168,10 @@ struct PeerHalo {
   int n_nbr, n_halo;
   unsigned long long timeout_ns;
   int send_ptr[kMaxPeers + 1];   // entries [send_ptr[k], send_ptr[k+1]) of send_idx go to neighbour k
-  LL16* peer_inbox[kMaxPeers];   // first element of MY range in neighbour k's halo inbox
-  LL16* my_inbox;                // [n_halo]
+  LL16* peer_inbox[kMaxPeers];   // first element of MY range in neighbour k's halo inbox (buffer 0)
+  int peer_half[kMaxPeers];      // elements per buffer of neighbour k's inbox (= its n_halo)
+  LL16* my_inbox;                // [2][n_halo]: double-buffered by the parity of the sequence number, so that a fast
+                                 // neighbour's exchange s+1 cannot overwrite values of exchange s that are still unread
 };
 // arguments of a SpMV that carries its own halo exchange (spmv.cu, HALO variants): the first wave of CTAs
 // stores this rank's boundary entries of x into the neighbours' inboxes, rows with halo columns read their

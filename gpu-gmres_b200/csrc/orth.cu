@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(const PeerHalo* __re
   for (int e = tid; e < total; e += nt) {
     int k = 0;
     while (e >= H->send_ptr[k + 1]) ++k;
-    ll_store(H->peer_inbox[k] + (e - H->send_ptr[k]), (double)v[idx[e]], seq);
+    ll_store(H->peer_inbox[k] + (size_t)(seq & 1u) * H->peer_half[k] + (e - H->send_ptr[k]), (double)v[idx[e]], seq);
   }
-  const LL16* in = H->my_inbox;
+  const LL16* in = H->my_inbox + (size_t)(seq & 1u) * max(nh, 1);
   for (int i = tid; i < nh; i += nt) halo_out[i] = (VT)ll_wait(in + i, seq, H->timeout_ns);
 }
 

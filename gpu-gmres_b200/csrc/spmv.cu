@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128, 8) spmv_sell_w(int n, int nslices, const 
       for (int e = tid; e < h.n_send; e += pushers) {
         int k = 0;
         while (e >= P->send_ptr[k + 1]) ++k;
-        ll_store(P->peer_inbox[k] + (e - P->send_ptr[k]), (double)x[h.send_idx[e]], h.seq);
+        ll_store(P->peer_inbox[k] + (size_t)(h.seq & 1u) * P->peer_half[k] + (e - P->send_ptr[k]), (double)x[h.send_idx[e]], h.seq);
       }
     }
   }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128, 8) spmv_sell_w(int n, int nslices, const 
       SV::idx(cc[k], ci);
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
-        if (HALO && ci[r] >= h.n_local) xv[k][r] = (VT)ll_wait(h.ph->my_inbox + (ci[r] - h.n_local), h.seq, h.ph->timeout_ns);
+        if (HALO && ci[r] >= h.n_local) xv[k][r] = (VT)ll_wait(h.ph->my_inbox + (size_t)(h.seq & 1u) * max(h.ph->n_halo, 1) + (ci[r] - h.n_local), h.seq, h.ph->timeout_ns);
         else xv[k][r] = x[ci[r]];
       }
     }

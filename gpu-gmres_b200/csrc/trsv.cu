@@ -189,41 +189,59 @@ template <class FT> struct LgArgs {
 };
 constexpr int kLgBS = 8;  // steps per block: granularity of staging, boundary hand-off and result flush
 template <class TIN, class TOUT, class FT, bool LOWER> constexpr size_t lg_smem_bytes(int NR) {
-  return (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN) + sizeof(TOUT)) + (size_t)NR * 8 + 3 * (size_t)(NR / kLgBS) * 8 + 64;
+  return (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN) + sizeof(TOUT)) + (size_t)NR * 8 + 64;
 }
-__device__ __forceinline__ void lg_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lg_smem_u32(bar)), "r"(count) : "memory");
+// progress counters in shared memory: the producer publishes "blocks finished" behind a CTA fence, the consumer
+// polls it (one 30-cycle LDS when the block is already there, an mbarrier try_wait costs three times that)
+__device__ __forceinline__ void lg_publish(volatile int* p, int v) {
+  __threadfence_block();
+  *p = v;
 }
-__device__ __forceinline__ void lg_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lg_smem_u32(bar)) : "memory");
-}
-// arrives (without raising the pending count) once all cp.async copies this thread issued so far have landed
-__device__ __forceinline__ void lg_cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(lg_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void lg_mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long timeout_ns) {
+template <bool SLEEP> __device__ __forceinline__ void lg_wait_progress(volatile int* p, int need, unsigned long long timeout_ns) {
   unsigned long long t0 = 0;
-  for (unsigned spin = 0;; ++spin) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(lg_smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) return;
-    if ((spin & 255u) == 255u) {  // a scheduling bug or a dead upstream strip must trap, never hang the GPU
+  for (unsigned spin = 0; *p < need; ++spin) {
+    if (SLEEP) __nanosleep(32);
+    if ((spin & 4095u) == 4095u) {  // a scheduling bug or a dead upstream strip must trap, never hang the GPU
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > timeout_ns) __trap();
     }
   }
+  __threadfence_block();
 }
-__device__ __forceinline__ void lg_wait_progress(volatile int* p, int need, unsigned long long timeout_ns) {
-  unsigned long long t0 = 0;
-  for (unsigned spin = 0; *p < need; ++spin) {
-    __nanosleep(64);
-    if ((spin & 1023u) == 1023u) {
-      const unsigned long long now = global_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > timeout_ns) __trap();
+
+// the 8 steps of one block on the chain warp.  INTERIOR: every lane is inside [0, ny) for all 8 steps and the strip
+// is full, so the operands need no masking.
+template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR, bool INTERIOR, class P>
+__device__ __forceinline__ void lg_chain_block(const P* s_pair, const FT* s_dinv, const TIN* s_rhs, TOUT* s_out, const double* s_bnd,
+                                               int lane, int t0, int tb, bool bnd, bool colok, int ny, int edge_in, CT& zprev) {
+  constexpr int BS = kLgBS;
+  CT ca[BS], cb[BS], r[BS], be[BS];
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    const int t = t0 + j;
+    const int slot = (t & (NR - 1)) * 32 + lane;  // always a valid ring address
+    const P c = s_pair[slot];
+    CT rr = (CT)s_rhs[slot];
+    if (!LOWER) rr *= (CT)s_dinv[slot];
+    if (INTERIOR) {
+      ca[j] = (CT)c.x; cb[j] = (CT)c.y; r[j] = rr;
+      be[j] = bnd ? (CT)s_bnd[(tb + j) & (NR - 1)] : (CT)0;  // same address for all lanes: broadcast
+    } else {
+      const bool act = colok && (unsigned)t < (unsigned)ny;
+      ca[j] = act ? (CT)c.x : (CT)0;
+      cb[j] = act ? (CT)c.y : (CT)0;
+      r[j] = act ? rr : (CT)0;
+      be[j] = bnd && tb + j < ny ? (CT)s_bnd[(tb + j) & (NR - 1)] : (CT)0;
     }
+  }
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
+    zn = lane == edge_in ? be[j] : zn;
+    const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
+    zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
+    s_out[((t0 + j) & (NR - 1)) * 32 + lane] = (TOUT)zprev;  // rows outside [0, ny) are never flushed
   }
 }
 
@@ -232,21 +250,21 @@ __device__ __forceinline__ void lg_wait_progress(volatile int* p, int need, unsi
 // lag = x (LOWER) / 31-x (UPPER).  A lone warp issues about one dependent instruction every four cycles, so
 // everything that is not the recurrence itself is moved off the chain warp:
 //   warp 1 LOADER    stages the coefficient pairs, 1/diag and the right-hand side of 8 time rows per block with
-//                    coalesced cp.async copies into a ring of NR rows, several blocks ahead of the chain, and lets
-//                    the copies arrive on the block's `full` mbarrier
+//                    coalesced cp.async copies into a ring of NR rows, several blocks ahead of the chain
 //   warp 2 BOUNDARY  polls the upstream strip's boundary column (flag-in-data packets in L2, warp-uniform vote
-//                    loop), drops the values into shared memory, arrives on `bfull`
-//   warp 0 CHAIN     per step: operands from shared memory (its own column), west/east value by shuffle (edge
-//                    lane: the boundary value), two FMAs, result to a ring in shared memory; one arrive per block
+//                    loop) and drops the values into shared memory
+//   warp 0 CHAIN     per step: operands from shared memory (its own column) into registers a block at a time,
+//                    west/east value by shuffle (edge lane: the boundary value), two FMAs, result to a ring
 //   warp 3 STORER    once all 32 lanes have passed a row: one coalesced 256-byte store of the row, and the edge
 //                    column of the block goes to the downstream strip as 8 packets
-// Rings are protected by two progress counters in shared memory (chain blocks done, storer blocks done).
+// Hand-offs are four "blocks finished" counters in shared memory: [0] chain, [1] storer, [2] loader, [3] boundary.
 template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR>
 __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
                                                            const int* skip) {
-  constexpr int BS = kLgBS, NS = NR / BS;
+  constexpr int BS = kLgBS;
   constexpr int AHEAD = (NR - 31) / BS - 1;  // blocks a producer may run ahead of the consumer that frees its ring rows
-  static_assert((NR & (NR - 1)) == 0 && AHEAD >= 2, "ring too small for the lane skew");
+  constexpr int INFLIGHT = AHEAD > 8 ? 6 : 2;  // cp.async groups (blocks) the loader keeps in flight
+  static_assert((NR & (NR - 1)) == 0 && AHEAD >= 2 && INFLIGHT < AHEAD, "ring too small for the lane skew");
   extern __shared__ __align__(16) unsigned char lg_smem[];
   using P = typename std::conditional<sizeof(FT) == 8, double2, float2>::type;
   unsigned char* sp = lg_smem;
@@ -255,18 +273,11 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
   TIN* s_rhs = reinterpret_cast<TIN*>(sp); sp += (size_t)NR * 32 * sizeof(TIN);
   TOUT* s_out = reinterpret_cast<TOUT*>(sp); sp += (size_t)NR * 32 * sizeof(TOUT);
   double* s_bnd = reinterpret_cast<double*>(sp); sp += (size_t)NR * 8;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sp); sp += (size_t)NS * 8;
-  uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(sp); sp += (size_t)NS * 8;
-  uint64_t* bar_done = reinterpret_cast<uint64_t*>(sp); sp += (size_t)NS * 8;
-  volatile int* prog = reinterpret_cast<volatile int*>(sp);  // [0] chain blocks done, [1] storer blocks done
+  volatile int* prog = reinterpret_cast<volatile int*>(sp);
   pdl_wait();
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { lg_mbar_init(&bar_full[i], 32); lg_mbar_init(&bar_bfull[i], 1); lg_mbar_init(&bar_done[i], 1); }
-    prog[0] = 0; prog[1] = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (threadIdx.x < 4) prog[threadIdx.x] = 0;
   __syncthreads();
   const int s = LOWER ? (int)blockIdx.x : a.strips - 1 - (int)blockIdx.x;  // CTAs in dependency order
   const int X = 32 * s + lane, nx = a.nx, ny = a.ny;
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
     const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
     const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
     for (int lb = 0; lb < nblk; ++lb) {
-      if (lb > AHEAD) lg_wait_progress(&prog[0], lb - AHEAD, tmo);  // the ring rows about to be overwritten are dead
+      if (lb > AHEAD) lg_wait_progress<true>(&prog[0], lb - AHEAD, tmo);  // the ring rows about to be overwritten are dead
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
         const int t = lb * BS + j;
@@ -292,14 +303,19 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
           if (colok) cp_async<sizeof(TIN)>(s_rhs + slot, in + (size_t)y * nx + X);
         }
       }
-      lg_cp_async_arrive(&bar_full[lb % NS]);
+      cp_async_commit();
+      cp_async_wait<INFLIGHT>();  // block lb - INFLIGHT (and everything older) has landed for this lane
+      __syncwarp();               // ... and for every lane
+      if (lane == 0 && lb >= INFLIGHT) lg_publish(&prog[2], lb - INFLIGHT + 1);
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    cp_async_wait<0>();
+    __syncwarp();
+    if (lane == 0) lg_publish(&prog[2], nblk);
   } else if (wid == 2) {  // --------------------------------------------------------- BOUNDARY IN
     if (has_up) {
       const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
       for (int b = 0; b * BS < ny; ++b) {
-        if (b > AHEAD) lg_wait_progress(&prog[0], b - AHEAD, tmo);
+        if (b > AHEAD) lg_wait_progress<true>(&prog[0], b - AHEAD, tmo);
         const int t = b * BS + lane;  // the edge lane has no lag: it reaches time row t at step t
         bool need = lane < BS && t < ny;
         LL16 pk = {0u, 0u, 0u, 0u};
@@ -315,53 +331,39 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
         }
         if (lane < BS && t < ny) s_bnd[t & (NR - 1)] = ll_val(pk);
         __syncwarp();
-        if (lane == 0) lg_mbar_arrive(&bar_bfull[b % NS]);
+        if (lane == 0) lg_publish(&prog[3], b + 1);
       }
     }
   } else if (wid == 0) {  // --------------------------------------------------------- CHAIN
     const int lag = LOWER ? lane : 31 - lane;
     CT zprev = (CT)0;
     for (int blk = 0; blk < nblk; ++blk) {
-      if (blk > AHEAD) lg_wait_progress(&prog[1], blk - AHEAD, tmo);  // the result ring rows about to be reused have left
-      const uint32_t par = (uint32_t)(blk / NS) & 1u;
-      lg_mbar_wait(&bar_full[blk % NS], par, tmo);
       const bool bnd = has_up && blk * BS < ny;
-      if (bnd) lg_mbar_wait(&bar_bfull[blk % NS], par, tmo);
+      {  // operands staged, boundary values here, result ring rows about to be reused have left: one poll loop, one fence
+        unsigned long long tw = 0;
+        for (unsigned spin = 0;; ++spin) {
+          const int p2 = prog[2], p3 = bnd ? prog[3] : blk + 1, p1 = blk > AHEAD ? prog[1] : blk;
+          if (p2 > blk && p3 > blk && p1 >= blk - AHEAD) break;
+          if ((spin & 4095u) == 4095u) {
+            const unsigned long long now = global_ns();
+            if (tw == 0) tw = now;
+            else if (now - tw > tmo) __trap();
+          }
+        }
+        __threadfence_block();
+      }
       const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
-      // every lane inside [0, ny) for all 8 steps and a full strip: no selects on the operands
-      const bool interior = blk * BS - 31 >= 0 && blk * BS + BS - 1 < ny && 32 * s + 31 < nx;
-      CT ca[BS], cb[BS], r[BS], be[BS];
-#pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        const int t = t0 + j;
-        const int slot = (t & (NR - 1)) * 32 + lane;  // always a valid ring address
-        const P c = s_pair[slot];
-        CT rr = (CT)s_rhs[slot];
-        if (!LOWER) rr *= (CT)s_dinv[slot];
-        const bool act = interior || (colok && (unsigned)t < (unsigned)ny);
-        ca[j] = act ? (CT)c.x : (CT)0;
-        cb[j] = act ? (CT)c.y : (CT)0;
-        r[j] = act ? rr : (CT)0;
-        be[j] = bnd && blk * BS + j < ny ? (CT)s_bnd[(blk * BS + j) & (NR - 1)] : (CT)0;  // same address for all lanes: broadcast
-      }
-#pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
-        zn = lane == edge_in ? be[j] : zn;
-        const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
-        zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
-        s_out[((t0 + j) & (NR - 1)) * 32 + lane] = (TOUT)zprev;  // rows outside [0, ny) are never flushed
-      }
+      if (blk * BS - 31 >= 0 && blk * BS + BS - 1 < ny && 32 * s + 31 < nx)
+        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, true>(s_pair, s_dinv, s_rhs, s_out, s_bnd, lane, t0, blk * BS, bnd, colok, ny, edge_in, zprev);
+      else
+        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, false>(s_pair, s_dinv, s_rhs, s_out, s_bnd, lane, t0, blk * BS, bnd, colok, ny, edge_in, zprev);
       __syncwarp();
-      if (lane == 0) {
-        lg_mbar_arrive(&bar_done[blk % NS]);
-        prog[0] = blk + 1;
-      }
+      if (lane == 0) lg_publish(&prog[0], blk + 1);
     }
   } else {  // ----------------------------------------------------------------------- STORER
     LL16* bnd_out = a.bnd + (size_t)s * ny;
     for (int b = 0; b < nblk; ++b) {
-      lg_mbar_wait(&bar_done[b % NS], (uint32_t)(b / NS) & 1u, tmo);
+      lg_wait_progress<true>(&prog[0], b + 1, tmo);
       // the rows the last lane finished in this block: every lane has passed them
       if (has_down && lane < BS) {
         const int tf = b * BS - 31 + lane;
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
         if (colok && (unsigned)tf < (unsigned)ny) out[(size_t)yrow(tf) * nx + X] = s_out[(tf & (NR - 1)) * 32 + lane];
       }
       __syncwarp();
-      if (lane == 0) prog[1] = b + 1;
+      if (lane == 0) lg_publish(&prog[1], b + 1);
     }
   }
 }
@@ -416,7 +418,7 @@ int launch_trsv_lattice_global(bg_context_t ctx, LatticeGlobalDev& S, int vec_dt
 // strips that can be resident at once (one CTA per strip, shared memory bound): beyond that the general kernel runs
 int lattice_global_capacity(bg_context_t ctx, int vec_dt, int fac_dt) {
   const size_t ct = (vec_dt == BG_F64 || fac_dt == BG_F64) ? 8 : 4, ft = dtype_size(fac_dt);
-  const size_t su = (size_t)64 * 32 * (3 * ft + 2 * ct) + 64 * 8 + 3 * 8 * 8 + 64 + 1024;  // the shallow ring
+  const size_t su = (size_t)64 * 32 * (3 * ft + 2 * ct) + 64 * 8 + 64 + 1024;  // the shallow ring
   const int per_sm = (int)std::min<size_t>(16, (size_t)(227 * 1024) / su);
   return ctx->sm_count * std::max(per_sm, 1);
 }
