@@ -193,8 +193,9 @@ template <class TIN, class TOUT, class FT, bool LOWER> constexpr size_t lg_smem_
 }
 // progress counters in shared memory: the producer publishes "blocks finished" behind a CTA fence, the consumer
 // polls it (one 30-cycle LDS when the block is already there, an mbarrier try_wait costs three times that)
+__device__ __forceinline__ void lg_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ void lg_publish(volatile int* p, int v) {
-  __threadfence_block();
+  lg_fence_cta();
   *p = v;
 }
 template <bool SLEEP> __device__ __forceinline__ void lg_wait_progress(volatile int* p, int need, unsigned long long timeout_ns) {
@@ -207,41 +208,41 @@ template <bool SLEEP> __device__ __forceinline__ void lg_wait_progress(volatile 
       else if (now - t0 > timeout_ns) __trap();
     }
   }
-  __threadfence_block();
+  lg_fence_cta();
 }
 
-// the 8 steps of one block on the chain warp.  INTERIOR: every lane is inside [0, ny) for all 8 steps and the strip
-// is full, so the operands need no masking.
+// the 8 steps of one block on the chain warp.  The rings are indexed by STEP (the loader puts lane x's element of
+// time row t where step t + lag will look for it), so the operands of the block's 8 steps sit at constant offsets
+// from one base address that never wraps inside a block: no address arithmetic on the chain warp.
+// INTERIOR: every lane is inside [0, ny) for all 8 steps and the strip is full, so the operands need no masking.
 template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR, bool INTERIOR, class P>
-__device__ __forceinline__ void lg_chain_block(const P* s_pair, const FT* s_dinv, const TIN* s_rhs, TOUT* s_out, const double* s_bnd,
-                                               int lane, int t0, int tb, bool bnd, bool colok, int ny, int edge_in, CT& zprev) {
+__device__ __forceinline__ void lg_chain_block(const P* __restrict__ pr, const FT* __restrict__ dv, const TIN* __restrict__ rh,
+                                               TOUT* __restrict__ ot, const double* __restrict__ bd, int t0, bool bnd, bool colok,
+                                               int ny, bool is_edge, CT& zprev) {
   constexpr int BS = kLgBS;
   CT ca[BS], cb[BS], r[BS], be[BS];
 #pragma unroll
   for (int j = 0; j < BS; ++j) {
-    const int t = t0 + j;
-    const int slot = (t & (NR - 1)) * 32 + lane;  // always a valid ring address
-    const P c = s_pair[slot];
-    CT rr = (CT)s_rhs[slot];
-    if (!LOWER) rr *= (CT)s_dinv[slot];
+    const P c = pr[j * 32];
+    CT rr = (CT)rh[j * 32];
+    if (!LOWER) rr *= (CT)dv[j * 32];
     if (INTERIOR) {
       ca[j] = (CT)c.x; cb[j] = (CT)c.y; r[j] = rr;
-      be[j] = bnd ? (CT)s_bnd[(tb + j) & (NR - 1)] : (CT)0;  // same address for all lanes: broadcast
     } else {
-      const bool act = colok && (unsigned)t < (unsigned)ny;
+      const bool act = colok && (unsigned)(t0 + j) < (unsigned)ny;
       ca[j] = act ? (CT)c.x : (CT)0;
       cb[j] = act ? (CT)c.y : (CT)0;
       r[j] = act ? rr : (CT)0;
-      be[j] = bnd && tb + j < ny ? (CT)s_bnd[(tb + j) & (NR - 1)] : (CT)0;
     }
+    be[j] = bnd ? (CT)bd[j] : (CT)0;  // same address for all lanes: broadcast (rows past ny-1 are never used by an active lane)
   }
 #pragma unroll
   for (int j = 0; j < BS; ++j) {
     CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
-    zn = lane == edge_in ? be[j] : zn;
+    zn = is_edge ? be[j] : zn;
     const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
     zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
-    s_out[((t0 + j) & (NR - 1)) * 32 + lane] = (TOUT)zprev;  // rows outside [0, ny) are never flushed
+    ot[j * 32] = (TOUT)zprev;            // steps outside [0, ny) are never flushed
   }
 }
 
@@ -291,13 +292,14 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
   if (wid == 1) {  // ---------------------------------------------------------------- LOADER
     const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
     const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
+    const int lag = LOWER ? lane : 31 - lane;  // ring row = the STEP at which this lane consumes the element
     for (int lb = 0; lb < nblk; ++lb) {
       if (lb > AHEAD) lg_wait_progress<true>(&prog[0], lb - AHEAD, tmo);  // the ring rows about to be overwritten are dead
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
         const int t = lb * BS + j;
         if (t < ny) {
-          const int y = yrow(t), slot = (t & (NR - 1)) * 32 + lane;
+          const int y = yrow(t), slot = ((t + lag) & (NR - 1)) * 32 + lane;
           cp_async<sizeof(P)>(s_pair + slot, gpair + (size_t)y * 32);
           if (!LOWER) cp_async<sizeof(FT)>(s_dinv + slot, gdinv + (size_t)y * 32);
           if (colok) cp_async<sizeof(TIN)>(s_rhs + slot, in + (size_t)y * nx + X);
@@ -350,29 +352,32 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
             else if (now - tw > tmo) __trap();
           }
         }
-        __threadfence_block();
+        lg_fence_cta();
       }
       const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
+      const int base = ((blk * BS) & (NR - 1)) * 32 + lane;
+      const double* bd = s_bnd + ((blk * BS) & (NR - 1));
       if (blk * BS - 31 >= 0 && blk * BS + BS - 1 < ny && 32 * s + 31 < nx)
-        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, true>(s_pair, s_dinv, s_rhs, s_out, s_bnd, lane, t0, blk * BS, bnd, colok, ny, edge_in, zprev);
+        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, true>(s_pair + base, s_dinv + base, s_rhs + base, s_out + base, bd, t0, bnd, colok, ny, lane == edge_in, zprev);
       else
-        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, false>(s_pair, s_dinv, s_rhs, s_out, s_bnd, lane, t0, blk * BS, bnd, colok, ny, edge_in, zprev);
+        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, false>(s_pair + base, s_dinv + base, s_rhs + base, s_out + base, bd, t0, bnd, colok, ny, lane == edge_in, zprev);
       __syncwarp();
       if (lane == 0) lg_publish(&prog[0], blk + 1);
     }
   } else {  // ----------------------------------------------------------------------- STORER
     LL16* bnd_out = a.bnd + (size_t)s * ny;
+    const int lag = LOWER ? lane : 31 - lane;
     for (int b = 0; b < nblk; ++b) {
       lg_wait_progress<true>(&prog[0], b + 1, tmo);
       // the rows the last lane finished in this block: every lane has passed them
       if (has_down && lane < BS) {
         const int tf = b * BS - 31 + lane;
-        if ((unsigned)tf < (unsigned)ny) ll_store(bnd_out + yrow(tf), (double)s_out[(tf & (NR - 1)) * 32 + edge_out], a.seq);
+        if ((unsigned)tf < (unsigned)ny) ll_store(bnd_out + yrow(tf), (double)s_out[((tf + 31) & (NR - 1)) * 32 + edge_out], a.seq);  // the edge lane lags 31 steps
       }
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
         const int tf = b * BS - 31 + j;
-        if (colok && (unsigned)tf < (unsigned)ny) out[(size_t)yrow(tf) * nx + X] = s_out[(tf & (NR - 1)) * 32 + lane];
+        if (colok && (unsigned)tf < (unsigned)ny) out[(size_t)yrow(tf) * nx + X] = s_out[((tf + lag) & (NR - 1)) * 32 + lane];
       }
       __syncwarp();
       if (lane == 0) lg_publish(&prog[1], b + 1);

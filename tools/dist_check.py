@@ -3,9 +3,11 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
 
-Every rank builds its plan, solves collectively (NCCL halo + allreduce, per-rank block-Jacobi ILU(0)),
-the pieces are gathered and compared with scipy's sparse LU; the iteration count is printed next to the
-one a single rank needs with the same tiles (iteration drift of the coarser block-Jacobi splitting)."""
+Every rank builds its plan, solves collectively (halo exchange + all-reduce, per-rank block-Jacobi ILU(0)), the
+pieces are gathered and compared (FP64 cases) with the CPU ORACLE -- the reference's host GMRES (src/gmres.cu:1904-2066)
+given the block-Jacobi ILU(0) of exactly the rank x tile partition the ranks used: same iteration count,
+|resid - resid_oracle| <= 1e-10, ||x - x_oracle|| <= 1e-8 ||x_oracle|| -- and with scipy's sparse LU; the iteration count
+is printed next to the one a single rank needs with the same tiles (iteration drift of the coarser splitting)."""
 import json
 import os
 import sys
@@ -13,7 +15,34 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gpu-gmres_b200", "python"))
+
+
+def rank_tile_blocks(bg, rp, ci, v, world, part, method, tile, nx, ys):
+    """block_of_row of the GLOBAL matrix as the ranks build it: rank q's diagonal block cut into its own tiles
+    (bg_dist_create: halo columns dropped, make_blocks with the rank's dims / METIS on the rank's pattern)."""
+    import scipy.sparse as sp
+
+    n = len(rp) - 1
+    blk = np.zeros(n, np.int32)
+    base = 0
+    for q in range(world):
+        plan = bg.DistPlan(rp, ci, v, world, q, part)
+        a = plan.arrays()
+        nl = plan.info.n_local
+        L = sp.csr_matrix((a["val"], a["col"], a["rowptr"]), shape=(nl, nl + plan.info.n_halo))[:, :nl].tocsr()
+        L.sort_indices()
+        rows = max(32, tile * tile)
+        nb = max(1, (nl + rows - 1) // rows)
+        if method == "strips":
+            nbq, bq = bg.host_block_partition(bg.PART_GRID2D, L.indptr, L.indices, nb, [nx, ys[q + 1] - ys[q], 1, tile, tile, 1])
+        else:
+            nbq, bq = bg.host_block_partition(bg.PART_METIS, L.indptr, L.indices, nb)
+        blk[a["l2g"]] = base + bq
+        base += nbq
+        plan.close()
+    return blk
 
 
 def main():
@@ -42,6 +71,7 @@ def main():
         tol = 1e-5 if dtn == "f32" else 1e-8
         rp, ci, v, b = synth.pg2d(nx, ny, seed=7)
         n = len(rp) - 1
+        ys = None
         if method == "strips":
             ys = [(r * ny) // world for r in range(world + 1)]
             part = np.repeat(np.arange(world, dtype=np.int32), np.diff(ys) * nx)
@@ -100,9 +130,22 @@ def main():
             r1 = S1.solve(A1, M1, d1b.data_ptr(), d1x.data_ptr(), opts)
             lim = (5e-3, 1e-4) if dtn == "f32" else (1e-6, 1e-7)
             good = r.flag == 0 and err < lim[0] and res < lim[1] and len({t["iters"] for t in per_transport.values()}) == 1
+            vs_oracle = None
+            if dtn == "f64":
+                # the oracle with the same rank x tile block-Jacobi ILU(0): north_star bars
+                from oracle import pyoracle as O
+
+                O.build()
+                blk = rank_tile_blocks(bg, rp, ci, v, world, part, method, tile, nx, ys if method == "strips" else None)
+                f = bg.host_ilu0(rp, ci, v, blk)
+                pc = O.Precond(O.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+                oflag, xo, oit, ores, _ = O.gmres(rp, ci, v, b, np.zeros(n), 32, 3000, tol, pc)
+                xerr = float(np.linalg.norm(x - xo) / np.linalg.norm(xo))
+                vs_oracle = dict(iters_oracle=int(oit), x_vs_oracle=xerr, resid_diff=abs(float(r.resid) - float(ores)))
+                good = good and r.iters == oit and xerr <= 1e-8 and abs(r.resid - ores) <= 1e-10
             ok = ok and good
             print(json.dumps(dict(case=f"pg2d {nx}x{ny} {method} {dtn} {orthn}", ranks=world, flag=r.flag, iters=r.iters, iters_1gpu=r1.iters, resid=r.resid,
-                                  true_rel_residual=res, x_err_vs_direct=err, halo_bytes=int(info.halo_bytes_per_exchange),
+                                  true_rel_residual=res, x_err_vs_direct=err, vs_oracle=vs_oracle, halo_bytes=int(info.halo_bytes_per_exchange),
                                   neighbors=int(info.n_neighbors), transport=("p2p" if info.transport == bg.TRANSPORT_P2P else "nccl"), transports=per_transport,
                                   solve_ms=round(r.solve_ms, 3),
                                   solve_ms_1gpu=round(r1.solve_ms, 3), ok=bool(good))), flush=True)
