@@ -245,6 +245,7 @@ struct bg_precond_s {
   int kind = BG_PRECOND_NONE, n = 0, dtype = BG_F64, factor_dtype = BG_F64, schedule = BG_TRSV_LEVEL;
   bool unit_lower = true, use_tma = true, allow_lattice = true;
   int lg_levels = 0;
+  bool device_factored = false;  // factor.cu built the streams
   int fb_chunk_bytes = 2048;
   int64_t nnzL = 0, nnzU = 0;
   bg::DevBuf dinv;                                 // DIAG, AINV (middle diagonal)
@@ -291,6 +292,11 @@ int gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precon
 int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
                            const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out);
 int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out);
+// factor.cu: block-Jacobi ILU(0) of the tiles of a 5-point grid factored and packed on the device (fills M->fb);
+// returns 1 when the matrix is not such a grid (the caller takes the host path)
+template <class T>
+int lattice_tiles_factor_device(bg_context_t ctx, bg_precond_t M, int n, const int* rp, const int* ci, const void* v, int vdt,
+                                const int* dims, uint64_t serial);
 }  // namespace bg
 
 struct bg_factors_s {

@@ -371,8 +371,10 @@ extern "C" void bg_precond_opts_default(bg_precond_opts* o) {
   o->stages = 2;
   o->warps_per_cta = 3;
   o->lattice = 1;
+  o->device_factor = 1;
 }
 
+static uint64_t g_order_serial = 0;
 template <class T> static int upload_syncfree_stream(bg_context_t ctx, const SyncFreeStream<T>& h, SyncFreeDev& d) {
   cudaStream_t s = ctx->stream;
   d.n = h.n; d.n_levels = h.n_levels; d.n_slices = h.n_slices; d.max_K = h.max_K; d.max_level_rows = h.max_level_rows;
@@ -395,7 +397,6 @@ template <class T> static int upload_lattice_global(bg_context_t ctx, const Latt
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }
-static uint64_t g_order_serial = 0;
 template <class T> static int upload_fused_stream(bg_context_t ctx, const FusedBlockStream<T>& h, FusedBlockDev& d) {
   cudaStream_t s = ctx->stream;
   d.n = h.n; d.nblocks = h.nblocks; d.max_rows = h.max_rows; d.max_levels_L = h.max_levels_L; d.max_levels_U = h.max_levels_U;
@@ -545,9 +546,6 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
   int nb = 1;
   const bool block = o.trsv_schedule == BG_TRSV_BLOCK;
   if (block) BG_TRY(make_blocks(o, n, rp, ci, blk, &nb));
-  Factors<T> F;
-  try { factor_dispatch<T>(use_ilut, n, rp, ci, v, vdt, o.ilut_tau, o.ilut_lfil, block ? blk.data() : nullptr, F); }
-  catch (const std::exception& e) { set_error("factorisation failed: %s", e.what()); return BG_ERR_ARG; }
   bg_precond_t M = precond_new(ctx, BG_PRECOND_LU, n, dtype);
   M->schedule = o.trsv_schedule;
   M->factor_dtype = o.factor_dtype < 0 ? dtype : o.factor_dtype;
@@ -556,6 +554,27 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
   M->fb_chunk_bytes = o.chunk_bytes > 0 ? o.chunk_bytes : 4096;
   M->fb.stages = std::min(8, std::max(2, o.stages > 0 ? o.stages : 2));
   M->fb.warps_per_cta = std::min(16, std::max(1, o.warps_per_cta > 0 ? o.warps_per_cta : 3));
+  // ILU(0) of grid tiles: factor AND pack on the device (factor.cu); anything else: host factorisation + host packers
+  static const bool dev_factor = [] { const char* e = getenv("BG_DEVICE_FACTOR"); return !(e && e[0] == '0'); }();
+  if (dev_factor && !use_ilut && block && o.block_method == BG_PART_GRID2D && M->allow_lattice && M->factor_dtype == dtype && o.device_factor != 0) {
+    int dims[6] = {o.dims[0], o.dims[1], o.dims[2], o.dims[3], o.dims[4], o.dims[5]};
+    if (dims[3] <= 0) dims[3] = dims[4] = std::max(1, (int)std::floor(std::sqrt((double)std::max(32, o.block_rows))));
+    const int stages = M->fb.stages, warps = M->fb.warps_per_cta;
+    int rc = lattice_tiles_factor_device<T>(ctx, M, n, rp, ci, v, vdt, dims, ++g_order_serial);
+    if (rc < 0) { delete M; return rc; }
+    if (rc == BG_OK) {
+      M->fb.stages = stages; M->fb.warps_per_cta = warps;
+      M->device_factored = true;
+      rc = M->tmp.alloc((size_t)n * 8);
+      if (rc < 0) { delete M; return rc; }
+      *out = M;
+      return BG_OK;
+    }
+    M->fb.stages = stages; M->fb.warps_per_cta = warps;  // not a 5-point grid in this numbering: the general path
+  }
+  Factors<T> F;
+  try { factor_dispatch<T>(use_ilut, n, rp, ci, v, vdt, o.ilut_tau, o.ilut_lfil, block ? blk.data() : nullptr, F); }
+  catch (const std::exception& e) { set_error("factorisation failed: %s", e.what()); delete M; return BG_ERR_ARG; }
   int rc = precond_install_dt<T>(M, F.L, F.U, true, block ? blk.data() : nullptr, nb);
   if (rc < 0) { delete M; return rc; }
   *out = M;
@@ -729,6 +748,7 @@ extern "C" int bg_precond_get_info(bg_precond_t M, bg_precond_info* o) {
       o->levelsL = M->fb.max_levels_L; o->levelsU = M->fb.max_levels_U; o->nblocks = M->fb.nblocks; o->max_block_rows = M->fb.max_rows;
       o->stream_bytes = M->fb.bytes;
       o->lattice = M->fb.lattice ? 1 : 0;
+      o->device_factored = M->device_factored ? 1 : 0;
     } else {
       o->levelsL = M->lg.on ? M->lg_levels : M->lsL.n_levels; o->levelsU = M->lg.on ? M->lg_levels : M->lsU.n_levels;
       o->nblocks = 1; o->max_block_rows = M->n;

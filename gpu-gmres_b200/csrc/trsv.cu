@@ -211,6 +211,18 @@ template <bool SLEEP> __device__ __forceinline__ void lg_wait_progress(volatile 
   lg_fence_cta();
 }
 
+#ifdef BG_SF_TIMING
+// development aid (make dbg): clock64 accounting of strip g_lg_probe's warps: [0] chain total [1] chain waiting
+// [2] chain waiting on the loader [3] ... on the boundary [4] ... on the storer [5] loader total [6] loader flow-control
+// [7] loader wait_group [8] storer total [9] storer waiting [10] boundary total [11] boundary polling
+__device__ long long g_lg_t[16];
+__device__ int g_lg_probe = 0;
+#define LG_T0(v) long long v = clock64()
+#define LG_ACC(k, v) do { if (s == g_lg_probe && lane == 0) g_lg_t[k] += clock64() - (v); } while (0)
+#else
+#define LG_T0(v) do {} while (0)
+#define LG_ACC(k, v) do {} while (0)
+#endif
 // the 8 steps of one block on the chain warp.  The rings are indexed by STEP (the loader puts lane x's element of
 // time row t where step t + lag will look for it), so the operands of the block's 8 steps sit at constant offsets
 // from one base address that never wraps inside a block: no address arithmetic on the chain warp.
@@ -293,8 +305,9 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
     const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
     const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
     const int lag = LOWER ? lane : 31 - lane;  // ring row = the STEP at which this lane consumes the element
+    LG_T0(tl);
     for (int lb = 0; lb < nblk; ++lb) {
-      if (lb > AHEAD) lg_wait_progress<true>(&prog[0], lb - AHEAD, tmo);  // the ring rows about to be overwritten are dead
+      { LG_T0(tf); if (lb > AHEAD) lg_wait_progress<true>(&prog[0], lb - AHEAD, tmo); LG_ACC(6, tf); }  // the ring rows about to be overwritten are dead
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
         const int t = lb * BS + j;
@@ -306,13 +319,14 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
         }
       }
       cp_async_commit();
-      cp_async_wait<INFLIGHT>();  // block lb - INFLIGHT (and everything older) has landed for this lane
+      { LG_T0(tw); cp_async_wait<INFLIGHT>(); LG_ACC(7, tw); }  // block lb - INFLIGHT (and everything older) has landed for this lane
       __syncwarp();               // ... and for every lane
       if (lane == 0 && lb >= INFLIGHT) lg_publish(&prog[2], lb - INFLIGHT + 1);
     }
     cp_async_wait<0>();
     __syncwarp();
     if (lane == 0) lg_publish(&prog[2], nblk);
+    LG_ACC(5, tl);
   } else if (wid == 2) {  // --------------------------------------------------------- BOUNDARY IN
     if (has_up) {
       const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
@@ -339,8 +353,15 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
   } else if (wid == 0) {  // --------------------------------------------------------- CHAIN
     const int lag = LOWER ? lane : 31 - lane;
     CT zprev = (CT)0;
+    LG_T0(tc);
     for (int blk = 0; blk < nblk; ++blk) {
       const bool bnd = has_up && blk * BS < ny;
+      LG_T0(tw);
+#ifdef BG_SF_TIMING
+      { LG_T0(t2); while (prog[2] <= blk) {} LG_ACC(2, t2); }
+      { LG_T0(t3); while (bnd && prog[3] <= blk) {} LG_ACC(3, t3); }
+      { LG_T0(t4); while (blk > AHEAD && prog[1] < blk - AHEAD) {} LG_ACC(4, t4); }
+#endif
       {  // operands staged, boundary values here, result ring rows about to be reused have left: one poll loop, one fence
         unsigned long long tw = 0;
         for (unsigned spin = 0;; ++spin) {
@@ -354,6 +375,7 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
         }
         lg_fence_cta();
       }
+      LG_ACC(1, tw);
       const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
       const int base = ((blk * BS) & (NR - 1)) * 32 + lane;
       const double* bd = s_bnd + ((blk * BS) & (NR - 1));
@@ -364,11 +386,13 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
       __syncwarp();
       if (lane == 0) lg_publish(&prog[0], blk + 1);
     }
+    LG_ACC(0, tc);
   } else {  // ----------------------------------------------------------------------- STORER
     LL16* bnd_out = a.bnd + (size_t)s * ny;
     const int lag = LOWER ? lane : 31 - lane;
+    LG_T0(ts);
     for (int b = 0; b < nblk; ++b) {
-      lg_wait_progress<true>(&prog[0], b + 1, tmo);
+      { LG_T0(tw); lg_wait_progress<true>(&prog[0], b + 1, tmo); LG_ACC(9, tw); }
       // the rows the last lane finished in this block: every lane has passed them
       if (has_down && lane < BS) {
         const int tf = b * BS - 31 + lane;
@@ -382,8 +406,17 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
       __syncwarp();
       if (lane == 0) lg_publish(&prog[1], b + 1);
     }
+    LG_ACC(8, ts);
   }
 }
+#ifdef BG_SF_TIMING
+}  // namespace bg
+extern "C" BG_API int bg_debug_lg_times(int probe, long long* out16) {
+  if (probe >= 0) { long long z[16] = {0}; cudaMemcpyToSymbol(bg::g_lg_t, z, sizeof(z)); return cudaMemcpyToSymbol(bg::g_lg_probe, &probe, sizeof(int)) == cudaSuccess ? 0 : -1; }
+  return cudaMemcpyFromSymbol(out16, bg::g_lg_t, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+namespace bg {
+#endif
 
 template <class VT, class FT, int NR>
 static int lattice_launch(bg_context_t ctx, LatticeGlobalDev& S, const void* in, void* tmp, void* out, const int* skip) {

@@ -60,14 +60,14 @@ class FactorsInfo(C.Structure):
 class PrecondOpts(C.Structure):
     _fields_ = [("trsv_schedule", C.c_int), ("block_method", C.c_int), ("block_rows", C.c_int), ("dims", C.c_int * 6),
                 ("factor_dtype", C.c_int), ("use_tma", C.c_int), ("ilut_lfil", C.c_int), ("ilut_tau", C.c_double),
-                ("chunk_bytes", C.c_int), ("stages", C.c_int), ("warps_per_cta", C.c_int), ("lattice", C.c_int)]
+                ("chunk_bytes", C.c_int), ("stages", C.c_int), ("warps_per_cta", C.c_int), ("lattice", C.c_int), ("device_factor", C.c_int)]
 
 
 class PrecondInfo(C.Structure):
     _fields_ = [("kind", C.c_int), ("n", C.c_int), ("dtype", C.c_int), ("factor_dtype", C.c_int), ("trsv_schedule", C.c_int),
                 ("nnzL", C.c_int64), ("nnzU", C.c_int64), ("levelsL", C.c_int), ("levelsU", C.c_int),
                 ("nblocks", C.c_int), ("max_block_rows", C.c_int), ("trsv_bytes", C.c_int64), ("stream_bytes", C.c_int64),
-                ("lattice", C.c_int)]
+                ("lattice", C.c_int), ("device_factored", C.c_int)]
 
 
 class GmresOpts(C.Structure):

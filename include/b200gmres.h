@@ -174,6 +174,8 @@ typedef struct {
   int warps_per_cta;   /* BG_TRSV_BLOCK: block solves per CTA (3)                                 */
   int lattice;         /* 1 (default): index-free wavefront layouts when the factors are those of a
                           5-point grid (detected from the pattern); 0: always the general streams  */
+  int device_factor;   /* 1 (default): ILU(0) of BG_PART_GRID2D tiles is factored and packed on the device
+                          (SURVEY 8f N2), bit-identical with the host path; 0: always the host path  */
 } bg_precond_opts;
 BG_API void bg_precond_opts_default(bg_precond_opts* o);
 /* MyNONE (preconditioner.h) */
@@ -220,6 +222,7 @@ typedef struct {
   int64_t trsv_bytes;          /* algorithmic bytes of one full application, SURVEY 8d           */
   int64_t stream_bytes;        /* bytes of the packed factor streams actually read per apply     */
   int lattice;                 /* 1: an index-free lattice layout is in use                       */
+  int device_factored;         /* 1: the factorisation and the stream packing ran on the device   */
 } bg_precond_info;
 BG_API int bg_precond_get_info(bg_precond_t M, bg_precond_info* info);
 /* level sets the device schedule was built from (BG_TRSV_LEVEL only), for parity tests */
