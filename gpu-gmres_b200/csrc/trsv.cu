@@ -193,7 +193,12 @@ template <class TIN, class TOUT, class FT, bool LOWER> constexpr size_t lg_smem_
 }
 // progress counters in shared memory: the producer publishes "blocks finished" behind a CTA fence, the consumer
 // polls it (one 30-cycle LDS when the block is already there, an mbarrier try_wait costs three times that)
-__device__ __forceinline__ void lg_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+// Hand-offs between the warps of one CTA go through shared memory only: data (st.shared / cp.async completed by
+// wait_group) first, then the volatile progress word, both from the same warp after a __syncwarp, and the consumer
+// reads the word before the data.  Shared-memory accesses of a warp are performed in program order, so no memory
+// fence is needed -- a MEMBAR.CTA here measured ~900 cycles per 8-step block on the chain warp, four times the
+// recurrence itself (tools/lg_probe.py) -- only the compiler must not reorder the accesses.
+__device__ __forceinline__ void lg_fence_cta() { asm volatile("" ::: "memory"); }
 __device__ __forceinline__ void lg_publish(volatile int* p, int v) {
   lg_fence_cta();
   *p = v;
