@@ -267,17 +267,21 @@ __device__ __forceinline__ void lg_chain_block(const P* __restrict__ pr, const F
 // to right) or ny-1-y (UPPER, strips right to left); lane x of the CHAIN warp reaches time row t at step t + lag,
 // lag = x (LOWER) / 31-x (UPPER).  A lone warp issues about one dependent instruction every four cycles, so
 // everything that is not the recurrence itself is moved off the chain warp:
-//   warp 1 LOADER    stages the coefficient pairs, 1/diag and the right-hand side of 8 time rows per block with
-//                    coalesced cp.async copies into a ring of NR rows, several blocks ahead of the chain
-//   warp 2 BOUNDARY  polls the upstream strip's boundary column (flag-in-data packets in L2, warp-uniform vote
+//   warps 3..6 LOADERS  stage the coefficient pairs, 1/diag and the right-hand side of 8 time rows per block (two
+//                    rows each) with coalesced cp.async copies into a ring of NR rows, several blocks ahead of the
+//                    chain.  Four of them because a lone warp needs ~900 cycles to issue a block's 24 copies with
+//                    their address arithmetic, three times what the chain needs to consume it (ncu: the chain
+//                    polled 22 times per block behind a single loader)
+//   warp 1 BOUNDARY  polls the upstream strip's boundary column (flag-in-data packets in L2, warp-uniform vote
 //                    loop) and drops the values into shared memory
 //   warp 0 CHAIN     per step: operands from shared memory (its own column) into registers a block at a time,
 //                    west/east value by shuffle (edge lane: the boundary value), two FMAs, result to a ring
-//   warp 3 STORER    once all 32 lanes have passed a row: one coalesced 256-byte store of the row, and the edge
+//   warp 2 STORER    once all 32 lanes have passed a row: one coalesced 256-byte store of the row, and the edge
 //                    column of the block goes to the downstream strip as 8 packets
-// Hand-offs are four "blocks finished" counters in shared memory: [0] chain, [1] storer, [2] loader, [3] boundary.
+// Hand-offs are "blocks finished" counters in shared memory: [0] chain, [1] storer, [3] boundary, [4..7] loaders.
+constexpr int kLgLoaders = 4, kLgThreads = 32 * (3 + kLgLoaders);
 template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR>
-__global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
+__global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, const TIN* __restrict__ in, TOUT* __restrict__ out,
                                                            const int* skip) {
   constexpr int BS = kLgBS;
   constexpr int AHEAD = (NR - 31) / BS - 1;  // blocks a producer may run ahead of the consumer that frees its ring rows
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
   pdl_wait();
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x < 4) prog[threadIdx.x] = 0;
+  if (threadIdx.x < 8) prog[threadIdx.x] = 0;
   __syncthreads();
   const int s = LOWER ? (int)blockIdx.x : a.strips - 1 - (int)blockIdx.x;  // CTAs in dependency order
   const int X = 32 * s + lane, nx = a.nx, ny = a.ny;
@@ -306,16 +310,18 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
   const unsigned long long tmo = a.timeout_ns;
   auto yrow = [&](int t) { return LOWER ? t : ny - 1 - t; };
 
-  if (wid == 1) {  // ---------------------------------------------------------------- LOADER
+  if (wid >= 3) {  // ---------------------------------------------------------------- LOADERS
+    constexpr int NL = kLgLoaders, RPL = BS / NL;  // rows of each block per loader warp
+    const int lw = wid - 3;
     const P* gpair = reinterpret_cast<const P*>(a.pair) + (size_t)s * ny * 32 + lane;
     const FT* gdinv = a.dinv + (size_t)s * ny * 32 + lane;
     const int lag = LOWER ? lane : 31 - lane;  // ring row = the STEP at which this lane consumes the element
     LG_T0(tl);
     for (int lb = 0; lb < nblk; ++lb) {
-      { LG_T0(tf); if (lb > AHEAD) lg_wait_progress<true>(&prog[0], lb - AHEAD, tmo); LG_ACC(6, tf); }  // the ring rows about to be overwritten are dead
+      { LG_T0(tf); if (lb > AHEAD) lg_wait_progress<false>(&prog[0], lb - AHEAD, tmo); LG_ACC(6, tf); }  // the ring rows about to be overwritten are dead
 #pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        const int t = lb * BS + j;
+      for (int j = 0; j < RPL; ++j) {
+        const int t = lb * BS + lw * RPL + j;
         if (t < ny) {
           const int y = yrow(t), slot = ((t + lag) & (NR - 1)) * 32 + lane;
           cp_async<sizeof(P)>(s_pair + slot, gpair + (size_t)y * 32);
@@ -326,17 +332,17 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
       cp_async_commit();
       { LG_T0(tw); cp_async_wait<INFLIGHT>(); LG_ACC(7, tw); }  // block lb - INFLIGHT (and everything older) has landed for this lane
       __syncwarp();               // ... and for every lane
-      if (lane == 0 && lb >= INFLIGHT) lg_publish(&prog[2], lb - INFLIGHT + 1);
+      if (lane == 0 && lb >= INFLIGHT) lg_publish(&prog[4 + lw], lb - INFLIGHT + 1);
     }
     cp_async_wait<0>();
     __syncwarp();
-    if (lane == 0) lg_publish(&prog[2], nblk);
+    if (lane == 0) lg_publish(&prog[4 + lw], nblk);
     LG_ACC(5, tl);
-  } else if (wid == 2) {  // --------------------------------------------------------- BOUNDARY IN
+  } else if (wid == 1) {  // --------------------------------------------------------- BOUNDARY IN
     if (has_up) {
       const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
       for (int b = 0; b * BS < ny; ++b) {
-        if (b > AHEAD) lg_wait_progress<true>(&prog[0], b - AHEAD, tmo);
+        if (b > AHEAD) lg_wait_progress<false>(&prog[0], b - AHEAD, tmo);
         const int t = b * BS + lane;  // the edge lane has no lag: it reaches time row t at step t
         bool need = lane < BS && t < ny;
         LL16 pk = {0u, 0u, 0u, 0u};
@@ -363,14 +369,16 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
       const bool bnd = has_up && blk * BS < ny;
       LG_T0(tw);
 #ifdef BG_SF_TIMING
-      { LG_T0(t2); while (prog[2] <= blk) {} LG_ACC(2, t2); }
+      { LG_T0(t2); while (min(min(prog[4], prog[5]), min(prog[6], prog[7])) <= blk) {} LG_ACC(2, t2); }
       { LG_T0(t3); while (bnd && prog[3] <= blk) {} LG_ACC(3, t3); }
       { LG_T0(t4); while (blk > AHEAD && prog[1] < blk - AHEAD) {} LG_ACC(4, t4); }
 #endif
       {  // operands staged, boundary values here, result ring rows about to be reused have left: one poll loop, one fence
         unsigned long long tw = 0;
         for (unsigned spin = 0;; ++spin) {
-          const int p2 = prog[2], p3 = bnd ? prog[3] : blk + 1, p1 = blk > AHEAD ? prog[1] : blk;
+          int4 pl;  // the four loaders' counters in one 16-byte shared load
+          asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pl.x), "=r"(pl.y), "=r"(pl.z), "=r"(pl.w) : "r"(lg_smem_u32(const_cast<int*>(prog + 4))) : "memory");
+          const int p2 = min(min(pl.x, pl.y), min(pl.z, pl.w)), p3 = bnd ? prog[3] : blk + 1, p1 = blk > AHEAD ? prog[1] : blk;
           if (p2 > blk && p3 > blk && p1 >= blk - AHEAD) break;
           if ((spin & 4095u) == 4095u) {
             const unsigned long long now = global_ns();
@@ -392,12 +400,12 @@ __global__ void __launch_bounds__(128) trsv_lattice_global(LgArgs<FT> a, const T
       if (lane == 0) lg_publish(&prog[0], blk + 1);
     }
     LG_ACC(0, tc);
-  } else {  // ----------------------------------------------------------------------- STORER
+  } else if (wid == 2) {  // --------------------------------------------------------- STORER
     LL16* bnd_out = a.bnd + (size_t)s * ny;
     const int lag = LOWER ? lane : 31 - lane;
     LG_T0(ts);
     for (int b = 0; b < nblk; ++b) {
-      { LG_T0(tw); lg_wait_progress<true>(&prog[0], b + 1, tmo); LG_ACC(9, tw); }
+      { LG_T0(tw); lg_wait_progress<false>(&prog[0], b + 1, tmo); LG_ACC(9, tw); }
       // the rows the last lane finished in this block: every lane has passed them
       if (has_down && lane < BS) {
         const int tf = b * BS - 31 + lane;
@@ -437,9 +445,9 @@ static int lattice_launch(bg_context_t ctx, LatticeGlobalDev& S, const void* in,
     attr_done[ctx->device & 63] = true;
   }
   LgArgs<FT> al{S.lower.as<FT>(), nullptr, S.bnd.as<LL16>(), S.nx, S.ny, S.strips, ++S.seq, tmo};
-  BG_CUDA(launch_pdl(kl, dim3(S.strips), dim3(128), sl, ctx->stream, al, (const VT*)in, (CT*)tmp, skip));
+  BG_CUDA(launch_pdl(kl, dim3(S.strips), dim3(kLgThreads), sl, ctx->stream, al, (const VT*)in, (CT*)tmp, skip));
   LgArgs<FT> au{S.upper.as<FT>(), S.udinv.as<FT>(), S.bnd.as<LL16>() + (size_t)S.strips * S.ny, S.nx, S.ny, S.strips, S.seq, tmo};
-  BG_CUDA(launch_pdl(ku, dim3(S.strips), dim3(128), su, ctx->stream, au, (const CT*)tmp, (VT*)out, skip));
+  BG_CUDA(launch_pdl(ku, dim3(S.strips), dim3(kLgThreads), su, ctx->stream, au, (const CT*)tmp, (VT*)out, skip));
   ctx->launches += 2;
   BG_CUDA(cudaGetLastError());
   return BG_OK;
