@@ -106,6 +106,8 @@ struct TrsvXform {      // prologue / epilogue of the split preconditioner
 struct SyncFreeDev {
   int n = 0, n_levels = 0, n_slices = 0, max_K = 0, max_level_rows = 0;
   DevBuf slice_slot, slice_off, rows, cols, vals, diag;
+  DevBuf slice_level, level_slices;  // level of every slice / slices per level
+  DevBuf lvl_cnt, lvl_done;          // per level: finished slices (reset by the last one), "level complete" packet
   int64_t bytes = 0;
   unsigned seq = 0;        // sequence number of the flag-in-data packets, one per launch
 };

@@ -381,7 +381,10 @@ template <class T> static int upload_syncfree_stream(bg_context_t ctx, const Syn
   BG_TRY(upload_vec(d.slice_slot, h.slice_slot, s)); BG_TRY(upload_vec(d.slice_off, h.slice_off, s));
   BG_TRY(upload_vec(d.rows, h.rows, s)); BG_TRY(upload_vec(d.cols, h.cols, s));
   BG_TRY(upload_vec(d.vals, h.vals, s)); BG_TRY(upload_vec(d.diag, h.diag, s));
-  d.bytes = (int64_t)h.cols.size() * (4 + sizeof(T)) + (int64_t)h.rows.size() * (4 + sizeof(T)) + (int64_t)h.slice_slot.size() * 12;
+  BG_TRY(upload_vec(d.slice_level, h.slice_level, s)); BG_TRY(upload_vec(d.level_slices, h.level_slices, s));
+  BG_TRY(d.lvl_cnt.alloc((size_t)std::max(1, h.n_levels) * 4)); BG_TRY(d.lvl_done.alloc((size_t)std::max(1, h.n_levels) * 16));
+  BG_CUDA(cudaMemsetAsync(d.lvl_cnt.p, 0, d.lvl_cnt.bytes, s)); BG_CUDA(cudaMemsetAsync(d.lvl_done.p, 0, d.lvl_done.bytes, s));
+  d.bytes = (int64_t)h.cols.size() * (4 + sizeof(T)) + (int64_t)h.rows.size() * (4 + sizeof(T)) + (int64_t)h.slice_slot.size() * 16;
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }

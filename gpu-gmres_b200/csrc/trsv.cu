@@ -67,24 +67,36 @@ __device__ __forceinline__ bool ll_ok(const LL16& v, unsigned seq) { return v.f0
 __device__ __forceinline__ double ll_val(const LL16& v) { return __hiloint2double((int)v.hi, (int)v.lo); }
 
 template <class FT> struct SfArgs {
-  const int *slice_slot, *rows, *cols;
+  const int *slice_slot, *rows, *cols, *slice_level, *level_slices;
   const int64_t* slice_off;
   const FT *vals, *diag;
+  int* lvl_cnt;     // finished slices per level; the slice that completes a level resets it and ...
+  LL16* lvl_done;   // ... publishes the level's "complete" packet (same sequence number as the row packets)
   int n_slices;
   unsigned seq;
   unsigned long long timeout_ns;
 };
 
 // One warp per slice (<= 32 rows of ONE level), slices taken in ascending order by a fixed set of resident warps:
-// a warp only ever waits for rows of earlier slices, which are finished or held by a running warp, so the walk
-// cannot deadlock as long as the whole grid is resident (launcher).  Everything that does not depend on other rows
-// (row ids, columns, values, right-hand side, diagonal) is loaded before the first poll; the packet loads of a
-// row leave together and the warp re-polls, AS A WHOLE, only the ones that were not ready yet, until a warp vote
-// says every lane has its operands.  The vote keeps the warp converged: 32 lanes spinning in private loops are
-// executed one divergent path after the other, which measured 10 us per dependency hop instead of one L2 round trip
-// (~0.4 us; tools/probe/relay_probe.cu, profiles/r02_syncfree_probe.txt).  Same operations in the same order as the
-// reference's host solve (acc = rhs; acc -= v_k x_k in stored order; acc /= diag).
+// a warp only ever waits for rows / levels of earlier slices, which are finished or held by a running warp, so the
+// walk cannot deadlock as long as the whole grid is resident (launcher: occupancy query).
+//  * Everything that does not depend on other rows (row ids, right-hand side, diagonal, the first group of columns and
+//    values, the metadata of the warp's NEXT slice) is loaded before the first wait.
+//  * GATE: a slice of level l first waits for the "level l-2 complete" packet -- one lane, one address, sleeping
+//    between polls.  Without it every warp ahead of the dependency front polls its operand packets continuously
+//    (thousands of warps x 32 lanes of 16-byte L2 loads per round trip), which inflated the hop of the warps AT the
+//    front from ~1 us to ~4 us per level on factors with many rows per level (ILU++ power-grid factors: 60 levels).
+//    Behind the gate only the slices of two levels poll packets.
+//  * A row's entries come in groups of KP, stored by ascending level of the operand (host packer): the operands that
+//    arrive last are in the last group.  The next group's columns and values are loaded BEFORE the current group is
+//    polled, so a group costs one L2 round trip, and only the last one lies on the critical path of the level.
+//  * The packet loads of a group leave together and the warp re-polls, AS A WHOLE, only the ones that were not ready,
+//    until a warp vote says every lane has its operands: 32 lanes spinning in private loops are executed one
+//    divergent path after the other, which measured 10 us per dependency hop instead of one L2 round trip
+//    (~0.4 us; tools/probe/relay_probe.cu, profiles/r02_syncfree_probe.txt).
+// Per row: acc = rhs; acc -= v_k x_k (k in the stored order of the stream); acc /= diag.
 constexpr int kSfKP = 4;
+constexpr int kSfGate = 2;  // levels between a slice and the completed level it waits for before polling packets
 #ifdef BG_SF_TIMING
 // development aid (make dbg): %globaltimer stamps of lane 0 of the warps that solve slices [g_sf_q0, g_sf_q0 + 2048):
 // [0] slice taken  [1] operands loaded  [2] all dependencies arrived  [3] result published  (+ SM id)
@@ -102,30 +114,70 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
   constexpr int KP = kSfKP;
   const int lane = threadIdx.x & 31;
   const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), G = (int)((gridDim.x * blockDim.x) >> 5);
+  if (g >= a.n_slices) return;
+  // metadata of the first slice; inside the loop it is fetched one slice ahead
+  int s0 = a.slice_slot[g], s1 = a.slice_slot[g + 1], lvl = a.slice_level[g];
+  int64_t off = a.slice_off[g], off1 = a.slice_off[g + 1];
   for (int q = g; q < a.n_slices; q += G) {
     SF_STAMP(0);
-    const int s0 = a.slice_slot[q], R = a.slice_slot[q + 1] - s0;
-    const int64_t off = a.slice_off[q];
-    const int K = (int)((a.slice_off[q + 1] - off) / R);
+    const int R = s1 - s0;
+    const int K = (int)((off1 - off) / R);
     const bool mine = lane < R;  // lanes beyond the slice stay in the loops with nothing to wait for
     const int t = mine ? lane : 0;
     const int r = a.rows[s0 + t];
+    const int64_t base = off + t;
+    int c[KP];
+    CT v[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {  // first group of the row
+      c[j] = (mine && j < K) ? a.cols[base + (int64_t)j * R] : -1;
+      v[j] = (mine && j < K) ? (CT)a.vals[base + (int64_t)j * R] : (CT)0;
+    }
     CT acc = load_rhs<VT, CT>(xf, in, r);
     const CT dg = UNIT ? (CT)1 : (CT)a.diag[s0 + t];
+    const int my_lvl = lvl;
+    {  // the warp's next slice
+      const int qn = q + G;
+      if (qn < a.n_slices) {
+        s0 = a.slice_slot[qn]; s1 = a.slice_slot[qn + 1]; lvl = a.slice_level[qn];
+        off = a.slice_off[qn]; off1 = a.slice_off[qn + 1];
+      }
+    }
 #ifdef BG_SF_TIMING
     if (acc == (CT)1.2345e300) return;  // forces the operand loads to complete before the stamp
     SF_STAMP(1);
     if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + 2048) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_sf_t[(q - g_sf_q0) * 5 + 4] = sm; }
 #endif
+    if (my_lvl >= kSfGate && K > 0) {  // GATE
+      if (lane == 0) {
+        const LL16* gp = a.lvl_done + (my_lvl - kSfGate);
+        unsigned long long t_start = 0;
+        for (unsigned spin = 0;; ++spin) {
+          const LL16 pk = ll_load(gp);
+          if (ll_ok(pk, a.seq)) break;
+          __nanosleep(200);
+          if ((spin & 1023u) == 1023u) {
+            const unsigned long long now = global_ns();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > a.timeout_ns) __trap();
+          }
+        }
+      }
+      __syncwarp();
+    }
     for (int k0 = 0; k0 < K; k0 += KP) {
-      int c[KP];
-      CT v[KP];
+      int cn[KP];
+      CT vn[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {  // next group: in flight while this one is polled
+        const bool has = mine && k0 + KP + j < K;
+        cn[j] = has ? a.cols[base + (int64_t)(k0 + KP + j) * R] : -1;
+        vn[j] = has ? (CT)a.vals[base + (int64_t)(k0 + KP + j) * R] : (CT)0;
+      }
       LL16 pk[KP];
       bool need[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        c[j] = (mine && k0 + j < K) ? a.cols[off + (int64_t)(k0 + j) * R + t] : -1;
-        v[j] = c[j] >= 0 ? (CT)a.vals[off + (int64_t)(k0 + j) * R + t] : (CT)0;
         need[j] = c[j] >= 0;
         pk[j] = LL16{0u, 0u, 0u, 0u};
       }
@@ -148,8 +200,11 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
         }
       }
 #pragma unroll
-      for (int j = 0; j < KP; ++j)
+      for (int j = 0; j < KP; ++j) {
         if (c[j] >= 0) acc -= v[j] * (CT)ll_val(pk[j]);
+        c[j] = cn[j];
+        v[j] = vn[j];
+      }
     }
     SF_STAMP(2);
     if (!UNIT) acc /= dg;
@@ -158,6 +213,14 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
       store_out<VT, CT>(xf, out, r, acc);
     }
     SF_STAMP(3);
+    if (lane == 0) {  // level accounting: the slice that completes its level re-arms the counter and opens the gate
+      const int total = a.level_slices[my_lvl];
+      const int old = total > 1 ? atomicAdd(a.lvl_cnt + my_lvl, 1) : 0;
+      if (old == total - 1) {
+        if (total > 1) a.lvl_cnt[my_lvl] = 0;
+        ll_store(a.lvl_done + my_lvl, 0.0, a.seq);
+      }
+    }
   }
 }
 #ifdef BG_SF_TIMING
@@ -223,10 +286,14 @@ template <bool SLEEP> __device__ __forceinline__ void lg_wait_progress(volatile 
 __device__ long long g_lg_t[16];
 __device__ int g_lg_probe = 0;
 #define LG_T0(v) long long v = clock64()
-#define LG_ACC(k, v) do { if (s == g_lg_probe && lane == 0) g_lg_t[k] += clock64() - (v); } while (0)
+#define LG_ACC(k, v) do { lg_acc[k] += clock64() - (v); } while (0)   // registers; flushed once at the end of the warp's role
+#define LG_DECL long long lg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define LG_FLUSH do { if (s == g_lg_probe && lane == 0) for (int k_ = 0; k_ < 12; ++k_) if (lg_acc[k_]) atomicAdd((unsigned long long*)&g_lg_t[k_], (unsigned long long)lg_acc[k_]); } while (0)
 #else
 #define LG_T0(v) do {} while (0)
 #define LG_ACC(k, v) do {} while (0)
+#define LG_DECL do {} while (0)
+#define LG_FLUSH do {} while (0)
 #endif
 // the 8 steps of one block on the chain warp.  The rings are indexed by STEP (the loader puts lane x's element of
 // time row t where step t + lag will look for it), so the operands of the block's 8 steps sit at constant offsets
@@ -309,6 +376,7 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
   const int edge_in = LOWER ? 0 : 31, edge_out = LOWER ? 31 : 0;
   const unsigned long long tmo = a.timeout_ns;
   auto yrow = [&](int t) { return LOWER ? t : ny - 1 - t; };
+  LG_DECL;
 
   if (wid >= 3) {  // ---------------------------------------------------------------- LOADERS
     constexpr int NL = kLgLoaders, RPL = BS / NL;  // rows of each block per loader warp
@@ -338,6 +406,7 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
     __syncwarp();
     if (lane == 0) lg_publish(&prog[4 + lw], nblk);
     LG_ACC(5, tl);
+    if (lw == 0) LG_FLUSH;
   } else if (wid == 1) {  // --------------------------------------------------------- BOUNDARY IN
     if (has_up) {
       const LL16* bnd_in = a.bnd + (size_t)(LOWER ? s - 1 : s + 1) * ny;
@@ -400,6 +469,7 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
       if (lane == 0) lg_publish(&prog[0], blk + 1);
     }
     LG_ACC(0, tc);
+    LG_FLUSH;
   } else if (wid == 2) {  // --------------------------------------------------------- STORER
     LL16* bnd_out = a.bnd + (size_t)s * ny;
     const int lag = LOWER ? lane : 31 - lane;
@@ -420,6 +490,7 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
       if (lane == 0) lg_publish(&prog[1], b + 1);
     }
     LG_ACC(8, ts);
+    LG_FLUSH;
   }
 }
 #ifdef BG_SF_TIMING
@@ -478,21 +549,30 @@ template <class VT, class FT, bool UNIT>
 static int syncfree_run(bg_context_t ctx, SyncFreeDev& S, const void* in, void* xs, void* out, const TrsvXform& x,
                         const int* skip) {
   using CT = decltype(VT() * FT());
-  SfArgs<FT> a{S.slice_slot.as<int>(), S.rows.as<int>(), S.cols.as<int>(), S.slice_off.as<int64_t>(), S.vals.as<FT>(),
-               S.diag.as<FT>(), S.n_slices, ++S.seq, 5ull * 1000000000ull};
+  SfArgs<FT> a{S.slice_slot.as<int>(), S.rows.as<int>(), S.cols.as<int>(), S.slice_level.as<int>(), S.level_slices.as<int>(),
+               S.slice_off.as<int64_t>(), S.vals.as<FT>(), S.diag.as<FT>(), S.lvl_cnt.as<int>(), S.lvl_done.as<LL16>(),
+               S.n_slices, ++S.seq, 5ull * 1000000000ull};
   // left-split and right-split never occur in the same solve, so one perm pointer suffices
   XformDev<VT> xf{x.pro, x.epi, x.pro == 1 ? x.perm : nullptr, x.epi == 1 ? x.perm : nullptr,
                   (const VT*)x.scale_pro, (const VT*)x.scale_epi};
-  // resident warps: deep enough to have the operands of the coming levels loaded before the dependency front
-  // arrives, shallow enough that the warps polling ahead of the front do not flood L2
-  static const int depth = [] { const char* e = getenv("BG_SF_DEPTH"); const int d = e ? atoi(e) : 8; return d > 0 ? d : 8; }();
+  // Resident warps.  The grid must be resident as a whole (warps wait for each other), hence the occupancy query.
+  // Beyond that: deep enough to have the operands of the coming levels loaded before the dependency front arrives
+  // (the gate keeps the warps ahead of the front quiet, so depth costs nothing but the level-complete polls).
+  auto kern = trsv_syncfree<VT, FT, CT, UNIT>;
+  static int per_sm_cache[64] = {};
+  int& per_sm = per_sm_cache[ctx->device & 63];
+  if (per_sm == 0) {
+    BG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+    if (per_sm < 1) { set_error("trsv_syncfree: no resident block"); return BG_ERR_CUDA; }
+  }
+  static const int depth = [] { const char* e = getenv("BG_SF_DEPTH"); const int d = e ? atoi(e) : 16; return d > 0 ? d : 16; }();
   const double per_level = (double)S.n_slices / std::max(1, S.n_levels);
-  int warps = (int)std::min<double>((double)ctx->sm_count * 32, std::max<double>(ctx->sm_count, per_level * depth));
+  const int max_warps = ctx->sm_count * std::min(per_sm, 8) * 4;
+  int warps = (int)std::min<double>((double)max_warps, std::max<double>(ctx->sm_count, per_level * depth));
   warps = std::min(warps, std::max(1, S.n_slices));
   const int threads = warps <= 4 * ctx->sm_count ? 32 : 128;
-  const int blocks = (warps * 32 + threads - 1) / threads;  // <= 16 CTAs per SM: always resident
-  BG_CUDA(launch_pdl(trsv_syncfree<VT, FT, CT, UNIT>, dim3(blocks), dim3(threads), 0, ctx->stream, a, xf, (const VT*)in,
-                     (LL16*)xs, (VT*)out, skip));
+  const int blocks = (warps * 32 + threads - 1) / threads;
+  BG_CUDA(launch_pdl(kern, dim3(blocks), dim3(threads), 0, ctx->stream, a, xf, (const VT*)in, (LL16*)xs, (VT*)out, skip));
   ctx->launches++;
   BG_CUDA(cudaGetLastError());
   return BG_OK;

@@ -498,9 +498,12 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
   out.n_levels = bucket_levels(n, out.sched_level.data(), lev_ptr, out.rows);
   out.slice_slot.assign(1, 0);
   out.slice_off.assign(1, 0);
+  out.slice_level.clear();
+  out.level_slices.assign(out.n_levels, 0);
   out.max_K = out.max_level_rows = 0;
   for (int l = 0; l < out.n_levels; ++l) {
     out.max_level_rows = std::max(out.max_level_rows, lev_ptr[l + 1] - lev_ptr[l]);
+    out.level_slices[l] = (lev_ptr[l + 1] - lev_ptr[l] + 31) / 32;
     for (int s0 = lev_ptr[l]; s0 < lev_ptr[l + 1]; s0 += 32) {
       const int R = std::min(32, lev_ptr[l + 1] - s0);
       int K = 0;
@@ -511,12 +514,14 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
       out.max_K = std::max(out.max_K, K);
       out.slice_slot.push_back(s0 + R);
       out.slice_off.push_back(out.slice_off.back() + (int64_t)K * R);
+      out.slice_level.push_back(l);
     }
   }
   out.n_slices = (int)out.slice_slot.size() - 1;
   out.cols.assign(out.slice_off.back(), -1);
   out.vals.assign(out.slice_off.back(), (T)0);
   out.diag.assign(n, (T)1);
+  std::vector<std::pair<int64_t, int>> ord;  // (level of the operand's row, column) -> position in the row
   for (int q = 0; q < out.n_slices; ++q) {
     const int s0 = out.slice_slot[q], R = out.slice_slot[q + 1] - s0;
     const int64_t off = out.slice_off[q];
@@ -526,12 +531,17 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
       if (ub <= lb) throw std::invalid_argument("triangular factor row without a diagonal");
       const int dpos = lower ? ub - 1 : lb;
       if (!unit) out.diag[s0 + t] = M.v[dpos];
-      int k = 0;
+      ord.clear();
       for (int p = lb; p < ub; ++p) {
         if (p == dpos) continue;
         if (lower ? M.ci[p] >= r : M.ci[p] <= r) throw std::invalid_argument("entry on the wrong side of the diagonal");
-        out.cols[off + (int64_t)k * R + t] = M.ci[p];
-        out.vals[off + (int64_t)k * R + t] = M.v[p];
+        ord.emplace_back(((int64_t)out.sched_level[M.ci[p]] << 32) | (uint32_t)M.ci[p], p);
+      }
+      std::sort(ord.begin(), ord.end());
+      int k = 0;
+      for (const auto& e : ord) {
+        out.cols[off + (int64_t)k * R + t] = M.ci[e.second];
+        out.vals[off + (int64_t)k * R + t] = M.v[e.second];
         ++k;
       }
     }

@@ -75,13 +75,18 @@ void trsv_levels_structural(bool lower, int n, const int* rp, const int* ci, int
 // levels, so a slice (= one warp) only ever waits for rows of earlier slices.  Slice q covers slots
 // [slice_slot[q], slice_slot[q+1]) = R rows; off-diagonal entry k of its t-th row sits at
 // cols/vals[slice_off[q] + k*R + t] (column -1 = padding); K_q = (slice_off[q+1] - slice_off[q]) / R.
-// diag[s] per slot (1 for unit-lower).
+// diag[s] per slot (1 for unit-lower).  The entries of a row are stored by ascending (level of the column's row,
+// column): the operands that arrive last sit in the row's LAST group of entries, so a warp that runs ahead of the
+// dependency front has consumed everything else when they appear.  slice_level[q] = level of slice q,
+// level_slices[l] = slices of level l (the device counts finished slices per level to publish "level l complete").
 template <class T> struct SyncFreeStream {
   int n = 0, n_levels = 0, n_slices = 0, max_K = 0, max_level_rows = 0;
   std::vector<int> level;        // per row: getLevel (parity API)
   std::vector<int> sched_level;  // per row: structural level the slices follow
   std::vector<int> slice_slot;   // n_slices + 1
   std::vector<int64_t> slice_off;  // n_slices + 1
+  std::vector<int> slice_level;  // n_slices
+  std::vector<int> level_slices; // n_levels
   std::vector<int> rows, cols;
   std::vector<T> vals, diag;
 };
