@@ -105,9 +105,10 @@ struct TrsvXform {      // prologue / epilogue of the split preconditioner
 // device copy of host_algos.h SyncFreeStream (BG_TRSV_LEVEL, any factor; trsv.cu trsv_syncfree)
 struct SyncFreeDev {
   int n = 0, n_levels = 0, n_slices = 0, max_K = 0, max_level_rows = 0;
-  DevBuf slice_slot, slice_off, rows, cols, vals, diag;
-  DevBuf slice_level, level_slices;  // level of every slice / slices per level
-  DevBuf lvl_cnt, lvl_done;          // per level: finished slices (reset by the last one), "level complete" packet
+  DevBuf meta, rows, cols, vals, diag;
+  DevBuf src_idx, dst_idx;           // per slot: where the right-hand side is read / the result written when the split
+                                     // preconditioner's permutations are folded into the solve (empty: the row itself)
+  std::vector<int> h_rows;           // host copy of rows (to build src_idx / dst_idx)
   int64_t bytes = 0;
   unsigned seq = 0;        // sequence number of the flag-in-data packets, one per launch
 };

@@ -378,13 +378,11 @@ static uint64_t g_order_serial = 0;
 template <class T> static int upload_syncfree_stream(bg_context_t ctx, const SyncFreeStream<T>& h, SyncFreeDev& d) {
   cudaStream_t s = ctx->stream;
   d.n = h.n; d.n_levels = h.n_levels; d.n_slices = h.n_slices; d.max_K = h.max_K; d.max_level_rows = h.max_level_rows;
-  BG_TRY(upload_vec(d.slice_slot, h.slice_slot, s)); BG_TRY(upload_vec(d.slice_off, h.slice_off, s));
+  BG_TRY(upload_vec(d.meta, h.meta, s));
   BG_TRY(upload_vec(d.rows, h.rows, s)); BG_TRY(upload_vec(d.cols, h.cols, s));
   BG_TRY(upload_vec(d.vals, h.vals, s)); BG_TRY(upload_vec(d.diag, h.diag, s));
-  BG_TRY(upload_vec(d.slice_level, h.slice_level, s)); BG_TRY(upload_vec(d.level_slices, h.level_slices, s));
-  BG_TRY(d.lvl_cnt.alloc((size_t)std::max(1, h.n_levels) * 4)); BG_TRY(d.lvl_done.alloc((size_t)std::max(1, h.n_levels) * 16));
-  BG_CUDA(cudaMemsetAsync(d.lvl_cnt.p, 0, d.lvl_cnt.bytes, s)); BG_CUDA(cudaMemsetAsync(d.lvl_done.p, 0, d.lvl_done.bytes, s));
-  d.bytes = (int64_t)h.cols.size() * (4 + sizeof(T)) + (int64_t)h.rows.size() * (4 + sizeof(T)) + (int64_t)h.slice_slot.size() * 16;
+  d.h_rows = h.rows;
+  d.bytes = (int64_t)h.cols.size() * (4 + sizeof(T)) + (int64_t)h.rows.size() * (4 + sizeof(T)) + (int64_t)h.meta.size() * 4;
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
 }
@@ -676,6 +674,12 @@ extern "C" int bg_precond_create_split(bg_context_t ctx, int n, const int* lp, c
   if (rc >= 0) rc = M->permRow.upload(permRow, sizeof(int) * n, s);
   if (rc >= 0) rc = M->permCol.upload(permCol, sizeof(int) * n, s);
   if (rc >= 0) rc = upload_vec(M->invPermCol, inv, s);
+  if (rc >= 0) {  // DevPrecond_left reads in[permRow[r]], DevPrecond_right writes out[invPermCol[r]]: composed with the slot order
+    std::vector<int> src(n), dst(n);
+    for (int k = 0; k < n; ++k) { src[k] = permRow[M->lsL.h_rows[k]]; dst[k] = inv[M->lsU.h_rows[k]]; }
+    rc = upload_vec(M->lsL.src_idx, src, s);
+    if (rc >= 0) rc = upload_vec(M->lsU.dst_idx, dst, s);
+  }
   if (rc >= 0) rc = upload_vec(M->u_rp, U.rp, s);
   if (rc >= 0) rc = upload_vec(M->u_ci, U.ci, s);
   if (rc >= 0) rc = M->factor_dtype == BG_F64 ? upload_vec(M->u_val, U.v, s) : upload_vec(M->u_val, to_vec<float>(U.v.data(), BG_F64, U.v.size()), s);

@@ -24,38 +24,18 @@
 namespace bg {
 
 // ------------------------------------------------------------------ prologue / epilogue
+// The split preconditioner's element-wise kernels, folded into the solve.  The permutations are composed with the
+// stream's slot order on the host (SyncFreeDev::src_idx / dst_idx), so the device sees one index per slot.
+//   pro 1: rhs = in[src] / s_pro[src]   kernel_divide_S + kernel_perm_precondLeft_S2D (preconditioner.cu:1439-1464)
+//   pro 2: rhs = in[src] * s_pro[src]   kernel_multiply_S2D (preconditioner.cu:1518-1531)
+//   epi 1: out[dst] = x / s_epi[dst]    kernel_perm_divide_precondRight_D2S (preconditioner.cu:1500-1516), as a scatter
 template <class VT> struct XformDev {
   int pro, epi;
-  const int* perm_pro;
-  const int* perm_epi;
+  const int* src_idx;  // per slot; null: the row itself
+  const int* dst_idx;
   const VT* s_pro;
   const VT* s_epi;
 };
-template <class VT, class CT>
-__device__ __forceinline__ CT load_rhs(const XformDev<VT>& xf, const VT* __restrict__ in, int r) {
-  if (xf.pro == 1) {  // kernel_divide_S + kernel_perm_precondLeft_S2D (preconditioner.cu:1439-1464)
-    const int p = xf.perm_pro[r];
-    const VT t = in[p] / xf.s_pro[p];
-    return (CT)t;
-  }
-  if (xf.pro == 2) {  // kernel_multiply_S2D (preconditioner.cu:1518-1531)
-    const VT t = in[r] * xf.s_pro[r];
-    return (CT)t;
-  }
-  return (CT)in[r];
-}
-template <class VT, class CT>
-__device__ __forceinline__ void store_out(const XformDev<VT>& xf, VT* __restrict__ out, int r, CT x) {
-  if (!out) return;
-  if (xf.epi == 1) {  // kernel_perm_divide_precondRight_D2S (preconditioner.cu:1500-1516), as a scatter
-    const int d = xf.perm_epi[r];
-    VT t = (VT)x;
-    t /= xf.s_epi[d];
-    out[d] = t;
-  } else {
-    out[r] = (VT)x;
-  }
-}
 
 // ------------------------------------------------------------------ sync-free LEVEL schedule (any factor)
 __device__ __forceinline__ LL16 ll_load(const LL16* p) {
@@ -67,11 +47,9 @@ __device__ __forceinline__ bool ll_ok(const LL16& v, unsigned seq) { return v.f0
 __device__ __forceinline__ double ll_val(const LL16& v) { return __hiloint2double((int)v.hi, (int)v.lo); }
 
 template <class FT> struct SfArgs {
-  const int *slice_slot, *rows, *cols, *slice_level, *level_slices;
-  const int64_t* slice_off;
+  const int4* meta;  // host_algos.h SyncFreeStream::meta
+  const int *rows, *cols;
   const FT *vals, *diag;
-  int* lvl_cnt;     // finished slices per level; the slice that completes a level resets it and ...
-  LL16* lvl_done;   // ... publishes the level's "complete" packet (same sequence number as the row packets)
   int n_slices;
   unsigned seq;
   unsigned long long timeout_ns;
@@ -80,34 +58,41 @@ template <class FT> struct SfArgs {
 // One warp per slice (<= 32 rows of ONE level), slices taken in ascending order by a fixed set of resident warps:
 // a warp only ever waits for rows / levels of earlier slices, which are finished or held by a running warp, so the
 // walk cannot deadlock as long as the whole grid is resident (launcher: occupancy query).
-//  * Everything that does not depend on other rows (row ids, right-hand side, diagonal, the first group of columns and
-//    values, the metadata of the warp's NEXT slice) is loaded before the first wait.
-//  * GATE: a slice of level l first waits for the "level l-2 complete" packet -- one lane, one address, sleeping
-//    between polls.  Without it every warp ahead of the dependency front polls its operand packets continuously
-//    (thousands of warps x 32 lanes of 16-byte L2 loads per round trip), which inflated the hop of the warps AT the
-//    front from ~1 us to ~4 us per level on factors with many rows per level (ILU++ power-grid factors: 60 levels).
-//    Behind the gate only the slices of two levels poll packets.
-//  * A row's entries come in groups of KP, stored by ascending level of the operand (host packer): the operands that
-//    arrive last are in the last group.  The next group's columns and values are loaded BEFORE the current group is
-//    polled, so a group costs one L2 round trip, and only the last one lies on the critical path of the level.
+//
+// A warp issues in order and stalls at the first USE of a load that has not landed, so the kernel is written as a
+// software pipeline in which every load is issued one stage before its first use:
+//   slice q+2G : metadata (one 16-byte load)
+//   slice q+G  : row id, source / destination index, diagonal, first group of columns and values   (needs metadata)
+//   slice q    : right-hand side and scales (need the indices), then per group of KP entries: packets of this group
+//                and columns / values of the next one in flight together, FMAs of this group behind the poll
+// so a slice costs one round trip per group and nothing else; measured before the pipeline: 2.2 us from "slice taken"
+// to "operands loaded" and 1.4 us from "dependencies arrived" to "published" (the epilogue's dependent loads), on top
+// of K/4 round trips.
+//  * Rows are right-aligned in the slice and their entries ordered by the operand's level (host packer): the operands
+//    that arrive last are in the LAST group of every lane, so when the warp runs ahead of the dependency front (the
+//    normal case on a thin level) only one group lies on the level's critical path.  With left-aligned rows the warp
+//    walked all K/4 groups after the front arrived: 10 us per level on the long rows of ILU++ factors.
 //  * The packet loads of a group leave together and the warp re-polls, AS A WHOLE, only the ones that were not ready,
 //    until a warp vote says every lane has its operands: 32 lanes spinning in private loops are executed one
 //    divergent path after the other, which measured 10 us per dependency hop instead of one L2 round trip
-//    (~0.4 us; tools/probe/relay_probe.cu, profiles/r02_syncfree_probe.txt).
+//    (tools/probe/relay_probe.cu, profiles/r02_syncfree_probe.txt).
+//  * Tried and dropped: gating the warps ahead of the front behind a per-level "complete" packet (one lane polling one
+//    address) to keep their packet polls off L2.  The completion signal (atomic count + packet) arrives later than the
+//    operands themselves: 346 us -> 446..542 us per L+U solve on the ILU++ factors of the 1304^2 grid.
 // Per row: acc = rhs; acc -= v_k x_k (k in the stored order of the stream); acc /= diag.
 constexpr int kSfKP = 4;
-constexpr int kSfGate = 2;  // levels between a slice and the completed level it waits for before polling packets
 #ifdef BG_SF_TIMING
-// development aid (make dbg): %globaltimer stamps of lane 0 of the warps that solve slices [g_sf_q0, g_sf_q0 + 2048):
-// [0] slice taken  [1] operands loaded  [2] all dependencies arrived  [3] result published  (+ SM id)
-__device__ unsigned long long g_sf_t[2048 * 5];
+// development aid (make dbg): %globaltimer stamps of lane 0 of the warps that solve slices [g_sf_q0, g_sf_q0 + kSfCap):
+// [0] slice taken  [1] right-hand side loaded  [2] all dependencies arrived  [3] result published  (+ SM id)
+constexpr int kSfCap = 65536;
+__device__ unsigned long long g_sf_t[kSfCap * 5];
 __device__ int g_sf_q0 = 0;
-#define SF_STAMP(k) do { if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + 2048) g_sf_t[(q - g_sf_q0) * 5 + (k)] = global_ns(); } while (0)
+#define SF_STAMP(k) do { if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + kSfCap) g_sf_t[(q - g_sf_q0) * 5 + (k)] = global_ns(); } while (0)
 #else
 #define SF_STAMP(k) do {} while (0)
 #endif
 template <class VT, class FT, class CT, bool UNIT>
-__global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> xf, const VT* __restrict__ in, LL16* xs,
+__global__ void __launch_bounds__(128, 5) trsv_syncfree(SfArgs<FT> a, XformDev<VT> xf, const VT* __restrict__ in, LL16* xs,
                                                      VT* out, const int* skip) {
   pdl_wait();
   if (skip && *skip) return;
@@ -115,64 +100,70 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
   const int lane = threadIdx.x & 31;
   const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), G = (int)((gridDim.x * blockDim.x) >> 5);
   if (g >= a.n_slices) return;
-  // metadata of the first slice; inside the loop it is fetched one slice ahead
-  int s0 = a.slice_slot[g], s1 = a.slice_slot[g + 1], lvl = a.slice_level[g];
-  int64_t off = a.slice_off[g], off1 = a.slice_off[g + 1];
+  const int last = a.n_slices;  // meta[n_slices] is a copy of the last slice: prefetches past the end stay in bounds
+
+  // stage "row" of a slice: everything that needs only the metadata
+  struct Row { int r, src, dst; CT dg; int c[KP]; CT v[KP]; };
+  auto load_row = [&](const int4& m, Row& w) {
+    const int R = m.y & 255, K = m.y >> 8;
+    const bool mine = lane < R;
+    const int slot = m.x + (mine ? lane : 0);
+    w.r = a.rows[slot];
+    w.src = xf.src_idx ? xf.src_idx[slot] : w.r;
+    w.dst = xf.dst_idx ? xf.dst_idx[slot] : w.r;
+    w.dg = UNIT ? (CT)1 : (CT)a.diag[slot];
+    const int64_t base = (int64_t)m.w * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      const bool has = mine && j < K;
+      w.c[j] = has ? a.cols[base + (int64_t)j * 32] : -1;
+      w.v[j] = has ? (CT)a.vals[base + (int64_t)j * 32] : (CT)0;
+    }
+  };
+
+  int4 m_cur = a.meta[g];
+  int4 m_nxt = a.meta[min(g + G, last)];
+  Row w_cur;
+  load_row(m_cur, w_cur);
   for (int q = g; q < a.n_slices; q += G) {
     SF_STAMP(0);
-    const int R = s1 - s0;
-    const int K = (int)((off1 - off) / R);
+    const int R = m_cur.y & 255, K = m_cur.y >> 8;
     const bool mine = lane < R;  // lanes beyond the slice stay in the loops with nothing to wait for
-    const int t = mine ? lane : 0;
-    const int r = a.rows[s0 + t];
-    const int64_t base = off + t;
+    const int64_t base = (int64_t)m_cur.w * 32 + lane;
+    const int r = w_cur.r, dst = w_cur.dst;
+    const CT dg = w_cur.dg;
+    // this slice: right-hand side and scales (in flight during the polls)
+    const VT rin = in[w_cur.src];
+    const VT spro = xf.pro ? xf.s_pro[w_cur.src] : (VT)1;
+    const VT sepi = xf.epi ? xf.s_epi[dst] : (VT)1;
     int c[KP];
     CT v[KP];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {  // first group of the row
-      c[j] = (mine && j < K) ? a.cols[base + (int64_t)j * R] : -1;
-      v[j] = (mine && j < K) ? (CT)a.vals[base + (int64_t)j * R] : (CT)0;
-    }
-    CT acc = load_rhs<VT, CT>(xf, in, r);
-    const CT dg = UNIT ? (CT)1 : (CT)a.diag[s0 + t];
-    const int my_lvl = lvl;
-    {  // the warp's next slice
-      const int qn = q + G;
-      if (qn < a.n_slices) {
-        s0 = a.slice_slot[qn]; s1 = a.slice_slot[qn + 1]; lvl = a.slice_level[qn];
-        off = a.slice_off[qn]; off1 = a.slice_off[qn + 1];
-      }
-    }
+    for (int j = 0; j < KP; ++j) { c[j] = w_cur.c[j]; v[j] = w_cur.v[j]; }
+    // the warp's next slice: row stage; the one after: metadata
+    const int4 m_nn = a.meta[min(q + 2 * G, last)];
+    Row w_nxt;
+    load_row(m_nxt, w_nxt);
+    auto rhs = [&]() -> CT {
+      if (xf.pro == 1) { const VT t = rin / spro; return (CT)t; }
+      if (xf.pro == 2) { const VT t = rin * spro; return (CT)t; }
+      return (CT)rin;
+    };
 #ifdef BG_SF_TIMING
-    if (acc == (CT)1.2345e300) return;  // forces the operand loads to complete before the stamp
+    if (rin == (VT)1.2345e30) return;  // forces the operand loads to complete before the stamp
     SF_STAMP(1);
-    if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + 2048) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_sf_t[(q - g_sf_q0) * 5 + 4] = sm; }
+    if (lane == 0 && q >= g_sf_q0 && q < g_sf_q0 + kSfCap) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_sf_t[(q - g_sf_q0) * 5 + 4] = sm; }
 #endif
-    if (my_lvl >= kSfGate && K > 0) {  // GATE
-      if (lane == 0) {
-        const LL16* gp = a.lvl_done + (my_lvl - kSfGate);
-        unsigned long long t_start = 0;
-        for (unsigned spin = 0;; ++spin) {
-          const LL16 pk = ll_load(gp);
-          if (ll_ok(pk, a.seq)) break;
-          __nanosleep(200);
-          if ((spin & 1023u) == 1023u) {
-            const unsigned long long now = global_ns();
-            if (t_start == 0) t_start = now;
-            else if (now - t_start > a.timeout_ns) __trap();
-          }
-        }
-      }
-      __syncwarp();
-    }
+    CT acc = (CT)0;
+    if (K == 0) acc = rhs();
     for (int k0 = 0; k0 < K; k0 += KP) {
       int cn[KP];
       CT vn[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {  // next group: in flight while this one is polled
         const bool has = mine && k0 + KP + j < K;
-        cn[j] = has ? a.cols[base + (int64_t)(k0 + KP + j) * R] : -1;
-        vn[j] = has ? (CT)a.vals[base + (int64_t)(k0 + KP + j) * R] : (CT)0;
+        cn[j] = has ? a.cols[base + (int64_t)(k0 + KP + j) * 32] : -1;
+        vn[j] = has ? (CT)a.vals[base + (int64_t)(k0 + KP + j) * 32] : (CT)0;
       }
       LL16 pk[KP];
       bool need[KP];
@@ -199,6 +190,7 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
           else if (now - t_start > a.timeout_ns) __trap();
         }
       }
+      if (k0 == 0) acc = rhs();
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
         if (c[j] >= 0) acc -= v[j] * (CT)ll_val(pk[j]);
@@ -210,24 +202,26 @@ __global__ void __launch_bounds__(128) trsv_syncfree(SfArgs<FT> a, XformDev<VT> 
     if (!UNIT) acc /= dg;
     if (mine) {
       ll_store(xs + r, (double)acc, a.seq);
-      store_out<VT, CT>(xf, out, r, acc);
-    }
-    SF_STAMP(3);
-    if (lane == 0) {  // level accounting: the slice that completes its level re-arms the counter and opens the gate
-      const int total = a.level_slices[my_lvl];
-      const int old = total > 1 ? atomicAdd(a.lvl_cnt + my_lvl, 1) : 0;
-      if (old == total - 1) {
-        if (total > 1) a.lvl_cnt[my_lvl] = 0;
-        ll_store(a.lvl_done + my_lvl, 0.0, a.seq);
+      if (out) {
+        if (xf.epi == 1) { VT t = (VT)acc; t /= sepi; out[dst] = t; }
+        else out[dst] = (VT)acc;
       }
     }
+    SF_STAMP(3);
+    m_cur = m_nxt;
+    m_nxt = m_nn;
+    w_cur = w_nxt;
   }
 }
 #ifdef BG_SF_TIMING
 }  // namespace bg
 extern "C" BG_API int bg_debug_sf_times(int q0, unsigned long long* out) {
-  if (q0 >= 0) return cudaMemcpyToSymbol(bg::g_sf_q0, &q0, sizeof(int)) == cudaSuccess ? 0 : -1;
-  return cudaMemcpyFromSymbol(out, bg::g_sf_t, sizeof(unsigned long long) * 2048 * 5) == cudaSuccess ? 0 : -1;
+  if (q0 >= 0) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, bg::g_sf_t) != cudaSuccess || cudaMemset(p, 0, sizeof(unsigned long long) * bg::kSfCap * 5) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(bg::g_sf_q0, &q0, sizeof(int)) == cudaSuccess ? 0 : -1;
+  }
+  return cudaMemcpyFromSymbol(out, bg::g_sf_t, sizeof(unsigned long long) * bg::kSfCap * 5) == cudaSuccess ? 0 : -1;
 }
 namespace bg {
 #endif
@@ -549,15 +543,14 @@ template <class VT, class FT, bool UNIT>
 static int syncfree_run(bg_context_t ctx, SyncFreeDev& S, const void* in, void* xs, void* out, const TrsvXform& x,
                         const int* skip) {
   using CT = decltype(VT() * FT());
-  SfArgs<FT> a{S.slice_slot.as<int>(), S.rows.as<int>(), S.cols.as<int>(), S.slice_level.as<int>(), S.level_slices.as<int>(),
-               S.slice_off.as<int64_t>(), S.vals.as<FT>(), S.diag.as<FT>(), S.lvl_cnt.as<int>(), S.lvl_done.as<LL16>(),
-               S.n_slices, ++S.seq, 5ull * 1000000000ull};
-  // left-split and right-split never occur in the same solve, so one perm pointer suffices
-  XformDev<VT> xf{x.pro, x.epi, x.pro == 1 ? x.perm : nullptr, x.epi == 1 ? x.perm : nullptr,
+  SfArgs<FT> a{S.meta.as<int4>(), S.rows.as<int>(), S.cols.as<int>(), S.vals.as<FT>(), S.diag.as<FT>(), S.n_slices, ++S.seq,
+               5ull * 1000000000ull};
+  if ((x.pro == 1 && !S.src_idx.p) || (x.epi == 1 && !S.dst_idx.p)) { set_error("trsv_syncfree: permutation not folded into the stream"); return BG_ERR_ARG; }
+  XformDev<VT> xf{x.pro, x.epi, x.pro == 1 ? S.src_idx.as<int>() : nullptr, x.epi == 1 ? S.dst_idx.as<int>() : nullptr,
                   (const VT*)x.scale_pro, (const VT*)x.scale_epi};
   // Resident warps.  The grid must be resident as a whole (warps wait for each other), hence the occupancy query.
   // Beyond that: deep enough to have the operands of the coming levels loaded before the dependency front arrives
-  // (the gate keeps the warps ahead of the front quiet, so depth costs nothing but the level-complete polls).
+  // and shallow enough that the warps polling ahead of the front do not flood L2.
   auto kern = trsv_syncfree<VT, FT, CT, UNIT>;
   static int per_sm_cache[64] = {};
   int& per_sm = per_sm_cache[ctx->device & 63];

@@ -496,11 +496,16 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
   trsv_levels_structural(lower, n, M.rp.data(), M.ci.data(), out.sched_level.data());
   std::vector<int> lev_ptr;
   out.n_levels = bucket_levels(n, out.sched_level.data(), lev_ptr, out.rows);
-  out.slice_slot.assign(1, 0);
-  out.slice_off.assign(1, 0);
-  out.slice_level.clear();
+  // inside a level: rows that need the same number of 4-entry groups share slices (a slice is as long as its longest
+  // row); stable, so rows of equal length keep their order (stencil factors are left as they are)
+  for (int l = 0; l < out.n_levels; ++l)
+    std::stable_sort(out.rows.begin() + lev_ptr[l], out.rows.begin() + lev_ptr[l + 1], [&](int a, int b) {
+      return (M.rp[a + 1] - M.rp[a] + 2) / 4 > (M.rp[b + 1] - M.rp[b] + 2) / 4;  // ceil((len - 1) / 4), len counts the diagonal
+    });
+  out.meta.clear();
   out.level_slices.assign(out.n_levels, 0);
   out.max_K = out.max_level_rows = 0;
+  int64_t off32 = 0;
   for (int l = 0; l < out.n_levels; ++l) {
     out.max_level_rows = std::max(out.max_level_rows, lev_ptr[l + 1] - lev_ptr[l]);
     out.level_slices[l] = (lev_ptr[l + 1] - lev_ptr[l] + 31) / 32;
@@ -511,20 +516,23 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
         const int r = out.rows[s0 + t];
         K = std::max(K, M.rp[r + 1] - M.rp[r] - 1);
       }
+      if (K >= (1 << 23) || off32 + K > 0x7fffffffLL) throw std::invalid_argument("factor too large for the sync-free stream");
       out.max_K = std::max(out.max_K, K);
-      out.slice_slot.push_back(s0 + R);
-      out.slice_off.push_back(out.slice_off.back() + (int64_t)K * R);
-      out.slice_level.push_back(l);
+      const int m[4] = {s0, R | (K << 8), l, (int)off32};
+      out.meta.insert(out.meta.end(), m, m + 4);
+      off32 += K;
     }
   }
-  out.n_slices = (int)out.slice_slot.size() - 1;
-  out.cols.assign(out.slice_off.back(), -1);
-  out.vals.assign(out.slice_off.back(), (T)0);
+  out.n_slices = (int)out.meta.size() / 4;
+  if (out.n_slices) out.meta.insert(out.meta.end(), out.meta.end() - 4, out.meta.end());
+  else out.meta.assign(4, 0);
+  out.cols.assign((size_t)off32 * 32, -1);
+  out.vals.assign((size_t)off32 * 32, (T)0);
   out.diag.assign(n, (T)1);
   std::vector<std::pair<int64_t, int>> ord;  // (level of the operand's row, column) -> position in the row
   for (int q = 0; q < out.n_slices; ++q) {
-    const int s0 = out.slice_slot[q], R = out.slice_slot[q + 1] - s0;
-    const int64_t off = out.slice_off[q];
+    const int s0 = out.meta[4 * q], R = out.meta[4 * q + 1] & 255, K = out.meta[4 * q + 1] >> 8;
+    const int64_t off = (int64_t)out.meta[4 * q + 3] * 32;
     for (int t = 0; t < R; ++t) {
       const int r = out.rows[s0 + t];
       const int lb = M.rp[r], ub = M.rp[r + 1];
@@ -538,10 +546,10 @@ void pack_syncfree_stream(bool lower, bool unit, const Csr<T>& M, SyncFreeStream
         ord.emplace_back(((int64_t)out.sched_level[M.ci[p]] << 32) | (uint32_t)M.ci[p], p);
       }
       std::sort(ord.begin(), ord.end());
-      int k = 0;
+      int k = K - (int)ord.size();  // right-aligned
       for (const auto& e : ord) {
-        out.cols[off + (int64_t)k * R + t] = M.ci[e.second];
-        out.vals[off + (int64_t)k * R + t] = M.v[e.second];
+        out.cols[off + (int64_t)k * 32 + t] = M.ci[e.second];
+        out.vals[off + (int64_t)k * 32 + t] = M.v[e.second];
         ++k;
       }
     }

@@ -71,21 +71,20 @@ int block_partition(int method, int n, const int* rp, const int* ci, int nblocks
 void trsv_levels_structural(bool lower, int n, const int* rp, const int* ci, int* level);
 
 // Sync-free stream (BG_TRSV_LEVEL, general factors; trsv.cu trsv_syncfree): rows sorted by (structural level,
-// row id) -- slot s holds row rows[s] -- and cut into SLICES of <= 32 consecutive slots that never span two
-// levels, so a slice (= one warp) only ever waits for rows of earlier slices.  Slice q covers slots
-// [slice_slot[q], slice_slot[q+1]) = R rows; off-diagonal entry k of its t-th row sits at
-// cols/vals[slice_off[q] + k*R + t] (column -1 = padding); K_q = (slice_off[q+1] - slice_off[q]) / R.
-// diag[s] per slot (1 for unit-lower).  The entries of a row are stored by ascending (level of the column's row,
-// column): the operands that arrive last sit in the row's LAST group of entries, so a warp that runs ahead of the
-// dependency front has consumed everything else when they appear.  slice_level[q] = level of slice q,
-// level_slices[l] = slices of level l (the device counts finished slices per level to publish "level l complete").
+// number of 4-entry groups descending, row id) -- slot s holds row rows[s] -- and cut into SLICES of <= 32 consecutive slots that never span two
+// levels, so a slice (= one warp) only ever waits for rows of earlier slices.  Slice q is described by
+// meta[4q..4q+3] = { first slot, R | K << 8, level, off32 }: R rows, K entries per row, and off-diagonal entry k of
+// its t-th row sits at cols/vals[(off32 + k) * 32 + t] (column -1 = padding; the lane stride is always 32, so every
+// group of a slice is one aligned 128/256-byte line).  Rows shorter than K are RIGHT-aligned (padding first) and a
+// row's entries are stored by ascending (level of the operand's row, column): the operands that arrive last sit in
+// the LAST entries of every row of the slice, so a warp that runs ahead of the dependency front has consumed
+// everything else when they appear and the level's critical path is one group, not K/4.
+// diag[s] per slot (1 for unit-lower).  level_slices[l] = slices of level l.
 template <class T> struct SyncFreeStream {
   int n = 0, n_levels = 0, n_slices = 0, max_K = 0, max_level_rows = 0;
   std::vector<int> level;        // per row: getLevel (parity API)
   std::vector<int> sched_level;  // per row: structural level the slices follow
-  std::vector<int> slice_slot;   // n_slices + 1
-  std::vector<int64_t> slice_off;  // n_slices + 1
-  std::vector<int> slice_level;  // n_slices
+  std::vector<int> meta;         // 4 * (n_slices + 1); the extra entry is a copy of the last slice (prefetch past the end)
   std::vector<int> level_slices; // n_levels
   std::vector<int> rows, cols;
   std::vector<T> vals, diag;

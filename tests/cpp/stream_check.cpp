@@ -44,12 +44,15 @@ static int run_syncfree(const Csr<T>& M, bool lower, bool unit, const std::vecto
   std::vector<char> ready(n, 0);
   int prev_level = -1;
   std::vector<char> seen(n, 0);
+  if ((int)S.meta.size() != 4 * (S.n_slices + 1)) { std::printf("%s: metadata size\n", what); return 1; }
+  std::vector<int> per_level(S.n_levels, 0);
   for (int q = 0; q < S.n_slices; ++q) {
-    const int s0 = S.slice_slot[q], R = S.slice_slot[q + 1] - s0;
+    const int s0 = S.meta[4 * q], R = S.meta[4 * q + 1] & 255, K = S.meta[4 * q + 1] >> 8;
     if (R < 1 || R > 32) { std::printf("%s: slice %d has %d rows\n", what, q, R); return 1; }
-    const int64_t off = S.slice_off[q];
-    const int K = (int)((S.slice_off[q + 1] - off) / R);
+    const int64_t off = (int64_t)S.meta[4 * q + 3] * 32;
     const int lev = S.sched_level[S.rows[s0]];
+    if (lev != S.meta[4 * q + 2]) { std::printf("%s: slice %d carries level %d, its rows are level %d\n", what, q, S.meta[4 * q + 2], lev); return 1; }
+    per_level[lev]++;
     if (lev < prev_level) { std::printf("%s: slices not in level order\n", what); return 1; }
     prev_level = lev;
     std::vector<double> res(R);
@@ -58,16 +61,27 @@ static int run_syncfree(const Csr<T>& M, bool lower, bool unit, const std::vecto
       if (S.sched_level[row] != lev) { std::printf("%s: slice %d spans two levels\n", what, q); return 1; }
       if (seen[row]++) { std::printf("%s: row %d scheduled twice\n", what, row); return 1; }
       double acc = r[row];
+      int plev = -1;
+      bool started = false;
       for (int k = 0; k < K; ++k) {
-        const int c = S.cols[off + (int64_t)k * R + t];
-        if (c < 0) continue;
+        const int c = S.cols[off + (int64_t)k * 32 + t];
+        if (c < 0) {
+          if (started) { std::printf("%s: row %d is not right-aligned in its slice\n", what, row); return 1; }
+          continue;
+        }
+        started = true;
         if (!ready[c]) { std::printf("%s: row %d reads row %d before it is published (deadlock on the device)\n", what, row, c); return 1; }
-        acc -= (double)S.vals[off + (int64_t)k * R + t] * x[c];
+        if (S.sched_level[c] < plev) { std::printf("%s: row %d: operands not in level order\n", what, row); return 1; }
+        plev = S.sched_level[c];
+        acc -= (double)S.vals[off + (int64_t)k * 32 + t] * x[c];
       }
+      if (K > 0 && M.rp[row + 1] - M.rp[row] - 1 > 0 && S.cols[off + (int64_t)(K - 1) * 32 + t] < 0) { std::printf("%s: row %d: last entry is padding\n", what, row); return 1; }
       res[t] = unit ? acc : acc / (double)S.diag[s0 + t];
     }
     for (int t = 0; t < R; ++t) { x[S.rows[s0 + t]] = res[t]; ready[S.rows[s0 + t]] = 1; }
   }
+  for (int l = 0; l < S.n_levels; ++l)
+    if (per_level[l] != S.level_slices[l]) { std::printf("%s: level %d has %d slices, level_slices says %d\n", what, l, per_level[l], S.level_slices[l]); return 1; }
   double err = 0, nrm = 0;
   for (int i = 0; i < n; ++i) {
     if (!seen[i]) { std::printf("%s: row %d never scheduled\n", what, i); return 1; }

@@ -1,54 +1,68 @@
 #!/usr/bin/env python
 """Development aid: where the warps of trsv_syncfree spend their time, from %globaltimer stamps compiled in with
--DBG_SF_TIMING (make -C gpu-gmres_b200 dbg):   python tools/sf_probe.py [nx] [q0]
-Per slice: taken -> operands loaded -> dependencies arrived -> published; and the pace of the dependency front."""
-import os, sys, ctypes as C
+-DBG_SF_TIMING (make -C gpu-gmres_b200 dbg):   python tools/sf_probe.py [--nx 652] [--ilupp]
+Per level: slices, first take, first / last publication; per slice: taken -> operands loaded -> dependencies arrived ->
+published.  --ilupp: the split preconditioner on ILU++ factors (input from the reference's producer, oracle/_ref)."""
+import argparse, os, sys, ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "gpu-gmres_b200", "python"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gpu-gmres_b200", "python"))
 import b200gmres as bg
 bg.LIB_PATH = os.path.join(ROOT, "gpu-gmres_b200", "build", "libb200gmres_dbg.so")
 import torch
 from b200gmres import synth
-nx = int(sys.argv[1]) if len(sys.argv) > 1 else 1304
-rp, ci, v, b = synth.pg2d(nx, nx, seed=synth.SEED_BASE + 2)
+ap = argparse.ArgumentParser()
+ap.add_argument("--nx", type=int, default=652)
+ap.add_argument("--ilupp", action="store_true")
+ap.add_argument("--every", type=int, default=1, help="print every k-th level")
+a = ap.parse_args()
+CAP = 65536
+rp, ci, v, b = synth.pg2d(a.nx, a.nx, seed=synth.SEED_BASE + 2)
 n = len(rp) - 1
 ctx = bg.Context(0)
-M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=bg.precond_opts(lattice=0))
-din = torch.from_numpy(b).cuda(); dout = torch.zeros(n, dtype=torch.float64, device="cuda")
 L = bg.lib()
-f = bg.host_ilu0(rp, ci, v)
-lev = bg.host_trsv_levels(1, f["lp"], f["li"], f["lv"])
-cnt = np.bincount(lev)
-slices_per_level = (cnt + 31) // 32
-first_slice = np.concatenate([[0], np.cumsum(slices_per_level)])
-q0 = int(sys.argv[2]) if len(sys.argv) > 2 else int(first_slice[len(cnt) // 2])
-for rep in range(3):
-    M.apply(bg.PC_FULL, din.data_ptr(), dout.data_ptr())
-ctx.sync()
-L.bg_debug_sf_times(C.c_int(q0), None)
-M.apply(bg.PC_FULL, din.data_ptr(), dout.data_ptr())   # note: the U solve overwrites the stamps of the L solve for the same q
-ctx.sync()
-t = (C.c_ulonglong * (2048 * 5))()
-L.bg_debug_sf_times(C.c_int(-1), t)
-t = np.array(t[:], dtype=np.int64).reshape(2048, 5)
-lm = len(cnt) // 2
-b0 = t[t[:, 0] > 0][:, 0].min()
-for l in range(lm, lm + 3):
-    a0, a1 = int(first_slice[l]) - q0, int(first_slice[l + 1]) - q0
-    rows = t[a0:a1]
-    print(f"  level {l}: {a1-a0} slices; taken(min..max) {rows[:,0].min()-b0}..{rows[:,0].max()-b0}  deps arrived {sorted((rows[:,2]-b0).tolist())[:6]} .. max {rows[:,2].max()-b0}  published min {rows[:,3].min()-b0} max {rows[:,3].max()-b0}")
-    print("     per slice (deps_arrived, published, sm):", [(int(r[2]-b0), int(r[3]-b0), int(r[4])) for r in rows[:12]])
-ok = t[:, 3] > 0
-t = t[ok]
-base = t[:, 0].min()
-print(f"nx={nx} q0={q0} slices stamped {len(t)}; SMs used {len(set(t[:,4]))}")
-d01, d12, d23 = t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2]
-for nm, d in (("taken->operands loaded", d01), ("operands->deps arrived", d12), ("deps->published", d23), ("taken->published", t[:, 3] - t[:, 0])):
-    print(f"  {nm:26s} ns: median {np.median(d):9.0f}  p10 {np.percentile(d,10):9.0f}  p90 {np.percentile(d,90):9.0f}  max {d.max():9.0f}")
-# pace of the front: publication time of consecutive slices
-pub = np.sort(t[:, 3]) - base
-print("  publication times of the first 48 stamped slices (ns from first take):", (pub[:48]).tolist())
-# three consecutive levels in detail: when each slice saw its dependencies arrive (t2) and published (t3)
-span = pub[-1] - pub[0]
-print(f"  {len(pub)} slices published over {span} ns -> {span/len(pub):.0f} ns per slice")
+if a.ilupp:
+    import scipy.sparse as sp
+    from oracle import pyoracle as O
+    Ac = sp.csr_matrix((v, ci, rp), shape=(n, n)).tocsc(); Ac.sort_indices()
+    fac = O.ilupp_factor(n, Ac.indptr, Ac.indices, Ac.data, threshold=1.2, mem_factor=1.0)
+    keys = ("lp", "li", "lv", "up", "ui", "uv", "middle", "lscale", "rscale", "permRow", "permCol")
+    M = bg.Precond.split(ctx, *[fac[k] for k in keys], dtype=bg.F64)
+    f = {k: np.asarray(fac[k]) for k in keys[:6]}
+    solves = (("L", bg.PC_LEFT, 1, "lp", "li", "lv"), ("U", bg.PC_RIGHT, 0, "up", "ui", "uv"))
+else:
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=bg.precond_opts(lattice=0))
+    f = bg.host_ilu0(rp, ci, v)
+    solves = (("L+U (stamps of U)", bg.PC_FULL, 0, "up", "ui", "uv"),)
+din = torch.from_numpy(b).cuda(); dout = torch.zeros(n, dtype=torch.float64, device="cuda")
+for name, which, lower, kp, ki, kv in solves:
+    lev = bg.host_trsv_levels(lower, f[kp], f[ki], f[kv])
+    cnt = np.bincount(lev)
+    spl = (cnt + 31) // 32
+    first = np.concatenate([[0], np.cumsum(spl)])
+    nsl = int(first[-1])
+    for _ in range(3):
+        M.apply(which, din.data_ptr(), dout.data_ptr())
+    ctx.sync()
+    L.bg_debug_sf_times(C.c_int(0), None)
+    M.apply(which, din.data_ptr(), dout.data_ptr())
+    ctx.sync()
+    t = (C.c_ulonglong * (CAP * 5))()
+    L.bg_debug_sf_times(C.c_int(-1), t)
+    t = np.frombuffer(t, dtype=np.uint64).astype(np.int64).reshape(CAP, 5)[:min(nsl, CAP)]
+    ok = t[:, 3] > 0
+    base = t[ok][:, 0].min()
+    print(f"== {name}: n={n} slices={nsl} levels={len(cnt)} stamped={int(ok.sum())} total {(t[ok][:,3].max()-base)/1e3:.1f} us, SMs {len(set(t[ok][:,4]))}")
+    d01, d12, d23 = t[ok][:, 1] - t[ok][:, 0], t[ok][:, 2] - t[ok][:, 1], t[ok][:, 3] - t[ok][:, 2]
+    for nm, d in (("taken->operands loaded", d01), ("operands->deps arrived", d12), ("deps->published", d23)):
+        print(f"  {nm:26s} ns: median {np.median(d):9.0f}  p10 {np.percentile(d,10):9.0f}  p90 {np.percentile(d,90):9.0f}  max {d.max():9.0f}")
+    prev_last = 0
+    for l in range(len(cnt)):
+        a0, a1 = int(first[l]), min(int(first[l + 1]), CAP)
+        if a0 >= CAP: break
+        r = t[a0:a1]
+        last = int(r[:, 3].max() - base)
+        if l % a.every == 0 or l == len(cnt) - 1:
+            print(f"  level {l:4d}: {a1-a0:6d} slices  first take {int(r[:,0].min()-base):8d}  last take {int(r[:,0].max()-base):8d}  first pub {int(r[:,3].min()-base):8d}  last pub {last:8d}  (+{last-prev_last:6d})  median wait {int(np.median(r[:,2]-r[:,1])):7d}")
+        prev_last = last
+M.close(); ctx.close()
