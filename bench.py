@@ -406,10 +406,16 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
         trsv_kernel: (st.trsv_ms, st.trsv_bytes, st.trsv_calls, trsv_moved_per * napply),
     }
     if orth_name == "mgs":
-        # strict MGS: i+1 (dot, axpy) launch pairs per inner iteration; each pair reads v_k and w twice and writes w
         it = max(rprof.iters_done, 1)
-        moved = sum((5 * (t % 32 + 1) + 3) * s8 * n for t in range(it))
-        kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls, moved)
+        if S.mgs_fused():
+            # one cooperative launch per inner iteration: every basis column read once, w read once, v_{i+1} written once
+            moved = sum(((t % 32 + 1) + 2) * s8 * n for t in range(it))
+            kernels["mgs_kernel (strict MGS, i+1 dependent dot/axpy pairs in one launch; w in registers, packet all-to-all sums)"] = (
+                st.orth_ms, st.orth_bytes, st.orth_calls, moved)
+        else:
+            # i+1 (dot, axpy) launch pairs per inner iteration; each pair reads v_k and w twice and writes w
+            moved = sum((5 * (t % 32 + 1) + 3) * s8 * n for t in range(it))
+            kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls, moved)
     elif st.dots_calls == 0:
         # fused step: one cooperative launch per inner iteration (projections + Givens epilogue + v_j)
         kernels["orth_kernel (fused: V^T w, w.w, Givens, v_j = (w - V h)/||.||; TMA-staged tiles reused from shared memory / L2)"] = (

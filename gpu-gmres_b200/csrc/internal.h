@@ -208,6 +208,12 @@ int launch_halo_exchange(bg_context_t ctx, int dtype, const PeerHalo* d_ph, int 
 // fused CGS step (adaptive or CGS2): projections + (peer all-reduce) + Givens epilogue + v_j, one cooperative launch
 int launch_orth(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, void* out,
                 const GmresDev& st, int inner_i, int orth_mode, const PeerAR* peer);
+// strict MGS step of inner iteration i as one cooperative launch (single GPU, vectors that fit the register-resident
+// layout: mgs_fused_supported); slots = mgs_slot_bytes() of zero-initialised device memory, seq = launch counter >= 1
+bool mgs_fused_supported(bg_context_t ctx, int n, int m);
+size_t mgs_slot_bytes(bg_context_t ctx, int m);
+int launch_mgs(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int i, const void* w, void* out, const GmresDev& st,
+               void* slots, unsigned seq);
 int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth,
                     int j, const double* red_in);
 int launch_pack(bg_context_t ctx, int dtype, int cnt, const int* idx, const void* v, void* buf, const int* skip);
@@ -270,6 +276,8 @@ struct bg_solver_s {
   int n = 0, m = 0, dtype = BG_F64;
   int64_t ld = 0;
   bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb, bp, xp, red;
+  bg::DevBuf mgs_slots;     // packets of the fused MGS step's grid-wide sums
+  unsigned mgs_seq = 0;
   bg::GmresDev dev{};
   void* pinned = nullptr;  // host mirror of flags+scal for polling
   cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;

@@ -709,6 +709,154 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* 
   }
 }
 
+// ---------------------------------------------------------------------------- fused strict MGS step
+// The reference's orthogonalisation (src/gmres.cu:2356-2362): for k = 0..i { H(k,i) = <w, v_k>; w -= H(k,i) v_k },
+// H(i+1,i) = ||w||, v_{i+1} = w / H(i+1,i) -- i+1 DEPENDENT dot/axpy pairs.  As separate kernels that is 2(i+2)
+// launches per inner iteration, each a few microseconds of work at power-grid sizes (337 us per iteration on the
+// 1.7 M-row grid, five times the fused CGS step).  Here the whole step is ONE cooperative launch:
+//  * CTA c owns rows [c*rows_per, (c+1)*rows_per); its slice of w lives in REGISTERS (1024 threads x 12 values)
+//    for the whole step and is written once, as v_{i+1};
+//  * the slices of v_k arrive by bulk-async copies into two shared-memory buffers, v_{k+2} being fetched while pair
+//    k+1 is computed, so every basis column is read from HBM exactly once and the copy hides behind the exchange;
+//  * the grid-wide sum of a pair is an all-to-all of flag-in-data packets: every CTA stores its partial sum (value +
+//    launch sequence number in one 16-byte store) and polls the packets of all CTAs -- one L2 round trip after the
+//    last store instead of an atomic ticket plus a broadcast -- and adds them in CTA order, so every CTA holds the same
+//    bits and the result does not depend on timing;
+//  * CTA 0 keeps the column of H and runs the Givens / residual / convergence epilogue.
+// Sums are accumulated in double whatever VT is; for VT = float w is rounded to float after every axpy, as the
+// separate kernels (and the reference's float w) do.
+constexpr int kMgsThreads = 1024, kMgsEPT = 12;
+struct MgsArgs {
+  LL16* slots;   // [(m + 2)][G] packets
+  unsigned seq;  // launch sequence number (never 0)
+  int rows_per;  // rows per CTA (multiple of 32)
+  unsigned long long timeout_ns;
+};
+template <class VT>
+__global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __restrict__ V, int64_t ld, int i, const VT* __restrict__ w_in,
+                                                             VT* __restrict__ out, GmresDev st, MgsArgs a) {
+  if (st.flags[F_CONV]) return;  // written by an earlier launch: uniform over the grid
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t full[2];
+  __shared__ double red_w[32];
+  __shared__ double s_sum;
+  __shared__ FinScratch fs;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
+  const int r0 = blockIdx.x * a.rows_per, rows = max(0, min(a.rows_per, n - r0));
+  const uint32_t buf_bytes = ((uint32_t)a.rows_per * sizeof(VT) + 127u) & ~127u;
+  const uint32_t bytes = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;  // columns are padded to ld: the tail stays in bounds
+  const int ncol = i + 1;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int k) {  // one thread
+    if (rows > 0) {
+      mbar_expect_tx(&full[k & 1], bytes);
+      bulk_g2s(dyn + (size_t)(k & 1) * buf_bytes, V + (size_t)k * ld + r0, bytes, &full[k & 1]);
+    }
+  };
+  if (tid == 0) { issue(0); if (ncol > 1) issue(1); }
+  double wr[kMgsEPT];
+#pragma unroll
+  for (int e = 0; e < kMgsEPT; ++e) {
+    const int r = tid + e * kMgsThreads;
+    wr[e] = r < rows ? (double)w_in[r0 + r] : 0.0;
+  }
+  if (blockIdx.x == 0) fin_prefetch(st, fs, i, tid);
+  const bool fast = st.m <= kFinMax;
+
+  // grid-wide sum of one value per thread; identical bits in every thread of every CTA
+  auto grid_sum = [&](double p, int k) -> double {
+    p = warp_sum(p);
+    if (lane == 0) red_w[wid] = p;
+    __syncthreads();
+    if (wid == 0) {
+      const double mine = warp_sum(red_w[lane]);
+      LL16* row = a.slots + (size_t)k * G;
+      if (lane == 0) ll_store(row + blockIdx.x, mine, a.seq);
+      constexpr int PER = 5;  // up to 160 CTAs (launcher)
+      LL16 pk[PER];
+      bool need[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) { need[u] = lane + 32 * u < G; pk[u] = LL16{0u, 0u, 0u, 0u}; }
+      unsigned long long t0 = 0;
+      for (unsigned spin = 0;; ++spin) {  // warp-uniform poll of everybody's packet
+        bool all = true;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          if (need[u]) {
+            const LL16* q = row + lane + 32 * u;
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[u].lo), "=r"(pk[u].f0), "=r"(pk[u].hi), "=r"(pk[u].f1) : "l"(q) : "memory");
+            need[u] = !(pk[u].f0 == a.seq && pk[u].f1 == a.seq);
+          }
+          all = all && !need[u];
+        }
+        if (__all_sync(0xffffffffu, all)) break;
+        if ((spin & 4095u) == 4095u) {
+          const unsigned long long now = global_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > a.timeout_ns) __trap();
+        }
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int u = 0; u < PER; ++u)
+        if (lane + 32 * u < G) acc += __hiloint2double((int)pk[u].hi, (int)pk[u].lo);
+      acc = warp_sum(acc);
+      if (lane == 0) s_sum = acc;
+    }
+    __syncthreads();
+    return s_sum;
+  };
+
+  for (int k = 0; k < ncol; ++k) {
+    if (rows > 0) mbar_wait(&full[k & 1], (uint32_t)(k >> 1) & 1u);
+    const VT* vk = reinterpret_cast<const VT*>(dyn + (size_t)(k & 1) * buf_bytes);
+    double p = 0.0;
+#pragma unroll
+    for (int e = 0; e < kMgsEPT; ++e) {
+      const int r = tid + e * kMgsThreads;
+      if (r < rows) p += (double)vk[r] * wr[e];
+    }
+    const double h = grid_sum(p, k);  // H(k,i) = <w, v_k>  (gmres.cu:2357)
+    if (blockIdx.x == 0 && tid == 0) {
+      if (fast) fs.col[k] = h; else st.H[(size_t)i * (st.m + 1) + k] = h;
+    }
+#pragma unroll
+    for (int e = 0; e < kMgsEPT; ++e) {
+      const int r = tid + e * kMgsThreads;
+      if (r < rows) wr[e] = (double)(VT)(wr[e] - h * (double)vk[r]);  // w -= H(k,i) v_k  (gmres.cu:2358)
+    }
+    __syncthreads();  // everybody is done with this buffer
+    if (tid == 0 && k + 2 < ncol) issue(k + 2);
+  }
+  double p = 0.0;
+#pragma unroll
+  for (int e = 0; e < kMgsEPT; ++e) p += wr[e] * wr[e];
+  const double ww = grid_sum(p, ncol);
+  const double hn = sqrt(ww);  // H(i+1,i) = ||w||  (gmres.cu:2360)
+  const double scale = hn > 0.0 ? 1.0 / hn : 0.0;
+#pragma unroll
+  for (int e = 0; e < kMgsEPT; ++e) {
+    const int r = tid + e * kMgsThreads;
+    if (r < rows) out[r0 + r] = (VT)(wr[e] * scale);  // v_{i+1} = w / H(i+1,i)  (gmres.cu:2361-2362)
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    st.scal[S_SCALE] = scale;
+    if (!(hn > 0.0)) st.flags[F_BREAK] = 1;
+    if (fast) {
+      fs.col[i + 1] = hn;
+      givens_column(st, i, &fs);
+    } else {
+      st.H[(size_t)i * (st.m + 1) + i + 1] = hn;
+      givens_column(st, i, nullptr);
+    }
+  }
+}
+
 // out = a * scale (no basis columns: v0 = r/beta, gmres.cu:2342-2343)
 template <class VT>
 __global__ void __launch_bounds__(256) scale_copy_kernel(int n, const VT* a, VT* out, GmresDev st, int use_scale, int force) {
@@ -928,6 +1076,38 @@ static int orth_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int j
   ctx->launches++;
   return BG_OK;
 }
+// rows per CTA of the fused MGS step, or 0 when the vector does not fit the register-resident layout
+static int mgs_rows_per(bg_context_t ctx, int n, int G) {
+  const int per = (((n + G - 1) / G) + 31) / 32 * 32;
+  return per <= kMgsThreads * kMgsEPT ? per : 0;
+}
+bool mgs_fused_supported(bg_context_t ctx, int n, int m) {
+  if (n < 1) return false;
+  const int G = std::max(1, std::min((n + 31) / 32, ctx->sm_count));
+  return G <= 160 && mgs_rows_per(ctx, n, G) > 0;
+}
+size_t mgs_slot_bytes(bg_context_t ctx, int m) { return (size_t)(m + 2) * 256 * sizeof(LL16); }
+template <class VT>
+static int mgs_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int i, const VT* w, VT* out, const GmresDev& st, void* slots,
+                        unsigned seq) {
+  const int G = std::max(1, std::min((n + 31) / 32, ctx->sm_count));
+  MgsArgs a{(LL16*)slots, seq, mgs_rows_per(ctx, n, G), 5ull * 1000000000ull};
+  if (a.rows_per == 0 || G > 160) { set_error("fused MGS: n=%d does not fit", n); return BG_ERR_UNSUPPORTED; }
+  const size_t smem = 2 * (((size_t)a.rows_per * sizeof(VT) + 127) & ~(size_t)127);
+  BG_TRY(pipe_smem_attr(mgs_kernel<VT>, ctx));
+  GmresDev stv = st;
+  void* args[] = {(void*)&n, (void*)&V, (void*)&ld, (void*)&i, (void*)&w, (void*)&out, (void*)&stv, (void*)&a};
+  // cooperative launch: the CTAs exchange partial sums inside the kernel, so co-residency must be guaranteed
+  BG_CUDA(cudaLaunchCooperativeKernel((const void*)mgs_kernel<VT>, dim3(G), dim3(kMgsThreads), args, smem, ctx->stream));
+  ctx->launches++;
+  return BG_OK;
+}
+int launch_mgs(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int i, const void* w, void* out, const GmresDev& st,
+               void* slots, unsigned seq) {
+  if (dtype == BG_F32) return mgs_dispatch<float>(ctx, n, (const float*)V, ld, i, (const float*)w, (float*)out, st, slots, seq);
+  return mgs_dispatch<double>(ctx, n, (const double*)V, ld, i, (const double*)w, (double*)out, st, slots, seq);
+}
+
 int launch_orth(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, void* out, const GmresDev& st,
                 int inner_i, int orth_mode, const PeerAR* peer) {
   if (dtype == BG_F32) return orth_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, (float*)out, st, inner_i, orth_mode, peer);

@@ -812,6 +812,8 @@ int bg::solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int ex
                o_sn = take((m + 1) * 8), o_t = take(16), o_hist = take((size_t)kHistCap * 8), o_p = take((size_t)nblk * pl * 8);
   if (rc >= 0) rc = S->state.alloc(off);
   if (rc >= 0) rc = S->red.alloc(sizeof(double) * (size_t)(m + 8));
+  if (rc >= 0) rc = S->mgs_slots.alloc(mgs_slot_bytes(ctx, m));
+  if (rc >= 0 && cudaMemset(S->mgs_slots.p, 0, S->mgs_slots.bytes) != cudaSuccess) rc = BG_ERR_CUDA;
   if (rc < 0) { delete S; return rc; }
   cudaMemset(S->state.p, 0, off);
   unsigned char* b = S->state.as<unsigned char>();
@@ -911,6 +913,8 @@ struct Driver {
     { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->ww.p, S->w.p, skip)); }
     Span sp(prof, PH_ORTH);
     if (o.orth == BG_ORTH_MGS) {
+      if (fused_orth && !dh && mgs_fused_supported(ctx, n, m))  // one cooperative launch for the i+1 dot/axpy pairs and the norm
+        return launch_mgs(ctx, S->dtype, n, col(0), ld, i, S->w.p, col(i + 1), st, S->mgs_slots.p, ++S->mgs_seq);
       for (int k = 0; k <= i; ++k) {
         BG_TRY(dots(col(k), 1, S->w.p, FIN_MGS_DOT, i, k, 0));
         BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(k), ld, 1, st.h, -1.0, S->w.p, st, 0, 0, 0));
@@ -1152,6 +1156,12 @@ extern "C" BG_API int bg_solver_bench_orth(bg_context_t ctx, bg_solver_t S, int 
   GmresDev st = S->dev;
   BG_TRY(launch_dots(ctx, S->dtype, S->n, S->V.p, S->ld, j, S->w.p, st, FIN_NONE, 0, 0, BG_ORTH_CGS_ADAPTIVE, 0));
   return launch_update(ctx, S->dtype, S->n, S->w.p, S->V.p, S->ld, j, st.h, -1.0, S->V.as<char>() + (size_t)j * S->ld * dtype_size(S->dtype), st, 1, 0, 0);
+}
+
+extern "C" int bg_solver_mgs_fused(bg_context_t ctx, bg_solver_t S) {
+  if (!ctx || !S) return BG_ERR_ARG;
+  const char* e = getenv("BG_FUSED_ORTH");  // read per call, like the solve does
+  return !(e && e[0] == '0') && mgs_fused_supported(ctx, S->n, S->m) ? 1 : 0;
 }
 
 extern "C" int bg_solver_profile(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,

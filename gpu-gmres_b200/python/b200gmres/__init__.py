@@ -429,6 +429,9 @@ class Solver:
     def bench_orth(self, j):
         _chk(lib().bg_solver_bench_orth(self.ctx.h, self.h, j))
 
+    def mgs_fused(self) -> bool:
+        return _chk(lib().bg_solver_mgs_fused(self.ctx.h, self.h)) == 1
+
     def close(self):
         if self.h:
             lib().bg_solver_destroy(self.h)

@@ -268,6 +268,9 @@ BG_API int bg_solver_get_hessenberg(bg_solver_t S, double* H, double* s, double*
 /* diagnostic: one fused orthogonalisation step (dots + update) against j basis columns on the
    solver's own workspace; used by bench.py to time the dominant kernel pair in isolation */
 BG_API int bg_solver_bench_orth(bg_context_t ctx, bg_solver_t S, int j);
+/* 1 when a strict-MGS step (BG_ORTH_MGS) of this solver runs as ONE cooperative launch (vector slices resident in
+   registers: single GPU, n up to 12288 rows per SM), 0 when it runs as i+1 dot/axpy launch pairs */
+BG_API int bg_solver_mgs_fused(bg_context_t ctx, bg_solver_t S);
 /* per-phase device time and algorithmic bytes of the last solve (≙ SUB_TIMER, gmres.h:64-80) */
 typedef struct {
   double spmv_ms, trsv_ms, orth_ms, other_ms;

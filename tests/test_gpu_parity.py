@@ -4,6 +4,8 @@ against the CPU oracle on the same seeded inputs and against the committed golde
 Tolerances (BASELINE.json north_star): integer artefacts (level sets) bit-exact; FP64 final
 residual within 1e-10 (absolute difference of the relative residuals) and solution within 1e-8
 relative; FP32 modes are compared at FP32 round-off level (reduction order differs by design)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -290,6 +292,42 @@ def run_gpu(bg, ctx, rp, ci, v, b, x0, M, dtc, **kw):
     S.close()
     A.close()
     return r, x, hist
+
+
+@pytest.mark.parametrize("dtc", [0, 1])
+@pytest.mark.parametrize("shape", [(96, 80), (33, 1), (400, 300)])
+def test_fused_mgs_step_equals_launch_pairs(bg, ctx, dtc, shape):
+    """Strict MGS (the reference's order, src/gmres.cu:2356-2362) as ONE cooperative launch (mgs_kernel: w in registers,
+    packet all-to-all sums) against the same step as i+1 dot/axpy launch pairs (BG_FUSED_ORTH=0): same stopping
+    iteration, same Hessenberg column by column up to summation order, same solution.  33 rows: one partial CTA;
+    120 000 rows: every SM owns a slice; restart 5 exercises the restart path through the fused kernel."""
+    from b200gmres import synth
+
+    rp, ci, v, b = synth.pg2d(shape[0], shape[1], seed=977)
+    n = len(rp) - 1
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=dtc)
+    tol = 1e-5 if dtc == 0 else 1e-9
+    res = {}
+    for m in (32, 5):
+        for fused in ("1", "0"):
+            os.environ["BG_FUSED_ORTH"] = fused
+            try:
+                A = bg.Matrix(ctx, rp, ci, v, dtype=dtc)
+                S = bg.Solver(ctx, n, m, dtype=dtc)
+                assert S.mgs_fused() == (fused == "1")
+                db, dx = dev(b, np_dt(dtc)), dev(np.zeros(n), np_dt(dtc))
+                r = S.solve(A, M, db.data_ptr(), dx.data_ptr(), bg.gmres_opts(m=m, tol=tol, max_iter=3000, orth=bg.ORTH_MGS, history_cap=4096))
+                res[(m, fused)] = (r, host(ctx, dx).astype(np.float64), S.history(), S.hessenberg()[0])
+                S.close(); A.close()
+            finally:
+                os.environ.pop("BG_FUSED_ORTH", None)
+        (r1, x1, h1, H1), (r0, x0, h0, H0) = res[(m, "1")], res[(m, "0")]
+        assert r1.flag == 0 and (r1.flag, r1.iters) == (r0.flag, r0.iters)
+        # rounding differences of the sums are amplified along the Krylov sequence: late columns agree to ~1e-8
+        assert np.allclose(h1, h0, rtol=2e-3 if dtc == 0 else 1e-6, atol=1e-14)
+        assert np.linalg.norm(x1 - x0) <= (5e-4 if dtc == 0 else 1e-9) * np.linalg.norm(x0)
+        assert np.allclose(H1, H0, rtol=0, atol=(1e-3 if dtc == 0 else 1e-7) * np.abs(H0).max())
+    M.close()
 
 
 @pytest.mark.parametrize("name", ["pg2d_24x20", "th3d_8x7x6", "rand_300"])
