@@ -92,6 +92,7 @@ struct FbArgs {
   int nblocks, max_rows, stages, tab_stride;
   uint32_t slot_bytes;  // ring slot stride (multiple of 128)
   uint32_t warp_smem;   // bytes of shared memory per warp (multiple of 128)
+  uint32_t tab_bytes;   // LATTICE: increment table at the end of the warp's area (multiple of 128)
 };
 
 template <class FT> struct PairOf;
@@ -172,53 +173,117 @@ __device__ __forceinline__ void run_steps_generic(int lane, int K, int nst, int 
   }
 }
 
+// LATTICE layout: per-warp table of the pair-pointer increments.  On anti-diagonal d of a tx x ty tile the active
+// lanes are [xlo_d, xlo_d + cnt_d) and lane x finds its pair at index u_d + x - xlo_d of the factor's stream (u_d =
+// pairs of the earlier diagonals), so from one step to the next every lane's pointer advances by the same, warp-
+// uniform amount cnt_d - (xlo_next - xlo_d).  tab[e] = that amount in bytes after step e of L (d = e), tab[nd + e]
+// after step e of U (d = D - e); filled once per tile shape.
+template <class FT>
+__device__ __forceinline__ void lattice_fill_tab(int lane, int tx, int ty, int* tab) {
+  using P = typename PairOf<FT>::type;
+  const int D = tx + ty - 2, ty1 = ty - 1, tx1 = tx - 1, nd = D + 1;
+  if (lane < 4) tab[lane] = 0;  // 16 zero bytes: the operands of lanes outside the wavefront
+  tab += 4;
+  for (int e = lane; e < nd; e += 32) {
+    {
+      const int d = e, xlo = max(0, d - ty1), cnt = min(d, tx1) - xlo + 1, xlo2 = max(0, d + 1 - ty1);
+      tab[e] = (cnt - (xlo2 - xlo)) * (int)sizeof(P);
+    }
+    {
+      const int d = D - e, xlo = max(0, d - ty1), cnt = min(d, tx1) - xlo + 1, xlo2 = max(0, d - 1 - ty1);
+      tab[nd + e] = (cnt - (xlo2 - xlo)) * (int)sizeof(P);
+    }
+  }
+}
+
 // one chunk of the LATTICE layout: whole anti-diagonals of a tx x ty tile, (west|east, south|north) value pairs.
-// Branch-free step: lanes off the current anti-diagonal compute with zero operands (their zprev is not read by
-// anybody: a lane's west/east neighbour is only consulted while that neighbour is inside the wavefront), so the
-// warp never diverges around the shuffle and the per-step instruction stream is two shuffles, two FMAs, two
-// shared loads for the NEXT step, one predicated store and a handful of warp-uniform index updates.
+// The wavefront step is the dependency chain of the whole solve (2 (tx + ty - 1) steps per tile, one warp), and a
+// lone warp issues one instruction every few cycles, so the step is cut down to what the recurrence needs: every
+// lane keeps RUNNING shared-memory addresses of its next right-hand side entry (+- tx elements per step) and of its
+// next pair (+ the table entry above), and its tile row y (+- 1); "active" is one unsigned compare on y.  No
+// per-step index arithmetic, no zeroing: the operand loads, the two FMAs and the store are predicated, a lane that
+// has not entered the wavefront yet holds z = 0 (never computed), and a lane's neighbour is only consulted while
+// that neighbour's value is the one the recurrence asks for (lane x is active on diagonal d exactly when lane x-1
+// was on d-1; the tile's first column / row carry zero coefficients).  Per step: 2 SHFL, 2 DFMA, 3 LDS (right-hand
+// side, pair, table entry for the step after next), 1 STS, four integer adds and two compares.
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <class CT> __device__ __forceinline__ CT lds_ct(uint32_t a);
+template <> __device__ __forceinline__ double lds_ct<double>(uint32_t a) { return lds_f64(a); }
+template <> __device__ __forceinline__ float lds_ct<float>(uint32_t a) { return lds_f32(a); }
+__device__ __forceinline__ void sts_ct(uint32_t a, double v) { sts_f64(a, v); }
+__device__ __forceinline__ void sts_ct(uint32_t a, float v) { sts_f32(a, v); }
+template <class CT, class FT> __device__ __forceinline__ void lds_pair(uint32_t a, CT& x, CT& y);
+template <> __device__ __forceinline__ void lds_pair<double, double>(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+template <> __device__ __forceinline__ void lds_pair<double, float>(uint32_t a, double& x, double& y) {
+  float fx, fy;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(fx), "=f"(fy) : "r"(a));
+  x = (double)fx; y = (double)fy;
+}
+template <> __device__ __forceinline__ void lds_pair<float, float>(uint32_t a, float& x, float& y) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
+}
+
 template <class FT, class CT, bool LOWER>
 __device__ __forceinline__ void lattice_steps(int lane, int nlev, int e0, const typename PairOf<FT>::type* __restrict__ pairs,
-                                              int tx, int ty, CT* xl, CT& zprev_io) {
+                                              int tx, int ty, CT* xl, CT& zprev_io, const int* tab) {
   using P = typename PairOf<FT>::type;
-  const int D = tx + ty - 2, ty1 = ty - 1, tx1 = tx - 1, step = LOWER ? tx : -tx;
-  int d = LOWER ? e0 : D - e0;        // anti-diagonal of the current step (warp-uniform)
-  int u = 0;                          // pairs of this chunk consumed by earlier steps (warp-uniform)
-  int xlo = max(0, d - ty1), cnt = min(d, tx1) - xlo + 1;
-  int li = lane + tx * (d - lane);    // this lane's row on the current anti-diagonal (meaningful while active)
-  bool act = (unsigned)(lane - xlo) < (unsigned)cnt;
-  CT r = (CT)0, ca = (CT)0, cb = (CT)0;
-  if (act) { r = xl[li]; const P c = pairs[u + lane - xlo]; ca = (CT)c.x; cb = (CT)c.y; }
-  CT zprev = zprev_io;
-#pragma unroll 2
-  for (int s = 0; s < nlev; ++s) {
-    // operands of the next step (independent of the dependency chain)
-    const int d2 = LOWER ? d + 1 : d - 1;
-    const int u2 = u + cnt;
-    const int xlo2 = max(0, d2 - ty1), cnt2 = min(d2, tx1) - xlo2 + 1;
-    const int li2 = li + step;
-    const bool act2 = (s + 1 < nlev) && (unsigned)(lane - xlo2) < (unsigned)cnt2;
-    CT r2 = (CT)0, ca2 = (CT)0, cb2 = (CT)0;
-    if (act2) { r2 = xl[li2]; const P c = pairs[u2 + lane - xlo2]; ca2 = (CT)c.x; cb2 = (CT)c.y; }
-    // the chain: own previous result (south / north) and the neighbour lane's (west / east)
-    const CT t = r - cb * zprev;
-    const CT zn = LOWER ? __shfl_up_sync(0xffffffffu, zprev, 1) : __shfl_down_sync(0xffffffffu, zprev, 1);
-    const CT z = t - ca * zn;
-    if (act) xl[li] = z;
-    zprev = z;  // inactive lanes: r = ca = cb = 0 gives z = 0
-    d = d2; u = u2; xlo = xlo2; cnt = cnt2; li = li2; act = act2; r = r2; ca = ca2; cb = cb2;
+  const int D = tx + ty - 2;
+  const int d0 = LOWER ? e0 : D - e0;
+  const int* tb = tab + 4 + (LOWER ? 0 : D + 1) + e0;  // tb[s]: pair-pointer increment after step s of this chunk
+  const uint32_t zero_a = smem_u32(tab);              // 16 zero bytes in front of the table
+  const uint32_t uty = (uint32_t)ty;
+  const int dxa = (LOWER ? tx : -tx) * (int)sizeof(CT), dy = LOWER ? 1 : -1;
+  int y = lane < tx ? d0 - lane : -0x40000000;  // lanes beyond the tile never become active
+  uint32_t pa = smem_u32(pairs) + (uint32_t)((lane - max(0, d0 - (ty - 1))) * (int)sizeof(P));
+  uint32_t xa = smem_u32(xl) + (uint32_t)((lane + tx * (d0 - lane)) * (int)sizeof(CT));
+  // operands of a step; a lane outside the wavefront reads zeros, so its z is 0 and nothing has to be predicated
+  // but the store
+  auto fetch = [&](bool act, CT& r, CT& ca, CT& cb) {
+    r = lds_ct<CT>(act ? xa : zero_a);
+    lds_pair<CT, FT>(act ? pa : zero_a, ca, cb);
+  };
+  CT z = zprev_io;
+  auto chain = [&](bool act, uint32_t xs, CT r, CT ca, CT cb) {
+    // neighbour lane's previous result (west / east), own previous result (south / north)
+    const CT zn = LOWER ? __shfl_up_sync(0xffffffffu, z, 1) : __shfl_down_sync(0xffffffffu, z, 1);
+    const CT t = r - cb * z;
+    z = t - ca * zn;
+    if (act) sts_ct(xs, z);
+  };
+  bool act = (uint32_t)y < uty;
+  CT r, ca, cb;
+  fetch(act, r, ca, cb);
+  int inc = tb[0];
+#pragma unroll 4
+  for (int s = 0; s + 1 < nlev; ++s) {
+    const uint32_t xs = xa;
+    const bool act_s = act;
+    pa += (uint32_t)inc; xa += (uint32_t)dxa; y += dy;
+    inc = tb[s + 1];  // used one step from now: the table load is off the address chain
+    act = (uint32_t)y < uty;
+    CT r2, ca2, cb2;
+    fetch(act, r2, ca2, cb2);  // next step's operands: in flight during this step's chain
+    chain(act_s, xs, r, ca, cb);
+    r = r2; ca = ca2; cb = cb2;
   }
-  zprev_io = zprev;
+  chain(act, xa, r, ca, cb);  // the successor of the chunk's last step sits in another ring slot
+  zprev_io = z;
 }
 template <class FT, class CT>
-__device__ __forceinline__ void run_lattice_chunk(int lane, const unsigned char* rec, int tx, int ty, CT* xl, CT& zprev) {
+__device__ __forceinline__ void run_lattice_chunk(int lane, const unsigned char* rec, int tx, int ty, CT* xl, CT& zprev, const int* tab) {
   using P = typename PairOf<FT>::type;
   const uint2 h = *reinterpret_cast<const uint2*>(rec);
   const int nlev = (int)(h.x & 0xffffu), e0 = (int)(h.x >> 16);
   const P* pairs = reinterpret_cast<const P*>(rec + 16);
   if (e0 == 0) zprev = (CT)0;  // first chunk of a factor
-  if ((h.y & 0xffffu) != 0) lattice_steps<FT, CT, true>(lane, nlev, e0, pairs, tx, ty, xl, zprev);
-  else lattice_steps<FT, CT, false>(lane, nlev, e0, pairs, tx, ty, xl, zprev);
+  if (nlev < 1) return;
+  if ((h.y & 0xffffu) != 0) lattice_steps<FT, CT, true>(lane, nlev, e0, pairs, tx, ty, xl, zprev, tab);
+  else lattice_steps<FT, CT, false>(lane, nlev, e0, pairs, tx, ty, xl, zprev, tab);
 }
 
 // GATHER: vectors in the caller's original row order, r scaled by 1/diag(U) while loading.
@@ -237,6 +302,8 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
   unsigned char* ring = mine + xl_bytes + coff_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * a.slot_bytes);
   uint64_t* bar_in = bars + a.stages;
+  int* ltab = reinterpret_cast<int*>(mine + a.warp_smem - a.tab_bytes);  // LATTICE: pair-pointer increments (lattice_fill_tab)
+  int ltx = -1, lty = -1;
   const FT* dinv = reinterpret_cast<const FT*>(a.dinv);
   constexpr bool kBulkVec = !GATHER && sizeof(VT) == sizeof(CT);  // rhs/result move as bulk copies
   if (lane == 0) {
@@ -263,6 +330,10 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
     if (LATTICE) {
       const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.blk + b) + 1);
       tx = d1.z; ty = d1.w;
+      if (tx != ltx || ty != lty) {  // a new tile shape (the tiles at the grid's right / top edge)
+        lattice_fill_tab<FT>(lane, tx, ty, ltab);
+        ltx = tx; lty = ty;
+      }
     }
     CT zprev = (CT)0;
     __syncwarp();
@@ -313,7 +384,7 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
       if (LATTICE) {
         // a lane's next read of xl (its own column) follows its own write: no warp barrier per step; the
         // next chunk's first operands may have been written by this lane only
-        run_lattice_chunk<FT, CT>(lane, rec, tx, ty, xl, zprev);
+        run_lattice_chunk<FT, CT>(lane, rec, tx, ty, xl, zprev, ltab);
         __syncwarp();  // every lane is past its last read of this ring slot
         TSTAMP(9 + 2 * c);
         if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
@@ -375,7 +446,8 @@ int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void*
   a.slot_bytes = ((uint32_t)S.max_chunk_bytes + 127u) & ~127u;
   const uint32_t xl_bytes = ((uint32_t)S.max_rows * sizeof(CT) + 127u) & ~127u;
   const uint32_t coff_bytes = ((uint32_t)S.tab_stride * 4u + 127u) & ~127u;
-  a.warp_smem = xl_bytes + coff_bytes + (uint32_t)a.stages * a.slot_bytes + 128u;
+  a.tab_bytes = S.lattice ? (((uint32_t)(S.max_levels_L + S.max_levels_U) * 4u + 16u + 127u) & ~127u) : 0u;
+  a.warp_smem = xl_bytes + coff_bytes + (uint32_t)a.stages * a.slot_bytes + 128u + a.tab_bytes;
   const int warps = S.warps_per_cta;
   const size_t smem = (size_t)warps * a.warp_smem;
   if (smem > ctx->smem_optin) {
