@@ -92,7 +92,7 @@ struct FbArgs {
   int nblocks, max_rows, stages, tab_stride;
   uint32_t slot_bytes;  // ring slot stride (multiple of 128)
   uint32_t warp_smem;   // bytes of shared memory per warp (multiple of 128)
-  uint32_t tab_bytes;   // LATTICE: increment table at the end of the warp's area (multiple of 128)
+  uint32_t tab_bytes;   // LATTICE: zero page at the end of the warp's area (multiple of 128)
 };
 
 template <class FT> struct PairOf;
@@ -173,39 +173,19 @@ __device__ __forceinline__ void run_steps_generic(int lane, int K, int nst, int 
   }
 }
 
-// LATTICE layout: per-warp table of the pair-pointer increments.  On anti-diagonal d of a tx x ty tile the active
-// lanes are [xlo_d, xlo_d + cnt_d) and lane x finds its pair at index u_d + x - xlo_d of the factor's stream (u_d =
-// pairs of the earlier diagonals), so from one step to the next every lane's pointer advances by the same, warp-
-// uniform amount cnt_d - (xlo_next - xlo_d).  tab[e] = that amount in bytes after step e of L (d = e), tab[nd + e]
-// after step e of U (d = D - e); filled once per tile shape.
-template <class FT>
-__device__ __forceinline__ void lattice_fill_tab(int lane, int tx, int ty, int* tab) {
-  using P = typename PairOf<FT>::type;
-  const int D = tx + ty - 2, ty1 = ty - 1, tx1 = tx - 1, nd = D + 1;
-  if (lane < 4) tab[lane] = 0;  // 16 zero bytes: the operands of lanes outside the wavefront
-  tab += 4;
-  for (int e = lane; e < nd; e += 32) {
-    {
-      const int d = e, xlo = max(0, d - ty1), cnt = min(d, tx1) - xlo + 1, xlo2 = max(0, d + 1 - ty1);
-      tab[e] = (cnt - (xlo2 - xlo)) * (int)sizeof(P);
-    }
-    {
-      const int d = D - e, xlo = max(0, d - ty1), cnt = min(d, tx1) - xlo + 1, xlo2 = max(0, d - 1 - ty1);
-      tab[nd + e] = (cnt - (xlo2 - xlo)) * (int)sizeof(P);
-    }
-  }
-}
-
 // one chunk of the LATTICE layout: whole anti-diagonals of a tx x ty tile, (west|east, south|north) value pairs.
 // The wavefront step is the dependency chain of the whole solve (2 (tx + ty - 1) steps per tile, one warp), and a
 // lone warp issues one instruction every few cycles, so the step is cut down to what the recurrence needs: every
 // lane keeps RUNNING shared-memory addresses of its next right-hand side entry (+- tx elements per step) and of its
-// next pair (+ the table entry above), and its tile row y (+- 1); "active" is one unsigned compare on y.  No
-// per-step index arithmetic, no zeroing: the operand loads, the two FMAs and the store are predicated, a lane that
-// has not entered the wavefront yet holds z = 0 (never computed), and a lane's neighbour is only consulted while
-// that neighbour's value is the one the recurrence asks for (lane x is active on diagonal d exactly when lane x-1
-// was on d-1; the tile's first column / row carry zero coefficients).  Per step: 2 SHFL, 2 DFMA, 3 LDS (right-hand
-// side, pair, table entry for the step after next), 1 STS, four integer adds and two compares.
+// next pair, and its tile row y (+- 1); "active" is one unsigned compare on y.  On anti-diagonal d the active lanes
+// are [xlo_d, xlo_d + cnt_d) and lane x finds its pair at index u_d + x - xlo_d of the factor's stream (u_d = pairs
+// of the earlier diagonals), so every lane's pair pointer advances by the same warp-uniform amount
+// cnt_d - (xlo_next - xlo_d) = min(d, tx-1) + 1 - max(0, d_next - (ty-1)), three integer operations.  A lane outside
+// the wavefront reads its operands from 16 zero bytes, so its z is 0 and only the store is predicated; a lane's
+// neighbour is only consulted while that neighbour's value is the one the recurrence asks for (lane x is active on
+// diagonal d exactly when lane x-1 was on d-1; the tile's first column / row carry zero coefficients).
+// Per step: 2 SHFL, 2 DFMA, 2 LDS (right-hand side, pair), 1 STS, two selects, a compare and a few integer adds.
+// The kernel is bound by the shared-memory pipe (ncu: 12 warps x ~10 wavefronts per step), not by issue or HBM.
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
@@ -230,12 +210,11 @@ template <> __device__ __forceinline__ void lds_pair<float, float>(uint32_t a, f
 
 template <class FT, class CT, bool LOWER>
 __device__ __forceinline__ void lattice_steps(int lane, int nlev, int e0, const typename PairOf<FT>::type* __restrict__ pairs,
-                                              int tx, int ty, CT* xl, CT& zprev_io, const int* tab) {
+                                              int tx, int ty, CT* xl, CT& zprev_io, const int* zero16) {
   using P = typename PairOf<FT>::type;
   const int D = tx + ty - 2;
   const int d0 = LOWER ? e0 : D - e0;
-  const int* tb = tab + 4 + (LOWER ? 0 : D + 1) + e0;  // tb[s]: pair-pointer increment after step s of this chunk
-  const uint32_t zero_a = smem_u32(tab);              // 16 zero bytes in front of the table
+  const uint32_t zero_a = smem_u32(zero16);
   const uint32_t uty = (uint32_t)ty;
   const int dxa = (LOWER ? tx : -tx) * (int)sizeof(CT), dy = LOWER ? 1 : -1;
   int y = lane < tx ? d0 - lane : -0x40000000;  // lanes beyond the tile never become active
@@ -258,13 +237,18 @@ __device__ __forceinline__ void lattice_steps(int lane, int nlev, int e0, const 
   bool act = (uint32_t)y < uty;
   CT r, ca, cb;
   fetch(act, r, ca, cb);
-  int inc = tb[0];
+  // warp-uniform, pre-scaled by the pair size: current diagonal, tx-1, and (ty-1) shifted by the step direction
+  constexpr int PS = (int)sizeof(P);
+  int dS = d0 * PS;
+  const int tx1S = (tx - 1) * PS, offS = (LOWER ? ty - 2 : ty) * PS;  // d_next - (ty-1) = d - (ty-2) going up, d - ty going down
 #pragma unroll 4
   for (int s = 0; s + 1 < nlev; ++s) {
     const uint32_t xs = xa;
     const bool act_s = act;
+    // inc = min(d, tx-1) + 1 - max(0, d_next - (ty-1)),  d_next = d +- 1
+    const int inc = min(dS, tx1S) + PS - max(0, dS - offS);
+    dS += LOWER ? PS : -PS;
     pa += (uint32_t)inc; xa += (uint32_t)dxa; y += dy;
-    inc = tb[s + 1];  // used one step from now: the table load is off the address chain
     act = (uint32_t)y < uty;
     CT r2, ca2, cb2;
     fetch(act, r2, ca2, cb2);  // next step's operands: in flight during this step's chain
@@ -275,15 +259,15 @@ __device__ __forceinline__ void lattice_steps(int lane, int nlev, int e0, const 
   zprev_io = z;
 }
 template <class FT, class CT>
-__device__ __forceinline__ void run_lattice_chunk(int lane, const unsigned char* rec, int tx, int ty, CT* xl, CT& zprev, const int* tab) {
+__device__ __forceinline__ void run_lattice_chunk(int lane, const unsigned char* rec, int tx, int ty, CT* xl, CT& zprev, const int* zero16) {
   using P = typename PairOf<FT>::type;
   const uint2 h = *reinterpret_cast<const uint2*>(rec);
   const int nlev = (int)(h.x & 0xffffu), e0 = (int)(h.x >> 16);
   const P* pairs = reinterpret_cast<const P*>(rec + 16);
   if (e0 == 0) zprev = (CT)0;  // first chunk of a factor
   if (nlev < 1) return;
-  if ((h.y & 0xffffu) != 0) lattice_steps<FT, CT, true>(lane, nlev, e0, pairs, tx, ty, xl, zprev, tab);
-  else lattice_steps<FT, CT, false>(lane, nlev, e0, pairs, tx, ty, xl, zprev, tab);
+  if ((h.y & 0xffffu) != 0) lattice_steps<FT, CT, true>(lane, nlev, e0, pairs, tx, ty, xl, zprev, zero16);
+  else lattice_steps<FT, CT, false>(lane, nlev, e0, pairs, tx, ty, xl, zprev, zero16);
 }
 
 // GATHER: vectors in the caller's original row order, r scaled by 1/diag(U) while loading.
@@ -302,8 +286,8 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
   unsigned char* ring = mine + xl_bytes + coff_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * a.slot_bytes);
   uint64_t* bar_in = bars + a.stages;
-  int* ltab = reinterpret_cast<int*>(mine + a.warp_smem - a.tab_bytes);  // LATTICE: pair-pointer increments (lattice_fill_tab)
-  int ltx = -1, lty = -1;
+  int* zero16 = reinterpret_cast<int*>(mine + a.warp_smem - a.tab_bytes);  // LATTICE: operands of lanes outside the wavefront
+  if (LATTICE && lane < 4) zero16[lane] = 0;
   const FT* dinv = reinterpret_cast<const FT*>(a.dinv);
   constexpr bool kBulkVec = !GATHER && sizeof(VT) == sizeof(CT);  // rhs/result move as bulk copies
   if (lane == 0) {
@@ -318,8 +302,10 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
   // descriptors, chunk tables, the factor stream) is touched, so the first chunks of every warp are already on
   // their way while the SpMV that produces `in` is still running.
   bool waited = false;
-  uint32_t g0 = 0;   // ring-global index of the current block's first chunk (monotone per warp)
-  uint32_t nin = 0;  // bulk loads of a right-hand side so far (phase of bar_in)
+  uint32_t st = 0;      // ring slot of the next chunk to consume (runs on across the blocks of this warp)
+  uint32_t phases = 0;  // bit s: parity of the next completion of slot s
+  uint32_t nin = 0;     // bulk loads of a right-hand side so far (phase of bar_in)
+  const uint32_t nst = (uint32_t)a.stages;
   for (int b = blockIdx.x * nw + wid; b < a.nblocks; b += gridDim.x * nw) {
     // descriptor and chunk table are fetched in one round trip (the table has a fixed stride)
     TSTAMP(0);
@@ -330,29 +316,28 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
     if (LATTICE) {
       const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.blk + b) + 1);
       tx = d1.z; ty = d1.w;
-      if (tx != ltx || ty != lty) {  // a new tile shape (the tiles at the grid's right / top edge)
-        lattice_fill_tab<FT>(lane, tx, ty, ltab);
-        ltx = tx; lty = ty;
-      }
     }
     CT zprev = (CT)0;
     __syncwarp();
     TSTAMP(1);
-    auto issue = [&](int c) {  // lane 0 only
-      const uint32_t st = (g0 + (uint32_t)c) % (uint32_t)a.stages;
+    auto issue = [&](int c, uint32_t slot) {  // lane 0 only
       const uint32_t o0 = coff[c], bytes = (coff[c + 1] - o0) * 16u;
-      mbar_expect_tx(&bars[st], bytes);
-      bulk_g2s(ring + (size_t)st * a.slot_bytes, a.stream + (size_t)o0 * 16u, bytes, &bars[st]);
+      mbar_expect_tx(&bars[slot], bytes);
+      bulk_g2s(ring + (size_t)slot * a.slot_bytes, a.stream + (size_t)o0 * 16u, bytes, &bars[slot]);
     };
     const bool bulk_vec = kBulkVec && (((uint32_t)row0 * sizeof(VT)) & 15u) == 0 && (((uint32_t)nb * sizeof(VT)) & 15u) == 0 && nb > 0;
-    if (lane == 0) {
-      for (int c = 0; c < nch && c < a.stages; ++c) issue(c);  // factor stream: constant data, may precede pdl_wait
+    if (lane == 0) {  // factor stream: constant data, may precede pdl_wait
+      uint32_t sl = st;
+      for (int c = 0; c < nch && c < a.stages; ++c) { issue(c, sl); sl = sl + 1 == nst ? 0u : sl + 1; }
     }
     if (!waited) {
       pdl_wait();
       waited = true;
       if (skip && *skip) {  // a skipped launch must still drain the bulk copies it started
-        if (lane == 0) for (int c = 0; c < nch && c < a.stages; ++c) mbar_wait(&bars[(g0 + (uint32_t)c) % (uint32_t)a.stages], ((g0 + (uint32_t)c) / (uint32_t)a.stages) & 1u);
+        if (lane == 0) {
+          uint32_t sl = st;
+          for (int c = 0; c < nch && c < a.stages; ++c) { mbar_wait(&bars[sl], (phases >> sl) & 1u); sl = sl + 1 == nst ? 0u : sl + 1; }
+        }
         return;
       }
     }
@@ -376,18 +361,18 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
       }
       __syncwarp();
     }
-    for (int c = 0; c < nch; ++c) {
-      const uint32_t g = g0 + (uint32_t)c, st = g % (uint32_t)a.stages;
-      mbar_wait(&bars[st], (g / (uint32_t)a.stages) & 1u);
+    for (int c = 0; c < nch; ++c, st = st + 1 == nst ? 0u : st + 1) {
+      mbar_wait(&bars[st], (phases >> st) & 1u);
+      phases ^= 1u << st;
       TSTAMP(8 + 2 * c);
       const unsigned char* rec = ring + (size_t)st * a.slot_bytes;
       if (LATTICE) {
         // a lane's next read of xl (its own column) follows its own write: no warp barrier per step; the
         // next chunk's first operands may have been written by this lane only
-        run_lattice_chunk<FT, CT>(lane, rec, tx, ty, xl, zprev, ltab);
+        run_lattice_chunk<FT, CT>(lane, rec, tx, ty, xl, zprev, zero16);
         __syncwarp();  // every lane is past its last read of this ring slot
         TSTAMP(9 + 2 * c);
-        if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
+        if (lane == 0 && c + a.stages < nch) issue(c + a.stages, st);
         continue;
       }
       const uint2 h = *reinterpret_cast<const uint2*>(rec);
@@ -409,7 +394,7 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
       }
       // every lane is past its last read of this ring slot: refill it
       TSTAMP(9 + 2 * c);
-      if (lane == 0 && c + a.stages < nch) issue(c + a.stages);
+      if (lane == 0 && c + a.stages < nch) issue(c + a.stages, st);
     }
     TSTAMP(4);
     if (bulk_vec) {
@@ -426,7 +411,6 @@ __global__ void __launch_bounds__(128) trsv_block_fused(FbArgs a, const VT* __re
     }
     __syncwarp();
     TSTAMP(5);
-    g0 += (uint32_t)nch;
   }
 #ifdef BG_TRSV_TIMING
   if (blockIdx.x * nw + wid == g_trsv_probe && lane == 0) { if (kBulkVec) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); g_trsv_t[6] = gt_ns(); }
@@ -446,7 +430,7 @@ int fused_run(bg_context_t ctx, const FusedBlockDev& S, bool gather, const void*
   a.slot_bytes = ((uint32_t)S.max_chunk_bytes + 127u) & ~127u;
   const uint32_t xl_bytes = ((uint32_t)S.max_rows * sizeof(CT) + 127u) & ~127u;
   const uint32_t coff_bytes = ((uint32_t)S.tab_stride * 4u + 127u) & ~127u;
-  a.tab_bytes = S.lattice ? (((uint32_t)(S.max_levels_L + S.max_levels_U) * 4u + 16u + 127u) & ~127u) : 0u;
+  a.tab_bytes = S.lattice ? 128u : 0u;
   a.warp_smem = xl_bytes + coff_bytes + (uint32_t)a.stages * a.slot_bytes + 128u + a.tab_bytes;
   const int warps = S.warps_per_cta;
   const size_t smem = (size_t)warps * a.warp_smem;
