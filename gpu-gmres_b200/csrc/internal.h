@@ -274,6 +274,7 @@ struct bg_precond_s {
 struct bg_solver_s {
   bg_context_t ctx = nullptr;
   int n = 0, m = 0, dtype = BG_F64;
+  int last_m = 0;  // restart length of the last solve (H is laid out with ld = last_m + 1)
   int64_t ld = 0;
   bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb, bp, xp, red;
   bg::DevBuf mgs_slots;     // packets of the fused MGS step's grid-wide sums

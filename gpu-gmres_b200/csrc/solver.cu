@@ -1025,6 +1025,7 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
   }
   GmresDev st = S->dev;
   st.m = m;  // H leading dimension follows the active restart length
+  S->last_m = m;
   st.hist_cap = std::min(std::max(o.history_cap, 0), kHistCap);
   const int chunk = std::max(1, o.poll_chunk);
 
@@ -1141,7 +1142,7 @@ extern "C" int bg_solver_get_history(bg_solver_t S, double* hist, int cap, int* 
 }
 extern "C" int bg_solver_get_hessenberg(bg_solver_t S, double* H, double* s, double* cs, double* sn) {
   if (!S) return BG_ERR_ARG;
-  const int m = S->m;
+  const int m = S->last_m > 0 ? S->last_m : S->m;  // the layout of the last solve (its restart length may be below the workspace's)
   BG_CUDA(cudaStreamSynchronize(S->ctx->stream));
   if (H) BG_CUDA(cudaMemcpy(H, S->dev.H, 8 * (size_t)(m + 1) * m, cudaMemcpyDeviceToHost));
   if (s) BG_CUDA(cudaMemcpy(s, S->dev.s, 8 * (size_t)(m + 1), cudaMemcpyDeviceToHost));

@@ -23,16 +23,33 @@ struct bg_transient_s {
   bg_precond_t M = nullptr;
   int n = 0, nsrc = 0, dtype = BG_F64;
   DevBuf pwl_ptr, pwl_t, pwl_v, u, bu, rhs, probe_idx, probe_out;
+  DevBuf pulse_of, pulse_t, pulse_v;  // per source: index of its PULSE record or -1 (piecewise linear); records: 5 times, 2 values
+  bool has_pulse = false;
   int nprobe = 0, probe_cap = 0;
 };
 
 namespace {
 // piecewise-linear sources, held at the end values outside the table (interp1, src/interp.cpp; gen_PWLut*, src/kernels.cu:154-230)
+// PULSE sources (gen_PULSEut_kernel, src/kernels.cu:224-246): record (td, tr, tf, tw, tp), (vlo, vhi); periodic in tp
 template <class VT>
 __global__ void pwl_eval_kernel(int nsrc, const int* __restrict__ ptr, const double* __restrict__ tt, const double* __restrict__ vv,
+                                const int* __restrict__ pulse_of, const double* __restrict__ pt, const double* __restrict__ pv,
                                 double t, VT* __restrict__ u) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nsrc) return;
+  const int pr = pulse_of ? pulse_of[k] : -1;
+  if (pr >= 0) {
+    const double td = pt[5 * pr], tr = pt[5 * pr + 1], tf = pt[5 * pr + 2], tw = pt[5 * pr + 3], tp = pt[5 * pr + 4];
+    const double vlo = pv[2 * pr], vhi = pv[2 * pr + 1];
+    double mt = t - floor(t / tp) * tp, value;
+    if (mt < td) value = vlo;
+    else if (mt < td + tr) value = vlo + (mt - td) * (vhi - vlo) / tr;
+    else if (mt < td + tr + tw) value = vhi;
+    else if (mt < td + tr + tw + tf) value = vhi - (mt - td - tr - tw) * (vhi - vlo) / tf;
+    else value = vlo;
+    u[k] = (VT)value;
+    return;
+  }
   const int lb = ptr[k], ub = ptr[k + 1];
   double val = 0.0;
   if (ub > lb) {
@@ -95,6 +112,25 @@ extern "C" int bg_transient_create(bg_context_t ctx, bg_solver_t S, bg_matrix_t 
   return BG_OK;
 }
 
+extern "C" int bg_transient_set_pulse(bg_transient_t T, int npulse, const int* src_index, const double* pulse_time, const double* pulse_val) {
+  if (!T || npulse < 0 || (npulse > 0 && (!src_index || !pulse_time || !pulse_val))) return BG_ERR_ARG;
+  BG_CUDA(cudaSetDevice(T->ctx->device));
+  std::vector<int> of(std::max(T->nsrc, 1), -1);
+  for (int k = 0; k < npulse; ++k) {
+    if (src_index[k] < 0 || src_index[k] >= T->nsrc) { set_error("bg_transient_set_pulse: source %d out of range", src_index[k]); return BG_ERR_ARG; }
+    const double* t = pulse_time + 5 * k;
+    if (!(t[4] > 0) || !(t[1] > 0) || !(t[2] > 0) || t[0] < 0 || t[3] < 0) { set_error("bg_transient_set_pulse: record %d needs tp, tr, tf > 0 and td, tw >= 0", k); return BG_ERR_ARG; }
+    of[src_index[k]] = k;
+  }
+  cudaStream_t s = T->ctx->stream;
+  BG_TRY(T->pulse_of.upload(of.data(), sizeof(int) * of.size(), s));
+  BG_TRY(T->pulse_t.upload(pulse_time, sizeof(double) * 5 * (size_t)std::max(npulse, 1), s));
+  BG_TRY(T->pulse_v.upload(pulse_val, sizeof(double) * 2 * (size_t)std::max(npulse, 1), s));
+  BG_CUDA(cudaStreamSynchronize(s));
+  T->has_pulse = npulse > 0;
+  return BG_OK;
+}
+
 extern "C" int bg_transient_destroy(bg_transient_t T) {
   if (!T) return BG_OK;
   if (T->ctx) cudaStreamSynchronize(T->ctx->stream);
@@ -125,8 +161,9 @@ extern "C" int bg_transient_run(bg_transient_t T, void* d_x, double t0, double h
     const double t = t0 + h * i;
     if (T->nsrc > 0) {
       const int g = (T->nsrc + 255) / 256;
-      if (T->dtype == BG_F32) pwl_eval_kernel<float><<<g, 256, 0, s>>>(T->nsrc, T->pwl_ptr.as<int>(), T->pwl_t.as<double>(), T->pwl_v.as<double>(), t, T->u.as<float>());
-      else pwl_eval_kernel<double><<<g, 256, 0, s>>>(T->nsrc, T->pwl_ptr.as<int>(), T->pwl_t.as<double>(), T->pwl_v.as<double>(), t, T->u.as<double>());
+      const int* pof = T->has_pulse ? T->pulse_of.as<int>() : nullptr;
+      if (T->dtype == BG_F32) pwl_eval_kernel<float><<<g, 256, 0, s>>>(T->nsrc, T->pwl_ptr.as<int>(), T->pwl_t.as<double>(), T->pwl_v.as<double>(), pof, T->pulse_t.as<double>(), T->pulse_v.as<double>(), t, T->u.as<float>());
+      else pwl_eval_kernel<double><<<g, 256, 0, s>>>(T->nsrc, T->pwl_ptr.as<int>(), T->pwl_t.as<double>(), T->pwl_v.as<double>(), pof, T->pulse_t.as<double>(), T->pulse_v.as<double>(), t, T->u.as<double>());
       ctx->launches++;
     } else {
       BG_CUDA(cudaMemsetAsync(T->u.p, 0, T->u.bytes, s));

@@ -420,8 +420,9 @@ class Solver:
         _chk(lib().bg_solver_get_history(self.h, _p(h), n.value, C.byref(n)))
         return h[: n.value]
 
-    def hessenberg(self):
-        m = self.m
+    def hessenberg(self, m=None):
+        """m = restart length of the last solve (default: the workspace's)"""
+        m = self.m if m is None else m
         H, s, cs, sn = np.zeros((m, m + 1)), np.zeros(m + 1), np.zeros(m + 1), np.zeros(m + 1)
         _chk(lib().bg_solver_get_hessenberg(self.h, _p(H), _p(s), _p(cs), _p(sn)))
         return H.T.copy(), s, cs, sn  # H[k, i]
@@ -461,6 +462,14 @@ class Transient:
         _chk(lib().bg_transient_create(ctx.h, S.h, A.h, M.h, n, _p(_i32(c_over_h[0])), _p(_i32(c_over_h[1])), _p(cv), len(pwl),
                                        _p(_i32(B[0])), _p(_i32(B[1])), _p(bv), F64, _p(ptr), _p(tt), _p(vv), len(pi),
                                        _p(pi) if len(pi) else None, C.byref(self.h)))
+
+    def set_pulse(self, src_index, pulse_time, pulse_val):
+        """sources src_index[k] become PULSE sources: pulse_time[k] = (td, tr, tf, tw, tp), pulse_val[k] = (vlo, vhi)"""
+        idx = np.ascontiguousarray(src_index, dtype=np.int32)
+        pt = np.ascontiguousarray(pulse_time, dtype=np.float64).reshape(-1)
+        pv = np.ascontiguousarray(pulse_val, dtype=np.float64).reshape(-1)
+        assert len(pt) == 5 * len(idx) and len(pv) == 2 * len(idx)
+        _chk(lib().bg_transient_set_pulse(self.h, len(idx), _p(idx), _p(pt), _p(pv)))
 
     def run(self, d_x, t0, h, nsteps, opts):
         st = TransientStats()

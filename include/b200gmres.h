@@ -263,7 +263,8 @@ BG_API int bg_gmres_solve(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_pre
 BG_API int bg_gmres_solve_host(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* h_b,
                                void* h_x, const bg_gmres_opts* o, bg_gmres_result* r);
 BG_API int bg_solver_get_history(bg_solver_t S, double* hist, int cap, int* len);
-/* Hessenberg / Givens state of the last cycle (H col-major ld=m+1, s, cs, sn) */
+/* Hessenberg / Givens state of the last cycle (H col-major, ld = m+1 with m = the restart length of the last solve,
+   i.e. bg_gmres_opts.m clamped to the workspace's; s, cs, sn: m+1 entries each) */
 BG_API int bg_solver_get_hessenberg(bg_solver_t S, double* H, double* s, double* cs, double* sn);
 /* diagnostic: one fused orthogonalisation step (dots + update) against j basis columns on the
    solver's own workspace; used by bench.py to time the dominant kernel pair in isolation */
@@ -300,6 +301,10 @@ BG_API int bg_transient_create(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, b
                                const double* pwl_t, const double* pwl_v, int nprobe, const int* probe_idx,
                                bg_transient_t* T);
 /* d_x: x(t0) on entry, x(t0 + nsteps h) on return; h_probe (may be NULL): [nsteps][nprobe] sampled node values */
+/* PULSE sources (gen_PULSEut_kernel, src/kernels.cu:224-246): source src_index[k] follows the periodic trapezoid
+   pulse_time[5k..] = (td, tr, tf, tw, tp), pulse_val[2k..] = (vlo, vhi) instead of its piecewise-linear table */
+BG_API int bg_transient_set_pulse(bg_transient_t T, int npulse, const int* src_index, const double* pulse_time,
+                                  const double* pulse_val);
 BG_API int bg_transient_run(bg_transient_t T, void* d_x, double t0, double h, int nsteps, const bg_gmres_opts* o,
                             bg_transient_stats* st, double* h_probe);
 BG_API int bg_transient_destroy(bg_transient_t T);

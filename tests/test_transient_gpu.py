@@ -72,3 +72,77 @@ def test_transient_matches_host_time_stepping(bg, ctx, dtc):
     r_dc = S.solve(Am, M, db.data_ptr(), dc.data_ptr(), bg.gmres_opts(m=32, tol=tol, max_iter=500, orth=bg.ORTH_MGS))
     assert st.iters_total / nsteps < r_dc.iters
     T.close(); S.close(); M.close(); Am.close()
+
+
+def pulse_value(t, td, tr, tf, tw, tp, vlo, vhi):
+    """gen_PULSEut_kernel (src/kernels.cu:224-246), restated for one time"""
+    mt = t - np.floor(t / tp) * tp
+    if mt < td:
+        return vlo
+    if mt < td + tr:
+        return vlo + (mt - td) * (vhi - vlo) / tr
+    if mt < td + tr + tw:
+        return vhi
+    if mt < td + tr + tw + tf:
+        return vhi - (mt - td - tr - tw) * (vhi - vlo) / tf
+    return vlo
+
+
+def test_transient_pulse_sources(bg, ctx):
+    """PULSE current sources (periodic trapezoids, src/kernels.cu:224-246) next to a piecewise-linear one, in the
+    device-resident loop, against host time stepping with direct solves."""
+    from b200gmres import synth
+
+    nx, ny = 32, 24
+    rp, ci, v, b0 = synth.pg2d(nx, ny, seed=47, c_over_h=0.3)
+    _, _, v0, _ = synth.pg2d(nx, ny, seed=47, c_over_h=0.0)
+    n = len(rp) - 1
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    Ch = sp.csr_matrix(A - sp.csr_matrix((v0, ci, rp), shape=(n, n)))
+    Ch.eliminate_zeros(); Ch.sort_indices()
+    rng = np.random.default_rng(9)
+    nsrc = 4
+    rows, cols, vals = [], [], []
+    for k in range(3):
+        nodes = rng.choice(n, size=20, replace=False)
+        rows += list(nodes); cols += [k] * len(nodes); vals += list(-rng.uniform(0.5e-3, 2e-3, size=len(nodes)))
+    nzb = np.flatnonzero(b0)
+    rows += list(nzb); cols += [3] * len(nzb); vals += list(b0[nzb])
+    B = sp.csr_matrix((vals, (rows, cols)), shape=(n, nsrc)); B.sort_indices()
+    pwl = [(np.array([0.0]), np.array([0.0])), (np.array([0.0, 4.0, 6.0]), np.array([0.0, 1.0, 0.5])),
+           (np.array([0.0]), np.array([0.0])), (np.array([0.0]), np.array([1.0]))]
+    pulses = {0: ((0.7, 0.5, 0.9, 1.3, 4.0), (0.1, 1.7)), 2: ((0.0, 0.25, 0.25, 0.5, 1.5), (-0.4, 0.8))}
+    h, nsteps = 0.3, 40
+
+    def u_of(t):
+        u = np.array([np.interp(t, tt, vv) for tt, vv in pwl])
+        for k, (tm, vl) in pulses.items():
+            u[k] = pulse_value(t, *tm, *vl)
+        return u
+
+    lu = spla.splu(A.tocsc())
+    x_ref = lu.solve(B @ u_of(0.0))
+    x0 = x_ref.copy()
+    probes = [1, n // 2]
+    probe_ref = np.zeros((nsteps, len(probes)))
+    for i in range(1, nsteps + 1):
+        x_ref = lu.solve(B @ u_of(h * i) + Ch @ x_ref)
+        probe_ref[i - 1] = x_ref[probes]
+    Am = bg.Matrix(ctx, rp, ci, v, dtype=1)
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=1)
+    S = bg.Solver(ctx, n, 32, dtype=1)
+    T = bg.Transient(ctx, S, Am, M, (Ch.indptr, Ch.indices, Ch.data), (B.indptr, B.indices, B.data), pwl, probes)
+    T.set_pulse(list(pulses), [pulses[k][0] for k in pulses], [pulses[k][1] for k in pulses])
+    with pytest.raises(bg.BgError):
+        T.set_pulse([nsrc], [(0, 1, 1, 1, 1)], [(0, 1)])       # source index out of range
+    with pytest.raises(bg.BgError):
+        T.set_pulse([0], [(0, 1, 1, 1, 0.0)], [(0, 1)])        # period must be positive
+    dx = torch.from_numpy(x0).cuda()
+    torch.cuda.synchronize()
+    rc, st, probe = T.run(dx.data_ptr(), 0.0, h, nsteps, bg.gmres_opts(m=32, tol=1e-10, max_iter=500, orth=bg.ORTH_MGS))
+    ctx.sync()
+    x = dx.cpu().numpy()
+    assert rc == 0 and st.not_converged == 0
+    assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+    assert np.abs(probe - probe_ref).max() <= 1e-7 * np.abs(probe_ref).max()
+    T.close(); S.close(); M.close(); Am.close()
