@@ -41,6 +41,17 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_JSON_FD = None  # N > 1: duplicate of the original stdout (descriptor 1 itself is pointed at stderr, see main)
+
+
+def emit(line):
+    """the ONE JSON line of this run, on the original stdout"""
+    text = json.dumps(line) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text.encode())
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gpu-gmres_b200", "python"))
 
@@ -235,7 +246,7 @@ def run_reference(args, rank):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -249,11 +260,15 @@ def main():
         return
 
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's log goes to stderr, at INFO so that the communicator's rank
-        # count and the transports it picked are visible to whoever runs this
+        # rank 0 prints ONE JSON line on stdout.  NCCL logs to the process's stdout, so file descriptor 1 is pointed at
+        # stderr for everything but that line (kept on a duplicate of the original descriptor); the log runs at INFO so
+        # that the communicator's rank count and the transports it picked are visible to whoever runs this
+        global _JSON_FD
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG", os.environ.get("BG_NCCL_DEBUG", "INFO"))
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import torch
     import torch.distributed as dist
@@ -289,7 +304,7 @@ def main():
         if not args.no_configs1:
             line["configs1"] = run_split_ilupp(args, local, 1304, min(args.steps, 10))
         line["configs0"] = run_configs0(args, local)
-    print(json.dumps(line))
+    emit(line)
 
 
 def _summary(sec, extra=()):
@@ -613,6 +628,7 @@ def run_dist(args, rank, world, local):
     part = np.repeat(np.arange(world, dtype=np.int32), np.diff(ys) * nx)
     t_setup = time.perf_counter()
     plan = bg.DistPlan(rp, ci, v, world, rank, part)
+    t_plan = time.perf_counter() - t_setup
     ids = [bg.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     ctx = bg.Context(local)
@@ -730,11 +746,11 @@ def run_dist(args, rank, world, local):
                      "backend": ("peer-memory kernels over NVLink (CUDA IPC windows): all-reduce fused into dots_kernel, halo = one gather+peer-store kernel"
                                  if info.transport == bg.TRANSPORT_P2P else "NCCL send/recv + allreduce on the solver stream")},
             "phases_rank0": phases, "comm_us_per_op_rank0": comm_us,
-            "roofline": None, "setup_s": t_setup,
+            "roofline": None, "setup_s": t_setup, "setup_plan_s": t_plan,
             "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     D.close(); plan.close(); ctx.close()
     dist.destroy_process_group()
 

@@ -31,6 +31,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -309,6 +311,17 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
   *out = nullptr;
   BG_CUDA(cudaSetDevice(ctx->device));
   const DistPlan<double>& p = P->p;
+  // B200GMRES_SETUP_TIMING=1: wall-clock of the setup stages on stderr (development aid)
+  static const bool timing = [] { const char* e = getenv("B200GMRES_SETUP_TIMING"); return e && e[0] == '1'; }();
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_prev = now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const double t = now();
+    std::fprintf(stderr, "[bg_dist_create rank %d] %-28s %.3f s\n", p.rank, what, t - t_prev);
+    t_prev = t;
+  };
   bg_dist_t D = new bg_dist_s;
   D->ctx = ctx; D->nranks = p.nranks; D->rank = p.rank; D->dtype = dtype; D->n_local = p.n_local; D->n_halo = p.n_halo;
   D->n_global = p.n_global; D->nbr = p.nbr; D->recv_ptr = p.recv_ptr; D->send_ptr = p.send_ptr;
@@ -322,9 +335,11 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
       ncclResult_t r = N.CommInitRank(&D->comm, p.nranks, uid, p.rank);
       if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", N.GetErrorString(r)); rc = BG_ERR_COMM; break; }
     }
+    lap("ncclCommInitRank");
     // local rows: own columns then halo slots
     rc = matrix_create_internal(ctx, p.n_local, p.n_local + p.n_halo, p.A.rp, p.A.ci, p.A.v.data(), BG_F64, dtype, BG_SPMV_AUTO, &D->A);
     if (rc < 0) break;
+    lap("local matrix");
     // block-Jacobi ILU of the own diagonal block (no communication in the triangular solves)
     std::vector<int> drp(p.n_local + 1, 0), dci;
     std::vector<double> dv;
@@ -333,6 +348,7 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
         if (p.A.ci[q] < p.n_local) { dci.push_back(p.A.ci[q]); dv.push_back(p.A.v[q]); }
       drp[i + 1] = (int)dci.size();
     }
+    lap("diagonal block");
     bg_precond_opts o;
     bg_precond_opts_default(&o);
     if (po) o = *po;
@@ -340,8 +356,10 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
     rc = use_ilut ? bg_precond_create_ilut(ctx, p.n_local, drp.data(), dci.data(), dv.data(), BG_F64, dtype, &o, &D->M)
                   : bg_precond_create_ilu0(ctx, p.n_local, drp.data(), dci.data(), dv.data(), BG_F64, dtype, &o, &D->M);
     if (rc < 0) break;
+    lap("block-Jacobi ILU");
     rc = solver_create_internal(ctx, p.n_local, m, dtype, p.n_halo, &D->S);
     if (rc < 0) break;
+    lap("workspace");
     // the solver works in the preconditioner's block-major order: send lists follow
     std::vector<int> inv(p.n_local), sidx(p.send_idx.size());
     for (int i = 0; i < p.n_local; ++i) inv[D->M->fb.h_perm[i]] = i;
@@ -353,6 +371,7 @@ extern "C" int bg_dist_create(bg_context_t ctx, bg_dist_plan_t P, const void* id
     D->send_count = (int)sidx.size();
     cudaStreamSynchronize(ctx->stream);
     if (p.nranks > 1) { rc = setup_p2p(D); if (rc < 0) break; }
+    lap("send lists + peer windows");
   } while (false);
   if (rc < 0) { bg_dist_destroy(D); return rc; }
   *out = D;
