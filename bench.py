@@ -83,6 +83,7 @@ def parse():
     ap.add_argument("--ilut-lfil", type=int, default=3)
     ap.add_argument("--factor-dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--orth", default="cgs", choices=["mgs", "cgs", "cgs2"])
+    ap.add_argument("--basis", default="f64", choices=["f64", "f32"], help="storage of the Krylov basis (f32: opt-in mixed precision, N=1, CGS)")
     ap.add_argument("--eta", type=float, default=0.1, help="CGS re-orthogonalisation threshold (DGKS): second pass when ||w'|| < eta ||w||")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1: peer-memory kernels over NVLink (default) or the NCCL baseline")
@@ -267,7 +268,8 @@ def main():
         sys.stdout.flush()
         _JSON_FD = os.dup(1)
         os.dup2(2, 1)
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("BG_NCCL_DEBUG", "INFO"))
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):  # (this image exports NCCL_DEBUG=VERSION)
+            os.environ["NCCL_DEBUG"] = os.environ.get("BG_NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
 
     import torch
@@ -279,7 +281,19 @@ def main():
         run_dist(args, rank, world, local)
         return
 
-    line = run_single(args, local, args.nx, "ilu0" if args.precond == "ilu0" else "ilut", args.schedule, args.orth, args.steps, headline=True)
+    line = run_single(args, local, args.nx, "ilu0" if args.precond == "ilu0" else "ilut", args.schedule, args.orth, args.steps, headline=True,
+                      keep_x=not args.quick, basis=args.basis)
+    x_head = line.pop("_x", None)
+    if not args.quick and args.basis == "f64" and args.orth != "mgs":
+        # opt-in mixed-precision Krylov basis (FP32 columns under FP64 vectors) on the headline system: never the headline,
+        # reported next to it with its distance from the all-FP64 run
+        mb = run_single(args, local, args.nx, "ilu0" if args.precond == "ilu0" else "ilut", args.schedule, args.orth, min(args.steps, 5),
+                        headline=False, keep_x=True, basis="f32")
+        sm = _summary(mb, extra=("iteration_roofline",))
+        sm["x_vs_fp64_basis"] = float(np.linalg.norm(mb["_x"] - x_head) / np.linalg.norm(x_head))
+        sm["true_rel_residual_fp64_basis"] = line["true_rel_residual"]
+        sm["iters_fp64_basis"] = line["iters"]
+        line["fp32_basis_opt_in"] = sm
     if not args.quick:
         other = "level" if args.schedule == "block" else "block"
         sec = run_single(args, local, args.nx, "ilu0", other, args.orth, min(args.steps, 5), headline=False)
@@ -338,7 +352,7 @@ def _time_solves(torch, ctx, stream, fn, k):
     return e0.elapsed_time(e1), r, ctx.launches - l0
 
 
-def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, keep_x=False):
+def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, keep_x=False, basis="f64"):
     import torch
 
     import b200gmres as bg
@@ -358,7 +372,7 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
         o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
-    S = bg.Solver(ctx, n, 32, dtype=bg.F64)
+    S = bg.Solver(ctx, n, 32, dtype=bg.F64, basis_dtype=bg.F32 if basis == "f32" else bg.F64)
     orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[orth_name]
     opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
 
@@ -433,8 +447,12 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
             kernels["dots_kernel+update_kernel (strict MGS, i+1 pairs)"] = (st.orth_ms, st.orth_bytes, st.orth_calls, moved)
     elif st.dots_calls == 0:
         # fused step: one cooperative launch per inner iteration (projections + Givens epilogue + v_j)
+        ob = st.dots_bytes + st.update_bytes
+        if basis == "f32":  # (2j) 4-byte basis reads, w twice, the new vector once as f64 and once as f32
+            it = max(rprof.iters_done, 1)
+            ob = sum((2 * (t % 32 + 1) * 4 + 2 * s8 + s8 + 4) * n for t in range(it))
         kernels["orth_kernel (fused: V^T w, w.w, Givens, v_j = (w - V h)/||.||; TMA-staged tiles reused from shared memory / L2)"] = (
-            st.orth_ms, st.dots_bytes + st.update_bytes, st.orth_calls, st.dots_bytes + st.update_bytes)
+            st.orth_ms, st.dots_bytes + st.update_bytes, st.orth_calls, ob)
     else:
         kernels["dots_kernel (V^T w and w.w, TMA-staged tiles)"] = (st.dots_ms, st.dots_bytes, st.dots_calls, st.dots_bytes)
         kernels["update_kernel (w - V h, normalised, TMA-staged tiles)"] = (st.update_ms, st.update_bytes, st.update_calls, st.update_bytes)
@@ -471,7 +489,7 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
                         "operator": ("block-Jacobi ILU tiles (changes the preconditioner: iteration drift reported through iters)" if schedule == "block"
                                      else "the reference's global factors, getLevel dependencies"),
                         "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "levels": [pinfo.levelsL, pinfo.levelsU],
-                        "factor_dtype": args.factor_dtype, "orth": orth_name, "reorth_eta": args.eta,
+                        "factor_dtype": args.factor_dtype, "basis_dtype": basis, "orth": orth_name, "reorth_eta": args.eta,
                         "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
                         "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
         "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),

@@ -214,6 +214,11 @@ bool mgs_fused_supported(bg_context_t ctx, int n, int m);
 size_t mgs_slot_bytes(bg_context_t ctx, int m);
 int launch_mgs(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int i, const void* w, void* out, const GmresDev& st,
                void* slots, unsigned seq);
+// mixed-precision basis (FP64 work vectors, FP32 basis columns; orth.cu)
+int launch_orth_mixed(bg_context_t ctx, int n, const float* V32, int64_t ld, int j, const double* w, double* out, float* out_b,
+                      const GmresDev& st, int inner_i, int orth_mode);
+int launch_round_store(bg_context_t ctx, int n, double* v, float* v32, const int* skip);
+int launch_axpy_basis(bg_context_t ctx, int n, const float* V32, int64_t ld, int k, const double* y, double* x, const GmresDev& st, int force);
 int launch_finalize(bg_context_t ctx, const GmresDev& st, int fin, int inner_i, int mgs_k, int orth_mode, int need_reorth,
                     int j, const double* red_in);
 int launch_pack(bg_context_t ctx, int dtype, int cnt, const int* idx, const void* v, void* buf, const int* skip);
@@ -275,6 +280,8 @@ struct bg_solver_s {
   bg_context_t ctx = nullptr;
   int n = 0, m = 0, dtype = BG_F64;
   int last_m = 0;  // restart length of the last solve (H is laid out with ld = last_m + 1)
+  int basis_dtype = BG_F64;  // storage type of V; != dtype: mixed-precision basis (FP64 work vectors, FP32 basis)
+  bg::DevBuf vcur;           // mixed basis: working (dtype) copy of the newest basis vector, the SpMV's input
   int64_t ld = 0;
   bg::DevBuf V, w, ww, r, rr, bb, yv, state, hx, hb, bp, xp, red;
   bg::DevBuf mgs_slots;     // packets of the fused MGS step's grid-wide sums
@@ -303,7 +310,7 @@ int gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precon
                        const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* out, DistHooks* dh);
 int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
                            const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out);
-int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out);
+int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out, int basis_dtype = -1);
 // factor.cu: block-Jacobi ILU(0) of the tiles of a 5-point grid factored and packed on the device (fills M->fb);
 // returns 1 when the matrix is not such a grid (the caller takes the host path)
 template <class T>

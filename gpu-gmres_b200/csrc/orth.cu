@@ -519,9 +519,21 @@ __device__ __forceinline__ void mbar_arrive_tx0(uint64_t* bar) {  // completes a
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(0u) : "memory");
 }
 
-template <class VT>
-__global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* __restrict__ V, int64_t ld, int j,
-                                                                const VT* w, VT* out, GmresDev st, int inner_i,
+// BT = storage type of the basis columns (V and the copy of the new vector in out_b), VT = type of w and of the working
+// copy `out` of the new vector.  BT == VT: out IS the basis column and out_b is null.  BT = float with VT = double is the
+// opt-in mixed-precision basis (bg_solver_create_ex): the j projections stream 4-byte columns, every sum, w and the
+// new vector stay FP64, and the new vector is rounded to BT before it is stored in EITHER place, so that the vector the
+// next SpMV multiplies is exactly the one the basis holds (the Arnoldi relation then holds for the stored basis).
+// float -> double by re-packing the bits (normal numbers exactly; zero and denormals become ~2^-127, which is below
+// anything the sums can resolve; the basis holds no infinities or NaNs while the solve is healthy)
+__device__ __forceinline__ double widen_f32(float x) {
+  const unsigned f = __float_as_uint(x);
+  const unsigned hi = (f & 0x80000000u) | (((f & 0x7fffffffu) >> 3) + 0x38000000u);
+  return __hiloint2double((int)hi, (int)(f << 29));
+}
+template <class VT, class BT>
+__global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const BT* __restrict__ V, int64_t ld, int j,
+                                                                const VT* w, VT* out, BT* out_b, GmresDev st, int inner_i,
                                                                 int orth_mode, Pipe pp, const PeerAR* peer) {
   if (st.flags[F_CONV]) return;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -559,13 +571,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* 
         const int t = blockIdx.x + q * G, s = q % S;
         if ((fany >> s) & 1u) mbar_wait(&empty[s], ((fbits >> s) & 1u) ^ 1u);
         const int rows = min(pp.R, n - t * pp.R);
-        const uint32_t col_bytes = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;
-        if (lane == 0) mbar_expect_tx(&full[s], col_bytes * (uint32_t)ncols);
+        const uint32_t cb_v = ((uint32_t)rows * sizeof(BT) + 15u) & ~15u, cb_w = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;
+        if (lane == 0) mbar_expect_tx(&full[s], cb_v * (uint32_t)j + cb_w);
         __syncwarp();
         unsigned char* tile = ring + (size_t)s * pp.stage_bytes;
         for (int c = lane; c < ncols; c += 32) {
-          const VT* src = (c < j ? V + (size_t)c * ld : extra) + (size_t)t * pp.R;
-          bulk_g2s(tile + (size_t)c * pp.R * sizeof(VT), src, col_bytes, &full[s]);
+          if (c < j) bulk_g2s(tile + (size_t)c * pp.R * sizeof(BT), V + (size_t)c * ld + (size_t)t * pp.R, cb_v, &full[s]);
+          else bulk_g2s(tile + (size_t)j * pp.R * sizeof(BT), extra + (size_t)t * pp.R, cb_w, &full[s]);
         }
         fbits ^= 1u << s; fany |= 1u << s;
       }
@@ -575,16 +587,37 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* 
       for (int q = 0; q < K; ++q) {
         const int t = blockIdx.x + q * G, s = q % S;
         mbar_wait(&full[s], (ubits >> s) & 1u);
-        const VT* tile = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes);
-        const VT* tw = tile + (size_t)j * pp.R;
+        const BT* tile = reinterpret_cast<const BT*>(ring + (size_t)s * pp.stage_bytes);
+        const VT* tw = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes + (size_t)j * pp.R * sizeof(BT));
         const int rows = min(pp.R, n - t * pp.R);
+        if constexpr (sizeof(BT) != sizeof(VT)) {
+          // mixed basis: FP32 products summed in FP32 over this tile's rows (<= 128 per thread), folded into the FP64
+          // accumulators once per tile; w.w stays FP64.  A float -> double conversion per ELEMENT (F2F.F64.F32) would
+          // make the step slower than the all-FP64 one; the stored basis carries 6e-8 rounding anyway.
+          float a32[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-        for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
-          const double wv = (double)tw[r];
+          for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
+            const double wv = (double)tw[r];
+            const float wf = (float)wv;
 #pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            const int c = cg + a * CW;
-            if (c < ncols) acc[a] += (double)tile[(size_t)c * pp.R + r] * wv;
+            for (int a = 0; a < 5; ++a) {
+              const int c = cg + a * CW;
+              if (c < j) a32[a] = fmaf((float)tile[(size_t)c * pp.R + r], wf, a32[a]);
+              else if (c == j) acc[a] += wv * wv;
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 5; ++a) acc[a] += (double)a32[a];
+        } else {
+#pragma unroll 4
+          for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
+            const double wv = (double)tw[r];
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+              const int c = cg + a * CW;
+              if (c < j) acc[a] += (double)tile[(size_t)c * pp.R + r] * wv;
+              else if (c == j) acc[a] += wv * wv;
+            }
           }
         }
         __syncwarp();
@@ -657,13 +690,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* 
           if (lane == 0) mbar_arrive_tx0(&full[s]);
         } else {
           const int rows = min(pp.R, n - t * pp.R);
-          const uint32_t col_bytes = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;
-          if (lane == 0) mbar_expect_tx(&full[s], col_bytes * (uint32_t)ncols);
+          const uint32_t cb_v = ((uint32_t)rows * sizeof(BT) + 15u) & ~15u, cb_w = ((uint32_t)rows * sizeof(VT) + 15u) & ~15u;
+          if (lane == 0) mbar_expect_tx(&full[s], cb_v * (uint32_t)j + cb_w);
           __syncwarp();
           unsigned char* tile = ring + (size_t)s * pp.stage_bytes;
           for (int c = lane; c < ncols; c += 32) {
-            const VT* src = (c < j ? V + (size_t)c * ld : extra) + (size_t)t * pp.R;
-            bulk_g2s(tile + (size_t)c * pp.R * sizeof(VT), src, col_bytes, &full[s]);
+            if (c < j) bulk_g2s(tile + (size_t)c * pp.R * sizeof(BT), V + (size_t)c * ld + (size_t)t * pp.R, cb_v, &full[s]);
+            else bulk_g2s(tile + (size_t)j * pp.R * sizeof(BT), extra + (size_t)t * pp.R, cb_w, &full[s]);
           }
         }
         fbits ^= 1u << s; fany |= 1u << s;
@@ -673,7 +706,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* 
       for (int q = 0; q < K; ++q) {
         const int qq = K - 1 - q, t = blockIdx.x + qq * G, s = qq % S;
         mbar_wait(&full[s], (ubits >> s) & 1u);
-        const VT* tile = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes);
+        const BT* tile = reinterpret_cast<const BT*>(ring + (size_t)s * pp.stage_bytes);
+        const VT* tw = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes + (size_t)j * pp.R * sizeof(BT));
         const int rows = min(pp.R, n - t * pp.R);
         const size_t base = (size_t)t * pp.R;
         for (int r0 = 0; r0 < rows; r0 += 1024) {
@@ -681,19 +715,37 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const VT* 
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int r = r0 + threadIdx.x + 256 * u;
-            av[u] = r < rows ? (double)tile[(size_t)j * pp.R + r] : 0.0;
+            av[u] = r < rows ? (double)tw[r] : 0.0;
           }
-          for (int k = 0; k < j; ++k) {
-            const double c = cs[k];
-            const VT* col = tile + (size_t)k * pp.R + r0 + threadIdx.x;
+          if constexpr (sizeof(BT) != sizeof(VT)) {
+            // mixed basis: w - V h cancels down to the (often much smaller) new direction, so the products and the sum
+            // must be exact to FP64 relative to w: FP64 FMAs on widened columns.  The widening is done with integer
+            // instructions (widen_f32): the conversion instruction F2F.F64.F32 is issued at a fraction of the FMA rate
+            // and made this step slower than the all-FP64 one (377 vs 360 us at 10 M rows).
+            for (int k = 0; k < j; ++k) {
+              const double c = cs[k];
+              const BT* col = tile + (size_t)k * pp.R + r0 + threadIdx.x;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (r0 + (int)threadIdx.x + 256 * u < rows) av[u] += c * (double)col[256 * u];
+              for (int u = 0; u < 4; ++u)
+                if (r0 + (int)threadIdx.x + 256 * u < rows) av[u] += c * widen_f32((float)col[256 * u]);
+            }
+          } else {
+            for (int k = 0; k < j; ++k) {
+              const double c = cs[k];
+              const BT* col = tile + (size_t)k * pp.R + r0 + threadIdx.x;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (r0 + (int)threadIdx.x + 256 * u < rows) av[u] += c * (double)col[256 * u];
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int r = r0 + threadIdx.x + 256 * u;
-            if (r < rows) out[base + r] = (VT)(av[u] * scale);
+            if (r < rows) {
+              const BT vb = (BT)(av[u] * scale);  // BT == VT: the value itself
+              out[base + r] = sizeof(BT) == sizeof(VT) ? (VT)(av[u] * scale) : (VT)vb;
+              if (out_b) out_b[base + r] = vb;
+            }
           }
         }
         __syncwarp();
@@ -1052,27 +1104,30 @@ int launch_update(bg_context_t ctx, int dtype, int n, const void* a, const void*
 }
 
 // ring geometry of the fused step: same stage budget, rows chosen so that every CTA owns the same number of tiles
-static Pipe orth_geometry(int ncols, size_t elem, int n, int G) {
-  Pipe p = pipe_geometry(ncols, elem);
+// j basis columns of elem_b bytes + one work column of elem_w bytes per row
+static Pipe orth_geometry(int j, size_t elem_b, size_t elem_w, int n, int G) {
+  const size_t row_bytes = (size_t)j * elem_b + elem_w;
+  Pipe p = pipe_geometry(1, row_bytes);
   const int64_t per = ((int64_t)n + G - 1) / G;                  // rows per CTA
   const int64_t k = std::max<int64_t>(1, (per + p.R - 1) / p.R); // tiles per CTA
   int R = (int)(((per + k - 1) / k + 31) / 32 * 32);
   p.R = std::max(32, std::min(R, p.R));
-  p.stage_bytes = (uint32_t)(((size_t)std::max(1, ncols) * p.R * elem + 127) / 128 * 128);
+  p.stage_bytes = (uint32_t)((row_bytes * p.R + 127) / 128 * 128);
   return p;
 }
-template <class VT>
-static int orth_dispatch(bg_context_t ctx, int n, const VT* V, int64_t ld, int j, const VT* w, VT* out, const GmresDev& st,
+template <class VT, class BT>
+static int orth_dispatch(bg_context_t ctx, int n, const BT* V, int64_t ld, int j, const VT* w, VT* out, BT* out_b, const GmresDev& st,
                          int i, int om, const PeerAR* peer) {
   if (j < 1 || j > kFinMax) { set_error("orth: j=%d outside 1..%d", j, kFinMax); return BG_ERR_ARG; }
   const int G = std::max(1, std::min((n + 31) / 32, ctx->sm_count));
-  Pipe pp = orth_geometry(j + 1, sizeof(VT), n, G);
+  Pipe pp = orth_geometry(j, sizeof(BT), sizeof(VT), n, G);
   const size_t smem = (size_t)pp.stages * pp.stage_bytes + 2 * sizeof(uint64_t) * pp.stages;
-  BG_TRY(pipe_smem_attr(orth_kernel<VT>, ctx));
+  auto kern = orth_kernel<VT, BT>;
+  BG_TRY(pipe_smem_attr(kern, ctx));
   GmresDev stv = st;
-  void* args[] = {(void*)&n, (void*)&V, (void*)&ld, (void*)&j, (void*)&w, (void*)&out, (void*)&stv, (void*)&i, (void*)&om, (void*)&pp, (void*)&peer};
+  void* args[] = {(void*)&n, (void*)&V, (void*)&ld, (void*)&j, (void*)&w, (void*)&out, (void*)&out_b, (void*)&stv, (void*)&i, (void*)&om, (void*)&pp, (void*)&peer};
   // cooperative launch: the CTAs wait for each other inside the kernel, so co-residency must be guaranteed
-  BG_CUDA(cudaLaunchCooperativeKernel((const void*)orth_kernel<VT>, dim3(G), dim3(kPipeThreads), args, smem, ctx->stream));
+  BG_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(G), dim3(kPipeThreads), args, smem, ctx->stream));
   ctx->launches++;
   return BG_OK;
 }
@@ -1110,8 +1165,52 @@ int launch_mgs(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, in
 
 int launch_orth(bg_context_t ctx, int dtype, int n, const void* V, int64_t ld, int j, const void* w, void* out, const GmresDev& st,
                 int inner_i, int orth_mode, const PeerAR* peer) {
-  if (dtype == BG_F32) return orth_dispatch<float>(ctx, n, (const float*)V, ld, j, (const float*)w, (float*)out, st, inner_i, orth_mode, peer);
-  return orth_dispatch<double>(ctx, n, (const double*)V, ld, j, (const double*)w, (double*)out, st, inner_i, orth_mode, peer);
+  if (dtype == BG_F32) return orth_dispatch<float, float>(ctx, n, (const float*)V, ld, j, (const float*)w, (float*)out, nullptr, st, inner_i, orth_mode, peer);
+  return orth_dispatch<double, double>(ctx, n, (const double*)V, ld, j, (const double*)w, (double*)out, nullptr, st, inner_i, orth_mode, peer);
+}
+// FP64 work vectors, FP32 basis storage: V32 = basis (ld floats per column), out = working copy of the new vector,
+// out_b = its column in the basis
+int launch_orth_mixed(bg_context_t ctx, int n, const float* V32, int64_t ld, int j, const double* w, double* out, float* out_b,
+                      const GmresDev& st, int inner_i, int orth_mode) {
+  return orth_dispatch<double, float>(ctx, n, V32, ld, j, w, out, out_b, st, inner_i, orth_mode, nullptr);
+}
+
+// mixed-precision basis, restart terms (once per cycle: plain grid-stride kernels)
+//   round_store: v <- (double)(float)v, v32 <- (float)v        (v0 = r / beta)
+//   axpy_basis:  x += sum_k y[k] V32[:,k]                       (x += V y, Update_GPU)
+__global__ void round_store_kernel(int n, double* __restrict__ v, float* __restrict__ v32, const int* skip) {
+  if (skip && *skip) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float f = (float)v[i];
+    v32[i] = f;
+    v[i] = (double)f;
+  }
+}
+__global__ void __launch_bounds__(256) axpy_basis_kernel(int n, const float* __restrict__ V32, int64_t ld, int k, const double* __restrict__ y,
+                                                         double* __restrict__ x, GmresDev st, int force) {
+  if (!force && st.flags[F_CONV]) return;
+  __shared__ double ys[kFinMax + 1];
+  if ((int)threadIdx.x < k) ys[threadIdx.x] = y[threadIdx.x];
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = x[i];
+#pragma unroll 8
+    for (int c = 0; c < k; ++c) acc += ys[c] * (double)V32[(size_t)c * ld + i];
+    x[i] = acc;
+  }
+}
+int launch_round_store(bg_context_t ctx, int n, double* v, float* v32, const int* skip) {
+  round_store_kernel<<<vec_grid(ctx, n, 1, 8), 256, 0, ctx->stream>>>(n, v, v32, skip);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
+}
+int launch_axpy_basis(bg_context_t ctx, int n, const float* V32, int64_t ld, int k, const double* y, double* x, const GmresDev& st, int force) {
+  if (k < 1 || k > kFinMax + 1) { set_error("axpy_basis: k=%d", k); return BG_ERR_ARG; }
+  axpy_basis_kernel<<<vec_grid(ctx, n, 1, 8), 256, 0, ctx->stream>>>(n, V32, ld, k, y, x, st, force);
+  ctx->launches++;
+  BG_CUDA(cudaGetLastError());
+  return BG_OK;
 }
 
 int launch_solve_y(bg_context_t ctx, const GmresDev& st, int k, int force) {

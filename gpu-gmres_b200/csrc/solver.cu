@@ -792,15 +792,25 @@ static const int kHistCap = 1 << 16;
 extern "C" int bg_solver_create(bg_context_t ctx, int n, int m, int dtype, bg_solver_t* out) {
   return solver_create_internal(ctx, n, m, dtype, 0, out);
 }
-int bg::solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out) {
+extern "C" int bg_solver_create_ex(bg_context_t ctx, int n, int m, int dtype, int basis_dtype, bg_solver_t* out) {
+  if (basis_dtype != dtype && !(dtype == BG_F64 && basis_dtype == BG_F32)) {
+    set_error("bg_solver_create_ex: the basis is stored in the vector type, or in FP32 under FP64 vectors");
+    return BG_ERR_UNSUPPORTED;
+  }
+  if (basis_dtype != dtype && m > 32) { set_error("bg_solver_create_ex: the mixed-precision basis runs the fused CGS step (m <= 32)"); return BG_ERR_UNSUPPORTED; }
+  return solver_create_internal(ctx, n, m, dtype, 0, out, basis_dtype);
+}
+int bg::solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out, int basis_dtype) {
   if (!ctx || !out || n < 0 || m < 1 || m > 1024 || extra_rows < 0) return BG_ERR_ARG;
   BG_CUDA(cudaSetDevice(ctx->device));
   bg_solver_t S = new bg_solver_s;
   S->ctx = ctx; S->n = n; S->m = m; S->dtype = dtype;
+  S->basis_dtype = basis_dtype < 0 ? dtype : basis_dtype;
   // every vector has room for `extra_rows` halo values behind its n own entries (row-partitioned runs)
   S->ld = ((int64_t)n + extra_rows + 31) / 32 * 32;
   const size_t s = dtype_size(dtype);
-  int rc = S->V.alloc((size_t)S->ld * (m + 1) * s);
+  int rc = S->V.alloc((size_t)S->ld * (m + 1) * dtype_size(S->basis_dtype));
+  if (rc >= 0 && S->basis_dtype != dtype) rc = S->vcur.alloc((size_t)S->ld * s);
   for (DevBuf* b : {&S->w, &S->ww, &S->r, &S->rr, &S->bb, &S->yv})
     if (rc >= 0) rc = b->alloc((size_t)S->ld * s);
   // state block: flags | scal | h | h2 | y | H | s | cs | sn | ticket | hist | partial
@@ -865,6 +875,7 @@ struct Driver {
   bool permuted = false;  // A, b, x and all work vectors are in the preconditioner's block-major row order
   DistHooks* dh = nullptr;  // row-partitioned run: halo exchange before every SpMV, allreduce inside every dots step
   bool fused_orth = true;   // BG_FUSED_ORTH=0 selects the separate dots / update kernels
+  bool mixed = false;       // FP32 basis columns under FP64 work vectors: the newest basis vector also lives in S->vcur
   // y = alpha A x (+ beta b): x must have room for the halo behind its n entries when dh is set
   int spmv(double alpha, void* xv, double beta, const void* bv, void* y, bool axpby) {
     if (dh) {
@@ -884,7 +895,9 @@ struct Driver {
     BG_TRY(dh->allreduce(red, j + 1));
     return launch_finalize(ctx, st, fin, i, mk, o.orth, nr, j, red);
   }
-  char* col(int k) const { return S->V.as<char>() + (size_t)k * ld * es; }
+  char* col(int k) const { return S->V.as<char>() + (size_t)k * ld * (mixed ? sizeof(float) : es); }
+  // the vector the operator is applied to in inner iteration i: basis column i, or its working copy (mixed basis)
+  void* vin(int i) const { return mixed ? S->vcur.p : (void*)col(i); }
   struct Span {
     Prof* p; int ph, a;
     Span(Prof* p_, int ph_) : p(p_), ph(ph_), a(p_ ? p_->mark() : 0) {}
@@ -899,16 +912,20 @@ struct Driver {
     { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->rr.p, S->r.p, skip)); }
     Span sp(prof, PH_OTHER);
     BG_TRY(dots(nullptr, 0, S->r.p, fin, 0, 0, 0));
+    if (mixed) {  // v0 = r / beta, rounded to the basis precision in both copies
+      BG_TRY(launch_update(ctx, S->dtype, n, S->r.p, nullptr, ld, 0, nullptr, 0.0, S->vcur.p, st, 1, 0, 0));
+      return launch_round_store(ctx, n, S->vcur.as<double>(), (float*)col(0), skip);
+    }
     return launch_update(ctx, S->dtype, n, S->r.p, nullptr, ld, 0, nullptr, 0.0, col(0), st, 1, 0, 0);
   }
   int iteration(int i) {
     // w = M_L^-1 A M_R^-1 v_i   (gmres.cu:2350-2354 / 2637-2640)
     if (split) {
-      { Span sp(prof, PH_TRSV); BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, col(i), S->w.p, skip, false)); }
+      { Span sp(prof, PH_TRSV); BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, vin(i), S->w.p, skip, false)); }
       { Span sp(prof, PH_SPMV); BG_TRY(spmv(1.0, S->w.p, 0.0, nullptr, S->ww.p, false)); }
     } else {
       Span sp(prof, PH_SPMV);
-      BG_TRY(spmv(1.0, col(i), 0.0, nullptr, S->ww.p, false));
+      BG_TRY(spmv(1.0, vin(i), 0.0, nullptr, S->ww.p, false));
     }
     { Span sp(prof, PH_TRSV); BG_TRY(apply_left(S->ww.p, S->w.p, skip)); }
     Span sp(prof, PH_ORTH);
@@ -923,6 +940,8 @@ struct Driver {
       return launch_update(ctx, S->dtype, n, S->w.p, nullptr, ld, 0, nullptr, 0.0, col(i + 1), st, 1, 0, 0);
     }
     const int j = i + 1;
+    if (mixed)  // FP32 basis columns, FP64 everything else; the new vector goes to the basis and to its working copy
+      return launch_orth_mixed(ctx, n, (const float*)col(0), ld, j, S->w.as<double>(), S->vcur.as<double>(), (float*)col(j), st, i, o.orth);
     // one cooperative launch: projections, (peer all-reduce,) Givens epilogue, v_j, conditional second pass
     if (fused_orth && (!dh || dh->peer_ar()))
       return launch_orth(ctx, S->dtype, n, col(0), ld, j, S->w.p, col(j), st, i, o.orth, dh ? dh->peer_ar() : nullptr);
@@ -937,7 +956,8 @@ struct Driver {
     const int* sk = force ? nullptr : skip;
     BG_TRY(launch_solve_y(ctx, st, k, force));
     void* tgt = split ? S->yv.p : x;
-    BG_TRY(launch_update(ctx, S->dtype, n, tgt, col(0), ld, k + 1, st.y, 1.0, tgt, st, 0, force, 0));
+    if (mixed) BG_TRY(launch_axpy_basis(ctx, n, (const float*)col(0), ld, k + 1, st.y, (double*)tgt, st, force));
+    else BG_TRY(launch_update(ctx, S->dtype, n, tgt, col(0), ld, k + 1, st.y, 1.0, tgt, st, 0, force, 0));
     if (split) BG_TRY(precond_apply(ctx, M, BG_PC_RIGHT, S->yv.p, x, sk, false));
     return BG_OK;
   }
@@ -1039,6 +1059,11 @@ static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_p
   if (dh && !permuted) { set_error("a row-partitioned solve needs a block-Jacobi (BG_TRSV_BLOCK) ILU preconditioner"); return BG_ERR_UNSUPPORTED; }
   Driver D{ctx, S, A, M, o, d_b, d_x, n, m, S->ld, dtype_size(S->dtype), M->kind == BG_PRECOND_SPLIT, st.flags + F_CONV, st, prof, permuted, dh};
   { const char* e = getenv("BG_FUSED_ORTH"); D.fused_orth = !(e && e[0] == '0'); }
+  D.mixed = S->basis_dtype != S->dtype;
+  if (D.mixed && (o.orth == BG_ORTH_MGS || dh || o.m > 32)) {
+    set_error("the mixed-precision basis supports the fused CGS step on one GPU (BG_ORTH_CGS_ADAPTIVE / BG_ORTH_CGS2, m <= 32)");
+    return BG_ERR_UNSUPPORTED;
+  }
   BG_TRY(launch_state_reset(ctx, st, o.tol, o.reorth_eta));
   // normb = || M_L^-1 b ||   (gmres.cu:2294-2296)
   BG_TRY(D.apply_left(d_b, S->bb.p, nullptr));
@@ -1154,6 +1179,7 @@ extern "C" int bg_solver_get_hessenberg(bg_solver_t S, double* H, double* s, dou
 // one orthogonalisation step against j basis columns on the solver's own workspace (bench hook)
 extern "C" BG_API int bg_solver_bench_orth(bg_context_t ctx, bg_solver_t S, int j) {
   if (!ctx || !S || j < 1 || j > std::min(S->m, 32)) return BG_ERR_ARG;
+  if (S->basis_dtype != S->dtype) { set_error("bg_solver_bench_orth: not for the mixed-precision basis"); return BG_ERR_UNSUPPORTED; }
   GmresDev st = S->dev;
   BG_TRY(launch_dots(ctx, S->dtype, S->n, S->V.p, S->ld, j, S->w.p, st, FIN_NONE, 0, 0, BG_ORTH_CGS_ADAPTIVE, 0));
   return launch_update(ctx, S->dtype, S->n, S->w.p, S->V.p, S->ld, j, st.h, -1.0, S->V.as<char>() + (size_t)j * S->ld * dtype_size(S->dtype), st, 1, 0, 0);

@@ -392,10 +392,14 @@ def gmres_opts(**kw) -> GmresOpts:
 
 
 class Solver:
-    def __init__(self, ctx, n, m=32, dtype=F64):
+    def __init__(self, ctx, n, m=32, dtype=F64, basis_dtype=None):
+        """basis_dtype=F32 with dtype=F64: the opt-in mixed-precision Krylov basis (bg_solver_create_ex)"""
         self.ctx, self.n, self.m, self.dtype = ctx, n, m, dtype
         self.h = C.c_void_p()
-        _chk(lib().bg_solver_create(ctx.h, n, m, dtype, C.byref(self.h)))
+        if basis_dtype is None or basis_dtype == dtype:
+            _chk(lib().bg_solver_create(ctx.h, n, m, dtype, C.byref(self.h)))
+        else:
+            _chk(lib().bg_solver_create_ex(ctx.h, n, m, dtype, basis_dtype, C.byref(self.h)))
 
     def solve(self, A, M, d_b, d_x, opts=None, host=False):
         """GMRES_GPU / GMRESilu_GPU through the C ABI.  d_b/d_x: device pointers (ints or torch

@@ -252,6 +252,14 @@ BG_API void bg_gmres_opts_default(bg_gmres_opts* o);
 /* workspace: replaces GMRES_GPU_Data::Initilize (src/gmres.h:89-105) and the workspace the PG
    path hides inside the Preconditioner (src/preconditioner.cu:1318-1331) */
 BG_API int bg_solver_create(bg_context_t ctx, int n, int m, int dtype, bg_solver_t* S);
+/* Opt-in mixed-precision Krylov basis: vectors, sums, w, x and every residual in `dtype` (BG_F64), the m+1 basis
+   columns stored in `basis_dtype` (BG_F32).  The orthogonalisation step is 60 % of the solve's HBM traffic and runs at
+   the roofline, so halving the bytes of the basis is the one lever left on a single GPU.  It changes the rounding of
+   the Arnoldi vectors (the reference mixes precisions the other way round: FP64 factors under FP32 vectors), so it is
+   never the default; each new vector is rounded to the basis precision before the operator is applied to it, i.e. the
+   Arnoldi relation holds for the stored basis, and the restart residual is always recomputed in `dtype`.
+   Fused CGS step only (BG_ORTH_CGS_ADAPTIVE / BG_ORTH_CGS2, m <= 32, one GPU).  basis_dtype == dtype: bg_solver_create. */
+BG_API int bg_solver_create_ex(bg_context_t ctx, int n, int m, int dtype, int basis_dtype, bg_solver_t* S);
 BG_API int bg_solver_destroy(bg_solver_t S);
 /* GMRES_GPU / GMRES_GPU_tran / GMRESilu_GPU (src/gmres.cu:2567-2732, 2736-2827, 2254-2446).
    M of kind SPLIT selects the GMRESilu_GPU algebra, anything else the left-preconditioned one.

@@ -294,6 +294,48 @@ def run_gpu(bg, ctx, rp, ci, v, b, x0, M, dtc, **kw):
     return r, x, hist
 
 
+@pytest.mark.parametrize("schedule", ["level", "block"])
+@pytest.mark.parametrize("shape", [(96, 80), (400, 300)])
+def test_mixed_precision_basis_reaches_the_fp64_answer(bg, ctx, schedule, shape):
+    """Opt-in FP32 Krylov basis under FP64 vectors (bg_solver_create_ex): same stopping rule, true residual still below the
+    tolerance (the restart residual is always recomputed in FP64), solution within 1e-7 of the all-FP64 run, iteration
+    count within 10 %; the combinations it does not cover are refused."""
+    from b200gmres import synth
+
+    nx, ny = shape
+    rp, ci, v, b = synth.pg2d(nx, ny, seed=613)
+    n = len(rp) - 1
+    A_h = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    o = None if schedule == "level" else bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_method=bg.PART_GRID2D, block_rows=1024,
+                                                         dims=[nx, ny, 1, 32, 32, 1])
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=1, opts=o)
+    A = bg.Matrix(ctx, rp, ci, v, dtype=1)
+    out = {}
+    for basis in (bg.F64, bg.F32):
+        S = bg.Solver(ctx, n, 32, dtype=bg.F64, basis_dtype=basis)
+        for orth in (bg.ORTH_CGS_ADAPTIVE, bg.ORTH_CGS2):
+            db, dx = dev(b, np.float64), dev(np.zeros(n), np.float64)
+            r = S.solve(A, M, db.data_ptr(), dx.data_ptr(), bg.gmres_opts(m=32, tol=1e-8, max_iter=5000, orth=orth, reorth_eta=0.1))
+            x = host(ctx, dx)
+            out[(basis, orth)] = (r, x, np.linalg.norm(b - A_h @ x) / np.linalg.norm(b))
+        if basis == bg.F32:
+            db, dx = dev(b, np.float64), dev(np.zeros(n), np.float64)
+            with pytest.raises(bg.BgError):  # strict MGS keeps the basis in the vector type
+                S.solve(A, M, db.data_ptr(), dx.data_ptr(), bg.gmres_opts(m=32, tol=1e-8, max_iter=10, orth=bg.ORTH_MGS))
+        S.close()
+    for orth in (bg.ORTH_CGS_ADAPTIVE, bg.ORTH_CGS2):
+        (r64, x64, t64), (r32, x32, t32) = out[(bg.F64, orth)], out[(bg.F32, orth)]
+        assert r64.flag == 0 and r32.flag == 0
+        assert t32 <= 2e-8, f"true relative residual {t32:.3e}"
+        assert abs(r32.iters - r64.iters) <= max(3, 0.1 * r64.iters), (r32.iters, r64.iters)
+        assert np.linalg.norm(x32 - x64) <= 1e-7 * np.linalg.norm(x64)
+    with pytest.raises(bg.BgError):
+        bg.Solver(ctx, n, 64, dtype=bg.F64, basis_dtype=bg.F32)   # the fused CGS step covers restarts up to 32
+    with pytest.raises(bg.BgError):
+        bg.Solver(ctx, n, 32, dtype=bg.F32, basis_dtype=bg.F64)
+    A.close(); M.close()
+
+
 @pytest.mark.parametrize("dtc", [0, 1])
 @pytest.mark.parametrize("shape", [(96, 80), (12, 9), (400, 300)])
 def test_fused_mgs_step_equals_launch_pairs(bg, ctx, dtc, shape):
