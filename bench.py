@@ -294,6 +294,13 @@ def main():
         sm["true_rel_residual_fp64_basis"] = line["true_rel_residual"]
         sm["iters_fp64_basis"] = line["iters"]
         line["fp32_basis_opt_in"] = sm
+        # the reference's own arithmetic and stopping rule: FP32 everywhere, tolerance 1e-6 (src/gmres.h:55,
+        # docs/tvlsi_3d_thermal.pdf p.578), same grid, same schedule
+        rp32 = run_single(args, local, args.nx, "ilu0", args.schedule, args.orth, min(args.steps, 5), headline=False, keep_x=True,
+                          vec="f32", tol=1e-6)
+        s32 = _summary(rp32, extra=("iteration_roofline",))
+        s32["x_vs_fp64_headline"] = float(np.linalg.norm(rp32["_x"] - x_head) / np.linalg.norm(x_head))
+        line["reference_precision_fp32_tol1e-6"] = s32
     if not args.quick:
         other = "level" if args.schedule == "block" else "block"
         sec = run_single(args, local, args.nx, "ilu0", other, args.orth, min(args.steps, 5), headline=False)
@@ -352,17 +359,20 @@ def _time_solves(torch, ctx, stream, fn, k):
     return e0.elapsed_time(e1), r, ctx.launches - l0
 
 
-def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, keep_x=False, basis="f64"):
+def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, keep_x=False, basis="f64", vec="f64", tol=None):
+    """vec = "f32": vectors, matrix and factors in FP32 (the reference's own arithmetic, src/gmres.h:55)"""
     import torch
 
     import b200gmres as bg
 
     rp, ci, v, b = workload(nx)
     n = len(rp) - 1
+    tol = args.tol if tol is None else tol
+    vdt, npdt, tdt, s8 = (bg.F64, np.float64, torch.float64, 8) if vec == "f64" else (bg.F32, np.float32, torch.float32, 4)
     ctx = bg.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    A = bg.Matrix(ctx, rp, ci, v, dtype=bg.F64)
-    fdt = bg.F32 if args.factor_dtype == "f32" else bg.F64
+    A = bg.Matrix(ctx, rp, ci, v, dtype=vdt)
+    fdt = bg.F32 if (args.factor_dtype == "f32" or vec == "f32") else bg.F64
     t_setup = time.perf_counter()
     if schedule == "block":
         o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=args.tile * args.tile_y, factor_dtype=fdt,
@@ -370,16 +380,17 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
                             dims=[nx, nx, 1, args.tile, args.tile_y, 1], ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
     else:
         o = bg.precond_opts(trsv_schedule=bg.TRSV_LEVEL, factor_dtype=fdt, ilut_tau=args.ilut_tau, ilut_lfil=args.ilut_lfil)
-    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=o, ilut=(precond == "ilut"))
+    M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=vdt, opts=o, ilut=(precond == "ilut"))
     t_setup = time.perf_counter() - t_setup
-    S = bg.Solver(ctx, n, 32, dtype=bg.F64, basis_dtype=bg.F32 if basis == "f32" else bg.F64)
+    S = bg.Solver(ctx, n, 32, dtype=vdt, basis_dtype=bg.F32 if (basis == "f32" and vec == "f64") else None)
     orth = {"mgs": bg.ORTH_MGS, "cgs": bg.ORTH_CGS_ADAPTIVE, "cgs2": bg.ORTH_CGS2}[orth_name]
-    opts = bg.gmres_opts(m=32, tol=args.tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
+    opts = bg.gmres_opts(m=32, tol=tol, max_iter=10000, orth=orth, reorth_eta=args.eta)
 
-    db = torch.from_numpy(b).cuda()
-    dx = torch.zeros(n, dtype=torch.float64, device="cuda")
-    hb = torch.from_numpy(b).pin_memory()
-    hx = torch.zeros(n, dtype=torch.float64).pin_memory()
+    bv = np.ascontiguousarray(b, dtype=npdt)
+    db = torch.from_numpy(bv).cuda()
+    dx = torch.zeros(n, dtype=tdt, device="cuda")
+    hb = torch.from_numpy(bv).pin_memory()
+    hx = torch.zeros(n, dtype=tdt).pin_memory()
     torch.cuda.synchronize()
 
     def step_device():
@@ -409,12 +420,11 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
     with torch.cuda.stream(stream):
         dx.zero_()
     rprof, st = S.profile(A, M, db.data_ptr(), dx.data_ptr(), opts)
-    x = dx.cpu().numpy()
+    x = dx.cpu().numpy().astype(np.float64)
     true_rel = float(np.linalg.norm(b - _spmv_host(rp, ci, v, x)) / np.linalg.norm(b))
 
     peak, which = peaks()
     info, pinfo = A.info(), M.info()
-    s8 = 8
     # bytes one preconditioner application really moves: the packed factor streams + the vectors it reads and writes
     # (block tiles: r in, z out; level strips: r in, tmp out, tmp in, z out; sync-free slices add the 16-byte packets)
     if schedule == "block":
@@ -430,7 +440,7 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
     # SpMV moves its sliced-ELL copy (values + 32-bit columns, padded) + x gathers (L2-served) + y
     spmv_moved_per = (info.sell_padded_nnz * (s8 + 4) if info.format == bg.SPMV_SELL else info.nnz * (s8 + 4) + 4 * (n + 1)) + 2 * s8 * n
     kernels = {
-        ("spmv_sell_w<double,5> (sliced ELL, fixed width, all loads in flight)" if info.format == bg.SPMV_SELL else "spmv_csr_vector"):
+        ("spmv_sell_w<%s,5> (sliced ELL, fixed width, all loads in flight)" % ("double" if vec == "f64" else "float") if info.format == bg.SPMV_SELL else "spmv_csr_vector"):
             (st.spmv_ms, st.spmv_bytes, st.spmv_calls, spmv_moved_per * st.spmv_calls),
         trsv_kernel: (st.trsv_ms, st.trsv_bytes, st.trsv_calls, trsv_moved_per * napply),
     }
@@ -483,15 +493,15 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
     line = {
         "metric": METRIC, "value": step_ms, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3) if headline else 2,
         "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_of(nx, n, info.nnz, args.tol),
+        "vs_baseline": None, "dtype": vec, "data": "synthetic",
+        "config": config_of(nx, n, info.nnz, tol),
         "impl_config": {"restart": 32, "precond": precond, "trsv_schedule": schedule, "lattice_layout": bool(pinfo.lattice),
                         "operator": ("block-Jacobi ILU tiles (changes the preconditioner: iteration drift reported through iters)" if schedule == "block"
                                      else "the reference's global factors, getLevel dependencies"),
                         "blocks": pinfo.nblocks, "block_rows": pinfo.max_block_rows, "levels": [pinfo.levelsL, pinfo.levelsU],
-                        "factor_dtype": args.factor_dtype, "basis_dtype": basis, "orth": orth_name, "reorth_eta": args.eta,
+                        "factor_dtype": "f32" if fdt == bg.F32 else "f64", "basis_dtype": basis if vec == "f64" else "f32", "orth": orth_name, "reorth_eta": args.eta,
                         "spmv_format": "sell" if info.format == bg.SPMV_SELL else "csr",
-                        "l2_policy": "working set (Krylov basis 33 x n x 8 B = %.0f MB) exceeds the 126 MB L2" % (33 * n * 8 / 1e6)},
+                        "l2_policy": "working set (Krylov basis 33 x n x %d B = %.0f MB) exceeds the 126 MB L2" % (s8, 33 * n * s8 / 1e6)},
         "iters": int(r.iters), "resid": float(r.resid), "true_rel_residual": true_rel, "reorths": int(r.reorths),
         "ms_per_iteration": step_ms / max(r.iters_done, 1),
         "iteration_roofline": {"bytes_per_iteration_moved": moved_bytes / itp, "moved_GBps": moved_bytes / (step_ms * 1e-3) / 1e9,
@@ -504,7 +514,7 @@ def run_single(args, local, nx, precond, schedule, orth_name, steps, headline, k
                                        "which the index-free layouts do not move"},
         "kernels": per_kernel, "setup_s": t_setup,
         "roofline": roofline,
-        "e2e": {"value": ms_e2e / steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8},
+        "e2e": {"value": ms_e2e / steps, "unit": UNIT, "h2d_bytes_per_step": 2 * n * s8, "d2h_bytes_per_step": n * s8},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if keep_x:

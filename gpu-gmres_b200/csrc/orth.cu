@@ -590,10 +590,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const BT* 
         const BT* tile = reinterpret_cast<const BT*>(ring + (size_t)s * pp.stage_bytes);
         const VT* tw = reinterpret_cast<const VT*>(ring + (size_t)s * pp.stage_bytes + (size_t)j * pp.R * sizeof(BT));
         const int rows = min(pp.R, n - t * pp.R);
-        if constexpr (sizeof(BT) != sizeof(VT)) {
-          // mixed basis: FP32 products summed in FP32 over this tile's rows (<= 128 per thread), folded into the FP64
-          // accumulators once per tile; w.w stays FP64.  A float -> double conversion per ELEMENT (F2F.F64.F32) would
-          // make the step slower than the all-FP64 one; the stored basis carries 6e-8 rounding anyway.
+        if constexpr (sizeof(BT) == 4) {
+          // FP32 basis columns (mixed basis, and the all-FP32 solver): FP32 products summed in FP32 over this tile's rows
+          // (<= 128 per thread), folded into the FP64 accumulators once per tile; w.w stays FP64.  A float -> double
+          // conversion per ELEMENT (F2F.F64.F32) would make the step slower than the all-FP64 one; the rounding errors
+          // of the products average out over the rows (the reference's cublasSdot sums everything in FP32).
           float a32[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
           for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
@@ -608,15 +609,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const BT* 
           }
 #pragma unroll
           for (int a = 0; a < 5; ++a) acc[a] += (double)a32[a];
-        } else {
+        } else {  // uniform tile: column j is w itself
 #pragma unroll 4
           for (int r = lane + 32 * rg; r < rows; r += 32 * RW) {
             const double wv = (double)tw[r];
 #pragma unroll
             for (int a = 0; a < 5; ++a) {
               const int c = cg + a * CW;
-              if (c < j) acc[a] += (double)tile[(size_t)c * pp.R + r] * wv;
-              else if (c == j) acc[a] += wv * wv;
+              if (c < ncols) acc[a] += (double)tile[(size_t)c * pp.R + r] * wv;
             }
           }
         }
@@ -717,8 +717,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const BT* 
             const int r = r0 + threadIdx.x + 256 * u;
             av[u] = r < rows ? (double)tw[r] : 0.0;
           }
-          if constexpr (sizeof(BT) != sizeof(VT)) {
-            // mixed basis: w - V h cancels down to the (often much smaller) new direction, so the products and the sum
+          if constexpr (sizeof(BT) == 4) {
+            // FP32 basis columns: w - V h cancels down to the (often much smaller) new direction, so the products and the sum
             // must be exact to FP64 relative to w: FP64 FMAs on widened columns.  The widening is done with integer
             // instructions (widen_f32): the conversion instruction F2F.F64.F32 is issued at a fraction of the FMA rate
             // and made this step slower than the all-FP64 one (377 vs 360 us at 10 M rows).
@@ -742,9 +742,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const BT* 
           for (int u = 0; u < 4; ++u) {
             const int r = r0 + threadIdx.x + 256 * u;
             if (r < rows) {
-              const BT vb = (BT)(av[u] * scale);  // BT == VT: the value itself
-              out[base + r] = sizeof(BT) == sizeof(VT) ? (VT)(av[u] * scale) : (VT)vb;
-              if (out_b) out_b[base + r] = vb;
+              if constexpr (sizeof(BT) == sizeof(VT)) {
+                out[base + r] = (VT)(av[u] * scale);
+              } else {  // rounded to the basis precision in both copies
+                const BT vb = (BT)(av[u] * scale);
+                out[base + r] = (VT)vb;
+                out_b[base + r] = vb;
+              }
             }
           }
         }
