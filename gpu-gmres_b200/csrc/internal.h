@@ -79,6 +79,7 @@ struct bg_matrix_s {
   bg::SpmvPlan plan;
   bg::DevBuf rp, ci, val;            // CSR
   bg::DevBuf s_ptr, s_col, s_val;    // sliced ELL
+  bg::DevBuf s_halo;                 // per slice: 1 when one of its columns is a halo slot (ncols > n only)
   int sell_rpt = 1, sell_height = 32, sell_slices = 0;
   int sell_width = 0;  // > 0: every slice has this many entries per row (stencils): kernels skip the slice pointers
   // host CSR (compute dtype) kept so that a symmetrically permuted copy P A P^T can be built when a
@@ -184,6 +185,7 @@ struct HaloArgs {
   const int* send_idx = nullptr;
   int n_send = 0, n_local = 0;
   unsigned seq = 0;
+  const unsigned char* slice_halo = nullptr;  // per slice of the matrix: reads a halo slot (filled in by launch_spmv)
 };
 
 // ---- launchers (defined in the .cu files) --------------------------------------------------

@@ -197,6 +197,13 @@ static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::ve
     BG_TRY(upload_vec(A->s_ptr, sp, s));
     BG_TRY(upload_vec(A->s_col, sc, s));
     BG_TRY(upload_vec(A->s_val, sv, s));
+    if (A->ncols > A->n) {  // local rows of a row-partitioned matrix: which slices read halo slots
+      std::vector<unsigned char> fl(std::max(1, A->sell_slices), 0);
+      for (int i = 0; i < A->n; ++i)
+        for (int p = rp[i]; p < rp[i + 1]; ++p)
+          if (ci[p] >= A->n) { fl[i / A->sell_height] = 1; break; }
+      BG_TRY(upload_vec(A->s_halo, fl, s));
+    }
   }
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
