@@ -257,6 +257,7 @@ __device__ __forceinline__ void pipe_produce(const Pipe& pp, unsigned char* ring
 // one all-reduce ahead of the slowest one, because finishing number s needs everybody's values of s.
 __device__ void peer_allreduce(const PeerAR* __restrict__ P, double* red, int cnt) {
   __shared__ unsigned s_seq;
+  __shared__ double s_val[kMaxPeers * (kFinMax + 2)];
   const int R = P->nranks, me = P->rank;
   if (threadIdx.x == 0) { s_seq = *P->seq + 1u; *P->seq = s_seq; }
   __syncthreads();
@@ -266,11 +267,18 @@ __device__ void peer_allreduce(const PeerAR* __restrict__ P, double* red, int cn
     const int r = t / cnt, k = t - r * cnt;
     ll_store(&P->inbox[r][(slot + me) * kArLd + k], red[k], seq);
   }
-  double v = 0.0;
-  if ((int)threadIdx.x < cnt)
-    for (int r = 0; r < R; ++r) v += ll_wait(&P->inbox[me][(slot + r) * kArLd + threadIdx.x], seq, P->timeout_ns);
+  // one thread per (rank, value): all packets are polled at once -- a thread walking the ranks of its value one after
+  // the other paid one memory round trip per rank (5 us of the 13 us all-reduce at 8 ranks)
+  for (int t = threadIdx.x; t < R * cnt; t += blockDim.x) {
+    const int r = t / cnt, k = t - r * cnt;
+    s_val[r * (kFinMax + 2) + k] = ll_wait(&P->inbox[me][(slot + r) * kArLd + k], seq, P->timeout_ns);
+  }
   __syncthreads();
-  if ((int)threadIdx.x < cnt) red[threadIdx.x] = v;
+  if ((int)threadIdx.x < cnt) {
+    double v = 0.0;
+    for (int r = 0; r < R; ++r) v += s_val[r * (kFinMax + 2) + threadIdx.x];  // rank order: identical bits on every rank
+    red[threadIdx.x] = v;
+  }
   __syncthreads();
 }
 
