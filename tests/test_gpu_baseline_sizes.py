@@ -178,3 +178,63 @@ def test_c3_th3d_64_level_and_tiles_match_oracle(bg, ctx, oracle):
     r, x = gpu_solve(bg, ctx, rp, ci, v, b, M, tol=1e-8, max_iter=10000, orth=bg.ORTH_CGS_ADAPTIVE)
     check(r, x, flag, it, res, xo, "C3 3-D tiles")
     M.close()
+
+
+def test_headline_10m_size_independent_properties(bg, ctx):
+    """The headline workload itself (pg2d 3162^2 = 10 M rows, bench.py's input), where a CPU solve takes a minute: the
+    CUDA path is checked through properties that do not need one.
+      * SpMV against scipy on the same CSR (every row, 1e-13);
+      * block-Jacobi preconditioner (factored AND packed on the device): linearity M(a u + b v) = a M u + b M v, and the
+        defining identity L U (M r) = r with the HOST factors of the same tiles (bit-exact twin of the device ones);
+      * the global (reference-order) ILU(0) through the wavefront-strip kernel: L U (M r) = r with the host factors;
+      * the solve: true relative residual below the tolerance, the pinned iteration count of this input (108 / 84),
+        and the solutions of the two operators agree to the accuracy the tolerance allows."""
+    from b200gmres import synth
+
+    nx = 3162
+    rp, ci, v, b = synth.pg2d(nx, nx, seed=synth.SEED_BASE + 2)
+    n = len(rp) - 1
+    A_h = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    rng = np.random.default_rng(1)
+    u, w = rng.standard_normal(n), rng.standard_normal(n)
+    A = bg.Matrix(ctx, rp, ci, v, dtype=bg.F64)
+    du, dy = dev(u), dev(np.zeros(n))
+    A.spmv(du.data_ptr(), dy.data_ptr())
+    ctx.sync()
+    want = A_h @ u
+    assert np.abs(dy.cpu().numpy() - want).max() <= 1e-13 * np.abs(want).max()
+
+    def lu_product(f, z):
+        L = sp.csr_matrix((f["lv"], f["li"], f["lp"]), shape=(n, n))
+        U = sp.csr_matrix((f["uv"], f["ui"], f["up"]), shape=(n, n))
+        return L @ (U @ z)
+
+    dims = [nx, nx, 1, 32, 32, 1]
+    nb, blk = bg.host_block_partition(bg.PART_GRID2D, rp, ci, 0, dims)
+    xs = {}
+    for name, opts, f, iters in (
+            ("block", bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_method=bg.PART_GRID2D, block_rows=1024, dims=dims), bg.host_ilu0(rp, ci, v, blk), 108),
+            ("level", None, bg.host_ilu0(rp, ci, v), 84)):
+        M = bg.Precond.ilu0(ctx, rp, ci, v, dtype=bg.F64, opts=opts)
+        info = M.info()
+        assert info.lattice == 1 and (name == "level" or (info.device_factored == 1 and info.nblocks == nb))
+        outs = []
+        for vec in (u, w, 0.75 * u - 2.5 * w):
+            din, dout = dev(vec), dev(np.zeros(n))
+            M.apply(bg.PC_FULL, din.data_ptr(), dout.data_ptr())
+            ctx.sync()
+            outs.append(dout.cpu().numpy())
+        zu, zw, zc = outs
+        assert np.linalg.norm(zc - (0.75 * zu - 2.5 * zw)) <= 1e-13 * np.linalg.norm(zc), name          # linearity
+        assert np.linalg.norm(lu_product(f, zu) - u) <= 1e-12 * np.linalg.norm(u), name                 # L U z = r
+        S = bg.Solver(ctx, n, 32, dtype=bg.F64)
+        db, dx = dev(b), dev(np.zeros(n))
+        r = S.solve(A, M, db.data_ptr(), dx.data_ptr(), bg.gmres_opts(m=32, tol=1e-8, max_iter=10000, orth=bg.ORTH_CGS_ADAPTIVE, reorth_eta=0.1))
+        ctx.sync()
+        x = dx.cpu().numpy()
+        S.close(); M.close()
+        assert r.flag == 0 and r.iters == iters, (name, r.iters)
+        assert np.linalg.norm(b - A_h @ x) <= 1e-8 * np.linalg.norm(b), name
+        xs[name] = x
+    A.close()
+    assert np.linalg.norm(xs["block"] - xs["level"]) <= 1e-6 * np.linalg.norm(xs["level"])
