@@ -938,7 +938,7 @@ struct Driver {
     Span sp(prof, PH_ORTH);
     if (o.orth == BG_ORTH_MGS) {
       if (fused_orth && !dh && mgs_fused_supported(ctx, n, m))  // one cooperative launch for the i+1 dot/axpy pairs and the norm
-        return launch_mgs(ctx, S->dtype, n, col(0), ld, i, S->w.p, col(i + 1), st, S->mgs_slots.p, ++S->mgs_seq);
+        return launch_mgs(ctx, S->dtype, n, col(0), ld, i, S->w.p, col(i + 1), st, S->mgs_slots.p, ++S->mgs_seq ? S->mgs_seq : ++S->mgs_seq);  // never 0
       for (int k = 0; k <= i; ++k) {
         BG_TRY(dots(col(k), 1, S->w.p, FIN_MGS_DOT, i, k, 0));
         BG_TRY(launch_update(ctx, S->dtype, n, S->w.p, col(k), ld, 1, st.h, -1.0, S->w.p, st, 0, 0, 0));
