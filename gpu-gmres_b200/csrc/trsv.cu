@@ -244,6 +244,8 @@ template <class FT> struct LgArgs {
   unsigned seq;
   unsigned long long timeout_ns;
 };
+// 8 steps per block: 4 were measured 30 % slower (the per-block cost -- progress polls, publication, the burst of
+// operand loads -- is ~480 cycles), 16 do not fit the shallow ring and lengthen every strip-to-strip offset by 16 steps
 constexpr int kLgBS = 8;  // steps per block: granularity of staging, boundary hand-off and result flush
 template <class TIN, class TOUT, class FT, bool LOWER> constexpr size_t lg_smem_bytes(int NR) {
   return (size_t)NR * 32 * ((LOWER ? 2 : 3) * sizeof(FT) + sizeof(TIN) + sizeof(TOUT)) + (size_t)NR * 8 + 64;
