@@ -790,6 +790,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) orth_kernel(int n, const BT* 
 // Sums are accumulated in double whatever VT is; for VT = float w is rounded to float after every axpy, as the
 // separate kernels (and the reference's float w) do.
 constexpr int kMgsThreads = 1024, kMgsEPT = 12;
+#ifdef BG_MGS_TIMING
+// development aid (make dbg): clock64 stamps (SM cycles) of thread 0 of CTA g_mgs_probe, per pair k < 40:
+// [0] tile there  [1] local sum done  [2] own packet stored  [3] all packets read  [4] pair done
+__device__ unsigned long long g_mgs_t[40 * 5];
+__device__ int g_mgs_probe = 0;
+// stamps go to shared memory and are flushed at the end of the kernel: a global store in front of the packet store
+// delayed the latter by a store round trip
+#define MGS_STAMP(k, w) do { if (threadIdx.x == 0 && (k) < 40) s_mgs_t[(k) * 5 + (w)] = (unsigned long long)clock64(); } while (0)  // SM clock: one CTA, one SM
+#else
+#define MGS_STAMP(k, w) do {} while (0)
+#endif
 struct MgsArgs {
   LL16* slots;   // [(m + 2)][G] packets
   unsigned seq;  // launch sequence number (never 0)
@@ -805,6 +816,9 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
   __shared__ double red_w[32];
   __shared__ double s_sum;
   __shared__ FinScratch fs;
+#ifdef BG_MGS_TIMING
+  __shared__ unsigned long long s_mgs_t[40 * 5];
+#endif
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
   const int r0 = blockIdx.x * a.rows_per, rows = max(0, min(a.rows_per, n - r0));
   const uint32_t buf_bytes = ((uint32_t)a.rows_per * sizeof(VT) + 127u) & ~127u;
@@ -839,8 +853,10 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
     __syncthreads();
     if (wid == 0) {
       const double mine = warp_sum(red_w[lane]);
+      MGS_STAMP(k, 1);  // (after the first use of data guarded by the barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on)
       LL16* row = a.slots + (size_t)k * G;
-      if (lane == 0) ll_store(row + blockIdx.x, mine, a.seq);
+      if (lane == 0) ll_store_gpu(row + blockIdx.x, mine, a.seq);
+      MGS_STAMP(k, 2);
       constexpr int PER = 5;  // up to 160 CTAs (launcher)
       LL16 pk[PER];
       bool need[PER];
@@ -853,7 +869,7 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
         for (int u = 0; u < PER; ++u) {
           if (need[u]) {
             const LL16* q = row + lane + 32 * u;
-            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[u].lo), "=r"(pk[u].f0), "=r"(pk[u].hi), "=r"(pk[u].f1) : "l"(q) : "memory");
+            pk[u] = ll_load_gpu(q);
             need[u] = !(pk[u].f0 == a.seq && pk[u].f1 == a.seq);
           }
           all = all && !need[u];
@@ -865,6 +881,7 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
           else if (now - t0 > a.timeout_ns) __trap();
         }
       }
+      MGS_STAMP(k, 3);
       double acc = 0.0;
 #pragma unroll
       for (int u = 0; u < PER; ++u)
@@ -877,7 +894,13 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
   };
 
   for (int k = 0; k < ncol; ++k) {
-    if (rows > 0) mbar_wait(&full[k & 1], (uint32_t)(k >> 1) & 1u);
+    // one lane per warp waits for the tile: 1024 threads polling one mbarrier serialise on it (the probe showed the
+    // CTA spending ~3000 cycles per pair between the tile's arrival and the end of the local dot products)
+    if (rows > 0) {
+      if (lane == 0) mbar_wait(&full[k & 1], (uint32_t)(k >> 1) & 1u);
+      __syncwarp();
+    }
+    MGS_STAMP(k, 0);
     const VT* vk = reinterpret_cast<const VT*>(dyn + (size_t)(k & 1) * buf_bytes);
     double p = 0.0;
 #pragma unroll
@@ -896,6 +919,7 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
     }
     __syncthreads();  // everybody is done with this buffer
     if (tid == 0 && k + 2 < ncol) issue(k + 2);
+    MGS_STAMP(k, 4);
   }
   double p = 0.0;
 #pragma unroll
@@ -908,6 +932,10 @@ __global__ void __launch_bounds__(kMgsThreads, 1) mgs_kernel(int n, const VT* __
     const int r = tid + e * kMgsThreads;
     if (r < rows) out[r0 + r] = (VT)(wr[e] * scale);  // v_{i+1} = w / H(i+1,i)  (gmres.cu:2361-2362)
   }
+#ifdef BG_MGS_TIMING
+  if ((int)blockIdx.x == g_mgs_probe && tid == 0)
+    for (int q = 0; q < 200; ++q) g_mgs_t[q] = s_mgs_t[q];
+#endif
   if (blockIdx.x == 0 && tid == 0) {
     st.scal[S_SCALE] = scale;
     if (!(hn > 0.0)) st.flags[F_BREAK] = 1;
@@ -1143,6 +1171,12 @@ static int orth_dispatch(bg_context_t ctx, int n, const BT* V, int64_t ld, int j
   ctx->launches++;
   return BG_OK;
 }
+#ifdef BG_MGS_TIMING
+extern "C" BG_API int bg_debug_mgs_times(int probe_cta, unsigned long long* out200) {
+  if (probe_cta >= 0) return cudaMemcpyToSymbol(g_mgs_probe, &probe_cta, sizeof(int)) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out200, g_mgs_t, sizeof(unsigned long long) * 200) == cudaSuccess ? 0 : -1;
+}
+#endif
 // rows per CTA of the fused MGS step, or 0 when the vector does not fit the register-resident layout
 static int mgs_rows_per(bg_context_t ctx, int n, int G) {
   const int per = (((n + G - 1) / G) + 31) / 32 * 32;

@@ -11,6 +11,18 @@ __device__ __forceinline__ void ll_store(LL16* p, double v, unsigned seq) {
                "r"((unsigned)__double2hiint(v)), "r"(seq)
                : "memory");
 }
+// The same packet between the SMs of ONE GPU (triangular-solve hand-offs, the fused MGS step's sums): GPU scope is
+// enough and cheaper than the system scope a volatile access implies (which also covers NVLink peers and the host).
+__device__ __forceinline__ void ll_store_gpu(LL16* p, double v, unsigned seq) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(seq),
+               "r"((unsigned)__double2hiint(v)), "r"(seq)
+               : "memory");
+}
+__device__ __forceinline__ LL16 ll_load_gpu(const LL16* p) {
+  LL16 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.lo), "=r"(v.f0), "=r"(v.hi), "=r"(v.f1) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

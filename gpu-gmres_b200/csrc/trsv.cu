@@ -38,11 +38,7 @@ template <class VT> struct XformDev {
 };
 
 // ------------------------------------------------------------------ sync-free LEVEL schedule (any factor)
-__device__ __forceinline__ LL16 ll_load(const LL16* p) {
-  LL16 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.lo), "=r"(v.f0), "=r"(v.hi), "=r"(v.f1) : "l"(p) : "memory");
-  return v;
-}
+__device__ __forceinline__ LL16 ll_load(const LL16* p) { return ll_load_gpu(p); }  // hand-offs stay inside one GPU
 __device__ __forceinline__ bool ll_ok(const LL16& v, unsigned seq) { return v.f0 == seq && v.f1 == seq; }
 __device__ __forceinline__ double ll_val(const LL16& v) { return __hiloint2double((int)v.hi, (int)v.lo); }
 
@@ -201,7 +197,7 @@ __global__ void __launch_bounds__(128, 5) trsv_syncfree(SfArgs<FT> a, XformDev<V
     SF_STAMP(2);
     if (!UNIT) acc /= dg;
     if (mine) {
-      ll_store(xs + r, (double)acc, a.seq);
+      ll_store_gpu(xs + r, (double)acc, a.seq);
       if (out) {
         if (xf.epi == 1) { VT t = (VT)acc; t /= sepi; out[dst] = t; }
         else out[dst] = (VT)acc;
@@ -475,7 +471,7 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
       // the rows the last lane finished in this block: every lane has passed them
       if (has_down && lane < BS) {
         const int tf = b * BS - 31 + lane;
-        if ((unsigned)tf < (unsigned)ny) ll_store(bnd_out + yrow(tf), (double)s_out[((tf + 31) & (NR - 1)) * 32 + edge_out], a.seq);  // the edge lane lags 31 steps
+        if ((unsigned)tf < (unsigned)ny) ll_store_gpu(bnd_out + yrow(tf), (double)s_out[((tf + 31) & (NR - 1)) * 32 + edge_out], a.seq);  // the edge lane lags 31 steps
       }
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
