@@ -12,9 +12,12 @@
 //        flag-in-data packets in L2 (value + sequence number in one 16-byte store), so a level costs one
 //        L2 hand-off instead of a launch / grid barrier, and independent chains overlap.
 //      - trsv_lattice_global (ILU(0) factors of a 5-point grid in natural order, detected on the host): one
-//        warp per 32-column strip walks the anti-diagonal wavefront with its operands in registers (south /
-//        north = own previous result, west / east = neighbour lane by shuffle); only the strip boundary
-//        column crosses L2.  No indices are stored; a level costs a shuffle and two FMAs.
+//        CTA per 32-column strip; its chain warp walks the anti-diagonal wavefront (south / north = own previous
+//        result, west / east = neighbour lane by shuffle) on operands that loader warps stage in shared memory,
+//        a storer warp writes the results back; only the strip boundary column crosses L2.  No indices are
+//        stored; a level costs a shuffle and two FMAs.
+//    The device schedules follow the STRUCTURAL levels (every stored entry is a dependency); getLevel itself, which
+//    stops at / skips entries below 1e-9, stays the parity artefact (bg_precond_get_levels).
 //  * BLOCK  -- block-Jacobi ILU, see trsv_block.cu.
 #include <type_traits>
 
