@@ -297,7 +297,7 @@ __device__ int g_lg_probe = 0;
 template <class TIN, class TOUT, class FT, class CT, bool LOWER, int NR, bool INTERIOR, class P>
 __device__ __forceinline__ void lg_chain_block(const P* __restrict__ pr, const FT* __restrict__ dv, const TIN* __restrict__ rh,
                                                TOUT* __restrict__ ot, const double* __restrict__ bd, int t0, bool bnd, bool colok,
-                                               int ny, bool is_edge, CT& zprev) {
+                                               int ny, bool is_edge, CT& zprev, LL16* edge_out, unsigned seq) {
   constexpr int BS = kLgBS;
   CT ca[BS], cb[BS], r[BS], be[BS];
 #pragma unroll
@@ -322,6 +322,10 @@ __device__ __forceinline__ void lg_chain_block(const P* __restrict__ pr, const F
     const CT tt = r[j] - cb[j] * zprev;  // south / north: own previous result
     zprev = tt - ca[j] * zn;             // west / east: neighbour lane (or the upstream strip)
     ot[j * 32] = (TOUT)zprev;            // steps outside [0, ny) are never flushed
+    // the strip's last lane hands its value to the downstream strip the moment it exists (edge_out: this lane's
+    // packet of time row t0 + j, null on every other lane); waiting for the storer's block flush kept every strip
+    // ~8 steps plus a shared-memory hand-off further behind its neighbour
+    if (edge_out && (INTERIOR || (unsigned)(t0 + j) < (unsigned)ny)) ll_store_gpu(edge_out + (LOWER ? j : -j), (double)zprev, seq);
   }
 }
 
@@ -456,26 +460,23 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
       const int t0 = blk * BS - lag;  // this lane's time row at the first step of the block
       const int base = ((blk * BS) & (NR - 1)) * 32 + lane;
       const double* bd = s_bnd + ((blk * BS) & (NR - 1));
+      // packet of this lane's first time row of the block in the strip's boundary column (edge lane of a strip with a
+      // downstream neighbour only); rows run upwards for L (y = t) and downwards for U (y = ny-1-t)
+      LL16* eo = (has_down && lane == edge_out) ? a.bnd + (size_t)s * ny + (LOWER ? t0 : ny - 1 - t0) : nullptr;
       if (blk * BS - 31 >= 0 && blk * BS + BS - 1 < ny && 32 * s + 31 < nx)
-        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, true>(s_pair + base, s_dinv + base, s_rhs + base, s_out + base, bd, t0, bnd, colok, ny, lane == edge_in, zprev);
+        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, true>(s_pair + base, s_dinv + base, s_rhs + base, s_out + base, bd, t0, bnd, colok, ny, lane == edge_in, zprev, eo, a.seq);
       else
-        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, false>(s_pair + base, s_dinv + base, s_rhs + base, s_out + base, bd, t0, bnd, colok, ny, lane == edge_in, zprev);
+        lg_chain_block<TIN, TOUT, FT, CT, LOWER, NR, false>(s_pair + base, s_dinv + base, s_rhs + base, s_out + base, bd, t0, bnd, colok, ny, lane == edge_in, zprev, eo, a.seq);
       __syncwarp();
       if (lane == 0) lg_publish(&prog[0], blk + 1);
     }
     LG_ACC(0, tc);
     LG_FLUSH;
   } else if (wid == 2) {  // --------------------------------------------------------- STORER
-    LL16* bnd_out = a.bnd + (size_t)s * ny;
     const int lag = LOWER ? lane : 31 - lane;
     LG_T0(ts);
     for (int b = 0; b < nblk; ++b) {
       { LG_T0(tw); lg_wait_progress<false>(&prog[0], b + 1, tmo); LG_ACC(9, tw); }
-      // the rows the last lane finished in this block: every lane has passed them
-      if (has_down && lane < BS) {
-        const int tf = b * BS - 31 + lane;
-        if ((unsigned)tf < (unsigned)ny) ll_store_gpu(bnd_out + yrow(tf), (double)s_out[((tf + 31) & (NR - 1)) * 32 + edge_out], a.seq);  // the edge lane lags 31 steps
-      }
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
         const int tf = b * BS - 31 + j;
