@@ -415,6 +415,8 @@ __global__ void __launch_bounds__(kLgThreads) trsv_lattice_global(LgArgs<FT> a, 
         bool need = lane < BS && t < ny;
         LL16 pk = {0u, 0u, 0u, 0u};
         unsigned long long t0 = 0;
+        // (three staggered polls in flight instead of one were measured: the priming delay costs more than the finer
+        // detection grain buys, 499 -> 691 us at 1304^2)
         for (unsigned spin = 0;; ++spin) {  // warp-uniform poll
           if (need) { pk = ll_load(bnd_in + yrow(t)); need = !ll_ok(pk, a.seq); }
           if (__all_sync(0xffffffffu, !need)) break;
