@@ -16,6 +16,8 @@
 #include <cmath>
 #include <stdexcept>
 
+#include <type_traits>
+
 #include "internal.h"
 
 namespace bg {
@@ -433,7 +435,11 @@ template <class T> static int upload_fused_stream(bg_context_t ctx, const FusedB
 template <class FH, class FT>
 static int precond_install(bg_precond_t M, const Csr<FH>& L, const Csr<FH>& U, bool unit_lower, const int* block_of_row,
                            int nblocks) {
-  Csr<FT> Lf = convert_csr<FH, FT>(L), Uf = convert_csr<FH, FT>(U);
+  // same storage type: use the caller's factors in place (a copy of 10 M-row factors costs ~0.3 s of setup)
+  Csr<FT> Lc, Uc;
+  if constexpr (!std::is_same<FH, FT>::value) { Lc = convert_csr<FH, FT>(L); Uc = convert_csr<FH, FT>(U); }
+  const Csr<FT>& Lf = [&]() -> const Csr<FT>& { if constexpr (std::is_same<FH, FT>::value) return L; else return Lc; }();
+  const Csr<FT>& Uf = [&]() -> const Csr<FT>& { if constexpr (std::is_same<FH, FT>::value) return U; else return Uc; }();
   M->nnzL = (int64_t)L.v.size(); M->nnzU = (int64_t)U.v.size();
   M->unit_lower = unit_lower;
   try {

@@ -2,6 +2,8 @@
 // SURVEY.md (appendix A) and cite the reference location whose integer artefacts they reproduce.
 #include "host_algos.h"
 
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -16,6 +18,26 @@ extern "C" int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj,
                                    int64_t* options, int64_t* edgecut, int64_t* part);
 
 namespace bg {
+// Setup of 10 M-row problems is bound by first-touch page faults and plain copies of several hundred megabytes:
+// independent index ranges are handed to a few host threads.  fn(begin, end) must only write its own range.
+template <class F> static void parallel_ranges(size_t n, F fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = n < (size_t)1 << 20 ? 1 : std::min<size_t>(8, hw ? hw : 1);
+  if (nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b < e) th.emplace_back([=] { fn(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
+template <class T> static void parallel_copy(std::vector<T>& dst, const T* src, size_t n) {
+  dst.resize(n);  // (value-initialises: the faults of the zero fill are what is parallelised below for the big arrays)
+  T* d = dst.data();
+  parallel_ranges(n, [=](size_t b, size_t e) { std::copy(src + b, src + e, d + b); });
+}
+
 
 // ------------------------------------------------------------------ level sets
 void factor_levels(int n, const int* rp, const int* ci, const float* v, int* level) {
@@ -74,6 +96,18 @@ namespace {
 template <class T>
 void sorted_copy(int n, const int* rp, const int* ci, const T* v, const int* block, Csr<T>& W) {
   W.n = n;
+  if (!block) {  // the common case -- every row already sorted, nothing to drop -- is a plain copy
+    bool sorted = true;
+    for (int i = 0; i < n && sorted; ++i)
+      for (int p = rp[i] + 1; p < rp[i + 1]; ++p)
+        if (ci[p] < ci[p - 1]) { sorted = false; break; }
+    if (sorted) {
+      W.rp.assign(rp, rp + n + 1);
+      parallel_copy(W.ci, ci, (size_t)rp[n]);
+      parallel_copy(W.v, v, (size_t)rp[n]);
+      return;
+    }
+  }
   W.rp.assign(n + 1, 0);
   W.ci.clear();
   W.v.clear();
@@ -115,16 +149,18 @@ template <class T> void split_lu(const Csr<T>& W, Factors<T>& F) {
   }
   F.L.ci.resize(F.L.rp[n]); F.L.v.resize(F.L.rp[n]);
   F.U.ci.resize(F.U.rp[n]); F.U.v.resize(F.U.rp[n]);
-  for (int i = 0; i < n; ++i) {
-    int a = F.L.rp[i], b = F.U.rp[i];
-    for (int p = W.rp[i]; p < W.rp[i + 1]; ++p) {
-      if (is_zero(W.v[p])) continue;
-      if (W.ci[p] < i) { F.L.ci[a] = W.ci[p]; F.L.v[a++] = W.v[p]; }
-      else { F.U.ci[b] = W.ci[p]; F.U.v[b++] = W.v[p]; }
+  parallel_ranges((size_t)n, [&](size_t r0, size_t r1) {  // every row writes its own segments of L and U
+    for (int i = (int)r0; i < (int)r1; ++i) {
+      int a = F.L.rp[i], b = F.U.rp[i];
+      for (int p = W.rp[i]; p < W.rp[i + 1]; ++p) {
+        if (is_zero(W.v[p])) continue;
+        if (W.ci[p] < i) { F.L.ci[a] = W.ci[p]; F.L.v[a++] = W.v[p]; }
+        else { F.U.ci[b] = W.ci[p]; F.U.v[b++] = W.v[p]; }
+      }
+      F.L.ci[a] = i;
+      F.L.v[a] = (T)1;
     }
-    F.L.ci[a] = i;
-    F.L.v[a] = (T)1;
-  }
+  });
   F.unit_lower = true;
 }
 }  // namespace
@@ -593,15 +629,17 @@ template <class T> void pack_lattice_global(const Csr<T>& L, const Csr<T>& U, in
   out.lower.assign(slots * 2, (T)0);
   out.upper.assign(slots * 2, (T)0);
   out.udinv.assign(slots, (T)0);
-  for (int r = 0; r < n; ++r) {
-    const int X = r % nx, y = r / nx;
-    const size_t q = ((size_t)(X / 32) * ny + y) * 32 + X % 32;
-    for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p) out.lower[2 * q + (L.ci[p] == r - 1 && X > 0 ? 0 : 1)] = L.v[p];
-    const double di = 1.0 / (double)U.v[U.rp[r]];
-    out.udinv[q] = (T)di;
-    for (int p = U.rp[r] + 1; p < U.rp[r + 1]; ++p)
-      out.upper[2 * q + (U.ci[p] == r + 1 && X < nx - 1 ? 0 : 1)] = (T)((double)U.v[p] * di);
-  }
+  parallel_ranges((size_t)n, [&](size_t r0, size_t r1) {  // a row owns its slot q
+    for (int r = (int)r0; r < (int)r1; ++r) {
+      const int X = r % nx, y = r / nx;
+      const size_t q = ((size_t)(X / 32) * ny + y) * 32 + X % 32;
+      for (int p = L.rp[r]; p < L.rp[r + 1] - 1; ++p) out.lower[2 * q + (L.ci[p] == r - 1 && X > 0 ? 0 : 1)] = L.v[p];
+      const double di = 1.0 / (double)U.v[U.rp[r]];
+      out.udinv[q] = (T)di;
+      for (int p = U.rp[r] + 1; p < U.rp[r + 1]; ++p)
+        out.upper[2 * q + (U.ci[p] == r + 1 && X < nx - 1 ? 0 : 1)] = (T)((double)U.v[p] * di);
+    }
+  });
 }
 template void pack_lattice_global<float>(const Csr<float>&, const Csr<float>&, int, LatticeGlobal<float>&);
 template void pack_lattice_global<double>(const Csr<double>&, const Csr<double>&, int, LatticeGlobal<double>&);
