@@ -310,7 +310,7 @@ int gmres_solve_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_
                      const bg_gmres_opts* opts, bg_gmres_result* res, DistHooks* dh);
 int gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
                        const bg_gmres_opts* o, bg_gmres_result* r, bg_phase_stats* out, DistHooks* dh);
-int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
+int matrix_create_internal(bg_context_t ctx, int n, int ncols, std::vector<int> rp, std::vector<int> ci,
                            const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out);
 int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out, int basis_dtype = -1);
 // factor.cu: block-Jacobi ILU(0) of the tiles of a 5-point grid factored and packed on the device (fills M->fb);

@@ -62,10 +62,15 @@ template <class T> static int upload_vec(DevBuf& d, const std::vector<T>& v, cud
 }
 
 // values of any supported dtype -> std::vector<T>
+template <class T> static void convert_into(T* o, const void* p, int dt, size_t n) {
+  parallel_ranges(n, [=](size_t b, size_t e) {
+    if (dt == BG_F64) { const double* s = (const double*)p; for (size_t i = b; i < e; ++i) o[i] = (T)s[i]; }
+    else { const float* s = (const float*)p; for (size_t i = b; i < e; ++i) o[i] = (T)s[i]; }
+  });
+}
 template <class T> static std::vector<T> to_vec(const void* p, int dt, size_t n) {
   std::vector<T> o(n);
-  if (dt == BG_F64) { const double* s = (const double*)p; for (size_t i = 0; i < n; ++i) o[i] = (T)s[i]; }
-  else { const float* s = (const float*)p; for (size_t i = 0; i < n; ++i) o[i] = (T)s[i]; }
+  convert_into(o.data(), p, dt, n);
   return o;
 }
 template <class A, class B> static Csr<B> convert_csr(const Csr<A>& M) {
@@ -162,14 +167,19 @@ extern "C" int bg_host_free_pinned(void* p) {
 
 // =========================================================================== matrix
 template <class T>
-static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::vector<int>& ci, const std::vector<T>& v,
+static int matrix_build(bg_matrix_t A, std::vector<int>&& rp_in, std::vector<int>&& ci_in, const void* val, int val_dtype,
                         int format) {
   cudaStream_t s = A->ctx->stream;
   A->requested_format = format;
-  A->h_rp = rp;
-  A->h_ci = ci;
-  A->h_val.resize(v.size() * sizeof(T));
-  if (!v.empty()) std::memcpy(A->h_val.data(), v.data(), A->h_val.size());
+  // the host copy (kept for the block-Jacobi reordering, build_permuted) takes the index arrays over and receives
+  // the values already converted to the compute type: one pass over the caller's data instead of three
+  A->h_rp = std::move(rp_in);
+  A->h_ci = std::move(ci_in);
+  const std::vector<int>&rp = A->h_rp, &ci = A->h_ci;
+  const size_t nnz = ci.size();
+  A->h_val.resize(nnz * sizeof(T));
+  T* const v = reinterpret_cast<T*>(A->h_val.data());
+  convert_into(v, val, val_dtype, nnz);
   if (A->ncols < A->n) A->ncols = A->n;
   A->plan = inspect_rows(A->n, rp.data());
   if (format == BG_SPMV_AUTO) format = A->plan.format;
@@ -178,19 +188,19 @@ static int matrix_build(bg_matrix_t A, const std::vector<int>& rp, const std::ve
   A->lanes = format == BG_SPMV_CSR_WARP ? 32 : mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
   BG_TRY(upload_vec(A->rp, rp, s));
   BG_TRY(upload_vec(A->ci, ci, s));
-  BG_TRY(upload_vec(A->val, v, s));
+  BG_TRY(A->val.upload(v, nnz * sizeof(T), s));
   if (format == BG_SPMV_SELL) {
     A->sell_rpt = sizeof(T) == 4 ? 4 : 2;
     A->sell_height = 32 * A->sell_rpt;
     std::vector<int64_t> sp;
     std::vector<int> sc;
     std::vector<T> sv;
-    build_sell(A->n, rp.data(), ci.data(), v.data(), A->sell_height, sp, sc, sv);
+    build_sell(A->n, rp.data(), ci.data(), v, A->sell_height, sp, sc, sv);
     A->sell_slices = (int)sp.size() - 1;
     // a few short slices (grid boundaries) must not cost the fixed-width kernels: pad every slice to the
     // longest row when that adds at most 5 % of storage
     if ((int64_t)A->plan.max_row * A->sell_height * A->sell_slices <= sp.back() + sp.back() / 20 && (int64_t)A->plan.max_row * A->sell_height * A->sell_slices != sp.back())
-      build_sell(A->n, rp.data(), ci.data(), v.data(), A->sell_height, sp, sc, sv, A->plan.max_row);
+      build_sell(A->n, rp.data(), ci.data(), v, A->sell_height, sp, sc, sv, A->plan.max_row);
     A->sell_width = A->sell_slices > 0 ? (int)((sp[1] - sp[0]) / A->sell_height) : 0;
     for (int q = 0; q < A->sell_slices; ++q)
       if (sp[q + 1] - sp[q] != (int64_t)A->sell_width * A->sell_height) { A->sell_width = 0; break; }
@@ -219,27 +229,30 @@ extern "C" int bg_matrix_create_csr(bg_context_t ctx, int n, int64_t nnz, const 
   *out = nullptr;
   BG_CUDA(cudaSetDevice(ctx->device));
   std::vector<int> rp(n + 1, 0), ci(nnz);
-  std::vector<unsigned char> hv(nnz * dtype_size(val_dtype));
+  std::vector<unsigned char> hv;  // staging for device-resident values only: host values are read in place
   if (mem == BG_DEVICE) {
+    hv.resize(nnz * dtype_size(val_dtype));
     if (n) BG_CUDA(cudaMemcpy(rp.data(), rowptr, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost));
     if (nnz) { BG_CUDA(cudaMemcpy(ci.data(), col, sizeof(int) * nnz, cudaMemcpyDeviceToHost)); BG_CUDA(cudaMemcpy(hv.data(), val, hv.size(), cudaMemcpyDeviceToHost)); }
+    val = hv.data();
   } else {
     if (n) std::memcpy(rp.data(), rowptr, sizeof(int) * (n + 1));
-    if (nnz) { std::memcpy(ci.data(), col, sizeof(int) * nnz); std::memcpy(hv.data(), val, hv.size()); }
+    int* d = ci.data();
+    parallel_ranges((size_t)nnz, [=](size_t b, size_t e) { std::copy(col + b, col + e, d + b); });
   }
   if (n && (rp[0] != 0 || rp[n] != nnz)) { set_error("rowptr[0] must be 0 and rowptr[n] == nnz"); return BG_ERR_ARG; }
-  return matrix_create_internal(ctx, n, n, rp, ci, hv.data(), val_dtype, compute_dtype, spmv_format, out);
+  return matrix_create_internal(ctx, n, n, std::move(rp), std::move(ci), val, val_dtype, compute_dtype, spmv_format, out);
 }
 namespace bg {
-int matrix_create_internal(bg_context_t ctx, int n, int ncols, const std::vector<int>& rp, const std::vector<int>& ci,
+int matrix_create_internal(bg_context_t ctx, int n, int ncols, std::vector<int> rp, std::vector<int> ci,
                            const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out) {
   const int64_t nnz = (int64_t)ci.size();
   for (int64_t p = 0; p < nnz; ++p)
     if (ci[p] < 0 || ci[p] >= ncols) { set_error("column index out of range at entry %lld", (long long)p); return BG_ERR_ARG; }
   bg_matrix_t A = new bg_matrix_s;
   A->ctx = ctx; A->n = n; A->ncols = ncols; A->nnz = nnz; A->dtype = compute_dtype;
-  int rc = compute_dtype == BG_F32 ? matrix_build<float>(A, rp, ci, to_vec<float>(val, val_dtype, nnz), spmv_format)
-                                   : matrix_build<double>(A, rp, ci, to_vec<double>(val, val_dtype, nnz), spmv_format);
+  int rc = compute_dtype == BG_F32 ? matrix_build<float>(A, std::move(rp), std::move(ci), val, val_dtype, spmv_format)
+                                   : matrix_build<double>(A, std::move(rp), std::move(ci), val, val_dtype, spmv_format);
   if (rc < 0) { delete A; return rc; }
   *out = A;
   return BG_OK;
@@ -1003,22 +1016,24 @@ template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev&
   std::vector<int> rp(n + 1, 0), ci(A->h_ci.size());
   std::vector<T> vv(A->h_ci.size());
   for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (A->h_rp[perm[i] + 1] - A->h_rp[perm[i]]);
-  std::vector<std::pair<int, T>> row;
-  for (int i = 0; i < n; ++i) {
-    const int o = perm[i];
-    row.clear();
-    const double di = fb.h_dinv[i];  // row scaling D^-1 (D = diag U): the device solves are unit solves
-    for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) {
-      const int c = A->h_ci[p];  // halo columns (>= n, row-partitioned matrices) keep their slot
-      row.emplace_back(c < n ? inv[c] : c, (T)((double)v[p] * di));
+  parallel_ranges((size_t)n, [&](size_t r0, size_t r1) {  // every permuted row writes its own segment
+    std::vector<std::pair<int, T>> row;
+    for (int i = (int)r0; i < (int)r1; ++i) {
+      const int o = perm[i];
+      row.clear();
+      const double di = fb.h_dinv[i];  // row scaling D^-1 (D = diag U): the device solves are unit solves
+      for (int p = A->h_rp[o]; p < A->h_rp[o + 1]; ++p) {
+        const int c = A->h_ci[p];  // halo columns (>= n, row-partitioned matrices) keep their slot
+        row.emplace_back(c < n ? inv[c] : c, (T)((double)v[p] * di));
+      }
+      std::sort(row.begin(), row.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
+      int q = rp[i];
+      for (auto& e : row) { ci[q] = e.first; vv[q++] = e.second; }
     }
-    std::sort(row.begin(), row.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
-    int q = rp[i];
-    for (auto& e : row) { ci[q] = e.first; vv[q++] = e.second; }
-  }
+  });
   bg_matrix_t P = new bg_matrix_s;
   P->ctx = A->ctx; P->n = n; P->ncols = A->ncols; P->nnz = A->nnz; P->dtype = A->dtype;
-  int rc = matrix_build<T>(P, rp, ci, vv, A->requested_format);
+  int rc = matrix_build<T>(P, std::move(rp), std::move(ci), vv.data(), sizeof(T) == 4 ? BG_F32 : BG_F64, A->requested_format);
   if (rc < 0) { delete P; return rc; }
   P->h_rp.clear(); P->h_rp.shrink_to_fit(); P->h_ci.clear(); P->h_ci.shrink_to_fit(); P->h_val.clear(); P->h_val.shrink_to_fit();
   delete A->permuted;

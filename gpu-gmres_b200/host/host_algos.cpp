@@ -2,8 +2,6 @@
 // SURVEY.md (appendix A) and cite the reference location whose integer artefacts they reproduce.
 #include "host_algos.h"
 
-#include <thread>
-
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -18,20 +16,6 @@ extern "C" int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj,
                                    int64_t* options, int64_t* edgecut, int64_t* part);
 
 namespace bg {
-// Setup of 10 M-row problems is bound by first-touch page faults and plain copies of several hundred megabytes:
-// independent index ranges are handed to a few host threads.  fn(begin, end) must only write its own range.
-template <class F> static void parallel_ranges(size_t n, F fn) {
-  const unsigned hw = std::thread::hardware_concurrency();
-  const size_t nt = n < (size_t)1 << 20 ? 1 : std::min<size_t>(8, hw ? hw : 1);
-  if (nt <= 1) { fn((size_t)0, n); return; }
-  std::vector<std::thread> th;
-  const size_t chunk = (n + nt - 1) / nt;
-  for (size_t t = 0; t < nt; ++t) {
-    const size_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b < e) th.emplace_back([=] { fn(b, e); });
-  }
-  for (auto& x : th) x.join();
-}
 template <class T> static void parallel_copy(std::vector<T>& dst, const T* src, size_t n) {
   dst.resize(n);  // (value-initialises: the faults of the zero fill are what is parallelised below for the big arrays)
   T* d = dst.data();
@@ -982,22 +966,30 @@ void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std:
     for (int i = s * slice; i < std::min(n, (s + 1) * slice); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
     slice_ptr[s + 1] = slice_ptr[s] + (int64_t)mx * slice;
   }
-  cols.assign(slice_ptr[ns], 0);
-  vals.assign(slice_ptr[ns], (T)0);
-  for (int s = 0; s < ns; ++s)
-    for (int t = 0; t < slice; ++t) {
-      const int i = s * slice + t;
-      if (i >= n) continue;
-      int k = 0;
-      for (int p = rp[i]; p < rp[i + 1]; ++p, ++k) {
-        cols[slice_ptr[s] + (int64_t)k * slice + t] = ci[p];
-        vals[slice_ptr[s] + (int64_t)k * slice + t] = v[p];
+  cols.resize(slice_ptr[ns]);
+  vals.resize(slice_ptr[ns]);
+  // slices are disjoint ranges of the output: filled by several threads at 10 M-row sizes (parallel_ranges)
+  parallel_ranges((size_t)ns, [&](size_t s0, size_t s1) {
+    for (size_t s = s0; s < s1; ++s) {
+      const int64_t base = slice_ptr[s], wid = (slice_ptr[s + 1] - base) / slice;
+      for (int t = 0; t < slice; ++t) {
+        const int64_t i = (int64_t)s * slice + t;
+        int64_t k = 0;
+        if (i < n)
+          for (int p = rp[i]; p < rp[i + 1]; ++p, ++k) {
+            cols[base + k * slice + t] = ci[p];
+            vals[base + k * slice + t] = v[p];
+          }
+        // padding keeps column = own row (a valid, cached address; row 0 past the end) and value 0
+        for (; k < wid; ++k) {
+          cols[base + k * slice + t] = i < n ? (int)i : 0;
+          vals[base + k * slice + t] = (T)0;
+        }
       }
-      // padding keeps column = own row (a valid, cached address) and value 0
-      const int64_t wid = (slice_ptr[s + 1] - slice_ptr[s]) / slice;
-      for (; k < wid; ++k) cols[slice_ptr[s] + (int64_t)k * slice + t] = i;
     }
+  }, ((size_t)1 << 20) / (size_t)slice);
 }
+
 template void build_sell<float>(int, const int*, const int*, const float*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<float>&, int);
 template void build_sell<double>(int, const int*, const int*, const double*, int, std::vector<int64_t>&, std::vector<int>&, std::vector<double>&, int);
 

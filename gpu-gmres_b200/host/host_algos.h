@@ -6,7 +6,26 @@
 #include <cstdint>
 #include <vector>
 
+#include <algorithm>
+#include <thread>
+
 namespace bg {
+
+// Setup of 10 M-row problems is bound by first-touch page faults and plain copies of several hundred megabytes:
+// independent index ranges are handed to a few host threads.  fn(begin, end) must only write its own range.
+template <class F> inline void parallel_ranges(size_t n, F fn, size_t min_parallel = (size_t)1 << 20) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = n < min_parallel ? 1 : std::min<size_t>(8, hw ? hw : 1);
+  if (nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b < e) th.emplace_back([=] { fn(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
+
 
 // |v| < 1e-9 counts as a structural zero (reference: src/defs.h:45-47)
 constexpr float kEps = 1e-9f;

@@ -159,6 +159,20 @@ def test_level_stream_packers(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
 
 
+def test_sell_packer(tmp_path):
+    """build_sell (the SpMV storage of every matrix) at single-thread and threaded sizes: entries in row order
+    at [slice_ptr + k*slice + t], zero padding with in-range columns, product identical to CSR."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "sell_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "sell_check.cpp"),
+                           os.path.join(root, "gpu-gmres_b200", "host", "host_algos.cpp"),
+                           "/usr/local/cuda/lib64/libmetis_static.a", "-lpthread", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_fused_block_stream_packer(tmp_path):
     """The packed factor stream of the block-Jacobi solve, interpreted on the host step by step the
     way trsv_block_fused consumes it, reproduces a plain CSR forward/backward solve."""
