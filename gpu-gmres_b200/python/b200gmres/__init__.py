@@ -444,6 +444,85 @@ class Solver:
 
 
 # ------------------------------------------------------------------ row-partitioned (multi-GPU) solve
+class NetlistInfo(C.Structure):
+    _fields_ = [("n_nodes", C.c_int), ("n_inductors", C.c_int), ("n_vsources", C.c_int), ("n_isources", C.c_int),
+                ("n_resistors", C.c_int), ("n_capacitors", C.c_int), ("size", C.c_int), ("size_mna", C.c_int),
+                ("n_sources", C.c_int), ("n_ports", C.c_int), ("formulation", C.c_int), ("n_eliminated", C.c_int),
+                ("n_pulse", C.c_int), ("dc", C.c_int), ("nnz_g", C.c_int64), ("nnz_c", C.c_int64), ("nnz_b", C.c_int64),
+                ("n_pwl_points", C.c_int64), ("n_lines", C.c_int64), ("tstep", C.c_double), ("tstop", C.c_double)]
+
+
+SRC_DC, SRC_PWL, SRC_PULSE = 0, 1, 2
+NETLIST_MNA, NETLIST_REDUCED = 0, 1
+
+
+class Netlist:
+    """SPICE-subset power-grid netlist -> G, C, B (CSR triples), source tables, ports (bg_netlist_*): what
+    Matrix / Transient take.  `source` is a path, or the netlist text itself when text=True."""
+
+    def __init__(self, source, formulation=NETLIST_MNA, text=False, include_dir=None):
+        self.h = C.c_void_p()
+        if text:
+            raw = source.encode() if isinstance(source, str) else bytes(source)
+            _chk(lib().bg_netlist_parse(raw, C.c_int64(len(raw)), include_dir.encode() if include_dir else None, int(formulation), C.byref(self.h)))
+        else:
+            _chk(lib().bg_netlist_read(str(source).encode(), int(formulation), C.byref(self.h)))
+        self.info = NetlistInfo()
+        _chk(lib().bg_netlist_get_info(self.h, C.byref(self.info)))
+        i = self.info
+        self.G, self.C, self.B = (self._matrix(w, nz) for w, nz in (("G", i.nnz_g), ("C", i.nnz_c), ("B", i.nnz_b)))
+        self.kind = np.zeros(i.n_sources, np.int32)
+        self.pwl_ptr = np.zeros(i.n_sources + 1, np.int32)
+        self.pwl_t, self.pwl_v = np.zeros(i.n_pwl_points), np.zeros(i.n_pwl_points)
+        self.pulse_src = np.zeros(i.n_pulse, np.int32)
+        self.pulse_time, self.pulse_val = np.zeros((i.n_pulse, 5)), np.zeros((i.n_pulse, 2))
+        _chk(lib().bg_netlist_get_sources(self.h, _p(self.kind), _p(self.pwl_ptr), _p(self.pwl_t), _p(self.pwl_v), _p(self.pulse_src),
+                                          _p(self.pulse_time), _p(self.pulse_val)))
+        self.ports = np.zeros(i.n_ports, np.int32)
+        _chk(lib().bg_netlist_get_ports(self.h, _p(self.ports)))
+        self.kept = np.zeros(i.size, np.int32)
+        self.elim_row, self.elim_src, self.elim_sign = np.zeros(i.n_eliminated, np.int32), np.zeros(i.n_eliminated, np.int32), np.zeros(i.n_eliminated)
+        _chk(lib().bg_netlist_get_reduction(self.h, _p(self.kept), _p(self.elim_row), _p(self.elim_src), _p(self.elim_sign)))
+
+    def _matrix(self, which, nnz):
+        rp, ci, v = np.zeros(self.info.size + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        _chk(lib().bg_netlist_get_matrix(self.h, ord(which), _p(rp), _p(ci), _p(v)))
+        return rp, ci, v
+
+    @property
+    def pwl(self):
+        """per source (times, values): the `pwl` argument of Transient"""
+        return [(self.pwl_t[a:b], self.pwl_v[a:b]) for a, b in zip(self.pwl_ptr[:-1], self.pwl_ptr[1:])]
+
+    def u(self, t):
+        """source values at time t (piecewise-linear tables, held at their end values outside)"""
+        return np.array([np.interp(t, tt, vv) if len(tt) else 0.0 for tt, vv in self.pwl])
+
+    def node_row(self, name) -> int:
+        """row of a node; -1 ground, -2 unknown, -3 eliminated by BG_NETLIST_REDUCED"""
+        return int(lib().bg_netlist_node_row(self.h, str(name).encode()))
+
+    def row_name(self, row) -> str:
+        buf = C.create_string_buffer(256)
+        _chk(lib().bg_netlist_row_name(self.h, int(row), buf, 256))
+        return buf.value.decode()
+
+    def expand(self, x, t=0.0):
+        """solution of the active formulation -> MNA numbering (node voltages; the currents of eliminated sources stay NaN)"""
+        full = np.full(self.info.size_mna, np.nan)
+        full[self.kept] = x
+        if len(self.elim_row):
+            full[self.elim_row] = self.elim_sign * self.u(t)[self.elim_src]
+        return full
+
+    def close(self):
+        if self.h:
+            lib().bg_netlist_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+
 class TransientStats(C.Structure):
     _fields_ = [("steps", C.c_int), ("iters_max", C.c_int), ("not_converged", C.c_int), ("iters_total", C.c_int64),
                 ("launches", C.c_int64), ("last_resid", C.c_double), ("device_ms", C.c_double)]

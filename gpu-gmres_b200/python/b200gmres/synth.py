@@ -63,6 +63,66 @@ def pg2d(nx: int, ny: int, seed: int = SEED_BASE + 1, pad_pitch: int = 16, c_ove
     return rowptr, col, val, b.ravel().copy()
 
 
+def pg2d_netlist(nx: int, ny: int, seed: int = SEED_BASE + 1, pad_pitch: int = 16, cap: float = 1e-12, tstep: float = 1e-11,
+                 nsteps: int = 0, load: str = "dc", ports=((0, 0),)):
+    """The pg2d() grid as an ibmpg-style SPICE netlist (text), for the netlist front end (bg_netlist_*).
+
+    Same random stream and therefore the same conductances, pads and loads as pg2d(): node n_{ix}_{iy} is grid node
+    iy*nx+ix and appears first on its capacitor line, so the parser's first-appearance numbering IS pg2d's row order;
+    a pad is an ideal 1.8 V source behind a 0.1 ohm package resistor (the Norton pad of pg2d after elimination);
+    a load is a current source node -> ground, DC or (load="pwl") a ramp 0 -> I over 10 steps, or (load="pulse") a
+    periodic trapezoid.  Capacitors to ground are U(1,2)*cap like pg2d(c_over_h = cap/tstep).  nsteps > 0 adds
+    ".tran tstep nsteps*tstep"; `ports` become ".print tran v(...)".
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    gh = 1.0 * (1.0 + 0.1 * rng.uniform(-1, 1, size=(ny, nx - 1)))
+    gv = 0.5 * (1.0 + 0.1 * rng.uniform(-1, 1, size=(ny - 1, nx)))
+    off = pad_pitch // 2
+    pad = np.zeros((ny, nx), dtype=bool)
+    pad[off::pad_pitch, off::pad_pitch] = True
+    is_load = rng.uniform(0, 1, size=(ny, nx)) < 0.2
+    amps = np.zeros((ny, nx))
+    amps[is_load] = rng.uniform(0, 1e-3, size=int(is_load.sum()))
+    cval = cap * rng.uniform(1, 2, size=(ny, nx))
+    name = lambda ix, iy: f"n_{ix}_{iy}"
+    out = [f"* pg2d {nx} x {ny}, seed {seed:#x}: synthetic power grid in the ibmpg netlist dialect"]
+    for iy in range(ny):
+        for ix in range(nx):
+            out.append(f"C{iy * nx + ix} {name(ix, iy)} 0 {float(cval[iy, ix])!r}")
+    k = 0
+    for iy in range(ny):
+        for ix in range(nx - 1):
+            out.append(f"Rh{k} {name(ix, iy)} {name(ix + 1, iy)} {float(1.0 / gh[iy, ix])!r}"); k += 1
+    k = 0
+    for iy in range(ny - 1):
+        for ix in range(nx):
+            out.append(f"Rv{k} {name(ix, iy)} {name(ix, iy + 1)} {float(1.0 / gv[iy, ix])!r}"); k += 1
+    k = 0
+    for iy, ix in zip(*np.nonzero(pad)):
+        out.append(f"Rp{k} {name(ix, iy)} _X_{name(ix, iy)} 0.1")
+        out.append(f"Vp{k} _X_{name(ix, iy)} 0 1.8"); k += 1
+    k = 0
+    tstop = nsteps * tstep
+    for iy, ix in zip(*np.nonzero(is_load)):
+        a = float(amps[iy, ix])
+        if load == "pwl":
+            if k % 2:  # both spellings the reference reads: one line, or "PWL(" followed by one pair per "+" line
+                out.append(f"Il{k} {name(ix, iy)} 0 PWL(0 0 {10 * tstep!r} {a!r} {max(tstop, 11 * tstep)!r} {a!r})")
+            else:
+                out += [f"Il{k} {name(ix, iy)} 0 PWL(", f"+ 0 0", f"+ {10 * tstep!r} {a!r}", f"+ {max(tstop, 11 * tstep)!r} {a!r}", "+ )"]
+        elif load == "pulse":
+            out.append(f"Il{k} {name(ix, iy)} 0 0 PULSE(0 {a!r} {2 * tstep!r} {3 * tstep!r} {3 * tstep!r} {4 * tstep!r} {16 * tstep!r})")
+        else:
+            out.append(f"Il{k} {name(ix, iy)} 0 {a!r}")
+        k += 1
+    if nsteps > 0:
+        out.append(f".tran {tstep!r} {tstop!r}")
+    if ports:
+        out.append(".print tran " + " ".join(f"v({name(ix, iy)})" for ix, iy in ports))
+    out.append(".end")
+    return "\n".join(out) + "\n"
+
+
 def th3d(nx: int, ny: int, nz: int, seed: int = SEED_BASE + 3, c_over_h: float = 0.05):
     """3-D IC thermal grid, 7-point, non-symmetric on the micro-channel layers (z % 4 == 1).
 

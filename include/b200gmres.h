@@ -160,6 +160,52 @@ BG_API int bg_host_write_csr(const char* path, int file_format, int n_rows, int 
 BG_API int bg_host_read_vector(const char* path, int n, int dtype, void* out);
 BG_API int bg_host_write_vector(const char* path, int n, int dtype, const void* x);
 
+/* ---- netlist ingest: SPICE-subset power-grid netlist -> MNA matrices and source tables ----
+   Replaces parser_sub + stampG / stampC / stampB behind parser_wrapper (src/etbr_wrapper.cpp:46-171,
+   src/parser.cpp:273-636, 1904-2886) and keeps their conventions: nodes numbered by first appearance on R/C/L/V/I
+   lines with "0"/"gnd" as ground, unknowns [node voltages | inductor currents | voltage-source currents], G x +
+   C dx/dt = B u(t) with the voltage sources in the first columns of B and the current sources after them, scale
+   letters t g k m(eg) u n p f, DC / PWL(..., "+ t v" continuations) / PULSE(v1 v2 td tr tf pw period) sources,
+   .tran tstep tstop, .print tran v(node) ..., .include.  Sub-circuits (.subckt / X) are BG_ERR_UNSUPPORTED; a
+   malformed element is BG_ERR_ARG with its line number in bg_last_error().  Matrices come back as CSR with sorted
+   columns (the reference hands out the same matrices column-compressed), duplicate stamps added in file order.
+   BG_NETLIST_REDUCED (not in the reference) eliminates the nodes a voltage source ties to ground together with
+   that source's current: the rows with a zero diagonal disappear, the known voltages move into B, and what is
+   left suits the ILU(0) paths; bg_netlist_get_reduction maps back to the MNA numbering. */
+typedef struct bg_netlist_s* bg_netlist_t;
+enum { BG_SRC_DC = 0, BG_SRC_PWL = 1, BG_SRC_PULSE = 2 };
+enum { BG_NETLIST_MNA = 0, BG_NETLIST_REDUCED = 1 };
+typedef struct {
+  int n_nodes, n_inductors, n_vsources, n_isources, n_resistors, n_capacitors;
+  int size;        /* unknowns of the formulation asked for (rows of G, C, B)            */
+  int size_mna;    /* n_nodes + n_inductors + n_vsources (src/etbr_wrapper.cpp:112)      */
+  int n_sources;   /* columns of B                                                        */
+  int n_ports;     /* nodes named by .print that exist and are not ground                 */
+  int formulation, n_eliminated, n_pulse, dc; /* dc: no .tran line (src/etbr_wrapper.cpp:77-81) */
+  int64_t nnz_g, nnz_c, nnz_b, n_pwl_points, n_lines;
+  double tstep, tstop;
+} bg_netlist_info;
+BG_API int bg_netlist_read(const char* path, int formulation, bg_netlist_t* N);
+BG_API int bg_netlist_parse(const char* text, int64_t len, const char* include_dir /* may be NULL */, int formulation,
+                            bg_netlist_t* N);
+BG_API int bg_netlist_get_info(bg_netlist_t N, bg_netlist_info* info);
+/* which = 'G', 'C' or 'B'; rowptr[size + 1], col/val[nnz_*] */
+BG_API int bg_netlist_get_matrix(bg_netlist_t N, int which, int* rowptr, int* col, double* val);
+/* per source (column of B): kind[n_sources]; the breakpoint table the reference keeps, pwl_ptr[n_sources + 1],
+   pwl_t / pwl_v[n_pwl_points] (DC: two points 0 and tstop; PWL: a point at t = 0 is added when the first time is not
+   0; PULSE: six per period up to tstop, src/parser.cpp:2497-2518) -- the arguments of bg_transient_create; and the
+   PULSE records pulse_src[n_pulse], pulse_time[5 n_pulse] = (td, tr, tf, pw, period), pulse_val[2 n_pulse] =
+   (v1, v2) -- the arguments of bg_transient_set_pulse.  Any pointer may be NULL. */
+BG_API int bg_netlist_get_sources(bg_netlist_t N, int* kind, int* pwl_ptr, double* pwl_t, double* pwl_v, int* pulse_src,
+                                  double* pulse_time, double* pulse_val);
+BG_API int bg_netlist_get_ports(bg_netlist_t N, int* rows /* [n_ports]; -1: a node BG_NETLIST_REDUCED eliminated */);
+/* row of a node in the active formulation; -1 ground, -2 unknown name, -3 eliminated */
+BG_API int bg_netlist_node_row(bg_netlist_t N, const char* name);
+BG_API int bg_netlist_row_name(bg_netlist_t N, int row, char* buf, int cap);
+/* kept_mna_row[size]: MNA row of every unknown; eliminated nodes: v(elim_mna_row[k]) = elim_sign[k] * u(elim_source[k]) */
+BG_API int bg_netlist_get_reduction(bg_netlist_t N, int* kept_mna_row, int* elim_mna_row, int* elim_source, double* elim_sign);
+BG_API int bg_netlist_destroy(bg_netlist_t N);
+
 /* ---- preconditioners ---- */
 typedef struct {
   int trsv_schedule;   /* BG_TRSV_LEVEL (default) or BG_TRSV_BLOCK                               */

@@ -10,3 +10,13 @@ typedef struct cs_dl_sparse {
   double* x;
   UF_long nz;
 } cs_dl;
+
+// the int flavour and the two allocators src/matrix.cpp (mat2cs / mat2csdl) uses; defined in oracle/ref_parser_wrap.cpp
+typedef struct cs_sparse {
+  int nzmax, m, n;
+  int *p, *i;
+  double* x;
+  int nz;
+} cs;
+cs* cs_spalloc(int m, int n, int nzmax, int values, int triplet);
+cs_dl* cs_dl_spalloc(UF_long m, UF_long n, UF_long nzmax, UF_long values, UF_long triplet);

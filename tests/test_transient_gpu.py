@@ -146,3 +146,71 @@ def test_transient_pulse_sources(bg, ctx):
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
     assert np.abs(probe - probe_ref).max() <= 1e-7 * np.abs(probe_ref).max()
     T.close(); S.close(); M.close(); Am.close()
+
+
+@pytest.mark.parametrize("load", ["pwl", "pulse"])
+def test_netlist_to_device_transient(bg, ctx, load):
+    """netlist text -> bg_netlist_* (reduced formulation) -> DC operating point + device-resident transient with the
+    .print nodes sampled, against host backward Euler with direct solves on the FULL MNA system of the same netlist
+    (voltage-source rows kept): the two formulations and the two code paths must describe the same circuit."""
+    from b200gmres import synth
+
+    nx, ny, nsteps = 48, 40, 30
+    text = synth.pg2d_netlist(nx, ny, seed=synth.SEED_BASE + 9, pad_pitch=8, nsteps=nsteps, load=load, ports=((0, 0), (24, 20), (47, 39)))
+    F = bg.Netlist(text, text=True)                                       # full MNA: the host reference
+    R = bg.Netlist(text, formulation=bg.NETLIST_REDUCED, text=True)     # what runs on the device
+    h = R.info.tstep
+    assert R.info.size == nx * ny and abs(R.info.tstop - nsteps * h) < 1e-25
+
+    def csr(t, shape):
+        return sp.csr_matrix((t[2], t[1], t[0]), shape=shape)
+
+    nf, nr, ns = F.info.size, R.info.size, R.info.n_sources
+    Gf, Cf, Bf = csr(F.G, (nf, nf)), csr(F.C, (nf, nf)), csr(F.B, (nf, ns))
+
+    def u_of(t):
+        u = F.u(t)
+        for k, (tm, pv) in zip(F.pulse_src, zip(F.pulse_time, F.pulse_val)):
+            u[k] = pulse_value(t, *tm, *pv)
+        return u
+
+    x_ref = spla.splu(Gf.tocsc()).solve(Bf @ u_of(0.0))
+    x0_full = x_ref.copy()
+    lu = spla.splu((Gf + Cf / h).tocsc())
+    probe_ref = np.zeros((nsteps, len(F.ports)))
+    for i in range(1, nsteps + 1):
+        x_ref = lu.solve(Bf @ u_of(h * i) + (Cf / h) @ x_ref)
+        probe_ref[i - 1] = x_ref[F.ports]
+
+    Gr, Cr = csr(R.G, (nr, nr)), csr(R.C, (nr, nr))
+    Ch = sp.csr_matrix(Cr / h); Ch.sort_indices()
+    At = sp.csr_matrix(Gr + Ch); At.sort_indices()
+    o = bg.precond_opts(trsv_schedule=bg.TRSV_BLOCK, block_rows=1024, block_method=bg.PART_GRID2D, dims=[nx, ny, 1, 32, 32, 1])
+    opts = bg.gmres_opts(m=32, tol=1e-11, max_iter=2000, orth=bg.ORTH_CGS_ADAPTIVE, reorth_eta=0.1)
+    S = bg.Solver(ctx, nr, 32, dtype=bg.F64)
+    # DC operating point on the device
+    A0 = bg.Matrix(ctx, *R.G, dtype=bg.F64)
+    M0 = bg.Precond.ilu0(ctx, *R.G, dtype=bg.F64, opts=o)
+    db = torch.from_numpy(csr(R.B, (nr, ns)) @ u_of(0.0)).cuda()
+    dx = torch.zeros(nr, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    r = S.solve(A0, M0, db.data_ptr(), dx.data_ptr(), opts)
+    ctx.sync()
+    assert r.flag == 0
+    nn = F.info.n_nodes
+    full0 = R.expand(dx.cpu().numpy(), 0.0)
+    assert np.abs(full0[:nn] - x0_full[:nn]).max() <= 1e-8 * np.abs(x0_full[:nn]).max()
+    # transient on the device, started from the device's own operating point
+    A1 = bg.Matrix(ctx, At.indptr, At.indices, At.data, dtype=bg.F64)
+    M1 = bg.Precond.ilu0(ctx, At.indptr, At.indices, At.data, dtype=bg.F64, opts=o)
+    T = bg.Transient(ctx, S, A1, M1, (Ch.indptr, Ch.indices, Ch.data), R.B, R.pwl, list(R.ports))
+    if R.info.n_pulse:
+        T.set_pulse(R.pulse_src, R.pulse_time, R.pulse_val)
+    rc, st, probe = T.run(dx.data_ptr(), 0.0, h, nsteps, opts)
+    ctx.sync()
+    assert rc == 0 and st.steps == nsteps and st.not_converged == 0
+    full = R.expand(dx.cpu().numpy(), h * nsteps)
+    assert np.abs(full[:nn] - x_ref[:nn]).max() <= 1e-7 * np.abs(x_ref[:nn]).max()
+    assert np.abs(probe - probe_ref).max() <= 1e-7 * np.abs(probe_ref).max()
+    assert np.ptp(probe_ref[:, 1]) > 1e-6        # the loads do move the grid: the comparison is not of a constant
+    T.close(); S.close(); M1.close(); A1.close(); M0.close(); A0.close()
