@@ -31,12 +31,13 @@
 // of this library are built for; bg_netlist_get_reduction maps solutions back.
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <unordered_map>
+#include <cstdint>
 #include <vector>
 
 #include "../../include/b200gmres.h"
@@ -65,12 +66,57 @@ struct Source {
   int line = 0;
 };
 struct Branch { int a, b; double value; int line; };
+
+// node name -> node number: open addressing over 64-bit hashes, the names themselves live in node_name (a netlist
+// of N nodes costs 3-7 lookups per line; std::unordered_map spent more than half of the parse time here)
+struct NameTable {
+  struct Slot { uint64_t hash; int id; int pad; };  // hash 0 = empty; one cache line miss per probe
+  std::vector<Slot> slot;
+  size_t used = 0;
+  static uint64_t hash_of(const char* p, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t k = 0; k < n; ++k) h = (h ^ (unsigned char)p[k]) * 0x100000001b3ull;
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+    return h ? h : 1;
+  }
+  void grow() {
+    const size_t cap = slot.empty() ? 1024 : slot.size() * 2;
+    std::vector<Slot> s2(cap, Slot{0, 0, 0});
+    for (const Slot& s : slot)
+      if (s.hash) {
+        size_t q = s.hash & (cap - 1);
+        while (s2[q].hash) q = (q + 1) & (cap - 1);
+        s2[q] = s;
+      }
+    slot.swap(s2);
+  }
+  // number of `name`, or -1 when absent; `add` >= 0 inserts it with that number
+  int find(const std::vector<std::string>& names, const char* p, size_t n, int add = -1) {
+    if (used * 2 >= slot.size()) grow();
+    const uint64_t h = hash_of(p, n);
+    const size_t mask = slot.size() - 1;
+    size_t q = h & mask;
+    for (; slot[q].hash; q = (q + 1) & mask)
+      if (slot[q].hash == h) {
+        const std::string& nm = names[(size_t)slot[q].id];
+        if (nm.size() == n && std::memcmp(nm.data(), p, n) == 0) return slot[q].id;
+      }
+    if (add >= 0) { slot[q] = Slot{h, add, 0}; ++used; }
+    return -1;
+  }
+};
+inline bool is_ground(const char* p, size_t n) { return (n == 1 && p[0] == '0') || (n == 3 && p[0] == 'g' && p[1] == 'n' && p[2] == 'd'); }
 }  // namespace
 
 struct bg_netlist_s {
   int formulation = BG_NETLIST_MNA;
   std::vector<std::string> node_name;  // by node number
-  std::unordered_map<std::string, int> node_of;  // name -> number or kGround
+  NameTable node_of;  // name -> number (ground is recognised by name)
+  int lookup(const char* p, size_t n) {  // -1 ground, -2 unknown
+    if (is_ground(p, n)) return kGround;
+    const int id = node_of.find(node_name, p, n);
+    return id < 0 ? -2 : id;
+  }
   std::vector<Branch> res, cap, ind;
   std::vector<Source> vs, is;
   std::vector<std::string> port_name;
@@ -90,18 +136,24 @@ struct bg_netlist_s {
 };
 
 namespace {
-// StrToNum: the scale letter follows the number directly (src/parser.cpp:30-66)
-bool parse_number(const std::string& s, double& out) {
-  const char* p = s.c_str();
+// StrToNum: the scale letter follows the number directly (src/parser.cpp:30-66).  Tokens point into the NUL-terminated
+// text and end at a separator, which also stops strtod.
+struct Tok {
+  const char* p;
+  size_t n;
+  std::string str() const { return std::string(p, n); }
+};
+bool parse_number(const Tok& tk, double& out) {
   char* end = nullptr;
-  const double x = std::strtod(p, &end);
-  if (end == p) return false;
+  const double x = std::strtod(tk.p, &end);
+  if (end == tk.p || end > tk.p + tk.n) return false;
+  const char c0 = end < tk.p + tk.n ? end[0] : '\0', c1 = end + 1 < tk.p + tk.n ? end[1] : '\0';
   int e = 0;
-  switch (end[0]) {
+  switch (c0) {
     case 'T': case 't': e = 12; break;
     case 'G': case 'g': e = 9; break;
     case 'K': case 'k': e = 3; break;
-    case 'M': case 'm': e = (end[1] == 'E' || end[1] == 'e') ? 6 : -3; break;
+    case 'M': case 'm': e = (c1 == 'E' || c1 == 'e') ? 6 : -3; break;
     case 'U': case 'u': e = -6; break;
     case 'N': case 'n': e = -9; break;
     case 'P': case 'p': e = -12; break;
@@ -111,38 +163,40 @@ bool parse_number(const std::string& s, double& out) {
   out = e ? x * std::pow(10.0, e) : x;  // value * pow(10.0, e) like the reference, so the doubles agree
   return true;
 }
-bool ieq(const std::string& s, const char* lit) {  // case-insensitive prefix match of the literal
+bool ieq(const char* p, size_t n, const char* lit) {  // case-insensitive prefix match of the literal
   size_t k = 0;
   for (; lit[k]; ++k)
-    if (k >= s.size() || std::tolower((unsigned char)s[k]) != lit[k]) return false;
+    if (k >= n || std::tolower((unsigned char)p[k]) != lit[k]) return false;
   return true;
 }
-std::vector<std::string> tokens_of(const std::string& line, bool split_punct) {
-  std::vector<std::string> out;
-  std::string cur;
-  for (char ch : line) {
-    const bool sep = ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n' || (split_punct && (ch == '(' || ch == ')' || ch == ',' || ch == '='));
-    if (sep) { if (!cur.empty()) { out.push_back(cur); cur.clear(); } }
-    else cur.push_back(ch);
+bool ieq(const Tok& t, const char* lit) { return ieq(t.p, t.n, lit); }
+void tokens_of(const char* p, size_t n, bool split_punct, std::vector<Tok>& out) {
+  out.clear();
+  size_t k = 0;
+  while (k < n) {
+    auto sep = [&](char ch) { return ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n' || (split_punct && (ch == '(' || ch == ')' || ch == ',' || ch == '=')); };
+    while (k < n && sep(p[k])) ++k;
+    const size_t b = k;
+    while (k < n && !sep(p[k])) ++k;
+    if (k > b) out.push_back({p + b, k - b});
   }
-  if (!cur.empty()) out.push_back(cur);
-  return out;
 }
 
 struct Parser {
   bg_netlist_s& N;
   std::string err;
-  Source* open_pwl = nullptr;  // the source "+ t v" continuation lines extend
+  bool open_pwl = false;  // "+ t v" continuation lines extend the last source (of the list open_is_v names)
+  bool open_is_v = false;
   int depth = 0;
+  std::vector<Tok> tk;
   explicit Parser(bg_netlist_s& n) : N(n) {}
 
-  int node(const std::string& name) {
-    auto it = N.node_of.find(name);
-    if (it != N.node_of.end()) return it->second;
-    int id = kGround;
-    if (name != "0" && name != "gnd") { id = N.n_nodes(); N.node_name.push_back(name); }
-    N.node_of.emplace(name, id);
-    return id;
+  int node(const Tok& t) {
+    if (is_ground(t.p, t.n)) return kGround;
+    const int id = N.node_of.find(N.node_name, t.p, t.n, N.n_nodes());
+    if (id >= 0) return id;
+    N.node_name.emplace_back(t.p, t.n);
+    return N.n_nodes() - 1;
   }
   bool fail(int line, const char* what, const std::string& text) {
     char buf[512];
@@ -155,9 +209,9 @@ struct Parser {
     s.t.push_back(t);
     s.v.push_back(v);
   }
-  bool source_line(const std::string& line, int ln, bool is_v) {
-    std::vector<std::string> tk = tokens_of(line, true);
-    if (tk.size() < 4) return fail(ln, "source needs two nodes and a value", line);
+  bool source_line(const char* lp, size_t ll, int ln, bool is_v) {
+    tokens_of(lp, ll, true, tk);
+    if (tk.size() < 4) return fail(ln, "source needs two nodes and a value", std::string(lp, ll));
     Source s;
     s.is_v = is_v;
     s.line = ln;
@@ -169,42 +223,41 @@ struct Parser {
     while (kw < tk.size() && !ieq(tk[kw], "pwl") && !ieq(tk[kw], "pu")) ++kw;
     if (kw < tk.size() && ieq(tk[kw], "pwl")) {
       s.kind = BG_SRC_PWL;
-      std::vector<double> num;
-      for (size_t q = kw + 1; q < tk.size(); ++q) {
-        double x;
-        if (!parse_number(tk[q], x)) return fail(ln, "bad number in PWL", line);
-        num.push_back(x);
+      if ((tk.size() - kw - 1) % 2) return fail(ln, "PWL needs time/value pairs", std::string(lp, ll));
+      for (size_t q = kw + 1; q < tk.size(); q += 2) {
+        double t, v;
+        if (!parse_number(tk[q], t) || !parse_number(tk[q + 1], v)) return fail(ln, "bad number in PWL", std::string(lp, ll));
+        pwl_point(s, t, v);
       }
-      if (num.size() % 2) return fail(ln, "PWL needs time/value pairs", line);
-      for (size_t q = 0; q < num.size(); q += 2) pwl_point(s, num[q], num[q + 1]);
     } else if (kw < tk.size()) {
       s.kind = BG_SRC_PULSE;
-      if (tk.size() - kw - 1 != 7) return fail(ln, "PULSE needs v1 v2 td tr tf pw period", line);
+      if (tk.size() - kw - 1 != 7) return fail(ln, "PULSE needs v1 v2 td tr tf pw period", std::string(lp, ll));
       for (int q = 0; q < 7; ++q)
-        if (!parse_number(tk[kw + 1 + q], s.pulse[q])) return fail(ln, "bad number in PULSE", line);
-      if (!(s.pulse[6] > 0)) return fail(ln, "PULSE period must be positive", line);
+        if (!parse_number(tk[kw + 1 + q], s.pulse[q])) return fail(ln, "bad number in PULSE", std::string(lp, ll));
+      if (!(s.pulse[6] > 0)) return fail(ln, "PULSE period must be positive", std::string(lp, ll));
     } else {
-      if (ieq(tk[k], "dc") && tk[k].size() == 2) ++k;
+      if (ieq(tk[k], "dc") && tk[k].n == 2) ++k;
       double x;
-      if (k >= tk.size() || !parse_number(tk[k], x)) return fail(ln, "bad source value", line);
+      if (k >= tk.size() || !parse_number(tk[k], x)) return fail(ln, "bad source value", std::string(lp, ll));
       s.kind = BG_SRC_DC;
       s.pulse[0] = x;
     }
-    std::vector<Source>& dst = is_v ? N.vs : N.is;
-    dst.push_back(std::move(s));
-    open_pwl = dst.back().kind == BG_SRC_PWL ? &dst.back() : nullptr;
+    open_pwl = s.kind == BG_SRC_PWL;
+    open_is_v = is_v;
+    (is_v ? N.vs : N.is).push_back(std::move(s));
     return true;
   }
-  bool branch_line(const std::string& line, int ln, std::vector<Branch>& dst, const char* what) {
-    std::vector<std::string> tk = tokens_of(line, false);
+  bool branch_line(const char* lp, size_t ll, int ln, std::vector<Branch>& dst, const char* what) {
+    tokens_of(lp, ll, false, tk);
     double x;
-    if (tk.size() < 4 || !parse_number(tk[3], x)) return fail(ln, what, line);
-    if (!(x > 0) || !std::isfinite(x)) return fail(ln, "element value must be positive and finite", line);
+    if (tk.size() < 4 || !parse_number(tk[3], x)) return fail(ln, what, std::string(lp, ll));
+    if (!(x > 0) || !std::isfinite(x)) return fail(ln, "element value must be positive and finite", std::string(lp, ll));
     const int a = node(tk[1]), b = node(tk[2]);
     dst.push_back({a, b, x, ln});
-    open_pwl = nullptr;
+    open_pwl = false;
     return true;
   }
+  // `p` must be NUL-terminated at p[len]
   bool text(const char* p, size_t len, const std::string& dir) {
     if (++depth > 16) { err = "netlist: .include nested deeper than 16"; return false; }
     size_t pos = 0;
@@ -212,38 +265,38 @@ struct Parser {
     while (pos < len) {
       size_t e = pos;
       while (e < len && p[e] != '\n') ++e;
-      std::string line(p + pos, e - pos);
+      const char* lp = p + pos;
+      size_t ll = e - pos;
       pos = e + 1;
       ++ln;
       ++N.n_lines;
-      size_t f = 0;
-      while (f < line.size() && (line[f] == ' ' || line[f] == '\t')) ++f;
-      if (f == line.size()) continue;
-      const char c0 = line[f];
-      if (f) line.erase(0, f);
-      switch (c0) {
-        case 'R': case 'r': if (!branch_line(line, ln, N.res, "resistor needs two nodes and a value")) return false; break;
-        case 'C': case 'c': if (!branch_line(line, ln, N.cap, "capacitor needs two nodes and a value")) return false; break;
-        case 'L': case 'l': if (!branch_line(line, ln, N.ind, "inductor needs two nodes and a value")) return false; break;
-        case 'V': case 'v': if (!source_line(line, ln, true)) return false; break;
-        case 'I': case 'i': if (!source_line(line, ln, false)) return false; break;
-        case 'X': case 'x': return fail(ln, "sub-circuit instances are not supported", line);
+      while (ll && (*lp == ' ' || *lp == '\t')) { ++lp; --ll; }
+      if (!ll) continue;
+      switch (*lp) {
+        case 'R': case 'r': if (!branch_line(lp, ll, ln, N.res, "resistor needs two nodes and a value")) return false; break;
+        case 'C': case 'c': if (!branch_line(lp, ll, ln, N.cap, "capacitor needs two nodes and a value")) return false; break;
+        case 'L': case 'l': if (!branch_line(lp, ll, ln, N.ind, "inductor needs two nodes and a value")) return false; break;
+        case 'V': case 'v': if (!source_line(lp, ll, ln, true)) return false; break;
+        case 'I': case 'i': if (!source_line(lp, ll, ln, false)) return false; break;
+        case 'X': case 'x': return fail(ln, "sub-circuit instances are not supported", std::string(lp, ll));
         case '+': {
           if (!open_pwl) break;  // continuation of something this subset ignores
-          std::vector<std::string> tk = tokens_of(line.substr(1), true);
-          if (tk.size() % 2) return fail(ln, "PWL continuation needs time/value pairs", line);
+          tokens_of(lp + 1, ll - 1, true, tk);
+          if (tk.size() % 2) return fail(ln, "PWL continuation needs time/value pairs", std::string(lp, ll));
+          Source& s = open_is_v ? N.vs.back() : N.is.back();
           for (size_t q = 0; q < tk.size(); q += 2) {
             double t, v;
-            if (!parse_number(tk[q], t) || !parse_number(tk[q + 1], v)) return fail(ln, "bad number in PWL continuation", line);
-            pwl_point(*open_pwl, t, v);
+            if (!parse_number(tk[q], t) || !parse_number(tk[q + 1], v)) return fail(ln, "bad number in PWL continuation", std::string(lp, ll));
+            pwl_point(s, t, v);
           }
           break;
         }
         case '.': {
-          if (ieq(line, ".tran")) {
-            std::vector<std::string> tk = tokens_of(line, false);
+          const std::string line(lp, ll);
+          if (ieq(lp, ll, ".tran")) {
+            tokens_of(lp, ll, false, tk);
             if (tk.size() < 3 || !parse_number(tk[1], N.tstep) || !parse_number(tk[2], N.tstop)) return fail(ln, ".tran needs tstep tstop", line);
-          } else if (ieq(line, ".print")) {
+          } else if (ieq(lp, ll, ".print")) {
             for (size_t q = 0; q < line.size(); ++q)
               if (line[q] == '(') {
                 const size_t r = line.find(')', q);
@@ -254,19 +307,19 @@ struct Parser {
                 N.port_name.push_back(nm);
                 q = r;
               }
-          } else if (ieq(line, ".include")) {
-            std::vector<std::string> tk = tokens_of(line, false);
+          } else if (ieq(lp, ll, ".include")) {
+            tokens_of(lp, ll, false, tk);
             if (tk.size() < 2) return fail(ln, ".include needs a file name", line);
             std::string name;
-            for (char ch : tk[1]) if (ch != '"' && ch != '\'') name.push_back(ch);
+            for (size_t q = 0; q < tk[1].n; ++q) if (tk[1].p[q] != '"' && tk[1].p[q] != '\'') name.push_back(tk[1].p[q]);
             const std::string path = (!name.empty() && name[0] == '/') ? name : dir + name;
             std::string sub;
             if (!slurp(path, sub)) return fail(ln, "cannot open included file", path);
             const size_t slash = path.find_last_of('/');
-            if (!text(sub.data(), sub.size(), slash == std::string::npos ? std::string() : path.substr(0, slash + 1))) return false;
-          } else if (ieq(line, ".subckt")) {
+            if (!text(sub.c_str(), sub.size(), slash == std::string::npos ? std::string() : path.substr(0, slash + 1))) return false;
+          } else if (ieq(lp, ll, ".subckt")) {
             return fail(ln, "sub-circuit definitions are not supported", line);
-          } else if (ieq(line, ".end") && !ieq(line, ".ends")) {
+          } else if (ieq(lp, ll, ".end") && !ieq(lp, ll, ".ends")) {
             --depth;
             return true;
           }
@@ -281,6 +334,11 @@ struct Parser {
   static bool slurp(const std::string& path, std::string& out) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+      const long sz = std::ftell(f);
+      if (sz > 0) out.reserve((size_t)sz + 1);
+      std::rewind(f);
+    }
     char buf[1 << 16];
     size_t got;
     while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, got);
@@ -447,9 +505,9 @@ int build(bg_netlist_s& N) {
   }
   N.port_row.clear();
   for (const std::string& nm : N.port_name) {  // like NodeList::pushPort: unknown names and ground are skipped (src/element.cpp:163-175)
-    auto it = N.node_of.find(nm);
-    if (it == N.node_of.end() || it->second == kGround) continue;
-    N.port_row.push_back(N.new_of_mna[it->second]);  // -1: the port is a fixed node of the reduced system
+    const int id = N.lookup(nm.data(), nm.size());
+    if (id < 0) continue;
+    N.port_row.push_back(N.new_of_mna[id]);  // -1: the port is a fixed node of the reduced system
   }
   return BG_OK;
 }
@@ -459,13 +517,21 @@ int parse_common(const char* text, size_t len, const std::string& dir, int formu
   bg_netlist_s* N = new bg_netlist_s;
   N->formulation = formulation;
   Parser P(*N);
-  if (!P.text(text, len, dir)) {
+  const char* te = std::getenv("B200GMRES_SETUP_TIMING");
+  const bool timing = te && te[0] == '1';
+  const auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (timing) std::fprintf(stderr, "[b200gmres] netlist %-10s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  };
+  if (!P.text(text, len, dir)) {  // text[len] == 0 (callers pass std::string storage)
     bg::set_error("%s", P.err.c_str());
     const bool unsupported = P.err.find("not supported") != std::string::npos;
     delete N;
     return unsupported ? BG_ERR_UNSUPPORTED : BG_ERR_ARG;
   }
+  lap("parsed");
   const int rc = build(*N);
+  lap("assembled");
   if (rc < 0) { delete N; return rc; }
   *out = N;
   return BG_OK;
@@ -479,14 +545,15 @@ extern "C" int bg_netlist_read(const char* path, int formulation, bg_netlist_t* 
   if (!Parser::slurp(path, text)) { bg::set_error("bg_netlist_read: cannot open %s", path); return BG_ERR_ARG; }
   const std::string p(path);
   const size_t slash = p.find_last_of('/');
-  return parse_common(text.data(), text.size(), slash == std::string::npos ? std::string() : p.substr(0, slash + 1), formulation, out);
+  return parse_common(text.c_str(), text.size(), slash == std::string::npos ? std::string() : p.substr(0, slash + 1), formulation, out);
 }
 extern "C" int bg_netlist_parse(const char* text, int64_t len, const char* include_dir, int formulation, bg_netlist_t* out) {
   if (!text || len < 0 || !out) { bg::set_error("bg_netlist_parse: bad argument"); return BG_ERR_ARG; }
   *out = nullptr;
   std::string dir = include_dir ? include_dir : "";
   if (!dir.empty() && dir.back() != '/') dir.push_back('/');
-  return parse_common(text, (size_t)len, dir, formulation, out);
+  const std::string copy(text, (size_t)len);  // the tokenizer wants a terminator after the last token
+  return parse_common(copy.c_str(), copy.size(), dir, formulation, out);
 }
 extern "C" int bg_netlist_get_info(bg_netlist_t N, bg_netlist_info* o) {
   if (!N || !o) return BG_ERR_ARG;
@@ -530,10 +597,9 @@ extern "C" int bg_netlist_get_ports(bg_netlist_t N, int* rows) {
 }
 extern "C" int bg_netlist_node_row(bg_netlist_t N, const char* name) {
   if (!N || !name) return -2;
-  auto it = N->node_of.find(name);
-  if (it == N->node_of.end()) return -2;
-  if (it->second == kGround) return -1;
-  const int r = N->new_of_mna[it->second];
+  const int id = N->lookup(name, std::strlen(name));
+  if (id < 0) return id;  // -1 ground, -2 unknown
+  const int r = N->new_of_mna[id];
   return r < 0 ? -3 : r;
 }
 extern "C" int bg_netlist_row_name(bg_netlist_t N, int row, char* buf, int cap) {
