@@ -93,7 +93,9 @@ extern "C" int bg_transient_create(bg_context_t ctx, bg_solver_t S, bg_matrix_t 
     const int npts = pwl_ptr[nsrc];
     for (int k = 0; k < nsrc; ++k)
       for (int p = pwl_ptr[k] + 1; p < pwl_ptr[k + 1]; ++p)
-        if (!(pwl_t[p] > pwl_t[p - 1])) { set_error("source %d: breakpoint times must increase", k); rc = BG_ERR_ARG; break; }
+        // repeated times are jumps (the reference's PULSE tables repeat the period boundary, src/parser.cpp:2503-2514);
+        // the lookup below lands on the later point of a pair and never divides by a zero interval
+        if (!(pwl_t[p] >= pwl_t[p - 1])) { set_error("source %d: breakpoint times must not decrease", k); rc = BG_ERR_ARG; break; }
     if (rc < 0) break;
     cudaStream_t s = ctx->stream;
     if ((rc = T->pwl_ptr.upload(pwl_ptr, sizeof(int) * (nsrc + 1), s)) < 0) break;

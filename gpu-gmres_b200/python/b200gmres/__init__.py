@@ -494,6 +494,15 @@ class Netlist:
         """per source (times, values): the `pwl` argument of Transient"""
         return [(self.pwl_t[a:b], self.pwl_v[a:b]) for a, b in zip(self.pwl_ptr[:-1], self.pwl_ptr[1:])]
 
+    @property
+    def transient_pwl(self):
+        """`pwl` for Transient when the PULSE sources go through set_pulse: their tables shrink to the base value (the
+        reference's six-points-per-period expansion is cut at tstop and need not be monotone in its last period)"""
+        out = self.pwl
+        for k, pv in zip(self.pulse_src, self.pulse_val):
+            out[k] = (np.zeros(1), np.array([pv[0]]))
+        return out
+
     def u(self, t):
         """source values at time t (piecewise-linear tables, held at their end values outside)"""
         return np.array([np.interp(t, tt, vv) if len(tt) else 0.0 for tt, vv in self.pwl])

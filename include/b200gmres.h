@@ -193,7 +193,8 @@ BG_API int bg_netlist_get_info(bg_netlist_t N, bg_netlist_info* info);
 BG_API int bg_netlist_get_matrix(bg_netlist_t N, int which, int* rowptr, int* col, double* val);
 /* per source (column of B): kind[n_sources]; the breakpoint table the reference keeps, pwl_ptr[n_sources + 1],
    pwl_t / pwl_v[n_pwl_points] (DC: two points 0 and tstop; PWL: a point at t = 0 is added when the first time is not
-   0; PULSE: six per period up to tstop, src/parser.cpp:2497-2518) -- the arguments of bg_transient_create; and the
+   0; PULSE: six per period, the last time cut to tstop like src/parser.cpp:2497-2518 does -- possibly below its
+   predecessor) -- the arguments of bg_transient_create (give PULSE sources a one-point table there); and the
    PULSE records pulse_src[n_pulse], pulse_time[5 n_pulse] = (td, tr, tf, pw, period), pulse_val[2 n_pulse] =
    (v1, v2) -- the arguments of bg_transient_set_pulse.  Any pointer may be NULL. */
 BG_API int bg_netlist_get_sources(bg_netlist_t N, int* kind, int* pwl_ptr, double* pwl_t, double* pwl_v, int* pulse_src,

@@ -203,7 +203,7 @@ def test_netlist_to_device_transient(bg, ctx, load):
     # transient on the device, started from the device's own operating point
     A1 = bg.Matrix(ctx, At.indptr, At.indices, At.data, dtype=bg.F64)
     M1 = bg.Precond.ilu0(ctx, At.indptr, At.indices, At.data, dtype=bg.F64, opts=o)
-    T = bg.Transient(ctx, S, A1, M1, (Ch.indptr, Ch.indices, Ch.data), R.B, R.pwl, list(R.ports))
+    T = bg.Transient(ctx, S, A1, M1, (Ch.indptr, Ch.indices, Ch.data), R.B, R.transient_pwl, list(R.ports))
     if R.info.n_pulse:
         T.set_pulse(R.pulse_src, R.pulse_time, R.pulse_val)
     rc, st, probe = T.run(dx.data_ptr(), 0.0, h, nsteps, opts)

@@ -85,7 +85,7 @@ def main():
     A2 = bg.Matrix(ctx, At.indptr, At.indices, At.data, dtype=bg.F64)
     M2 = bg.Precond.ilu0(ctx, At.indptr, At.indices, At.data, dtype=bg.F64, opts=popts)
     probes = [p for p in N.ports if p >= 0]
-    T = bg.Transient(ctx, S, A2, M2, (Ch.indptr, Ch.indices, Ch.data), N.B, N.pwl, probes)
+    T = bg.Transient(ctx, S, A2, M2, (Ch.indptr, Ch.indices, Ch.data), N.B, N.transient_pwl, probes)
     if i.n_pulse:
         T.set_pulse(N.pulse_src, N.pulse_time, N.pulse_val)
     rc, st, probe = T.run(dx.data_ptr(), 0.0, h, nsteps, opts)
