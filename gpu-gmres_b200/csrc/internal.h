@@ -246,6 +246,11 @@ int launch_trsv_block(bg_context_t ctx, const FusedBlockDev& S, int vec_dt, int 
 int launch_gather(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out, const void* scale = nullptr,
                   int scale_dt = BG_F64);
 int launch_scatter(bg_context_t ctx, int dtype, int n, const int* perm, const void* in, void* out);
+// setup on the device (spmv.cu): sliced-ELL fill from the CSR arrays in HBM; rows of D^-1 P A P^T from those of A
+int launch_sell_fill(bg_context_t ctx, int dtype, int n, int nslices, int slice, const int* rp, const int* ci, const void* v,
+                     const int64_t* sp, int* cols, void* vals);
+int launch_permute_rows(bg_context_t ctx, int dtype, int n, const int* rp_old, const int* ci_old, const void* v_old, const int* perm,
+                        const int* inv, const double* dinv, const int* rp_new, int* ci_new, void* v_new);
 int launch_diag_scale(bg_context_t ctx, int dtype, int n, const void* in, const void* d, void* out,
                       const int* skip_flag);
 // out[perm[i]] = in[i]*scale[i]  (warm-start scatter), out[i] = in[i]/scale[i]
@@ -313,6 +318,7 @@ int gmres_profile_dist(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precon
 int matrix_create_internal(bg_context_t ctx, int n, int ncols, std::vector<int> rp, std::vector<int> ci,
                            const void* val, int val_dtype, int compute_dtype, int spmv_format, bg_matrix_t* out);
 int solver_create_internal(bg_context_t ctx, int n, int m, int dtype, int extra_rows, bg_solver_t* out, int basis_dtype = -1);
+int prepare_solve(bg_matrix_t A, bg_precond_t M);  // one-time host work of the first solve (block-major copy of A)
 // factor.cu: block-Jacobi ILU(0) of the tiles of a 5-point grid factored and packed on the device (fills M->fb);
 // returns 1 when the matrix is not such a grid (the caller takes the host path)
 template <class T>

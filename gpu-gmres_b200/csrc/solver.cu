@@ -166,6 +166,57 @@ extern "C" int bg_host_free_pinned(void* p) {
 }
 
 // =========================================================================== matrix
+// B200GMRES_HOST_SETUP=1 keeps the sliced-ELL fill and the block-major reordering on the host (the round-1 path)
+static bool host_setup() {
+  const char* e = getenv("B200GMRES_HOST_SETUP");
+  return e && e[0] == '1';
+}
+// SpMV plan and storage of a matrix whose CSR arrays are already on the device (A->rp, A->ci, A->val); rp = host row
+// pointers.  The sliced-ELL copy is filled on the device (sell_fill_kernel) unless host arrays are handed in.
+template <class T>
+static int matrix_finish(bg_matrix_t A, const int* rp, int format, const int* h_ci, const T* h_v) {
+  cudaStream_t s = A->ctx->stream;
+  A->plan = inspect_rows(A->n, rp);
+  if (format == BG_SPMV_AUTO) format = A->plan.format;
+  A->format = format;
+  const double mean = A->plan.mean_row;
+  A->lanes = format == BG_SPMV_CSR_WARP ? 32 : mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
+  if (format != BG_SPMV_SELL) return BG_OK;
+  A->sell_rpt = sizeof(T) == 4 ? 4 : 2;
+  A->sell_height = 32 * A->sell_rpt;
+  std::vector<int64_t> sp;
+  sell_slice_ptr(A->n, rp, A->sell_height, 0, sp);
+  A->sell_slices = (int)sp.size() - 1;
+  // a few short slices (grid boundaries) must not cost the fixed-width kernels: pad every slice to the
+  // longest row when that adds at most 5 % of storage
+  int min_width = 0;
+  if ((int64_t)A->plan.max_row * A->sell_height * A->sell_slices <= sp.back() + sp.back() / 20 && (int64_t)A->plan.max_row * A->sell_height * A->sell_slices != sp.back()) {
+    min_width = A->plan.max_row;
+    sell_slice_ptr(A->n, rp, A->sell_height, min_width, sp);
+  }
+  A->sell_width = A->sell_slices > 0 ? (int)((sp[1] - sp[0]) / A->sell_height) : 0;
+  for (int q = 0; q < A->sell_slices; ++q)
+    if (sp[q + 1] - sp[q] != (int64_t)A->sell_width * A->sell_height) { A->sell_width = 0; break; }
+  A->plan.sell_padded = sp.back();
+  A->plan.slice = A->sell_height;
+  BG_TRY(upload_vec(A->s_ptr, sp, s));
+  if (h_ci && h_v) {
+    std::vector<int> sc;
+    std::vector<T> sv;
+    build_sell(A->n, rp, h_ci, h_v, A->sell_height, sp, sc, sv, min_width);
+    BG_TRY(upload_vec(A->s_col, sc, s));
+    BG_TRY(upload_vec(A->s_val, sv, s));
+    BG_CUDA(cudaStreamSynchronize(s));  // sc, sv leave scope
+    return BG_OK;
+  }
+  BG_TRY(A->s_col.alloc(sizeof(int) * (size_t)std::max<int64_t>(sp.back(), 1)));
+  BG_TRY(A->s_val.alloc(sizeof(T) * (size_t)std::max<int64_t>(sp.back(), 1)));
+  BG_TRY(launch_sell_fill(A->ctx, A->dtype, A->n, A->sell_slices, A->sell_height, A->rp.as<int>(), A->ci.as<int>(), A->val.p,
+                          A->s_ptr.as<int64_t>(), A->s_col.as<int>(), A->s_val.p));
+  BG_CUDA(cudaStreamSynchronize(s));  // sp leaves scope (its upload is asynchronous)
+  return BG_OK;
+}
+
 template <class T>
 static int matrix_build(bg_matrix_t A, std::vector<int>&& rp_in, std::vector<int>&& ci_in, const void* val, int val_dtype,
                         int format) {
@@ -181,41 +232,16 @@ static int matrix_build(bg_matrix_t A, std::vector<int>&& rp_in, std::vector<int
   T* const v = reinterpret_cast<T*>(A->h_val.data());
   convert_into(v, val, val_dtype, nnz);
   if (A->ncols < A->n) A->ncols = A->n;
-  A->plan = inspect_rows(A->n, rp.data());
-  if (format == BG_SPMV_AUTO) format = A->plan.format;
-  A->format = format;
-  const double mean = A->plan.mean_row;
-  A->lanes = format == BG_SPMV_CSR_WARP ? 32 : mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
   BG_TRY(upload_vec(A->rp, rp, s));
   BG_TRY(upload_vec(A->ci, ci, s));
   BG_TRY(A->val.upload(v, nnz * sizeof(T), s));
-  if (format == BG_SPMV_SELL) {
-    A->sell_rpt = sizeof(T) == 4 ? 4 : 2;
-    A->sell_height = 32 * A->sell_rpt;
-    std::vector<int64_t> sp;
-    std::vector<int> sc;
-    std::vector<T> sv;
-    build_sell(A->n, rp.data(), ci.data(), v, A->sell_height, sp, sc, sv);
-    A->sell_slices = (int)sp.size() - 1;
-    // a few short slices (grid boundaries) must not cost the fixed-width kernels: pad every slice to the
-    // longest row when that adds at most 5 % of storage
-    if ((int64_t)A->plan.max_row * A->sell_height * A->sell_slices <= sp.back() + sp.back() / 20 && (int64_t)A->plan.max_row * A->sell_height * A->sell_slices != sp.back())
-      build_sell(A->n, rp.data(), ci.data(), v, A->sell_height, sp, sc, sv, A->plan.max_row);
-    A->sell_width = A->sell_slices > 0 ? (int)((sp[1] - sp[0]) / A->sell_height) : 0;
-    for (int q = 0; q < A->sell_slices; ++q)
-      if (sp[q + 1] - sp[q] != (int64_t)A->sell_width * A->sell_height) { A->sell_width = 0; break; }
-    A->plan.sell_padded = sp.back();
-    A->plan.slice = A->sell_height;
-    BG_TRY(upload_vec(A->s_ptr, sp, s));
-    BG_TRY(upload_vec(A->s_col, sc, s));
-    BG_TRY(upload_vec(A->s_val, sv, s));
-    if (A->ncols > A->n) {  // local rows of a row-partitioned matrix: which slices read halo slots
-      std::vector<unsigned char> fl(std::max(1, A->sell_slices), 0);
-      for (int i = 0; i < A->n; ++i)
-        for (int p = rp[i]; p < rp[i + 1]; ++p)
-          if (ci[p] >= A->n) { fl[i / A->sell_height] = 1; break; }
-      BG_TRY(upload_vec(A->s_halo, fl, s));
-    }
+  BG_TRY(matrix_finish<T>(A, rp.data(), format, host_setup() ? ci.data() : nullptr, host_setup() ? v : nullptr));
+  if (A->format == BG_SPMV_SELL && A->ncols > A->n) {  // local rows of a row-partitioned matrix: which slices read halo slots
+    std::vector<unsigned char> fl(std::max(1, A->sell_slices), 0);
+    for (int i = 0; i < A->n; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p)
+        if (ci[p] >= A->n) { fl[i / A->sell_height] = 1; break; }
+    BG_TRY(upload_vec(A->s_halo, fl, s));
   }
   BG_CUDA(cudaStreamSynchronize(s));
   return BG_OK;
@@ -1007,7 +1033,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 // perm[i], D = diag(U) in that order); built once per ordering and cached inside A.  With b scaled
 // the same way the left-preconditioned operator M^-1 A and M^-1 b are unchanged, but the device
 // triangular solves become unit solves (trsv_block.cu).
-template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev& fb) {
+template <class T> static int build_permuted_host(bg_matrix_t A, const FusedBlockDev& fb) {
   const int n = A->n;
   const std::vector<int>& perm = fb.h_perm;
   std::vector<int> inv(n);
@@ -1041,6 +1067,40 @@ template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev&
   A->permuted_serial = fb.serial;
   return BG_OK;
 }
+// the same matrix built on the device from A's CSR arrays in HBM (permute_rows_kernel): only the new row pointers are
+// computed on the host.  Square matrices only (row-partitioned ones need the per-slice halo flags of the host path).
+template <class T> static int build_permuted_device(bg_matrix_t A, const FusedBlockDev& fb) {
+  const int n = A->n;
+  cudaStream_t s = A->ctx->stream;
+  const std::vector<int>& perm = fb.h_perm;
+  std::vector<int> rp((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) rp[(size_t)i + 1] = rp[i] + (A->h_rp[(size_t)perm[i] + 1] - A->h_rp[perm[i]]);
+  bg_matrix_t P = new bg_matrix_s;
+  P->ctx = A->ctx; P->n = n; P->ncols = A->ncols; P->nnz = A->nnz; P->dtype = A->dtype;
+  P->requested_format = A->requested_format;
+  int rc = BG_OK;
+  do {
+    DevBuf dinv;
+    if ((rc = dinv.upload(fb.h_dinv.data(), sizeof(double) * (size_t)n, s)) < 0) break;
+    if ((rc = upload_vec(P->rp, rp, s)) < 0) break;
+    if ((rc = P->ci.alloc(sizeof(int) * (size_t)std::max<int64_t>(A->nnz, 1))) < 0) break;
+    if ((rc = P->val.alloc(sizeof(T) * (size_t)std::max<int64_t>(A->nnz, 1))) < 0) break;
+    if ((rc = launch_permute_rows(A->ctx, A->dtype, n, A->rp.as<int>(), A->ci.as<int>(), A->val.p, fb.perm.as<int>(), fb.iperm.as<int>(),
+                                  dinv.as<double>(), P->rp.as<int>(), P->ci.as<int>(), P->val.p)) < 0) break;
+    if ((rc = matrix_finish<T>(P, rp.data(), A->requested_format, nullptr, nullptr)) < 0) break;
+    cudaError_t e = cudaStreamSynchronize(s);  // dinv is released at the end of this scope
+    if (e != cudaSuccess) { rc = cuda_fail(e, "build_permuted_device", __FILE__, __LINE__); break; }
+  } while (false);
+  if (rc < 0) { delete P; return rc; }
+  delete A->permuted;
+  A->permuted = P;
+  A->permuted_serial = fb.serial;
+  return BG_OK;
+}
+template <class T> static int build_permuted(bg_matrix_t A, const FusedBlockDev& fb) {
+  if (host_setup() || A->ncols != A->n || !fb.perm.p || !fb.iperm.p || (int)fb.h_dinv.size() != A->n) return build_permuted_host<T>(A, fb);
+  return build_permuted_device<T>(A, fb);
+}
 static int permuted_matrix(bg_matrix_t A, const FusedBlockDev& fb, bg_matrix_t* out) {
   if (!A->permuted || A->permuted_serial != fb.serial) {
     if ((int)fb.h_perm.size() != A->n) { set_error("preconditioner ordering does not match the matrix"); return BG_ERR_ARG; }
@@ -1049,6 +1109,17 @@ static int permuted_matrix(bg_matrix_t A, const FusedBlockDev& fb, bg_matrix_t* 
   *out = A->permuted;
   return BG_OK;
 }
+
+namespace bg {
+// one-time work of the first solve with a block-Jacobi preconditioner (the block-major copy of A), done ahead of it
+int prepare_solve(bg_matrix_t A, bg_precond_t M) {
+  if (!A || !M) return BG_ERR_ARG;
+  if (M->kind != BG_PRECOND_LU || M->schedule != BG_TRSV_BLOCK || M->n != A->n) return BG_OK;
+  BG_CUDA(cudaSetDevice(A->ctx->device));
+  bg_matrix_t P;
+  return permuted_matrix(A, M->fb, &P);
+}
+}  // namespace bg
 
 static int gmres_solve_impl(bg_context_t ctx, bg_solver_t S, bg_matrix_t A, bg_precond_t M, const void* d_b, void* d_x,
                             const bg_gmres_opts* opts, bg_gmres_result* res, Prof* prof, DistHooks* dh = nullptr) {

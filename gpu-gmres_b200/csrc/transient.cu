@@ -82,6 +82,7 @@ extern "C" int bg_transient_create(bg_context_t ctx, bg_solver_t S, bg_matrix_t 
   T->ctx = ctx; T->S = S; T->A = A; T->M = M; T->n = n; T->nsrc = nsrc; T->dtype = S->dtype; T->nprobe = nprobe;
   int rc = BG_OK;
   do {
+    if ((rc = prepare_solve(A, M)) < 0) break;  // keep one-time setup out of the time loop
     // C/h: square, any format; B: n x nsrc, CSR only (sliced-ELL padding points at the own row, which may exceed nsrc)
     std::vector<int> rp(c_rowptr, c_rowptr + n + 1), ci(c_col, c_col + c_rowptr[n]);
     rc = matrix_create_internal(ctx, n, n, rp, ci, c_val, val_dtype, T->dtype, BG_SPMV_AUTO, &T->Ch);

@@ -956,16 +956,21 @@ SpmvPlan inspect_rows(int n, const int* rp) {
   return p;
 }
 
-template <class T>
-void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std::vector<int64_t>& slice_ptr,
-                std::vector<int>& cols, std::vector<T>& vals, int min_width) {
+void sell_slice_ptr(int n, const int* rp, int slice, int min_width, std::vector<int64_t>& slice_ptr) {
   const int ns = (n + slice - 1) / slice;
-  slice_ptr.assign(ns + 1, 0);
+  slice_ptr.assign((size_t)ns + 1, 0);
   for (int s = 0; s < ns; ++s) {
     int mx = min_width;
     for (int i = s * slice; i < std::min(n, (s + 1) * slice); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
     slice_ptr[s + 1] = slice_ptr[s] + (int64_t)mx * slice;
   }
+}
+
+template <class T>
+void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std::vector<int64_t>& slice_ptr,
+                std::vector<int>& cols, std::vector<T>& vals, int min_width) {
+  const int ns = (n + slice - 1) / slice;
+  sell_slice_ptr(n, rp, slice, min_width, slice_ptr);
   cols.resize(slice_ptr[ns]);
   vals.resize(slice_ptr[ns]);
   // slices are disjoint ranges of the output: filled by several threads at 10 M-row sizes (parallel_ranges)

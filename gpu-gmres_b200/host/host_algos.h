@@ -210,6 +210,8 @@ struct SpmvPlan {
 };
 SpmvPlan inspect_rows(int n, const int* rp);
 // sliced ELL (slices padded to max(their own longest row, min_width)); slice_ptr in entries.
+// slice_ptr of the sliced-ELL layout alone (the fill may then happen on the device: spmv.cu sell_fill_kernel)
+void sell_slice_ptr(int n, const int* rp, int slice, int min_width, std::vector<int64_t>& slice_ptr);
 template <class T>
 void build_sell(int n, const int* rp, const int* ci, const T* v, int slice, std::vector<int64_t>& slice_ptr,
                 std::vector<int>& cols, std::vector<T>& vals, int min_width = 0);
