@@ -327,31 +327,37 @@ extern "C" int bg_host_bucket_levels(int n, const int* level, int* n_levels, int
   if (nodes) std::copy(nd.begin(), nd.end(), nodes);
   return BG_OK;
 }
+enum { FACTOR_ILU0 = 0, FACTOR_ILUT = 1, FACTOR_ILUK = 2 };  // `lfil`: ILUT row budget / ILU(k) level
 template <class T>
-static void factor_dispatch(bool use_ilut, int n, const int* rp, const int* ci, const void* v, int dt, double tau, int lfil,
+static void factor_dispatch(int method, int n, const int* rp, const int* ci, const void* v, int dt, double tau, int lfil,
                             const int* blk, Factors<T>& F) {
   std::vector<T> vv = to_vec<T>(v, dt, (size_t)rp[n]);
-  if (use_ilut) ilut<T>(n, rp, ci, vv.data(), tau, lfil, blk, F);
+  if (method == FACTOR_ILUT) ilut<T>(n, rp, ci, vv.data(), tau, lfil, blk, F);
+  else if (method == FACTOR_ILUK) iluk<T>(n, rp, ci, vv.data(), lfil, blk, F);
   else ilu0<T>(n, rp, ci, vv.data(), blk, F);
 }
-static int host_factor(bool use_ilut, int n, const int* rp, const int* ci, const void* v, int dt, double tau, int lfil,
+static int host_factor(int method, int n, const int* rp, const int* ci, const void* v, int dt, double tau, int lfil,
                        const int* blk, bg_factors_t* out) {
   if (!out || n < 0 || (n && (!rp || !ci || !v))) return BG_ERR_ARG;
   bg_factors_t F = new bg_factors_s;
   F->n = n; F->dtype = dt;
   try {
-    if (dt == BG_F64) factor_dispatch<double>(use_ilut, n, rp, ci, v, dt, tau, lfil, blk, F->f64);
-    else factor_dispatch<float>(use_ilut, n, rp, ci, v, dt, tau, lfil, blk, F->f32);
+    if (dt == BG_F64) factor_dispatch<double>(method, n, rp, ci, v, dt, tau, lfil, blk, F->f64);
+    else factor_dispatch<float>(method, n, rp, ci, v, dt, tau, lfil, blk, F->f32);
   } catch (const std::exception& e) { set_error("factorisation failed: %s", e.what()); delete F; return BG_ERR_ARG; }
   *out = F;
   return BG_OK;
 }
 extern "C" int bg_host_ilu0(int n, const int* rp, const int* ci, const void* v, int dt, const int* blk, bg_factors_t* F) {
-  return host_factor(false, n, rp, ci, v, dt, 0, 0, blk, F);
+  return host_factor(FACTOR_ILU0, n, rp, ci, v, dt, 0, 0, blk, F);
 }
 extern "C" int bg_host_ilut(int n, const int* rp, const int* ci, const void* v, int dt, double tau, int lfil, const int* blk, bg_factors_t* F) {
   if (lfil < 0 || tau < 0) return BG_ERR_ARG;
-  return host_factor(true, n, rp, ci, v, dt, tau, lfil, blk, F);
+  return host_factor(FACTOR_ILUT, n, rp, ci, v, dt, tau, lfil, blk, F);
+}
+extern "C" int bg_host_iluk(int n, const int* rp, const int* ci, const void* v, int dt, int level, const int* blk, bg_factors_t* F) {
+  if (level < 0) { set_error("bg_host_iluk: level of fill must be >= 0"); return BG_ERR_ARG; }
+  return host_factor(FACTOR_ILUK, n, rp, ci, v, dt, 0, level, blk, F);
 }
 extern "C" int bg_host_ainv(int n, const int* rp, const int* ci, const void* v, int dt, double droptol, bg_factors_t* out) {
   if (!out || n < 0 || droptol < 0 || (n && (!rp || !ci || !v))) return BG_ERR_ARG;
@@ -593,8 +599,9 @@ static int make_blocks(const bg_precond_opts& o, int n, const int* rp, const int
 }
 
 template <class T>
-static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp, const int* ci, const void* v, int vdt,
-                           int dtype, const bg_precond_opts& o, bg_precond_t* out) {
+static int create_factored(bg_context_t ctx, int method, int n, const int* rp, const int* ci, const void* v, int vdt,
+                           int dtype, const bg_precond_opts& o, bg_precond_t* out, int iluk_level = 0) {
+  const bool use_ilut = method != FACTOR_ILU0;  // anything but ILU(0) of grid tiles is factored on the host
   std::vector<int> blk;
   int nb = 1;
   const bool block = o.trsv_schedule == BG_TRSV_BLOCK;
@@ -626,7 +633,7 @@ static int create_factored(bg_context_t ctx, bool use_ilut, int n, const int* rp
     M->fb.stages = stages; M->fb.warps_per_cta = warps;  // not a 5-point grid in this numbering: the general path
   }
   Factors<T> F;
-  try { factor_dispatch<T>(use_ilut, n, rp, ci, v, vdt, o.ilut_tau, o.ilut_lfil, block ? blk.data() : nullptr, F); }
+  try { factor_dispatch<T>(method, n, rp, ci, v, vdt, o.ilut_tau, method == FACTOR_ILUK ? iluk_level : o.ilut_lfil, block ? blk.data() : nullptr, F); }
   catch (const std::exception& e) { set_error("factorisation failed: %s", e.what()); delete M; return BG_ERR_ARG; }
   int rc = precond_install_dt<T>(M, F.L, F.U, true, block ? blk.data() : nullptr, nb);
   if (rc < 0) { delete M; return rc; }
@@ -641,8 +648,8 @@ extern "C" int bg_precond_create_ilu0(bg_context_t ctx, int n, const int* rp, co
   bg_precond_opts d;
   bg_precond_opts_default(&d);
   if (o) d = *o;
-  return dtype == BG_F32 ? create_factored<float>(ctx, false, n, rp, ci, v, vdt, dtype, d, out)
-                         : create_factored<double>(ctx, false, n, rp, ci, v, vdt, dtype, d, out);
+  return dtype == BG_F32 ? create_factored<float>(ctx, FACTOR_ILU0, n, rp, ci, v, vdt, dtype, d, out)
+                         : create_factored<double>(ctx, FACTOR_ILU0, n, rp, ci, v, vdt, dtype, d, out);
 }
 extern "C" int bg_precond_create_ilut(bg_context_t ctx, int n, const int* rp, const int* ci, const void* v, int vdt,
                                       int dtype, const bg_precond_opts* o, bg_precond_t* out) {
@@ -651,8 +658,18 @@ extern "C" int bg_precond_create_ilut(bg_context_t ctx, int n, const int* rp, co
   bg_precond_opts d;
   bg_precond_opts_default(&d);
   if (o) d = *o;
-  return dtype == BG_F32 ? create_factored<float>(ctx, true, n, rp, ci, v, vdt, dtype, d, out)
-                         : create_factored<double>(ctx, true, n, rp, ci, v, vdt, dtype, d, out);
+  return dtype == BG_F32 ? create_factored<float>(ctx, FACTOR_ILUT, n, rp, ci, v, vdt, dtype, d, out)
+                         : create_factored<double>(ctx, FACTOR_ILUT, n, rp, ci, v, vdt, dtype, d, out);
+}
+extern "C" int bg_precond_create_iluk(bg_context_t ctx, int n, const int* rp, const int* ci, const void* v, int vdt,
+                                      int dtype, int level, const bg_precond_opts* o, bg_precond_t* out) {
+  if (!ctx || !out || n < 0 || level < 0 || (n && (!rp || !ci || !v))) return BG_ERR_ARG;
+  BG_CUDA(cudaSetDevice(ctx->device));
+  bg_precond_opts d;
+  bg_precond_opts_default(&d);
+  if (o) d = *o;
+  return dtype == BG_F32 ? create_factored<float>(ctx, FACTOR_ILUK, n, rp, ci, v, vdt, dtype, d, out, level)
+                         : create_factored<double>(ctx, FACTOR_ILUK, n, rp, ci, v, vdt, dtype, d, out, level);
 }
 
 template <class T> static Csr<T> csr_from(int n, const int* rp, const int* ci, const void* v, int vdt) {

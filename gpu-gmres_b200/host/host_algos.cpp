@@ -183,6 +183,93 @@ void ilu0(int n, const int* rp, const int* ci, const T* v, const int* block, Fac
 template void ilu0<float>(int, const int*, const int*, const float*, const int*, Factors<float>&);
 template void ilu0<double>(int, const int*, const int*, const double*, const int*, Factors<double>&);
 
+// ILU(k): level-of-fill incomplete factorisation.  The symbolic phase follows the rule of ITSOL's lofC, which the
+// reference vendors (src/iluk.cpp:193-335): entries of A have level 0, eliminating row i with pivot row k gives
+// position (i, j) the level lev(i,k) + lev(k,j) + 1, the smallest level offered wins, positions above `lfil` are not
+// created, pivots are taken in ascending column order (fill left of the diagonal becomes a pivot itself), the
+// diagonal is always kept.  The numeric phase is the IKJ sweep of ilu0 above on that pattern (multipliers divided by
+// the pivot, where ITSOL multiplies by a stored reciprocal), so lfil = 0 reproduces ilu0 bit for bit.
+template <class T>
+void iluk(int n, const int* rp, const int* ci, const T* v, int lfil, const int* block, Factors<T>& F) {
+  Csr<T> A;
+  sorted_copy(n, rp, ci, v, block, A);
+  // factored rows: columns ascending, values, level of every position; udiag[i] = position of the diagonal
+  Csr<T> W;
+  W.n = n;
+  W.rp.assign((size_t)n + 1, 0);
+  W.ci.reserve(A.ci.size() * (size_t)(lfil > 0 ? 2 : 1));
+  W.v.reserve(A.ci.size() * (size_t)(lfil > 0 ? 2 : 1));
+  std::vector<int> lev;
+  lev.reserve(W.ci.capacity());
+  std::vector<int> udiag(n, -1);
+  std::vector<int> slot(n, -1);      // column -> index in the row under construction
+  std::vector<int> cols, levs;       // the row under construction, in discovery order
+  std::vector<T> vals;
+  std::vector<int> heap;             // columns left of the diagonal still to be used as pivots (min-heap)
+  std::vector<int> order;
+  F.zero_pivots = 0;
+  auto heap_cmp = [](int a, int b) { return a > b; };
+  for (int i = 0; i < n; ++i) {
+    cols.clear(); levs.clear(); vals.clear(); heap.clear();
+    bool has_diag = false;
+    for (int p = A.rp[i]; p < A.rp[i + 1]; ++p) {
+      const int c = A.ci[p];
+      if (c == i) has_diag = true;
+      slot[c] = (int)cols.size();
+      cols.push_back(c); levs.push_back(0); vals.push_back(A.v[p]);
+      if (c < i) heap.push_back(c);
+    }
+    if (!has_diag) { slot[i] = (int)cols.size(); cols.push_back(i); levs.push_back(0); vals.push_back((T)0); }
+    // symbolic: the complete pattern of row i first -- a position refused at one pivot (level too high) may be
+    // created by a later one, and the numeric sweep must then see the earlier pivot's contribution as well
+    std::make_heap(heap.begin(), heap.end(), heap_cmp);
+    while (!heap.empty()) {
+      std::pop_heap(heap.begin(), heap.end(), heap_cmp);
+      const int k = heap.back();
+      heap.pop_back();
+      const int lk = levs[slot[k]];
+      for (int q = udiag[k] + 1; q < W.rp[k + 1]; ++q) {
+        const int c = W.ci[q];
+        const int it = lev[q] + lk + 1;
+        if (it > lfil) continue;
+        const int sc = slot[c];
+        if (sc < 0) {
+          slot[c] = (int)cols.size();
+          cols.push_back(c); levs.push_back(it); vals.push_back((T)0);
+          if (c < i) { heap.push_back(c); std::push_heap(heap.begin(), heap.end(), heap_cmp); }
+        } else if (it < levs[sc]) {
+          levs[sc] = it;
+        }
+      }
+    }
+    order.resize(cols.size());
+    for (size_t q = 0; q < cols.size(); ++q) order[q] = (int)q;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return cols[a] < cols[b]; });
+    // numeric: a_ij -= l_ik u_kj over the pivots k < i of the row in ascending order, on the positions the row stores
+    for (int q : order) {
+      const int k = cols[q];
+      if (k >= i) break;
+      const T ukk = W.v[udiag[k]];
+      const T lik = is_zero(ukk) ? (T)0 : vals[q] / ukk;  // a vanishing pivot zeroes the column like ilu0
+      vals[q] = lik;
+      for (int r = udiag[k] + 1; r < W.rp[k + 1]; ++r) {
+        const int sc = slot[W.ci[r]];
+        if (sc >= 0) vals[sc] -= lik * W.v[r];
+      }
+    }
+    for (int q : order) {
+      if (cols[q] == i) udiag[i] = (int)W.ci.size();
+      W.ci.push_back(cols[q]); W.v.push_back(vals[q]); lev.push_back(levs[q]);
+      slot[cols[q]] = -1;
+    }
+    W.rp[(size_t)i + 1] = (int)W.ci.size();
+    if (is_zero(W.v[udiag[i]])) F.zero_pivots++;
+  }
+  split_lu(W, F);
+}
+template void iluk<float>(int, const int*, const int*, const float*, int, const int*, Factors<float>&);
+template void iluk<double>(int, const int*, const int*, const double*, int, const int*, Factors<double>&);
+
 template <class T>
 void ilut(int n, const int* rp, const int* ci, const T* v, double tau, int lfil, const int* block,
           Factors<T>& F) {

@@ -58,6 +58,9 @@ int bucket_levels(int n, const int* level, std::vector<int>& levelPtr, std::vect
 // row and column share a block (block-Jacobi ILU).
 template <class T>
 void ilu0(int n, const int* rp, const int* ci, const T* v, const int* block, Factors<T>& F);
+// ILU(k), level-of-fill rule of ITSOL's lofC (src/iluk.cpp:193-335, vendored by the reference); lfil = 0 is ilu0
+template <class T>
+void iluk(int n, const int* rp, const int* ci, const T* v, int lfil, const int* block, Factors<T>& F);
 // ILUT(tau, lfil): dual-threshold incomplete LU (Saad), same output layout, L unit lower.
 template <class T>
 void ilut(int n, const int* rp, const int* ci, const T* v, double tau, int lfil, const int* block,

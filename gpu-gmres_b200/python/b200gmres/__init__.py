@@ -188,6 +188,16 @@ def host_ilut(rowptr, col, val, tau, lfil, block_of_row=None):
     return _factors_out(h)
 
 
+def host_iluk(rowptr, col, val, level, block_of_row=None):
+    """ILU(level) on the host: level-of-fill rule of ITSOL's lofC (the reference's vendored ILUK); level 0 is host_ilu0"""
+    n = len(rowptr) - 1
+    val = np.ascontiguousarray(val)
+    h = C.c_void_p()
+    blk = None if block_of_row is None else _i32(block_of_row)
+    _chk(lib().bg_host_iluk(n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), int(level), _p(blk), C.byref(h)))
+    return _factors_out(h)
+
+
 FILE_TRIPLETS, FILE_CSR_F32, FILE_CSR_F64 = 0, 1, 2
 
 
@@ -339,6 +349,16 @@ class Precond:
         f = lib().bg_precond_create_ilut if ilut else lib().bg_precond_create_ilu0
         _chk(f(ctx.h, n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), dtype,
                C.byref(opts) if opts is not None else None, C.byref(h)))
+        return cls(ctx, h, n)
+
+    @classmethod
+    def iluk(cls, ctx, rowptr, col, val, level, dtype=F64, opts=None):
+        """ILU(level): level-of-fill factors (bg_host_iluk) behind the same triangular-solve schedules"""
+        n = len(rowptr) - 1
+        val = np.ascontiguousarray(val)
+        h = C.c_void_p()
+        _chk(lib().bg_precond_create_iluk(ctx.h, n, _p(_i32(rowptr)), _p(_i32(col)), _p(val), dtype_code(val.dtype), dtype, int(level),
+                                          C.byref(opts) if opts is not None else None, C.byref(h)))
         return cls(ctx, h, n)
 
     @classmethod

@@ -115,6 +115,12 @@ BG_API int bg_host_ilu0(int n, const int* rowptr, const int* col, const void* va
    (src/mna_solve_gpu_gmres.cpp:316-344) and hands them to bg_precond_create_split. */
 BG_API int bg_host_ilut(int n, const int* rowptr, const int* col, const void* val, int val_dtype,
                         double tau, int lfil, const int* block_of_row, bg_factors_t* F);
+/* ILU(k): level-of-fill factorisation with the symbolic rule of ITSOL's lofC / ilukC, which the reference vendors
+   for its ILUK preconditioner type (src/iluk.cpp:56-335, src/defs.h:14; the reference then discards ITSOL's result
+   and applies ILU(0), SURVEY quirk Q7 -- here the type does what its name says).  level = 0 is bg_host_ilu0 bit for
+   bit; the fill pattern equals lofC's for every level (tests/test_host_logic.py against the vendored code). */
+BG_API int bg_host_iluk(int n, const int* rowptr, const int* col, const void* val, int val_dtype,
+                        int level, const int* block_of_row, bg_factors_t* F);
 /* sparse approximate inverse A^-1 ~ Z D^-1 W^T by left-looking biconjugation with drop tolerance (Benzi-Tuma AINV):
    the role CUSP's nonsym_bridson_ainv(A, 0.1) plays in MyAINV::Initilize (src/preconditioner.cu:140-201; CUSP itself
    is outside the replaced layer, so the factors are this library's own -- parity with CUSP's pattern is not claimed).
@@ -243,6 +249,10 @@ BG_API int bg_precond_create_ilu0(bg_context_t ctx, int n, const int* h_rowptr, 
                                   bg_precond_t* M);
 BG_API int bg_precond_create_ilut(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
                                   const void* h_val, int val_dtype, int dtype, const bg_precond_opts* o,
+                                  bg_precond_t* M);
+/* ILU(level) factors (bg_host_iluk) behind the same triangular-solve schedules */
+BG_API int bg_precond_create_iluk(bg_context_t ctx, int n, const int* h_rowptr, const int* h_col,
+                                  const void* h_val, int val_dtype, int dtype, int level, const bg_precond_opts* o,
                                   bg_precond_t* M);
 /* M^-1 = U^-1 L^-1 from caller-supplied CSR factors in the reference's ILU0 layout (unit-lower L
    with its diagonal stored last, U with the diagonal first): what MyILU0/MyILUK::DevPrecond

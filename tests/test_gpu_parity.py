@@ -481,6 +481,28 @@ def test_gmres_matches_oracle_on_fresh_inputs(bg, ctx, oracle, name):
     M.close()
 
 
+@pytest.mark.parametrize("name", ["pg2d_61x47", "th3d_13x11x9", "rand_2000"])
+@pytest.mark.parametrize("level", [1, 2])
+def test_gmres_iluk_matches_oracle(bg, ctx, oracle, name, level):
+    """ILU(k) factors (bg_precond_create_iluk: ITSOL's level-of-fill rule, pinned on the host against the code the
+    reference vendors) through the general reference-order triangular solves: same iteration count as the oracle
+    given the same factors, fewer iterations than ILU(0)."""
+    rp, ci, v, b = CASES[name]
+    n = len(rp) - 1
+    f = bg.host_iluk(rp, ci, v, level)
+    pc = oracle.Precond(oracle.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+    flag, xo, it, res, hist = oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 5000, 1e-8, pc, hist_cap=5000)
+    _, pc0 = oracle_ilu0_pc(oracle, bg, rp, ci, v, "f64")
+    it0 = oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 5000, 1e-8, pc0)[2]
+    assert it < it0
+    M = bg.Precond.iluk(ctx, rp, ci, v, level, dtype=1)
+    r, x, h = run_gpu(bg, ctx, rp, ci, v, b, np.zeros(n), M, 1, tol=1e-8, max_iter=5000, orth=0)
+    assert (r.flag, r.iters) == (flag, it)
+    assert abs(r.resid - res) <= RESID_ATOL_F64
+    assert np.linalg.norm(x - xo) <= X_RTOL_F64 * np.linalg.norm(xo)
+    M.close()
+
+
 def test_block_jacobi_gmres_converges_and_reports_drift(bg, ctx, oracle):
     rp, ci, v, b = CASES["pg2d_61x47"]
     n = len(rp) - 1

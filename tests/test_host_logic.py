@@ -143,6 +143,107 @@ def test_ilut_reduces_to_ilu_and_improves(bg, oracle):
     assert it_ilut < g["f64_meta"][1]
 
 
+def itsol_iluk(rp, ci, v, level):
+    """ILU(level) of the ITSOL code the reference vendors (src/iluk.cpp ilukC / lofC, compiled unchanged into
+    oracle/_ref/libref_iluk.so): per row the strictly-lower and strictly-upper columns and float values, and 1/diag"""
+    L = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_iluk.so"))
+    n = len(rp) - 1
+    rp32, ci32, v32 = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32), np.ascontiguousarray(v, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.refk_factor(n, p(rp32), p(ci32), p(v32), int(level)) == 0
+    nl, nu = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    assert L.refk_row_counts(p(nl), p(nu)) == 0
+    lc, lv = np.zeros(nl.sum(), np.int32), np.zeros(nl.sum(), np.float32)
+    uc, uv = np.zeros(nu.sum(), np.int32), np.zeros(nu.sum(), np.float32)
+    dinv = np.zeros(n, np.float32)
+    assert L.refk_get(p(lc), p(lv), p(uc), p(uv), p(dinv)) == 0
+    return nl, lc, lv, nu, uc, uv, dinv
+
+
+REF_ILUK = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_iluk.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ILUK), reason="oracle/_ref/libref_iluk.so not built (needs /root/reference)")
+@pytest.mark.parametrize("case", ["pg2d", "th3d", "random"])
+def test_iluk_pattern_equals_vendored_itsol(bg, case):
+    """bg_host_iluk against the ILU(k) the reference vendors: fill pattern identical for every level (integer
+    artefact: bit-exact), values within float round-off (ITSOL multiplies by a stored reciprocal pivot, the product
+    divides), level 0 identical with bg_host_ilu0, L U = A on the pattern."""
+    from b200gmres import synth
+
+    if case == "pg2d":
+        rp, ci, v, _ = synth.pg2d(21, 17, seed=11)
+    elif case == "th3d":
+        rp, ci, v, _ = synth.th3d(7, 6, 5, seed=12)
+    else:  # unstructured, non-symmetric pattern, diagonally dominant
+        rng = np.random.default_rng(3)
+        n = 300
+        M = sp.random(n, n, density=0.012, random_state=7, format="csr") + sp.random(n, n, density=0.004, random_state=8, format="csr").T
+        M = sp.csr_matrix(M)
+        M.data = rng.uniform(-1, 1, size=M.nnz)
+        M = sp.csr_matrix(M + sp.diags(np.asarray(abs(M).sum(axis=1)).ravel() + 1.0))
+        M.sort_indices()
+        rp, ci, v = M.indptr, M.indices, M.data
+    n = len(rp) - 1
+    v = np.asarray(v, np.float64)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    f0 = bg.host_ilu0(rp, ci, v)
+    k0 = bg.host_iluk(rp, ci, v, 0)
+    assert all(np.array_equal(f0[k], k0[k]) for k in ("lp", "li", "lv", "up", "ui", "uv"))
+    prev_nnz = 0
+    for level in (0, 1, 2, 3, 5):
+        f = bg.host_iluk(rp, ci, v.astype(np.float32), level)          # ITSOL's precision
+        nl, lc, lv, nu, uc, uv, dinv = itsol_iluk(rp, ci, v, level)
+        lp, up = f["lp"], f["up"]      # L carries its unit diagonal last, U its diagonal first
+        a = b = 0
+        dropped = 0
+        for i in range(n):
+            for mine_c, mine_v, ref_c, ref_v in ((f["li"][lp[i]:lp[i + 1] - 1], f["lv"][lp[i]:lp[i + 1] - 1], lc[a:a + nl[i]], lv[a:a + nl[i]]),
+                                                 (f["ui"][up[i] + 1:up[i + 1]], f["uv"][up[i] + 1:up[i + 1]], uc[b:b + nu[i]], uv[b:b + nu[i]])):
+                order = np.argsort(ref_c, kind="stable")        # ITSOL keeps U rows in discovery order
+                ref_c, ref_v = ref_c[order], ref_v[order]
+                if len(mine_c) != len(ref_c):
+                    # the library's structural-zero rule (|v| < 1e-9, SURVEY Q5, splitLU_csr) removes vanishing fill
+                    keep = np.isin(ref_c, mine_c)
+                    assert np.all(np.abs(ref_v[~keep]) < 2e-9), (level, i)
+                    dropped += int((~keep).sum())
+                    ref_c, ref_v = ref_c[keep], ref_v[keep]
+                assert np.array_equal(mine_c, ref_c), (level, i)
+                assert np.allclose(mine_v, ref_v, rtol=2e-5, atol=1e-6)
+            assert np.isclose(1.0 / f["uv"][up[i]], dinv[i], rtol=2e-5)
+            a += nl[i]; b += nu[i]
+        assert dropped == 0 or case == "random"      # the grids have no vanishing fill: their patterns are lofC's exactly
+        # FP64 factors on the same pattern: the product reproduces A wherever the factors store an entry
+        d = bg.host_iluk(rp, ci, v, level)
+        assert dropped or (np.array_equal(d["li"], f["li"]) and np.array_equal(d["ui"], f["ui"]))
+        L = sp.csr_matrix((d["lv"], d["li"], d["lp"]), shape=(n, n))
+        U = sp.csr_matrix((d["uv"], d["ui"], d["up"]), shape=(n, n))
+        P = sp.csr_matrix(abs(L) + abs(U)); P.data[:] = 1
+        assert abs((L @ U - A).multiply(P)).max() <= (1e-8 if dropped else 1e-12) * abs(A).max()   # dropped fill: |v| < 1e-9 each
+        assert L.nnz + U.nnz >= prev_nnz
+        prev_nnz = L.nnz + U.nnz
+
+
+def test_iluk_improves_convergence_and_respects_blocks(bg, oracle):
+    g = load_golden("pg2d_24x20")
+    rp, ci, v, b = g["rowptr"], g["col"], g["val"], g["b"]
+    n = len(rp) - 1
+    its = []
+    for level in (0, 1, 2, 4):
+        f = bg.host_iluk(rp, ci, v, level)
+        pc = oracle.Precond(oracle.PC_ILU0, n, "f64", **{k: f[k] for k in ("lp", "li", "lv", "up", "ui", "uv")})
+        its.append(oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 500, 1e-8, pc)[2])
+    assert its[0] == g["f64_meta"][1] and its[0] > its[1] > its[2] > its[3]
+    blk = (np.arange(n) * 7 // n).astype(np.int32)
+    f = bg.host_iluk(rp, ci, v, 2, blk)
+    rows = np.repeat(np.arange(n), np.diff(f["lp"]))
+    assert np.all(blk[rows] == blk[f["li"]])
+    rows = np.repeat(np.arange(n), np.diff(f["up"]))
+    assert np.all(blk[rows] == blk[f["ui"]])
+    with pytest.raises(bg.BgError):
+        bg.host_iluk(rp, ci, v, -1)
+
+
 def test_level_stream_packers(tmp_path):
     """The two BG_TRSV_LEVEL streams (sync-free slices for any factor, index-free strips for 5-point ILU(0)),
     interpreted on the host the way trsv_syncfree / trsv_lattice_global consume them: no row is read before it
