@@ -22,6 +22,16 @@ def test_library_exports_every_declared_symbol(bg):
     assert not missing, missing
 
 
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/b200gmres.h must compile as C99 (no C++ types in the signatures)"""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200gmres.h"\nint main(void) { bg_gmres_opts o; bg_netlist_info i; (void)o; (void)i; return BG_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)])
+
+
 def test_no_cpu_fallback(bg):
     if bg.device_count() > 0:
         pytest.skip("GPU present")
