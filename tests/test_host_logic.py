@@ -234,6 +234,28 @@ def test_iluk_pattern_equals_vendored_itsol(bg, case):
         prev_nnz = L.nnz + U.nnz
 
 
+@pytest.mark.parametrize("name", ["iluk_pg2d_13x11", "iluk_th3d_6x5x4"])
+def test_iluk_equals_committed_itsol_output(bg, name):
+    """the same pin against the committed output of the vendored ITSOL code (tests/golden/make_frontend_golden.py)"""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    rp, ci, v = g["rowptr"], g["col"], g["val"]
+    n = len(rp) - 1
+    for level in range(4):
+        f = bg.host_iluk(rp, ci, v.astype(np.float32), level)
+        nl, lc, lv, nu, uc, uv, dinv = (g[f"k{level}_{k}"] for k in ("nl", "lc", "lv", "nu", "uc", "uv", "dinv"))
+        lp, up = f["lp"], f["up"]
+        assert np.array_equal(np.diff(lp) - 1, nl) and np.array_equal(np.diff(up) - 1, nu)
+        a = b = 0
+        for i in range(n):
+            order = np.argsort(uc[b:b + nu[i]], kind="stable")
+            assert np.array_equal(f["li"][lp[i]:lp[i + 1] - 1], lc[a:a + nl[i]])
+            assert np.array_equal(f["ui"][up[i] + 1:up[i + 1]], uc[b:b + nu[i]][order])
+            assert np.allclose(f["lv"][lp[i]:lp[i + 1] - 1], lv[a:a + nl[i]], rtol=2e-5, atol=1e-6)
+            assert np.allclose(f["uv"][up[i] + 1:up[i + 1]], uv[b:b + nu[i]][order], rtol=2e-5, atol=1e-6)
+            assert np.isclose(1.0 / f["uv"][up[i]], dinv[i], rtol=2e-5)
+            a += nl[i]; b += nu[i]
+
+
 def test_iluk_improves_convergence_and_respects_blocks(bg, oracle):
     g = load_golden("pg2d_24x20")
     rp, ci, v, b = g["rowptr"], g["col"], g["val"], g["b"]

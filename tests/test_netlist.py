@@ -81,15 +81,11 @@ def same_matrix(mine, ref):
             and np.array_equal(a.col[ka], b.col[kb]) and np.array_equal(a.data[ka], b.data[kb]))
 
 
-def assert_matches_reference(text, tmp_path, name="case.sp"):
-    path = tmp_path / name
-    path.write_text(text)
-    N = bg.Netlist(path)
-    R = ref_parse(path)
+def compare_with_reference(N, R):
     i = N.info
     assert (i.n_nodes, i.n_inductors, i.n_vsources, i.n_isources, i.size) == (R["n_nodes"], R["n_l"], R["n_vs"], R["n_is"], R["size"])
     assert (i.tstep, i.tstop) == (R["tstep"], R["tstop"])
-    assert [N.row_name(r) for r in range(i.n_nodes)] == R["names"]
+    assert [N.row_name(r) for r in range(i.n_nodes)] == list(R["names"])
     for w in "GCB":
         assert same_matrix(dense(N, w), R[w]), w
     assert np.array_equal(N.ports, R["ports"])
@@ -98,7 +94,39 @@ def assert_matches_reference(text, tmp_path, name="case.sp"):
         # (src/parser.cpp:2367-2370, 2858-2867); otherwise it stays padded to a multiple of PWL_SIZE = 800
         assert len(rt) == len(t) or (len(rt) % 800 == 0 and len(rt) > len(t)), k
         assert np.array_equal(t, rt[:len(t)]) and np.array_equal(v, rv[:len(t)]), k
+
+
+def assert_matches_reference(text, tmp_path, name="case.sp"):
+    path = tmp_path / name
+    path.write_text(text)
+    N = bg.Netlist(path)
+    R = ref_parse(path)
+    compare_with_reference(N, R)
     return N, R
+
+
+def load_reference_golden(name):
+    """tests/golden/netlist_*.npz (tests/golden/make_frontend_golden.py): what the reference's compiled parser produced"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    nn, nl, nv, ni = (int(x) for x in g["counts"])
+    R = dict(n_nodes=nn, n_l=nl, n_vs=nv, n_is=ni, size=nn + nl + nv, tstep=float(g["tran"][0]), tstop=float(g["tran"][1]),
+             ports=g["ports"], names=[str(x) for x in g["names"]], pulse_time=g["pulse_time"], pulse_val=g["pulse_val"])
+    for w in "GCB":
+        R[w] = sp.csc_matrix((g[w + "_x"], g[w + "_i"], g[w + "_p"]), shape=tuple(int(x) for x in g[w + "_shape"]))
+    ptr = g["src_ptr"]
+    R["sources"] = [(g["src_t"][a:b], g["src_v"][a:b]) for a, b in zip(ptr[:-1], ptr[1:])]
+    return str(g["text"]), R
+
+
+@pytest.mark.parametrize("name", ["netlist_grid_pwl", "netlist_grid_pulse", "netlist_mixed"])
+def test_equals_committed_reference_output(name):
+    """the same comparison against the committed output of the reference's parser (runs without /root/reference)"""
+    text, R = load_reference_golden(name)
+    N = bg.Netlist(text, text=True)
+    compare_with_reference(N, R)
+    if len(R["pulse_time"]):      # the reference records the PULSE parameters of current sources only
+        cur = N.pulse_src >= N.info.n_vsources
+        assert np.array_equal(N.pulse_time[cur], R["pulse_time"]) and np.array_equal(N.pulse_val[cur], R["pulse_val"])
 
 
 TINY = """* two nodes, an inductor, a pad and a load
@@ -155,10 +183,11 @@ def test_equals_reference_parser_on_grids(tmp_path, load):
         assert np.array_equal(N.pulse_src, N.info.n_vsources + np.arange(N.info.n_isources))
 
 
-@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libref_parser.so not built (needs /root/reference)")
-def test_equals_reference_parser_on_mixed_elements(tmp_path):
+def mixed_netlist():
     """inductors, floating and grounded sources in both orientations, every scale letter, parallel and repeated
-    elements (duplicate stamps add up in file order), continuation lines, upper/lower case keywords"""
+    elements, continuation lines, upper/lower case keywords.  (A PULSE source sits last in its list: the reference cuts
+    a PULSE table that a PWL source follows down to the previous PWL's length, src/parser.cpp:2553-2556 -- a defect
+    the product does not share.)"""
     rng = np.random.default_rng(5)
     names = [f"n{k}" for k in range(30)]
     lines = ["* mixed"]
@@ -172,9 +201,14 @@ def test_equals_reference_parser_on_mixed_elements(tmp_path):
               "V5 n5 gnd 0 PULSE(0 1.2 1n 0.1n 0.1n 2n 5n)",
               "I1 n6 0 PWL(0 0 1n 1m 3n 0)", "i2 0 n7 pwl(0.5n 2m 1n 3m)", "I4 n10 0 PWL(0 1m 4n 2m)", "I3 n8 n9 0 PULSE(0 5m 0 1n 1n 3n 10n)",
               ".TRAN 0.1n 20n", ".print tran v(n3) v(n29) v(n0)", ".end"]
-    # (a PULSE source sits last in its list: the reference cuts a PULSE table that a PWL source follows down to the
-    # previous PWL's length, src/parser.cpp:2553-2556 -- a defect the product does not share)
-    N, R = assert_matches_reference("\n".join(lines) + "\n", tmp_path)
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libref_parser.so not built (needs /root/reference)")
+def test_equals_reference_parser_on_mixed_elements(tmp_path):
+    """inductors, floating and grounded sources in both orientations, every scale letter, parallel and repeated
+    elements (duplicate stamps add up in file order), continuation lines, upper/lower case keywords"""
+    N, R = assert_matches_reference(mixed_netlist(), tmp_path)
     assert np.array_equal(N.pulse_time, [[1e-9, 0.1 * 10.0 ** -9, 0.1 * 10.0 ** -9, 2 * 10.0 ** -9, 5 * 10.0 ** -9], [0, 1e-9, 1e-9, 3 * 10.0 ** -9, 10 * 10.0 ** -9]])
     assert list(N.pulse_src) == [4, 5 + 3]
     assert np.array_equal(R["pulse_time"][0], N.pulse_time[1])   # the reference records current sources only
