@@ -156,6 +156,35 @@ def test_c2_split_ilupp_factors_match_oracle(bg, ctx, oracle, nx, c2):
     oracle.ilupp_free(fac)
 
 
+def test_netlist_mna_system_through_the_power_grid_path(bg, ctx, oracle):
+    """The reference's power-grid flow from the netlist on: parser -> full MNA system (voltage-source rows with a zero
+    diagonal, src/mna.cpp:204-218) -> ILU++ factors with pivoting (threshold 1.2) -> setPrecondPG / GMRESilu_GPU.
+    bg_netlist_* (bit-exact with the reference's parser, tests/test_netlist.py) feeds bg_precond_create_split; the
+    device solve equals the oracle's GMRESilu on the same factors."""
+    if oracle.ilupp() is None:
+        pytest.skip("oracle/_ref/libilupp.so not present")
+    from b200gmres import synth
+
+    N = bg.Netlist(synth.pg2d_netlist(40, 36, seed=synth.SEED_BASE + 31, pad_pitch=8), text=True)
+    n = N.info.size
+    rp, ci, v = N.G
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    assert int((A.diagonal() == 0).sum()) == N.info.n_vsources > 0
+    b = sp.csr_matrix((N.B[2], N.B[1], N.B[0]), shape=(n, N.info.n_sources)) @ N.u(0.0)
+    Ac = A.tocsc()
+    Ac.sort_indices()
+    fac = oracle.ilupp_factor(n, Ac.indptr, Ac.indices, Ac.data, threshold=1.2, mem_factor=1.0)
+    keys = ("lp", "li", "lv", "up", "ui", "uv", "middle", "lscale", "rscale", "permRow", "permCol")
+    pc = oracle.Precond(oracle.PC_SPLIT, n, "f64", **{k: fac[k] for k in keys})
+    flag, xo, it, res, _ = oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, 1e-8, pc)
+    assert flag == 0
+    M = bg.Precond.split(ctx, *[fac[k] for k in keys], dtype=bg.F64)
+    r, x = gpu_solve(bg, ctx, rp, ci, v, b, M, tol=1e-8, max_iter=10000, orth=bg.ORTH_MGS)
+    check(r, x, flag, it, res, xo, "netlist MNA + ILU++")
+    M.close()
+    oracle.ilupp_free(fac)
+
+
 def test_c3_th3d_64_level_and_tiles_match_oracle(bg, ctx, oracle):
     from b200gmres import synth
 

@@ -246,6 +246,32 @@ def test_reduced_formulation_solves_the_same_circuit():
         bg.Netlist("V1 a 0 1\nV2 a 0 2\nR1 a 0 1\n.end\n", formulation=bg.NETLIST_REDUCED, text=True)
 
 
+def test_mna_system_is_solvable_the_reference_way():
+    """full MNA formulation (zero diagonal on the voltage-source rows) + the reference's ILU++ with pivoting + its
+    GMRESilu (CPU oracle): the flow of mna_solve_gpu_gmres.cpp from the parser on, checked against a direct solve"""
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as oracle
+
+    oracle.build()
+    if oracle.ilupp() is None:
+        pytest.skip("oracle/_ref/libilupp.so not built (needs /root/reference)")
+    N = bg.Netlist(synth.pg2d_netlist(40, 36, seed=synth.SEED_BASE + 31, pad_pitch=8), text=True)
+    n = N.info.size
+    rp, ci, v = N.G
+    A = dense(N, "G")
+    assert int((A.diagonal() == 0).sum()) == N.info.n_vsources == 20
+    b = dense(N, "B") @ N.u(0.0)
+    Ac = A.tocsc()
+    Ac.sort_indices()
+    fac = oracle.ilupp_factor(n, Ac.indptr, Ac.indices, Ac.data, threshold=1.2, mem_factor=1.0)
+    keys = ("lp", "li", "lv", "up", "ui", "uv", "middle", "lscale", "rscale", "permRow", "permCol")
+    pc = oracle.Precond(oracle.PC_SPLIT, n, "f64", **{k: fac[k] for k in keys})
+    flag, xo, it, res, _ = oracle.gmres(rp, ci, v, b, np.zeros(n), 32, 10000, 1e-8, pc)
+    oracle.ilupp_free(fac)
+    xd = spl.spsolve(Ac, b)
+    assert flag == 0 and it < 40 and np.linalg.norm(xo - xd) <= 1e-6 * np.linalg.norm(xd)
+
+
 def test_include_and_errors(tmp_path):
     (tmp_path / "sub").mkdir()
     (tmp_path / "sub" / "grid.inc").write_text("R2 b 0 2\nR3 b c 3\n* end of include\n")
