@@ -578,6 +578,26 @@ extern "C" int bg_netlist_get_matrix(bg_netlist_t N, int which, int* rowptr, int
   std::copy(M->v.begin(), M->v.end(), val);
   return BG_OK;
 }
+// the same matrix column-compressed with 64-bit indices and rows ascending inside a column: exactly the p / i / x
+// arrays of the cs_dl the reference's parser_wrapper hands on (matrix::sort + mat2csdl, src/matrix.cpp:127-135, 343-362)
+extern "C" int bg_netlist_get_matrix_csc(bg_netlist_t N, int which, int64_t* colptr, int64_t* row, double* val) {
+  if (!N || !colptr) return BG_ERR_ARG;
+  const Csr* M = which == 'G' || which == 'g' ? &N->G : which == 'C' || which == 'c' ? &N->C : which == 'B' || which == 'b' ? &N->B : nullptr;
+  if (!M) { bg::set_error("bg_netlist_get_matrix_csc: which must be 'G', 'C' or 'B'"); return BG_ERR_ARG; }
+  if (!M->ci.empty() && (!row || !val)) return BG_ERR_ARG;
+  const int nc = M->n_cols;
+  for (int j = 0; j <= nc; ++j) colptr[j] = 0;
+  for (int c : M->ci) colptr[(size_t)c + 1]++;
+  for (int j = 0; j < nc; ++j) colptr[(size_t)j + 1] += colptr[j];
+  std::vector<int64_t> next(colptr, colptr + nc);
+  for (int i = 0; i < M->n_rows; ++i)   // rows visited in ascending order: every column comes out sorted
+    for (int p = M->rp[i]; p < M->rp[(size_t)i + 1]; ++p) {
+      const int64_t q = next[(size_t)M->ci[p]]++;
+      row[q] = i;
+      val[q] = M->v[p];
+    }
+  return BG_OK;
+}
 extern "C" int bg_netlist_get_sources(bg_netlist_t N, int* kind, int* pwl_ptr, double* pwl_t, double* pwl_v, int* pulse_src,
                                       double* pulse_time, double* pulse_val) {
   if (!N) return BG_ERR_ARG;

@@ -509,6 +509,15 @@ class Netlist:
         _chk(lib().bg_netlist_get_matrix(self.h, ord(which), _p(rp), _p(ci), _p(v)))
         return rp, ci, v
 
+    def csc(self, which):
+        """(colptr, row, val) with int64 indices: the cs_dl arrays the reference's parser_wrapper returns for 'G', 'C', 'B'"""
+        i = self.info
+        ncol = i.n_sources if which == "B" else i.size
+        nnz = {"G": i.nnz_g, "C": i.nnz_c, "B": i.nnz_b}[which]
+        cp, ri, x = np.zeros(ncol + 1, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz)
+        _chk(lib().bg_netlist_get_matrix_csc(self.h, ord(which), _p(cp), _p(ri), _p(x)))
+        return cp, ri, x
+
     @property
     def pwl(self):
         """per source (times, values): the `pwl` argument of Transient"""

@@ -197,6 +197,9 @@ BG_API int bg_netlist_parse(const char* text, int64_t len, const char* include_d
 BG_API int bg_netlist_get_info(bg_netlist_t N, bg_netlist_info* info);
 /* which = 'G', 'C' or 'B'; rowptr[size + 1], col/val[nnz_*] */
 BG_API int bg_netlist_get_matrix(bg_netlist_t N, int which, int* rowptr, int* col, double* val);
+/* the same matrix as the p / i / x arrays of the cs_dl (column-compressed, 64-bit indices, rows ascending inside a
+   column) parser_wrapper returns as Gs, Cs, Bs: colptr[columns + 1], row / val[nnz_*] */
+BG_API int bg_netlist_get_matrix_csc(bg_netlist_t N, int which, int64_t* colptr, int64_t* row, double* val);
 /* per source (column of B): kind[n_sources]; the breakpoint table the reference keeps, pwl_ptr[n_sources + 1],
    pwl_t / pwl_v[n_pwl_points] (DC: two points 0 and tstop; PWL: a point at t = 0 is added when the first time is not
    0; PULSE: six per period, the last time cut to tstop like src/parser.cpp:2497-2518 does -- possibly below its

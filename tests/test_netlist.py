@@ -88,6 +88,9 @@ def compare_with_reference(N, R):
     assert [N.row_name(r) for r in range(i.n_nodes)] == list(R["names"])
     for w in "GCB":
         assert same_matrix(dense(N, w), R[w]), w
+        cp, ri, x = N.csc(w)      # the cs_dl arrays themselves, element for element
+        ref = R[w].tocsc()
+        assert np.array_equal(cp, ref.indptr) and np.array_equal(ri, ref.indices) and np.array_equal(x, ref.data), w
     assert np.array_equal(N.ports, R["ports"])
     for k, ((t, v), (rt, rv)) in enumerate(zip(N.pwl, R["sources"])):
         # the reference trims a PWL table only when the next source of the list is PWL too or at .end
