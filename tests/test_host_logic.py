@@ -234,6 +234,33 @@ def test_iluk_pattern_equals_vendored_itsol(bg, case):
         prev_nnz = L.nnz + U.nnz
 
 
+@pytest.mark.skipif(not os.path.exists(REF_ILUK), reason="oracle/_ref/libref_iluk.so not built (needs /root/reference)")
+def test_iluk_fuzz_against_vendored_itsol(bg):
+    """40 random sparse matrices (non-symmetric patterns, random row lengths, well-scaled values so that no fill
+    vanishes): strictly-lower and strictly-upper patterns of every row identical with lofC's for levels 0..3"""
+    for seed in range(40):
+        rng = np.random.default_rng(500 + seed)
+        n = int(rng.integers(20, 160))
+        M = sp.random(n, n, density=float(rng.uniform(0.02, 0.08)), random_state=int(seed), format="csr")
+        M.data = rng.uniform(0.5, 1.5, size=M.nnz) * rng.choice([-1.0, 1.0], size=M.nnz)
+        M = sp.csr_matrix(M + sp.diags(np.asarray(abs(M).sum(axis=1)).ravel() + 1.0))
+        M.sort_indices()
+        rp, ci, v = M.indptr, M.indices, M.data
+        for level in range(4):
+            f = bg.host_iluk(rp, ci, v, level)
+            nl, lc, lv, nu, uc, uv, dinv = itsol_iluk(rp, ci, v, level)
+            lp, up = f["lp"], f["up"]
+            small = min(np.abs(lv).min() if len(lv) else 1.0, np.abs(uv).min() if len(uv) else 1.0)
+            if small < 1e-8:
+                continue        # a vanishing fill entry: the structural-zero rule would remove it (covered above)
+            assert np.array_equal(np.diff(lp) - 1, nl) and np.array_equal(np.diff(up) - 1, nu), (seed, level)
+            a = b = 0
+            for i in range(n):
+                assert np.array_equal(f["li"][lp[i]:lp[i + 1] - 1], lc[a:a + nl[i]]), (seed, level, i)
+                assert np.array_equal(f["ui"][up[i] + 1:up[i + 1]], np.sort(uc[b:b + nu[i]])), (seed, level, i)
+                a += nl[i]; b += nu[i]
+
+
 @pytest.mark.parametrize("name", ["iluk_pg2d_13x11", "iluk_th3d_6x5x4"])
 def test_iluk_equals_committed_itsol_output(bg, name):
     """the same pin against the committed output of the vendored ITSOL code (tests/golden/make_frontend_golden.py)"""
