@@ -15,7 +15,7 @@
 //   B200GMRES_DEVICE=<id>      device ordinal (default 0; the reference hard-codes 1, setGPUdevice.cu:24)
 //   B200GMRES_TRSV=block       block-Jacobi ILU(0) solves (performance mode) instead of the
 //                              reference-exact global level schedule, for MyILU0 / MyILUK
-//   B200GMRES_ORTH=mgs|cgs     strict modified Gram-Schmidt (reference order) or fused CGS (default)
+//   B200GMRES_ORTH=mgs|cgs     strict modified Gram-Schmidt (reference order, default) or fused CGS (restart <= 32)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
