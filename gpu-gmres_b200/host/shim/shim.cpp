@@ -121,9 +121,20 @@ int run_gmres(bg_solver_t S, bg_matrix_t A, Preconditioner& M, const float* d_b,
   bg_gmres_opts o;
   bg_gmres_opts_default(&o);
   o.m = m; o.max_iter = *max_iter; o.tol = (double)*tol; o.orth = orth_mode(o.m);
+  // the reference's GMRES_SHOW_RESID_PROGRESS build prints one "DEV---resid" line per inner iteration
+  // (src/gmres.cu:2373-2397); here the device records the residual history and the lines are printed after the solve
+  const char* show = std::getenv("B200GMRES_SHOW_RESID_PROGRESS");
+  const bool progress = show && show[0] == '1';
+  if (progress) o.history_cap = 4096;
   bg_gmres_result r;
   const int rc = bg_gmres_solve(ctx(), S, A, (bg_precond_t)M.bg_handle, d_b, d_x, &o, &r);
   if (rc < 0) die("bg_gmres_solve");
+  if (progress) {
+    std::vector<double> hist(4096);
+    int len = 0;
+    if (bg_solver_get_history(S, hist.data(), (int)hist.size(), &len) >= 0)
+      for (int k = 0; k < len; ++k) std::printf("DEV---resid: %e < %e\n", hist[k], (double)*tol);
+  }
   *max_iter = r.iters;
   *tol = (float)r.resid;
   return rc;  // BG_OK (0) or BG_NOT_CONVERGED (1)
