@@ -249,6 +249,32 @@ def test_reduced_formulation_solves_the_same_circuit():
         bg.Netlist("V1 a 0 1\nV2 a 0 2\nR1 a 0 1\n.end\n", formulation=bg.NETLIST_REDUCED, text=True)
 
 
+REF_CONV_SO = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_SO) and os.path.exists(REF_CONV_SO)), reason="oracle/_ref not built (needs /root/reference)")
+def test_handover_to_the_solver_equals_the_reference_chain(tmp_path):
+    """the reference hands its parser's cs_dl matrices to the GPU solver through
+    LDcsc2csrMySpMatrix (src/formatConvert.cpp:300-334: COO, cycle-chasing COO->CSR, per-row bubble sort, values cast
+    to float).  The CSR bg_netlist_get_matrix returns, cast to float, is that matrix element for element."""
+    L = C.CDLL(REF_CONV_SO)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k, text in enumerate((synth.pg2d_netlist(14, 11, seed=synth.SEED_BASE + 41, pad_pitch=4, nsteps=8, load="pwl"), mixed_netlist(), random_netlist(77))):
+        path = tmp_path / f"h{k}.sp"
+        path.write_text(text)
+        N, R = bg.Netlist(path), ref_parse(path)
+        for w in "GC":
+            M = R[w].tocsc()          # the reference parser's own arrays
+            if M.nnz == 0:
+                continue
+            n = M.shape[0]
+            cp, ri, x = M.indptr.astype(np.int64), M.indices.astype(np.int64), np.ascontiguousarray(M.data)
+            rp, ci, v = np.zeros(n + 1, np.int32), np.zeros(M.nnz, np.int32), np.zeros(M.nnz, np.float32)
+            L.ref_LDcsc2csr(C.c_long(n), C.c_long(n), p(cp), p(ri), p(x), p(rp), p(ci), p(v))
+            mine = getattr(N, w)
+            assert np.array_equal(rp, mine[0]) and np.array_equal(ci, mine[1]) and np.array_equal(v, mine[2].astype(np.float32)), (k, w)
+
+
 def random_netlist(seed):
     """a random flat netlist inside the dialect both parsers accept (no PWL left open on its first line, no PULSE source
     followed by a PWL one -- the reference's defects listed in DESIGN.md)"""
