@@ -533,8 +533,23 @@ class Netlist:
         return out
 
     def u(self, t):
-        """source values at time t (piecewise-linear tables, held at their end values outside)"""
-        return np.array([np.interp(t, tt, vv) if len(tt) else 0.0 for tt, vv in self.pwl])
+        """source values at time t: piecewise-linear tables held at their end values outside; PULSE sources from their
+        records like the device does (gen_PULSEut_kernel, src/kernels.cu:224-246) -- their tables are the reference's
+        expansion, whose last breakpoint is cut to tstop and need not be monotone"""
+        u = np.array([np.interp(t, tt, vv) if len(tt) else 0.0 for tt, vv in self.pwl])
+        for k, (td, tr, tf, tw, tp), (vlo, vhi) in zip(self.pulse_src, self.pulse_time, self.pulse_val):
+            mt = t - np.floor(t / tp) * tp
+            if mt < td:
+                u[k] = vlo
+            elif mt < td + tr:
+                u[k] = vlo + (mt - td) * (vhi - vlo) / tr
+            elif mt < td + tr + tw:
+                u[k] = vhi
+            elif mt < td + tr + tw + tf:
+                u[k] = vhi - (mt - td - tr - tw) * (vhi - vlo) / tf
+            else:
+                u[k] = vlo
+        return u
 
     def node_row(self, name) -> int:
         """row of a node; -1 ground, -2 unknown, -3 eliminated by BG_NETLIST_REDUCED"""

@@ -374,6 +374,16 @@ def test_mna_system_is_solvable_the_reference_way():
     assert flag == 0 and it < 40 and np.linalg.norm(xo - xd) <= 1e-6 * np.linalg.norm(xd)
 
 
+def test_source_values_follow_tables_and_pulse_records():
+    N = bg.Netlist("R1 a 0 1\nV1 a 0 0 PULSE(0.2 1.2 1n 0.5n 0.25n 2n 5n)\nI1 a 0 PWL(1n 1m 3n 3m)\n.tran 0.1n 7n\n.end\n", text=True)
+    (tv, vv), (ti, vi) = N.pwl
+    assert len(tv) == 12 and tv[-1] == 7 * 10.0 ** -9 and tv[-2] > tv[-1]      # the reference's cut last period
+    for t, want in ((0.0, 0.2), (1.25e-9, 0.7), (2e-9, 1.2), (3.625e-9, 0.7), (4.9e-9, 0.2), (6.25e-9, 0.7), (6.9e-9, 1.2)):
+        assert abs(N.u(t)[0] - want) < 1e-12, t
+    assert np.allclose(N.u(0.0)[1], 1e-3) and np.allclose(N.u(2e-9)[1], 2e-3) and np.allclose(N.u(9e-9)[1], 3e-3)
+    assert [len(t) for t, _ in N.transient_pwl] == [1, 3]
+
+
 def test_include_and_errors(tmp_path):
     (tmp_path / "sub").mkdir()
     (tmp_path / "sub" / "grid.inc").write_text("R2 b 0 2\nR3 b c 3\n* end of include\n")
