@@ -32,6 +32,24 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)])
 
 
+def test_c_example_builds_and_fails_loudly_without_a_gpu(bg, tmp_path):
+    """examples/solve_csr.c: plain C99 against the C ABI; without a device it must stop at bg_context_create with the
+    library's message (exit status 3) -- never compute on the CPU; with a device it solves (status 0)"""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "solve_csr")
+    libdir = os.path.join(root, "gpu-gmres_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "solve_csr.c"),
+                           "-L", libdir, "-lb200gmres", "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    out = subprocess.run([exe, "40"], capture_output=True, text=True)
+    assert out.returncode in (0, 3), out.stdout + out.stderr
+    if out.returncode == 3:
+        assert "no CPU fallback" in out.stderr
+    else:
+        assert "flag 0" in out.stdout
+
+
 def test_no_cpu_fallback(bg):
     if bg.device_count() > 0:
         pytest.skip("GPU present")
