@@ -15,6 +15,8 @@ sys.path.insert(0, os.path.join(ROOT, "gpu-gmres_b200", "python"))
 import b200gmres as bg  # noqa: E402
 from b200gmres import synth  # noqa: E402
 
+bg.build()  # make -C gpu-gmres_b200 when the library is not there yet (host code only is exercised here)
+
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_parser.so")
 
 
